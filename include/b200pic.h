@@ -1,0 +1,209 @@
+/* b200pic.h — C-ABI of libb200pic.so: a B200 (sm_100a) implementation of runko's
+ * per-timestep PIC hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one
+ * method of the reference's pybind11-exposed C++ tile API; the reference
+ * interface each one stands in for is cited as `file:line` relative to
+ * /root/reference.  INTEGRATION.md shows the pybind11-side stubs a runko
+ * maintainer would add to `src/runko/bindings/py{emf,pic}.c++` to call these.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *  - every function returns 0 on success, non-zero on failure; the message is
+ *    retrievable with b2p_last_error() (thread-local).  B2P_ERR_LOGIC mirrors
+ *    the reference's std::logic_error, everything else std::runtime_error;
+ *  - all device work is enqueued on one CUDA stream per process and is
+ *    asynchronous; getters and b2p_sync() synchronise (SURVEY.md §8b
+ *    "Threading");
+ *  - field arrays crossing the boundary are fp32, component-major
+ *    `buf[c*N + (i*Ny + j)*Nz + k]` (k fastest), the reference's own layout
+ *    (external/tyvi/src/tyvi/mdgrid_buffer.h:61-65);
+ *  - particle arrays are SoA fp32 + uint64 ids (src/runko/pic/particle.h:73-78).
+ */
+#ifndef B200PIC_H
+#define B200PIC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2P_MAX_SPECIES 8
+#define B2P_HALO 3 /* src/runko/emf/common.h:9 */
+
+enum { B2P_OK = 0, B2P_ERR_RUNTIME = 1, B2P_ERR_LOGIC = 2, B2P_ERR_CUDA = 3 };
+
+/* src/runko/communication_common.h:30-38 */
+enum {
+  B2P_COMM_EMF_J               = 0,
+  B2P_COMM_EMF_E               = 1,
+  B2P_COMM_EMF_B               = 2,
+  B2P_COMM_PIC_PARTICLE        = 3,
+  B2P_COMM_PIC_PARTICLE_EXTRA  = 4,
+  B2P_COMM_NUMBER_OF_PARTICLES = 5,
+  B2P_COMM_EMF_J_EXCHANGE      = 6
+};
+
+enum { B2P_PROPAGATOR_FDTD2 = 0, B2P_PROPAGATOR_STENCIL = 1 };          /* emf/tile.h:27 */
+enum { B2P_FILTER_NONE = -1, B2P_FILTER_BINOMIAL2 = 0, B2P_FILTER_BINOMIAL2_UNROLLED = 1 }; /* emf/tile.h:28 */
+enum { B2P_PUSHER_NONE = -1, B2P_PUSHER_BORIS = 0, B2P_PUSHER_HIGUERA_CARY = 1, B2P_PUSHER_FARADAY = 2 }; /* pic/tile.h:34 */
+enum { B2P_INTERP_LINEAR_1ST = 0, B2P_INTERP_LINEAR_1ST_UNROLLED = 1 }; /* pic/tile.h:35 */
+enum { B2P_DEPOSIT_ZIGZAG_1ST = 0, B2P_DEPOSIT_ZIGZAG_1ST_ATOMIC = 1 }; /* pic/tile.h:36 */
+
+/* Flat POD form of the Python config object the reference parses with
+ * toolbox::ConfigParser (src/runko/tools/config_parser.c++:14-95); the keys are
+ * the ones emf::Tile / pic::Tile read (emf/tile.c++:86-142, pic/tile.c++:28-147). */
+typedef struct b2p_config {
+  int32_t  n_tiles[3];          /* "n_tiles" */
+  int32_t  n_cells[3];          /* "n_cells_per_tile" (each >= 3) */
+  double   cfl;                 /* "cfl" */
+  int32_t  field_propagator;    /* B2P_PROPAGATOR_* */
+  int32_t  current_filter;      /* B2P_FILTER_* */
+  /* stencil[a] is emf::StencilAxisCoeffs::M for axis a (emf/stencil_coefficients.h:30-64);
+   * entry [a][0][0] (alpha) is ignored on input and recomputed from the others. */
+  float    stencil[3][3][5];
+  int32_t  n_species;           /* number of contiguous q<i>/m<i> pairs; 0 = emf-only tile */
+  double   q[B2P_MAX_SPECIES];  /* "q<i>" signed charge */
+  double   m[B2P_MAX_SPECIES];  /* "m<i>" |m/q| */
+  int32_t  particle_pusher;     /* B2P_PUSHER_* */
+  int32_t  field_interpolator;  /* B2P_INTERP_* */
+  int32_t  current_depositer;   /* B2P_DEPOSIT_* */
+  uint64_t prealloc_per_species;/* "prealloc_per_species" */
+} b2p_config;
+
+/* runko::ParticleState<float> — the 32-byte AoS migration wire format
+ * (src/runko/particles_common.h:26-34). */
+typedef struct b2p_particle_state {
+  float    pos[3];
+  float    vel[3];
+  uint64_t id;
+} b2p_particle_state;
+
+typedef struct b2p_tile b2p_tile;
+typedef struct b2p_grid b2p_grid;
+
+/* ---- process-level ------------------------------------------------------ */
+const char* b2p_last_error(void);
+const char* b2p_version(void);
+/* Select the CUDA device for this process (one process per GPU). Fails loudly
+ * when no CUDA device is usable — there is no CPU fallback. */
+int b2p_init(int device);
+int b2p_sync(void);
+/* tools._get_gpu_mem_kB (src/runko/tools/gpu_memory.h:16-28) */
+int64_t b2p_gpu_mem_kB(void);
+
+/* ---- tile life cycle ---------------------------------------------------- */
+/* emf::Tile / pic::Tile constructor (emf/tile.c++:82-181, pic/tile.c++:119-147). */
+int  b2p_tile_create(const b2p_config* cfg, const int32_t idx[3], b2p_tile** out);
+void b2p_tile_destroy(b2p_tile* t);
+/* corgi::Tile mins/maxs (emf/tile.c++:162-170), as doubles. */
+int  b2p_tile_bounds(const b2p_tile* t, double mins[3], double maxs[3]);
+
+/* ---- fields (emf::Tile) ------------------------------------------------- */
+/* YeeLattice::set_EBJ (emf/yee_lattice.h:519-553): upload interior (with_halo=0,
+ * arrays of 3*Nx*Ny*Nz floats) or the full haloed lattice (with_halo=1,
+ * 3*(Nx+6)(Ny+6)(Nz+6)). Any of E,B,J may be NULL (left untouched). */
+int b2p_tile_set_fields(b2p_tile* t, const float* E, const float* B, const float* J, int with_halo);
+/* YeeLattice::get_EBJ / get_EBJ_with_halo (emf/yee_lattice.c++:91-168). */
+int b2p_tile_get_fields(b2p_tile* t, float* E, float* B, float* J, int with_halo);
+int b2p_tile_push_half_b(b2p_tile* t);   /* emf::Tile::push_half_b  emf/tile.c++:359-375 */
+int b2p_tile_push_e(b2p_tile* t);        /* emf::Tile::push_e       emf/tile.c++:379-394 */
+int b2p_tile_add_current(b2p_tile* t);   /* emf::Tile::add_current  emf/yee_lattice.c++:171-179 */
+int b2p_tile_filter_current(b2p_tile* t);/* emf::Tile::filter_current emf/tile.c++:405-426 */
+int b2p_tile_clear_current(b2p_tile* t); /* YeeLattice::clear_current emf/yee_lattice.c++:317-321 */
+/* YeeLattice::total_energy_{B,E} (emf/yee_lattice.c++:383-428). */
+int b2p_tile_field_energy(b2p_tile* t, double* energy_B, double* energy_E);
+
+/* ---- particles (pic::Tile) ---------------------------------------------- */
+/* pic::Tile::inject / batch_inject_* after the Python generator has run
+ * (pic/tile.c++:207-322): doubles are narrowed to fp32 and ids
+ * (tile_tag<<40)|ordinal are assigned here (pic/tile.c++:470-481). */
+int b2p_tile_inject(b2p_tile* t, int sp, uint64_t n,
+                    const double* x, const double* y, const double* z,
+                    const double* ux, const double* uy, const double* uz);
+/* Raw container upload including dead slots (id == UINT64_MAX); replaces the
+ * container. Test / restart hook; no reference equivalent. */
+int b2p_tile_set_particles(b2p_tile* t, int sp, uint64_t n,
+                           const float* x, const float* y, const float* z,
+                           const float* ux, const float* uy, const float* uz,
+                           const uint64_t* id);
+/* ParticleContainer::size (dead or alive) — pic/particle.c++:63-67. */
+int b2p_tile_container_size(b2p_tile* t, int sp, uint64_t* n);
+/* get_positions/get_velocities/get_ids (pic/particle.c++:82-168): alive_only=1
+ * returns alive particles in container order; alive_only=0 returns the raw
+ * container. Output arrays must hold container_size entries; NULL = skip. */
+int b2p_tile_get_particles(b2p_tile* t, int sp, int alive_only,
+                           float* x, float* y, float* z,
+                           float* ux, float* uy, float* uz,
+                           uint64_t* id, uint64_t* n_out);
+int b2p_tile_push_particles(b2p_tile* t);          /* pic/tile.c++:326-365 */
+int b2p_tile_deposit_current(b2p_tile* t);         /* pic/tile.c++:369-415 */
+int b2p_tile_sort_particles(b2p_tile* t);          /* pic/tile.c++:419-438 */
+int b2p_tile_pack_outgoing_particles(b2p_tile* t); /* pic/tile_communication.c++:68-96 */
+/* The sort score of every slot (pic/tile.c++:430-435, pic/particle.h:607-614). */
+int b2p_tile_sort_keys(b2p_tile* t, int sp, uint32_t* keys);
+/* Outgoing AoS buffer and the 27*n_species cumulative end offsets
+ * (pic/tile.h:84-85). buf may be NULL to query only ends / n_out. */
+int b2p_tile_get_outgoing(b2p_tile* t, b2p_particle_state* buf, uint64_t cap,
+                          uint64_t* ends, uint64_t* n_out);
+/* ParticleContainer::total_kinetic_energy (pic/particle.c++:352-377). */
+int b2p_tile_kinetic_energy(b2p_tile* t, int sp, double* energy, uint64_t* container_size);
+
+/* ---- grid (corgi::Grid surface used by runko/simulation.py) -------------- */
+int  b2p_grid_create(const b2p_config* cfg, b2p_grid** out);
+void b2p_grid_destroy(b2p_grid* g);
+/* corgi::Grid::add_tile (external/corgi/src/corgi/corgi.h:434-467): the grid
+ * borrows the tile; the caller keeps ownership. */
+int  b2p_grid_add_tile(b2p_grid* g, b2p_tile* t);
+/* corgi::Grid::local_communication (corgi.h:1697-1718) for all local tiles,
+ * mode = B2P_COMM_*. */
+int  b2p_grid_local_communication(b2p_grid* g, int mode);
+/* The `for tile in local_tiles: tile.<method>()` loops of
+ * runko/simulation.py:235-253, batched into one enqueue per phase. */
+int b2p_grid_push_half_b(b2p_grid* g);
+int b2p_grid_push_e(b2p_grid* g);
+int b2p_grid_add_current(b2p_grid* g);
+int b2p_grid_filter_current(b2p_grid* g);
+int b2p_grid_push_particles(b2p_grid* g);
+int b2p_grid_pack_outgoing_particles(b2p_grid* g);
+int b2p_grid_sort_particles(b2p_grid* g);
+int b2p_grid_deposit_current(b2p_grid* g);
+/* One lap of projects/pic-turbulence/pic.py:187-221 (diagnostics/IO excluded);
+ * sort when lap % 5 == 0. */
+int b2p_grid_step_pic(b2p_grid* g, int64_t lap);
+/* One lap of projects/emf-wave/emf.py:48-62. */
+int b2p_grid_step_emf(b2p_grid* g);
+/* Σ over local tiles of total_energy_{B,E}, Σ kinetic energy and Σ container
+ * sizes per species (io/pic_average_kinetic_energy.h:24-155,
+ * io/emf_average_field_energy_density.h). */
+int b2p_grid_energies(b2p_grid* g, double* energy_B, double* energy_E,
+                      double* kinetic /*n_species*/, uint64_t* sizes /*n_species*/);
+/* Synthetic uniform thermal plasma generated on the device (bench workloads
+ * too large to stage through the host): ppc particles per cell per species,
+ * positions cell corner + U[0,1)^3, momenta Maxwellian with spread `delgam`,
+ * counter-based RNG seeded by (seed, tile, species). No reference equivalent. */
+int b2p_grid_inject_thermal(b2p_grid* g, int ppc, double delgam, uint64_t seed);
+int b2p_grid_set_uniform_B(b2p_grid* g, float bx, float by, float bz);
+
+/* ---- multi-GPU (replaces corgi's MPI transport, corgi.h:1560-1692) ------- */
+/* 128-byte NCCL unique id, created on rank 0 and distributed by the caller. */
+int b2p_nccl_unique_id(void* id128);
+/* owner[cid] = rank owning tile cid = i + Nx*(j + Ny*k) (corgi.h:283-315),
+ * i.e. pycorgi Grid.get_mpi_grid. Creates the communicator and the exchange plan. */
+int b2p_grid_comm_init(b2p_grid* g, int rank, int nranks, const void* id128, const int32_t* owner);
+/* recv_data + send_data + wait_data of one mode (runko/simulation.py:295-319),
+ * including the number_of_particles handshake for B2P_COMM_PIC_PARTICLE. */
+int b2p_grid_external_communication(b2p_grid* g, int mode);
+
+/* ---- timing helpers for bench.py (CUDA events on the library's stream) --- */
+int b2p_timer_start(void);
+int b2p_timer_stop(float* ms);
+/* number of kernels this library has launched since process start */
+uint64_t b2p_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PIC_H */

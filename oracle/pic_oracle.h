@@ -1,0 +1,81 @@
+/* pic_oracle.h — C-ABI of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a single-source, dependency-free CPU
+ * restatement of the reference's PIC-step arithmetic (runko @ e302899e) used
+ * as the parity checker by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs.  Nothing under runko_b200/ may import,
+ * link or execute it.
+ *
+ * Parity pin: the reference ships no numeric golden vectors for this path
+ * (SURVEY.md §8c); the oracle is pinned against the reference's own
+ * known-answer / behavioural tests (tests/py/test_emf_fdtd2.py,
+ * test_emf_stencil.py, test_emf_current_filter_binomial2.py,
+ * test_pic_particle_pusher.py, test_pic_current_depositer_zigzag_1st*.py,
+ * test_pic_particle_sorting.py, tests/py-multirank/test_{emf,pic}_simulation.py),
+ * re-expressed in tests/test_oracle_reference_kats.py.  The reference itself
+ * cannot be compiled here (needs MPI, kokkos mdspan, rocThrust, GCC>=14 —
+ * see DESIGN.md).
+ */
+#ifndef PIC_ORACLE_H
+#define PIC_ORACLE_H
+#include "../include/b200pic.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_grid orc_grid;
+
+const char* orc_last_error(void);
+/* Builds ALL n_tiles tiles of the global periodic grid in this process. */
+orc_grid* orc_create(const b2p_config* cfg);
+void      orc_destroy(orc_grid* g);
+int       orc_num_tiles(const orc_grid* g);
+/* tile handle = corgi cid = i + Nx*(j + Ny*k) */
+int       orc_tile_cid(const orc_grid* g, int i, int j, int k);
+
+int orc_tile_set_fields(orc_grid* g, int t, const float* E, const float* B, const float* J, int with_halo);
+int orc_tile_get_fields(orc_grid* g, int t, float* E, float* B, float* J, int with_halo);
+int orc_tile_push_half_b(orc_grid* g, int t);
+int orc_tile_push_e(orc_grid* g, int t);
+int orc_tile_add_current(orc_grid* g, int t);
+int orc_tile_filter_current(orc_grid* g, int t);
+int orc_tile_clear_current(orc_grid* g, int t);
+int orc_tile_field_energy(orc_grid* g, int t, double* eB, double* eE);
+
+int orc_tile_inject(orc_grid* g, int t, int sp, uint64_t n,
+                    const double* x, const double* y, const double* z,
+                    const double* ux, const double* uy, const double* uz);
+int orc_tile_set_particles(orc_grid* g, int t, int sp, uint64_t n,
+                           const float* x, const float* y, const float* z,
+                           const float* ux, const float* uy, const float* uz,
+                           const uint64_t* id);
+int orc_tile_container_size(orc_grid* g, int t, int sp, uint64_t* n);
+int orc_tile_get_particles(orc_grid* g, int t, int sp, int alive_only,
+                           float* x, float* y, float* z,
+                           float* ux, float* uy, float* uz,
+                           uint64_t* id, uint64_t* n_out);
+int orc_tile_push_particles(orc_grid* g, int t);
+int orc_tile_deposit_current(orc_grid* g, int t);
+int orc_tile_sort_particles(orc_grid* g, int t);
+int orc_tile_pack_outgoing_particles(orc_grid* g, int t);
+int orc_tile_sort_keys(orc_grid* g, int t, int sp, uint32_t* keys);
+int orc_tile_get_outgoing(orc_grid* g, int t, b2p_particle_state* buf, uint64_t cap,
+                          uint64_t* ends, uint64_t* n_out);
+int orc_tile_kinetic_energy(orc_grid* g, int t, int sp, double* energy, uint64_t* container_size);
+/* Interpolated E,B at n positions (global coordinates) on tile t: out is [n][6]. */
+int orc_tile_interpolate(orc_grid* g, int t, uint64_t n, const float* x, const float* y,
+                         const float* z, float* out);
+
+int orc_local_communication(orc_grid* g, int mode);
+/* all-tile phases, `threads` workers over tiles (one tile per worker at a time:
+ * the reference's CPU execution model, serial inside a tile). */
+int orc_grid_phase(orc_grid* g, const char* phase, int threads);
+int orc_step_pic(orc_grid* g, int64_t lap, int threads);
+int orc_step_emf(orc_grid* g, int threads);
+int orc_energies(orc_grid* g, double* eB, double* eE, double* kinetic, uint64_t* sizes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

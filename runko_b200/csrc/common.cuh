@@ -1,0 +1,94 @@
+// common.cuh — shared host/device declarations of libb200pic (sm_100a).
+// Memory layout:
+//   fields   : per tile, E/B/J each 3*Ch fp32, component-major, k fastest:
+//              buf[c*Ch + (i*Hy + j)*Hz + k], H* = N* + 6 (halo 3 each side)
+//   particles: per (tile, species) SoA streams x,y,z,ux,uy,uz (fp32) + id (u64)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b200pic.h"
+
+namespace b2p {
+
+constexpr int H = B2P_HALO;
+constexpr unsigned long long DEAD = ~0ull;
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define B2P_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      throw ::b2p::Error(B2P_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+// process context: one device, one stream (all work is stream-ordered)
+struct Context {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  unsigned long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+Context& ctx();          // initialises lazily on device 0; throws if no GPU
+void count_launch(int n = 1);
+#define B2P_LAUNCH_CHECK()                  \
+  do {                                      \
+    ::b2p::count_launch();                  \
+    B2P_CUDA(cudaGetLastError());           \
+  } while (0)
+
+void* dmalloc(size_t bytes);   // stream-ordered (cudaMallocAsync)
+void dfree(void* p);
+template <class T> T* dalloc(size_t n) { return static_cast<T*>(dmalloc(n * sizeof(T))); }
+
+// growable device array bound to the context stream
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~DBuf() { release(); }
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
+    return *this;
+  }
+  void release() { if (p) { dfree(p); p = nullptr; cap = 0; } }
+  // ensure capacity >= n; contents are NOT preserved unless keep > 0 (first `keep` elements)
+  void reserve(size_t n, size_t keep = 0) {
+    if (n <= cap) return;
+    size_t ncap = n + n / 8 + 64;
+    T* q = dalloc<T>(ncap);
+    if (keep && p) B2P_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, ctx().stream));
+    if (p) dfree(p);
+    p = q; cap = ncap;
+  }
+};
+
+// ---- device-visible descriptors -------------------------------------------
+struct Geom {                 // identical for every tile of a grid
+  int N[3];                   // interior cells
+  int Hx[3];                  // with halo
+  unsigned Ch;                // Hx*Hy*Hz
+};
+
+struct FieldPtrs { float* E; float* B; float* J; };
+
+struct Species {              // one particle container on the device
+  float* x; float* y; float* z; float* ux; float* uy; float* uz;
+  unsigned long long* id;
+  unsigned n;                 // container size (dead or alive)
+};
+
+}  // namespace b2p

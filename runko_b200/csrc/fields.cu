@@ -1,0 +1,348 @@
+// fields.cu — Yee-lattice kernels: FDTD2 / extended-stencil B push, E push,
+// add_current, binomial current filter, halo fill, J exchange, field energy.
+// All kernels are batched over a device-resident tile table (blockIdx.z spans
+// tiles), read/write fp32 component-major lattices with k fastest, and use
+// no FMA contraction (-fmad=false) so results are bit-identical to the
+// reference's unfused CPU arithmetic.
+#include "fields.cuh"
+
+namespace b2p {
+
+// thread <-> cell mapping shared by the interior sweeps: x->k, y->j, z->(tile,i)
+#define INTERIOR_CELL_OR_RETURN()                                              \
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;                         \
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;                         \
+  const int tile = blockIdx.z / g.N[0];                                        \
+  const int i = blockIdx.z - tile * g.N[0];                                    \
+  if (k >= g.N[2] || j >= g.N[1]) return;                                      \
+  const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2];                   \
+  const size_t n = (size_t(i + H) * g.Hx[1] + (j + H)) * g.Hx[2] + (k + H);    \
+  const FieldPtrs f = tiles[tile];                                             \
+  const size_t Ch = g.Ch;
+
+// emf/yee_lattice_fdtd2.c++:43-57 — the reference's three per-component sweeps
+// fused into one pass (each B component depends on E only, so fusing does not
+// change any operand): 36 B/cell algorithmic.
+__global__ void __launch_bounds__(256)
+k_push_b_fdtd2(const FieldPtrs* __restrict__ tiles, const Geom g, const float dt) {
+  INTERIOR_CELL_OR_RETURN();
+  const float* __restrict__ Ex = f.E;
+  const float* __restrict__ Ey = f.E + Ch;
+  const float* __restrict__ Ez = f.E + 2 * Ch;
+  const float ex = Ex[n], ey = Ey[n], ez = Ez[n];
+  const float DkEy = Ey[n + 1] - ey;
+  const float DjEz = Ez[n + sj] - ez;
+  const float DiEz = Ez[n + si] - ez;
+  const float DkEx = Ex[n + 1] - ex;
+  const float DjEx = Ex[n + sj] - ex;
+  const float DiEy = Ey[n + si] - ey;
+  f.B[n] = f.B[n] + dt * (DkEy - DjEz);
+  f.B[Ch + n] = f.B[Ch + n] + dt * (DiEz - DkEx);
+  f.B[2 * Ch + n] = f.B[2 * Ch + n] + dt * (DjEx - DiEy);
+}
+
+// emf/yee_lattice_fdtd2.c++:96-110, optionally followed by add_current
+// (emf/yee_lattice.c++:176-178): E1 = E + dt*curl; E2 = E1 - J, same two roundings.
+template <bool ADD_CURRENT>
+__global__ void __launch_bounds__(256)
+k_push_e_fdtd2(const FieldPtrs* __restrict__ tiles, const Geom g, const float dt) {
+  INTERIOR_CELL_OR_RETURN();
+  const float* __restrict__ Bx = f.B;
+  const float* __restrict__ By = f.B + Ch;
+  const float* __restrict__ Bz = f.B + 2 * Ch;
+  const float bx = Bx[n], by = By[n], bz = Bz[n];
+  const float DkBy = By[n - 1] - by;
+  const float DjBz = Bz[n - sj] - bz;
+  const float DiBz = Bz[n - si] - bz;
+  const float DkBx = Bx[n - 1] - bx;
+  const float DjBx = Bx[n - sj] - bx;
+  const float DiBy = By[n - si] - by;
+  float e0 = f.E[n] + dt * (DkBy - DjBz);
+  float e1 = f.E[Ch + n] + dt * (DiBz - DkBx);
+  float e2 = f.E[2 * Ch + n] + dt * (DjBx - DiBy);
+  if (ADD_CURRENT) {
+    e0 = e0 - f.J[n];
+    e1 = e1 - f.J[Ch + n];
+    e2 = e2 - f.J[2 * Ch + n];
+  }
+  f.E[n] = e0; f.E[Ch + n] = e1; f.E[2 * Ch + n] = e2;
+}
+
+// emf/yee_lattice.c++:171-179
+__global__ void __launch_bounds__(256)
+k_add_current(const FieldPtrs* __restrict__ tiles, const Geom g) {
+  INTERIOR_CELL_OR_RETURN();
+  f.E[n] = f.E[n] - f.J[n];
+  f.E[Ch + n] = f.E[Ch + n] - f.J[Ch + n];
+  f.E[2 * Ch + n] = f.E[2 * Ch + n] - f.J[2 * Ch + n];
+  (void)sj; (void)si;
+}
+
+struct StencilM { float M[3][3][5]; };   // axis, row, col (emf/stencil_coefficients.h:30-64)
+
+// One extended-stencil derivative, the 15-term sum of
+// emf/yee_lattice_stencil.c++:55-85 in source order (left-associated).
+__device__ __forceinline__ float stencil_deriv(const float* __restrict__ F, const long c, const float (&M)[3][5],
+                                               const long sa, const long s1, const long s2) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const long hi = c + (r + 1) * sa, lo = c - r * sa;
+    const float t0 = M[r][0] * (F[hi] - F[lo]);
+    const float t1 = M[r][1] * ((F[hi + s1] + F[hi - s1]) - (F[lo + s1] + F[lo - s1]));
+    const float t2 = M[r][2] * ((F[hi + s2] + F[hi - s2]) - (F[lo + s2] + F[lo - s2]));
+    const float t3 = M[r][3] * ((F[hi + 2 * s1] + F[hi - 2 * s1]) - (F[lo + 2 * s1] + F[lo - 2 * s1]));
+    const float t4 = M[r][4] * ((F[hi + 2 * s2] + F[hi - 2 * s2]) - (F[lo + 2 * s2] + F[lo - 2 * s2]));
+    acc = (r == 0) ? t0 : acc + t0;
+    acc = acc + t1; acc = acc + t2; acc = acc + t3; acc = acc + t4;
+  }
+  return acc;
+}
+
+// emf/yee_lattice_stencil.c++:18-295
+__global__ void __launch_bounds__(256)
+k_push_b_stencil(const FieldPtrs* __restrict__ tiles, const Geom g, const float dt, const StencilM c) {
+  INTERIOR_CELL_OR_RETURN();
+  const float* __restrict__ Ex = f.E;
+  const float* __restrict__ Ey = f.E + Ch;
+  const float* __restrict__ Ez = f.E + 2 * Ch;
+  const long s[3] = { long(si), long(sj), 1 };
+  const long m = long(n);
+  // D*_a uses axis[a] with perp1=(a+1)%3, perp2=(a+2)%3
+  const float DzEy = stencil_deriv(Ey, m, c.M[2], s[2], s[0], s[1]);
+  const float DyEz = stencil_deriv(Ez, m, c.M[1], s[1], s[2], s[0]);
+  const float DxEz = stencil_deriv(Ez, m, c.M[0], s[0], s[1], s[2]);
+  const float DzEx = stencil_deriv(Ex, m, c.M[2], s[2], s[0], s[1]);
+  const float DyEx = stencil_deriv(Ex, m, c.M[1], s[1], s[2], s[0]);
+  const float DxEy = stencil_deriv(Ey, m, c.M[0], s[0], s[1], s[2]);
+  f.B[n] = f.B[n] + dt * (DzEy - DyEz);
+  f.B[Ch + n] = f.B[Ch + n] + dt * (DxEz - DzEx);
+  f.B[2 * Ch + n] = f.B[2 * Ch + n] + dt * (DyEx - DxEy);
+}
+
+// ---- binomial current filter --------------------------------------------------
+// Both variants write every cell of dst: the region [1,H-1)^3 gets the filtered
+// value, the outermost layer gets 0 (binomial2: the reference move-assigns a
+// value-initialised grid, ..._binomial2.c++:43,75) or the old J (binomial2_unrolled
+// filters in place, :139-156).
+struct FilterTile { const float* src; float* dst; };
+
+template <bool UNROLLED>
+__global__ void __launch_bounds__(256)
+k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int tile = blockIdx.z / (3 * g.Hx[0]);
+  const int rem = blockIdx.z - tile * 3 * g.Hx[0];
+  const int c = rem / g.Hx[0];
+  const int i = rem - c * g.Hx[0];
+  if (k >= g.Hx[2] || j >= g.Hx[1]) return;
+  const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2];
+  const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
+  const float* __restrict__ J = tiles[tile].src + size_t(c) * g.Ch;
+  float* __restrict__ out = tiles[tile].dst + size_t(c) * g.Ch;
+  const bool edge = (i == 0) | (j == 0) | (k == 0) | (i == g.Hx[0] - 1) | (j == g.Hx[1] - 1) | (k == g.Hx[2] - 1);
+  if (edge) { out[n] = UNROLLED ? J[n] : 0.0f; return; }
+  if (UNROLLED) {
+    // separable z, y, x passes (..._binomial2.c++:118-156) evaluated on the fly;
+    // same products and the same left-associated 3-term sums per pass.
+    float t2[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float t1[3];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const float* p = J + n + (a - 1) * long(si) + (b - 1) * long(sj);
+        t1[b] = 0.25f * p[-1] + 0.5f * p[0] + 0.25f * p[1];
+      }
+      t2[a] = 0.25f * t1[0] + 0.5f * t1[1] + 0.25f * t1[2];
+    }
+    out[n] = 0.25f * t2[0] + 0.5f * t2[1] + 0.25f * t2[2];
+  } else {
+    // 27-point sum accumulated from 0 in index_space order, a slowest (:58-73)
+    float acc = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float w = ((a == 1) ? 2.f : 1.f) * ((b == 1) ? 2.f : 1.f) * ((d == 1) ? 2.f : 1.f) / 64.f;
+          acc = acc + w * J[n + (a - 1) * long(si) + (b - 1) * long(sj) + (d - 1)];
+        }
+    out[n] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_zero(float* __restrict__ p, const size_t n) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = 0.0f;
+}
+
+// ---- halo fill / J exchange (corgi local_communication, Moore order) ----------
+// Per axis, region of direction d (emf/yee_lattice.h:493-517, 580-602):
+//   subregion(d):               d=-1 [0,3)   d=0 [3,3+N)   d=+1 [3+N,6+N)
+//   corresponding_subregion(d): d=-1 [N,N+3) d=0 [3,3+N)   d=+1 [3,6)
+__device__ __forceinline__ int dir_of_halo(int a, int N) { return a < H ? -1 : (a >= H + N ? 1 : 0); }
+
+// me.subregion(dir) <- neighbour(dir).corresponding_subregion(dir) for all 26
+// directions of every tile (emf/yee_lattice.c++:206-239). One thread per lattice
+// cell and component; interior cells exit. `which` selects E/B/J.
+__global__ void __launch_bounds__(256)
+k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, const Geom g, const int which) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int tile = blockIdx.z / g.Hx[0];
+  const int i = blockIdx.z - tile * g.Hx[0];
+  if (k >= g.Hx[2] || j >= g.Hx[1]) return;
+  const int di = dir_of_halo(i, g.N[0]), dj = dir_of_halo(j, g.N[1]), dk = dir_of_halo(k, g.N[2]);
+  if (di == 0 && dj == 0 && dk == 0) return;
+  const int o = nbr[tile * 27 + ((di + 1) * 3 + (dj + 1)) * 3 + (dk + 1)];
+  if (o < 0) return;   // remote neighbour: filled by the external exchange
+  // my halo index a in subregion(d) maps to a - d*N in the neighbour (same formula for d=-1,0,+1)
+  const int si_ = i - di * g.N[0], sj_ = j - dj * g.N[1], sk_ = k - dk * g.N[2];
+  const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
+  const size_t m = (size_t(si_) * g.Hx[1] + sj_) * g.Hx[2] + sk_;
+  const FieldPtrs me = tiles[tile], ot = tiles[o];
+  float* dst = which == 0 ? me.E : (which == 1 ? me.B : me.J);
+  const float* src = which == 0 ? ot.E : (which == 1 ? ot.B : ot.J);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) dst[size_t(c) * g.Ch + n] = src[size_t(c) * g.Ch + m];
+}
+
+// me.corresponding_subregion(-dir) += neighbour(dir).subregion(-dir) for the 26
+// directions in Moore order kr->jr->ir (emf/yee_lattice.c++:249-261,
+// corgi cellular_automata.h:48-62), so every cell accumulates its up-to-7
+// contributions in the reference's order. One thread per interior cell/component.
+__global__ void __launch_bounds__(256)
+k_J_exchange(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, const Geom g) {
+  INTERIOR_CELL_OR_RETURN();
+  (void)sj; (void)si;
+  const int a[3] = { i + H, j + H, k + H };
+  // along one axis, cell a (haloed index) lies in corresponding_subregion(-d) for
+  //   d=+1: a in [N, N+3)  -> neighbour cell a - N  (its lower halo)
+  //   d=-1: a in [3, 6)    -> neighbour cell a + N  (its upper halo)
+  //   d= 0: always         -> neighbour cell a
+  bool lo[3], hi[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { lo[d] = a[d] < 2 * H; hi[d] = a[d] >= g.N[d]; }
+  if (!(lo[0] | hi[0] | lo[1] | hi[1] | lo[2] | hi[2])) return;
+  float acc[3] = { f.J[n], f.J[Ch + n], f.J[2 * Ch + n] };
+  for (int kr = -1; kr <= 1; ++kr)
+    for (int jr = -1; jr <= 1; ++jr)
+      for (int ir = -1; ir <= 1; ++ir) {
+        if (ir == 0 && jr == 0 && kr == 0) continue;
+        const int dr[3] = { ir, jr, kr };
+        bool in = true;
+        int s[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          in = in && (dr[d] == 0 || (dr[d] == 1 ? hi[d] : lo[d]));
+          s[d] = a[d] - dr[d] * g.N[d];
+        }
+        if (!in) continue;
+        const int o = nbr[tile * 27 + ((ir + 1) * 3 + (jr + 1)) * 3 + (kr + 1)];
+        if (o < 0) continue;
+        const float* oJ = tiles[o].J;
+        const size_t m = (size_t(s[0]) * g.Hx[1] + s[1]) * g.Hx[2] + s[2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] = acc[c] + oJ[size_t(c) * Ch + m];
+      }
+  f.J[n] = acc[0]; f.J[Ch + n] = acc[1]; f.J[2 * Ch + n] = acc[2];
+}
+
+// emf/yee_lattice.c++:383-428 — Σ(Fx²+Fy²+Fz²) over the interior, accumulated in
+// double (the reference's serial fp32 sum is reproduced only to tolerance).
+__global__ void __launch_bounds__(256)
+k_field_energy(const FieldPtrs* __restrict__ tiles, const Geom g, double* __restrict__ out /*[ntiles][2]*/) {
+  const int tile = blockIdx.y;
+  const size_t Ni = size_t(g.N[0]) * g.N[1] * g.N[2];
+  double sB = 0, sE = 0;
+  const FieldPtrs f = tiles[tile];
+  for (size_t q = size_t(blockIdx.x) * blockDim.x + threadIdx.x; q < Ni; q += size_t(gridDim.x) * blockDim.x) {
+    const int k = q % g.N[2];
+    const int j = (q / g.N[2]) % g.N[1];
+    const int i = q / (size_t(g.N[2]) * g.N[1]);
+    const size_t n = (size_t(i + H) * g.Hx[1] + (j + H)) * g.Hx[2] + (k + H);
+    const float bx = f.B[n], by = f.B[g.Ch + n], bz = f.B[2 * size_t(g.Ch) + n];
+    const float ex = f.E[n], ey = f.E[g.Ch + n], ez = f.E[2 * size_t(g.Ch) + n];
+    sB += double(bx * bx + by * by + bz * bz);
+    sE += double(ex * ex + ey * ey + ez * ez);
+  }
+  for (int o = 16; o > 0; o >>= 1) { sB += __shfl_xor_sync(0xffffffffu, sB, o); sE += __shfl_xor_sync(0xffffffffu, sE, o); }
+  __shared__ double shB[8], shE[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { shB[w] = sB; shE[w] = sE; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0, e = 0;
+    for (int q = 0; q < int(blockDim.x >> 5); ++q) { b += shB[q]; e += shE[q]; }
+    atomicAdd(&out[2 * tile], b);
+    atomicAdd(&out[2 * tile + 1], e);
+  }
+}
+
+// ------------------------------------------------------------------ launchers --
+static dim3 cell_block() { return dim3(32, 8, 1); }
+static dim3 interior_grid(const Geom& g, int ntiles) {
+  return dim3((g.N[2] + 31) / 32, (g.N[1] + 7) / 8, unsigned(ntiles) * g.N[0]);
+}
+
+void launch_push_b_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt) {
+  if (!ntiles) return;
+  k_push_b_fdtd2<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
+  B2P_LAUNCH_CHECK();
+}
+void launch_push_b_stencil(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, const float M[3][3][5]) {
+  if (!ntiles) return;
+  StencilM c;
+  for (int a = 0; a < 3; ++a) for (int r = 0; r < 3; ++r) for (int q = 0; q < 5; ++q) c.M[a][r][q] = M[a][r][q];
+  k_push_b_stencil<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt, c);
+  B2P_LAUNCH_CHECK();
+}
+void launch_push_e_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, bool add_current) {
+  if (!ntiles) return;
+  if (add_current) k_push_e_fdtd2<true><<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
+  else k_push_e_fdtd2<false><<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
+  B2P_LAUNCH_CHECK();
+}
+void launch_add_current(const FieldPtrs* tiles, int ntiles, const Geom& g) {
+  if (!ntiles) return;
+  k_add_current<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g);
+  B2P_LAUNCH_CHECK();
+}
+void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unrolled) {
+  if (!ntiles) return;
+  const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, unsigned(ntiles) * 3 * g.Hx[0]);
+  const FilterTile* ft = static_cast<const FilterTile*>(filter_tiles);
+  if (unrolled) k_filter_binomial2<true><<<grid, cell_block(), 0, ctx().stream>>>(ft, g);
+  else k_filter_binomial2<false><<<grid, cell_block(), 0, ctx().stream>>>(ft, g);
+  B2P_LAUNCH_CHECK();
+}
+void launch_zero(float* p, size_t n) {
+  if (!n) return;
+  const unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, size_t(ctx().sm_count) * 16));
+  k_zero<<<blocks, 256, 0, ctx().stream>>>(p, n);
+  B2P_LAUNCH_CHECK();
+}
+void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which) {
+  if (!ntiles) return;
+  const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, unsigned(ntiles) * g.Hx[0]);
+  k_halo_fill<<<grid, cell_block(), 0, ctx().stream>>>(tiles, nbr, g, which);
+  B2P_LAUNCH_CHECK();
+}
+void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g) {
+  if (!ntiles) return;
+  k_J_exchange<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, nbr, g);
+  B2P_LAUNCH_CHECK();
+}
+void launch_field_energy(const FieldPtrs* tiles, int ntiles, const Geom& g, double* out) {
+  if (!ntiles) return;
+  B2P_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 2 * ntiles, ctx().stream));
+  const size_t Ni = size_t(g.N[0]) * g.N[1] * g.N[2];
+  const unsigned bx = unsigned(std::min<size_t>((Ni + 255) / 256, 64));
+  k_field_energy<<<dim3(bx, ntiles), 256, 0, ctx().stream>>>(tiles, g, out);
+  B2P_LAUNCH_CHECK();
+}
+
+}  // namespace b2p

@@ -1,0 +1,17 @@
+// fields.cuh — launchers of the Yee-lattice kernels (fields.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b2p {
+void launch_push_b_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt);
+void launch_push_b_stencil(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, const float M[3][3][5]);
+void launch_push_e_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, bool add_current);
+void launch_add_current(const FieldPtrs* tiles, int ntiles, const Geom& g);
+// filter_tiles: device array of {const float* src; float* dst;} per tile
+void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unrolled);
+void launch_zero(float* p, size_t n);
+// which: 0=E 1=B 2=J; nbr: device int[ntiles][27] (tile-table index of the neighbour, -1 = remote)
+void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which);
+void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g);
+void launch_field_energy(const FieldPtrs* tiles, int ntiles, const Geom& g, double* out);
+}  // namespace b2p

@@ -1,0 +1,867 @@
+// host.cu — process context, tile/grid objects and the per-phase orchestration
+// (what runko/simulation.py + corgi do around the kernels, batched per phase).
+#include "host.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace b2p {
+
+// ------------------------------------------------------------------ context --
+static Context g_ctx;
+static bool g_ctx_ready = false;
+
+static void init_context(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw Error(B2P_ERR_CUDA, std::string("libb200pic: no usable CUDA device (") + cudaGetErrorString(e) +
+                                "); this library has no CPU fallback");
+  if (device < 0 || device >= count) throw Error(B2P_ERR_CUDA, "libb200pic: device index out of range");
+  B2P_CUDA(cudaSetDevice(device));
+  g_ctx.device = device;
+  B2P_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+  B2P_CUDA(cudaDeviceGetAttribute(&g_ctx.sm_count, cudaDevAttrMultiProcessorCount, device));
+  B2P_CUDA(cudaEventCreate(&g_ctx.ev0));
+  B2P_CUDA(cudaEventCreate(&g_ctx.ev1));
+  // keep freed blocks in the stream-ordered pool instead of returning them to the OS
+  cudaMemPool_t pool;
+  B2P_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long thr = ~0ull;
+  B2P_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  g_ctx_ready = true;
+}
+void init(int device) {
+  if (g_ctx_ready) {
+    if (device != g_ctx.device) throw Error(B2P_ERR_RUNTIME, "libb200pic: device already selected for this process");
+    return;
+  }
+  init_context(device);
+}
+Context& ctx() {
+  if (!g_ctx_ready) init_context(0);
+  return g_ctx;
+}
+void count_launch(int n) { g_ctx.launches += n; }
+
+void* dmalloc(size_t bytes) {
+  void* p = nullptr;
+  B2P_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, ctx().stream));
+  return p;
+}
+void dfree(void* p) {
+  if (p && g_ctx_ready) cudaFreeAsync(p, g_ctx.stream);
+}
+static void sync() { B2P_CUDA(cudaStreamSynchronize(ctx().stream)); }
+template <class T> static void h2d(T* dst, const T* src, size_t n) {
+  if (n) B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+}
+template <class T> static void d2h(T* dst, const T* src, size_t n) {
+  if (n) B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream));
+}
+
+// process-level scratch shared by all tiles (all work is ordered on one stream)
+struct Scratch {
+  DBuf<float4> nodal;
+  DBuf<unsigned> keys[2], vals[2];
+  DBuf<unsigned char> cub_temp;
+  DBuf<unsigned long long> list[2];
+  DBuf<unsigned> counters;        // [0]=list count, then per-container last_alive, then counts[ncont][27]
+  DBuf<unsigned char> table;      // device staging for job / out-tile tables
+  DBuf<double> energy;
+  Container spare;                // gather target of the sort (swapped with the container)
+};
+static Scratch& scratch() { static Scratch* s = new Scratch; return *s; }
+
+// ---------------------------------------------------------------- container --
+void Container::reserve(size_t cap) {
+  if (cap <= capacity()) return;
+  x.reserve(cap, n); y.reserve(cap, n); z.reserve(cap, n);
+  ux.reserve(cap, n); uy.reserve(cap, n); uz.reserve(cap, n);
+  id.reserve(cap, n);
+}
+
+static void swap_storage(Container& a, Container& b) {
+  std::swap(a.x.p, b.x.p); std::swap(a.x.cap, b.x.cap);
+  std::swap(a.y.p, b.y.p); std::swap(a.y.cap, b.y.cap);
+  std::swap(a.z.p, b.z.p); std::swap(a.z.cap, b.z.cap);
+  std::swap(a.ux.p, b.ux.p); std::swap(a.ux.cap, b.ux.cap);
+  std::swap(a.uy.p, b.uy.p); std::swap(a.uy.cap, b.uy.cap);
+  std::swap(a.uz.p, b.uz.p); std::swap(a.uz.cap, b.uz.cap);
+  std::swap(a.id.p, b.id.p); std::swap(a.id.cap, b.id.cap);
+}
+
+// P = 1 + last alive slot (pic/particle.h:469-488); full pass when not cached
+static unsigned find_P(Container& c) {
+  if (c.P_valid) return c.P;
+  unsigned P = 0;
+  if (c.n) {
+    Scratch& s = scratch();
+    s.counters.reserve(64);
+    B2P_CUDA(cudaMemsetAsync(s.counters.p, 0, sizeof(unsigned), ctx().stream));
+    launch_last_alive(c.id.p, c.n, s.counters.p);
+    d2h(&P, s.counters.p, 1);
+    sync();
+  }
+  c.P = P; c.P_valid = true;
+  return P;
+}
+
+}  // namespace b2p
+
+using namespace b2p;
+
+// --------------------------------------------------------------------- tile --
+const FieldPtrs* b2p_tile::device_entry() {
+  d_fp.reserve(1);
+  if (fp_dirty) {
+    const FieldPtrs f = ptrs();
+    h2d(d_fp.p, &f, 1);
+    fp_dirty = false;
+  }
+  return d_fp.p;
+}
+
+const FieldPtrs* b2p_grid::device_table() {
+  if (table_dirty) {
+    std::vector<FieldPtrs> h(tiles.size());
+    for (size_t i = 0; i < tiles.size(); ++i) h[i] = tiles[i]->ptrs();
+    d_tiles.reserve(std::max<size_t>(1, h.size()));
+    h2d(d_tiles.p, h.data(), h.size());
+    table_dirty = false;
+  }
+  return d_tiles.p;
+}
+
+static int wrapi(int v, int n) { while (v < 0) v += n; while (v >= n) v -= n; return v; }   // corgi/tile.h:126-136
+
+const int* b2p_grid::device_nbr() {
+  if (nbr_dirty) {
+    std::vector<int> h(tiles.size() * 27, -1);
+    for (size_t t = 0; t < tiles.size(); ++t)
+      for (int ir = -1; ir <= 1; ++ir) for (int jr = -1; jr <= 1; ++jr) for (int kr = -1; kr <= 1; ++kr) {
+        const int* T = cfg.n_tiles;
+        const int c = cid(wrapi(tiles[t]->idx[0] + ir, T[0]), wrapi(tiles[t]->idx[1] + jr, T[1]), wrapi(tiles[t]->idx[2] + kr, T[2]));
+        h[t * 27 + ((ir + 1) * 3 + (jr + 1)) * 3 + (kr + 1)] = slot_of_cid[c];
+      }
+    d_nbr.reserve(std::max<size_t>(1, h.size()));
+    h2d(d_nbr.p, h.data(), h.size());
+    nbr_dirty = false;
+  }
+  return d_nbr.p;
+}
+
+namespace b2p {
+
+// emf/stencil_coefficients.h:43-64
+static float stencil_alpha(const float M[3][5]) {
+  float sum = 0.0f;
+  sum += 3.0f * (M[1][0] + 2.0f * (M[1][1] + M[1][2] + M[1][3] + M[1][4]));
+  sum += 5.0f * (M[2][0] + 2.0f * (M[2][1] + M[2][2] + M[2][3] + M[2][4]));
+  sum += 1.0f * 2.0f * (M[0][1] + M[0][2] + M[0][3] + M[0][4]);
+  return 1.0f - sum;
+}
+
+static void validate_config(const b2p_config& c) {
+  for (int d = 0; d < 3; ++d) {
+    if (c.n_cells[d] < H)
+      throw Error(B2P_ERR_RUNTIME, "Yee Lattice extents (" + std::to_string(c.n_cells[0]) + ", " + std::to_string(c.n_cells[1]) +
+                                     ", " + std::to_string(c.n_cells[2]) + ") are assumed to be at least halo size: 3");
+    if (c.n_tiles[d] < 1) throw Error(B2P_ERR_RUNTIME, "n_tiles must be positive");
+  }
+  if (c.field_propagator != B2P_PROPAGATOR_FDTD2 && c.field_propagator != B2P_PROPAGATOR_STENCIL)
+    throw Error(B2P_ERR_RUNTIME, "not supported field propagator.");
+  if (c.n_species < 0 || c.n_species > B2P_MAX_SPECIES) throw Error(B2P_ERR_RUNTIME, "unsupported number of species");
+  if (size_t(c.n_tiles[0]) * c.n_tiles[1] * c.n_tiles[2] >= (size_t(1) << 24))
+    throw Error(B2P_ERR_RUNTIME, "PIC tile does not support this many tiles.");   // pic/tile.c++:138-140
+  const size_t Ch = size_t(c.n_cells[0] + 6) * (c.n_cells[1] + 6) * (c.n_cells[2] + 6);
+  if (Ch >= (size_t(1) << 31)) throw Error(B2P_ERR_RUNTIME, "tile lattice too large for 32-bit cell indexing");
+}
+
+static Geom make_geom(const b2p_config& c) {
+  Geom g;
+  g.Ch = 1;
+  for (int d = 0; d < 3; ++d) { g.N[d] = c.n_cells[d]; g.Hx[d] = c.n_cells[d] + 2 * H; g.Ch *= unsigned(g.Hx[d]); }
+  return g;
+}
+
+static b2p_tile* create_tile(const b2p_config& cfg, const int32_t idx[3]) {
+  validate_config(cfg);
+  for (int d = 0; d < 3; ++d)
+    if (idx[d] < 0 || idx[d] >= cfg.n_tiles[d])
+      throw Error(B2P_ERR_RUNTIME, "Trying to create tile outside of configured grid.");   // emf/tile.c++:155-157
+  ctx();
+  std::unique_ptr<b2p_tile> t(new b2p_tile);
+  t->cfg = cfg;
+  t->g = make_geom(cfg);
+  std::memcpy(t->stencilM, cfg.stencil, sizeof(t->stencilM));
+  for (int a = 0; a < 3; ++a) t->stencilM[a][0][0] = stencil_alpha(t->stencilM[a]);
+  for (int d = 0; d < 3; ++d) {
+    t->idx[d] = idx[d];
+    t->mins[d] = double(size_t(idx[d]) * size_t(cfg.n_cells[d]));              // emf/tile.c++:162-170
+    t->maxs[d] = double((size_t(idx[d]) + 1) * size_t(cfg.n_cells[d]));
+    t->origo[d] = static_cast<float>(t->mins[d]) - float(H);
+  }
+  const size_t nf = t->lattice_floats();
+  t->E.reserve(nf); t->B.reserve(nf); t->Jbuf[0].reserve(nf); t->Jbuf[1].reserve(nf);
+  launch_zero(t->E.p, nf); launch_zero(t->B.p, nf); launch_zero(t->Jbuf[0].p, nf); launch_zero(t->Jbuf[1].p, nf);
+  t->sp.resize(cfg.n_species);
+  t->next_ordinal.assign(cfg.n_species, 0);
+  for (int s = 0; s < cfg.n_species; ++s) {
+    t->sp[s].charge = cfg.q[s]; t->sp[s].mass = cfg.m[s];
+    if (cfg.prealloc_per_species) {                                               // pic/particle.c++:39-61
+      if (cfg.prealloc_per_species >= (1ull << 32)) throw Error(B2P_ERR_RUNTIME, "prealloc_per_species exceeds uint32 indexing");
+      t->sp[s].reserve(cfg.prealloc_per_species);
+      t->sp[s].n = unsigned(cfg.prealloc_per_species);
+      launch_fill_dead(t->sp[s].id.p, 0, t->sp[s].n);
+      t->sp[s].P = 0; t->sp[s].P_valid = true;
+    } else {
+      t->sp[s].P = 0; t->sp[s].P_valid = true;
+    }
+  }
+  t->tile_tag = (static_cast<unsigned long long>(idx[0]) * cfg.n_tiles[1] + idx[1]) * cfg.n_tiles[2] + idx[2];   // pic/tile.c++:141-143
+  return t.release();
+}
+
+// ----------------------------------------------------------- field phases --
+static float half_dt(const b2p_config& c) { return static_cast<float>(c.cfl / 2); }    // emf/tile.c++:365
+static float full_dt(const b2p_config& c) { return static_cast<float>(c.cfl); }        // emf/tile.c++:384
+
+void phase_push_half_b(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table) {
+  if (tiles.empty()) return;
+  b2p_tile* t0 = tiles[0];
+  if (t0->cfg.field_propagator == B2P_PROPAGATOR_STENCIL)
+    launch_push_b_stencil(table, int(tiles.size()), t0->g, half_dt(t0->cfg), t0->stencilM);
+  else
+    launch_push_b_fdtd2(table, int(tiles.size()), t0->g, half_dt(t0->cfg));
+}
+void phase_push_e(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table, bool add_current) {
+  if (tiles.empty()) return;
+  launch_push_e_fdtd2(table, int(tiles.size()), tiles[0]->g, full_dt(tiles[0]->cfg), add_current);
+}
+void phase_add_current(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table) {
+  if (tiles.empty()) return;
+  launch_add_current(table, int(tiles.size()), tiles[0]->g);
+}
+
+// emf/tile.c++:405-426; out of place into the tile's second J buffer, then swap
+void phase_filter(const std::vector<b2p_tile*>& tiles) {
+  if (tiles.empty()) return;
+  const int cf = tiles[0]->cfg.current_filter;
+  if (cf != B2P_FILTER_BINOMIAL2 && cf != B2P_FILTER_BINOMIAL2_UNROLLED)
+    throw Error(B2P_ERR_LOGIC, "Trying to filter current without specifying `current_filter`!");
+  struct FT { const float* src; float* dst; };
+  std::vector<FT> h(tiles.size());
+  for (size_t i = 0; i < tiles.size(); ++i) h[i] = FT{ tiles[i]->Jbuf[tiles[i]->jcur].p, tiles[i]->Jbuf[1 - tiles[i]->jcur].p };
+  Scratch& s = scratch();
+  s.table.reserve(h.size() * sizeof(FT));
+  h2d(reinterpret_cast<FT*>(s.table.p), h.data(), h.size());
+  launch_filter(s.table.p, int(tiles.size()), tiles[0]->g, cf == B2P_FILTER_BINOMIAL2_UNROLLED);
+  for (b2p_tile* t : tiles) {
+    t->jcur = 1 - t->jcur;
+    t->fp_dirty = true;
+    if (t->grid) t->grid->table_dirty = true;
+  }
+}
+
+// -------------------------------------------------------- particle phases --
+static int sign_of(double v) { return (0.0 < v) - (v < 0.0); }   // tools/math.h:181-183
+
+// pic/tile.c++:326-365
+void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
+  Scratch& s = scratch();
+  for (b2p_tile* t : tiles) {
+    bool any = false;
+    for (const Container& c : t->sp) any = any || c.n;
+    if (!any) continue;
+    s.nodal.reserve(size_t(2) * t->g.Ch);
+    launch_nodal_means(t->E.p, t->B.p, t->g, s.nodal.p);
+    for (Container& c : t->sp) {
+      const float qm = static_cast<float>(sign_of(c.charge) / c.mass);
+      launch_push(t->cfg.particle_pusher, c.view(), s.nodal.p, t->g, t->origo, static_cast<float>(t->cfg.cfl), qm);
+    }
+  }
+}
+
+// pic/tile.c++:369-415.  clear_current + scratch accumulate + `J += scratch`
+// collapse to "zero J, accumulate into J" (0 + x == x).
+void phase_deposit(const std::vector<b2p_tile*>& tiles) {
+  for (b2p_tile* t : tiles) {
+    launch_zero(t->J(), t->lattice_floats());
+    for (Container& c : t->sp)
+      launch_deposit(c.view(), t->J(), t->g, t->origo, static_cast<float>(t->cfg.cfl), static_cast<float>(c.charge));
+  }
+}
+
+// pic/tile.c++:419-438 + pic/particle.h:575-703: stable sort by cell key, dead last
+void phase_sort(const std::vector<b2p_tile*>& tiles) {
+  Scratch& s = scratch();
+  for (b2p_tile* t : tiles)
+    for (Container& c : t->sp) {
+      if (c.n < 2) continue;
+      for (int b = 0; b < 2; ++b) { s.keys[b].reserve(c.n); s.vals[b].reserve(c.n); }
+      launch_sort_keys(c.view(), t->g, t->origo, s.keys[0].p, s.vals[0].p, 0xFFFFFFFFu);
+      const size_t tb = sort_pairs_temp_bytes(c.n, 32);
+      s.cub_temp.reserve(tb);
+      unsigned* k[2] = { s.keys[0].p, s.keys[1].p };
+      unsigned* v[2] = { s.vals[0].p, s.vals[1].p };
+      const int sel = sort_pairs(s.cub_temp.p, tb, k, v, c.n, 32);
+      s.spare.reserve(c.capacity());
+      s.spare.n = c.n;
+      launch_gather(c.view(), s.spare.view(), v[sel]);
+      swap_storage(c, s.spare);
+      c.P_valid = false;
+    }
+}
+
+// pic/tile_communication.c++:68-96 + pic/particle.c++:199-348, batched over tiles
+void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles) {
+  if (tiles.empty()) return;
+  Scratch& s = scratch();
+  std::vector<Container*> conts;
+  std::vector<b2p_tile*> owner;
+  size_t total_slots = 0;
+  for (b2p_tile* t : tiles)
+    for (Container& c : t->sp) { conts.push_back(&c); owner.push_back(t); total_slots += c.n; }
+  const size_t nc = conts.size();
+  for (b2p_tile* t : tiles) { t->out_ends.assign(27 * t->sp.size(), 0); t->out_count = 0; }
+  if (nc == 0) return;
+  if (nc >= (size_t(1) << 26)) throw Error(B2P_ERR_RUNTIME, "too many containers in one pack call");
+  // device counters: [0] list length | [1..nc] P per container | [1+nc..1+2nc) leavers per container | counts[nc][27]
+  const size_t ncounters = 1 + 2 * nc + nc * 27;
+  s.counters.reserve(ncounters);
+  std::vector<unsigned> hc(1 + 2 * nc);
+  size_t cap = std::max<size_t>(total_slots / 8 + 65536, s.list[0].cap);
+  for (;;) {
+    s.list[0].reserve(cap); s.list[1].reserve(cap);
+    B2P_CUDA(cudaMemsetAsync(s.counters.p, 0, ncounters * sizeof(unsigned), ctx().stream));
+    for (size_t c = 0; c < nc; ++c) {
+      const b2p_tile* t = owner[c];
+      const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
+      const float mx[3] = { float(t->maxs[0]), float(t->maxs[1]), float(t->maxs[2]) };
+      launch_detect_leavers(conts[c]->view(), mn, mx, unsigned(c), s.list[0].p, s.counters.p,
+                            unsigned(std::min<size_t>(s.list[0].cap, 0xFFFFFFFFu)), s.counters.p + 1 + c,
+                            s.counters.p + 1 + nc + c);
+    }
+    d2h(hc.data(), s.counters.p, 1 + 2 * nc);
+    sync();
+    if (hc[0] <= s.list[0].cap) break;
+    cap = hc[0];   // overflow: nothing was modified yet, redo with a larger list
+  }
+  const unsigned total = hc[0];
+  for (size_t c = 0; c < nc; ++c) { conts[c]->P = hc[1 + c]; conts[c]->P_valid = true; }
+  if (total == 0) return;
+  // restore the reference's (species, subregion, container order) order
+  int cbits = 1;
+  while ((size_t(1) << cbits) < nc) ++cbits;
+  const int end_bit = 37 + cbits;
+  const size_t tb = sort_keys64_temp_bytes(total, end_bit);
+  s.cub_temp.reserve(tb);
+  unsigned long long* k[2] = { s.list[0].p, s.list[1].p };
+  const int sel = sort_keys64(s.cub_temp.p, tb, k, total, end_bit);
+  const unsigned* cont_count = hc.data() + 1 + nc;
+  std::vector<OutTileHost> ot(nc);
+  unsigned long long run = 0;
+  size_t c = 0;
+  for (b2p_tile* t : tiles) {
+    unsigned long long tile_total = 0;
+    for (size_t q = 0; q < t->sp.size(); ++q) tile_total += cont_count[c + q];
+    t->out_buf.reserve(std::max<size_t>(tile_total, 1));
+    t->out_count = tile_total;
+    for (size_t q = 0; q < t->sp.size(); ++q) ot[c + q] = OutTileHost{ t->out_buf.p, run, conts[c + q]->view() };
+    run += tile_total;
+    c += t->sp.size();
+  }
+  s.table.reserve(nc * sizeof(OutTileHost));
+  h2d(reinterpret_cast<OutTileHost*>(s.table.p), ot.data(), nc);
+  unsigned* counts = s.counters.p + 1 + 2 * nc;
+  launch_gather_outgoing(k[sel], total, s.table.p, counts);
+  std::vector<unsigned> hcounts(nc * 27);
+  d2h(hcounts.data(), counts, nc * 27);
+  sync();
+  c = 0;
+  for (b2p_tile* t : tiles) {
+    unsigned long long next = 0;                                   // pic/particle.c++:327-343
+    for (size_t q = 0; q < t->sp.size(); ++q, ++c)
+      for (int r = 0; r < 27; ++r) {
+        if (r != 13) next += hcounts[c * 27 + r];
+        t->out_ends[27 * q + r] = next;
+      }
+  }
+}
+
+// ---------------------------------------------------------- communication --
+struct SpanRef { const b2p_particle_state* p; unsigned n; };
+
+static void append_spans(std::vector<Container*>& conts, std::vector<std::vector<SpanRef>>& spans, bool wrap,
+                         const float wmin[3], const float wmax[3]) {
+  // pic/particle.h:454-572 for many containers at once
+  std::vector<AppendJobHost> jobs;
+  unsigned max_count = 0;
+  for (size_t c = 0; c < conts.size(); ++c) {
+    if (spans[c].empty()) continue;
+    Container& ct = *conts[c];
+    const unsigned P = find_P(ct);
+    size_t total = 0;
+    for (const SpanRef& sr : spans[c]) total += sr.n;
+    if (size_t(P) + total >= (size_t(1) << 32)) throw Error(B2P_ERR_RUNTIME, "particle container exceeds uint32 indexing");
+    ct.reserve(size_t(P) + total);
+    // keep only [0,P): slots beyond are dead and get overwritten or dropped
+    ct.n = unsigned(P + total);
+    unsigned off = P;
+    for (const SpanRef& sr : spans[c]) {
+      if (sr.n) { jobs.push_back(AppendJobHost{ sr.p, sr.n, off, ct.view() }); max_count = std::max(max_count, sr.n); }
+      off += sr.n;
+    }
+    ct.P = ct.n; ct.P_valid = true;   // either the last appended slot is alive, or n == P
+  }
+  if (jobs.empty()) return;
+  Scratch& s = scratch();
+  s.table.reserve(jobs.size() * sizeof(AppendJobHost));
+  h2d(reinterpret_cast<AppendJobHost*>(s.table.p), jobs.data(), jobs.size());
+  for (size_t b = 0; b < jobs.size(); b += 65535) {
+    const int nj = int(std::min<size_t>(65535, jobs.size() - b));
+    launch_append(reinterpret_cast<AppendJobHost*>(s.table.p) + b, nj, max_count, wrap, wmin, wmax);
+  }
+}
+
+// corgi::Grid::local_communication (external/corgi/src/corgi/corgi.h:1697-1718)
+void grid_local_communication(b2p_grid* g, int mode) {
+  const int nt = int(g->tiles.size());
+  if (!nt) return;
+  switch (mode) {
+    case B2P_COMM_EMF_E: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 0); return;
+    case B2P_COMM_EMF_B: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 1); return;
+    case B2P_COMM_EMF_J: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 2); return;
+    case B2P_COMM_EMF_J_EXCHANGE: launch_J_exchange(g->device_table(), g->device_nbr(), nt, g->g); return;
+    case B2P_COMM_PIC_PARTICLE: break;
+    default:
+      throw Error(B2P_ERR_LOGIC, "local_communication does not support given communication mode: " + std::to_string(mode));
+  }
+  // pic/tile_communication.c++:121-195: for every Moore direction (kr, jr, ir order) take
+  // the neighbour's span for the inverted direction; then the postlude appends (:100-117)
+  std::vector<Container*> conts;
+  std::vector<std::vector<SpanRef>> spans;
+  const int* T = g->cfg.n_tiles;
+  for (b2p_tile* me : g->tiles) {
+    const size_t base = conts.size();
+    for (Container& c : me->sp) { conts.push_back(&c); spans.emplace_back(); }
+    for (int kr = -1; kr <= 1; ++kr) for (int jr = -1; jr <= 1; ++jr) for (int ir = -1; ir <= 1; ++ir) {
+      if (!ir && !jr && !kr) continue;
+      const int oc = g->cid(wrapi(me->idx[0] + ir, T[0]), wrapi(me->idx[1] + jr, T[1]), wrapi(me->idx[2] + kr, T[2]));
+      const int os = g->slot_of_cid[oc];
+      if (os < 0) continue;   // remote neighbour: its particles arrive through the external exchange
+      b2p_tile* other = g->tiles[os];
+      if (other->out_ends.size() != 27 * other->sp.size())
+        throw Error(B2P_ERR_LOGIC, "pic_particle communication requires pack_outgoing_particles first");
+      const int inv = ((-ir + 1) * 3 + (-jr + 1)) * 3 + (-kr + 1);
+      for (size_t q = 0; q < me->sp.size(); ++q) {
+        const size_t index = 27 * q + inv;
+        const unsigned long long end = other->out_ends[index];
+        const unsigned long long begin = index == 0 ? 0 : other->out_ends[index - 1];
+        spans[base + q].push_back(SpanRef{ other->out_buf.p + begin, unsigned(end - begin) });
+      }
+    }
+  }
+  float wmin[3], wmax[3];
+  for (int d = 0; d < 3; ++d) { wmin[d] = 0.0f; wmax[d] = static_cast<float>(double(size_t(T[d]) * size_t(g->cfg.n_cells[d]))); }
+  append_spans(conts, spans, true, wmin, wmax);
+  for (b2p_tile* t : g->tiles) t->out_ends.clear();
+}
+
+}  // namespace b2p
+
+// ==================================================================== C ABI ==
+static thread_local std::string g_last_error;
+#define B2P_TRY try {
+#define B2P_CATCH                                                              \
+  }                                                                            \
+  catch (const b2p::Error& e) { g_last_error = e.what(); return e.code; }     \
+  catch (const std::exception& e) { g_last_error = e.what(); return B2P_ERR_RUNTIME; } \
+  return B2P_OK;
+
+static b2p_tile* T(b2p_tile* t) { if (!t) throw Error(B2P_ERR_RUNTIME, "null tile handle"); return t; }
+static b2p_grid* G(b2p_grid* g) { if (!g) throw Error(B2P_ERR_RUNTIME, "null grid handle"); return g; }
+static Container& C(b2p_tile* t, int sp) {
+  if (sp < 0 || sp >= int(T(t)->sp.size())) throw Error(B2P_ERR_RUNTIME, "particle type " + std::to_string(sp) + " is not configured");
+  return t->sp[sp];
+}
+namespace b2p { void init(int device); }
+
+extern "C" {
+
+const char* b2p_last_error(void) { return g_last_error.c_str(); }
+const char* b2p_version(void) { return "b200pic 0.1 (sm_100a)"; }
+int b2p_init(int device) { B2P_TRY b2p::init(device); B2P_CATCH }
+int b2p_sync(void) { B2P_TRY sync(); B2P_CATCH }
+int64_t b2p_gpu_mem_kB(void) {
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return -1;
+  return int64_t((tot - fr) / 1024);
+}
+
+int b2p_tile_create(const b2p_config* cfg, const int32_t idx[3], b2p_tile** out) {
+  B2P_TRY
+  if (!cfg || !idx || !out) throw Error(B2P_ERR_RUNTIME, "null argument");
+  *out = create_tile(*cfg, idx);
+  B2P_CATCH
+}
+void b2p_tile_destroy(b2p_tile* t) {
+  if (!t) return;
+  if (t->grid) {
+    b2p_grid* g = t->grid;
+    auto it = std::find(g->tiles.begin(), g->tiles.end(), t);
+    if (it != g->tiles.end()) {
+      g->tiles.erase(it);
+      std::fill(g->slot_of_cid.begin(), g->slot_of_cid.end(), -1);
+      for (size_t i = 0; i < g->tiles.size(); ++i) {
+        g->tiles[i]->slot = int(i);
+        g->slot_of_cid[g->cid(g->tiles[i]->idx[0], g->tiles[i]->idx[1], g->tiles[i]->idx[2])] = int(i);
+      }
+      g->table_dirty = g->nbr_dirty = true;
+    }
+  }
+  delete t;
+}
+int b2p_tile_bounds(const b2p_tile* t, double mins[3], double maxs[3]) {
+  B2P_TRY
+  for (int d = 0; d < 3; ++d) { mins[d] = t->mins[d]; maxs[d] = t->maxs[d]; }
+  B2P_CATCH
+}
+
+static void upload_field(b2p_tile* t, float* dev, const float* host, int with_halo) {
+  if (!host) return;
+  const Geom& g = t->g;
+  if (with_halo) { h2d(dev, host, t->lattice_floats()); sync(); return; }
+  std::vector<float> tmp(t->lattice_floats());
+  d2h(tmp.data(), dev, tmp.size());
+  sync();
+  const size_t Ni = size_t(g.N[0]) * g.N[1] * g.N[2];
+  for (int c = 0; c < 3; ++c)
+    for (int i = 0; i < g.N[0]; ++i) for (int j = 0; j < g.N[1]; ++j)
+      std::memcpy(&tmp[c * size_t(g.Ch) + (size_t(i + H) * g.Hx[1] + (j + H)) * g.Hx[2] + H],
+                  &host[c * Ni + (size_t(i) * g.N[1] + j) * g.N[2]], sizeof(float) * g.N[2]);
+  h2d(dev, tmp.data(), tmp.size());
+  sync();
+}
+static void download_field(b2p_tile* t, const float* dev, float* host, int with_halo) {
+  if (!host) return;
+  const Geom& g = t->g;
+  if (with_halo) { d2h(host, dev, t->lattice_floats()); sync(); return; }
+  std::vector<float> tmp(t->lattice_floats());
+  d2h(tmp.data(), dev, tmp.size());
+  sync();
+  const size_t Ni = size_t(g.N[0]) * g.N[1] * g.N[2];
+  for (int c = 0; c < 3; ++c)
+    for (int i = 0; i < g.N[0]; ++i) for (int j = 0; j < g.N[1]; ++j)
+      std::memcpy(&host[c * Ni + (size_t(i) * g.N[1] + j) * g.N[2]],
+                  &tmp[c * size_t(g.Ch) + (size_t(i + H) * g.Hx[1] + (j + H)) * g.Hx[2] + H], sizeof(float) * g.N[2]);
+}
+
+int b2p_tile_set_fields(b2p_tile* t, const float* E, const float* B, const float* J, int with_halo) {
+  B2P_TRY
+  T(t);
+  upload_field(t, t->E.p, E, with_halo); upload_field(t, t->B.p, B, with_halo); upload_field(t, t->J(), J, with_halo);
+  B2P_CATCH
+}
+int b2p_tile_get_fields(b2p_tile* t, float* E, float* B, float* J, int with_halo) {
+  B2P_TRY
+  T(t);
+  download_field(t, t->E.p, E, with_halo); download_field(t, t->B.p, B, with_halo); download_field(t, t->J(), J, with_halo);
+  B2P_CATCH
+}
+int b2p_tile_push_half_b(b2p_tile* t) { B2P_TRY phase_push_half_b({ T(t) }, t->device_entry()); B2P_CATCH }
+int b2p_tile_push_e(b2p_tile* t) { B2P_TRY phase_push_e({ T(t) }, t->device_entry(), false); B2P_CATCH }
+int b2p_tile_add_current(b2p_tile* t) { B2P_TRY phase_add_current({ T(t) }, t->device_entry()); B2P_CATCH }
+int b2p_tile_filter_current(b2p_tile* t) { B2P_TRY phase_filter({ T(t) }); B2P_CATCH }
+int b2p_tile_clear_current(b2p_tile* t) { B2P_TRY launch_zero(T(t)->J(), t->lattice_floats()); B2P_CATCH }
+int b2p_tile_field_energy(b2p_tile* t, double* eB, double* eE) {
+  B2P_TRY
+  T(t);
+  Scratch& s = scratch();
+  s.energy.reserve(2);
+  launch_field_energy(t->device_entry(), 1, t->g, s.energy.p);
+  double h[2];
+  d2h(h, s.energy.p, 2);
+  sync();
+  if (eB) *eB = h[0] / 2.0;                                                       // emf/yee_lattice.c++:402-403
+  if (eE) *eE = h[1] / 2.0;
+  B2P_CATCH
+}
+
+int b2p_tile_inject(b2p_tile* t, int sp, uint64_t n, const double* x, const double* y, const double* z,
+                    const double* ux, const double* uy, const double* uz) {
+  B2P_TRY
+  Container& c = C(t, sp);
+  // pic/tile.c++:207-217 + pic/particle.h:258-287: narrow, assign ids, append after the last alive slot
+  const unsigned P = find_P(c);
+  if (size_t(P) + n >= (size_t(1) << 32)) throw Error(B2P_ERR_RUNTIME, "particle container exceeds uint32 indexing");
+  c.reserve(size_t(P) + n);
+  c.n = unsigned(P + n);
+  if (n) {
+    std::vector<float> f(n);
+    const double* src[6] = { x, y, z, ux, uy, uz };
+    float* dst[6] = { c.x.p, c.y.p, c.z.p, c.ux.p, c.uy.p, c.uz.p };
+    for (int a = 0; a < 6; ++a) {
+      for (uint64_t i = 0; i < n; ++i) f[i] = static_cast<float>(src[a][i]);
+      h2d(dst[a] + P, f.data(), n);
+      sync();
+    }
+    std::vector<unsigned long long> ids(n);
+    for (uint64_t i = 0; i < n; ++i) {
+      const unsigned long long ordinal = t->next_ordinal[sp]++;
+      if (ordinal >= (2ull << 40)) throw Error(B2P_ERR_RUNTIME, "PIC tile ran out of particle ids (2^40 per species)!");
+      ids[i] = (t->tile_tag << 40) | ordinal;                                     // pic/tile.c++:470-481
+    }
+    h2d(c.id.p + P, ids.data(), n);
+    sync();
+  }
+  c.P = c.n; c.P_valid = true;
+  B2P_CATCH
+}
+
+int b2p_tile_set_particles(b2p_tile* t, int sp, uint64_t n, const float* x, const float* y, const float* z,
+                           const float* ux, const float* uy, const float* uz, const uint64_t* id) {
+  B2P_TRY
+  Container& c = C(t, sp);
+  if (n >= (1ull << 32)) throw Error(B2P_ERR_RUNTIME, "particle container exceeds uint32 indexing");
+  c.n = 0;
+  c.reserve(n);
+  c.n = unsigned(n);
+  h2d(c.x.p, x, n); h2d(c.y.p, y, n); h2d(c.z.p, z, n);
+  h2d(c.ux.p, ux, n); h2d(c.uy.p, uy, n); h2d(c.uz.p, uz, n);
+  h2d(c.id.p, reinterpret_cast<const unsigned long long*>(id), n);
+  sync();
+  c.P_valid = false;
+  B2P_CATCH
+}
+int b2p_tile_container_size(b2p_tile* t, int sp, uint64_t* n) { B2P_TRY *n = C(t, sp).n; B2P_CATCH }
+int b2p_tile_get_particles(b2p_tile* t, int sp, int alive_only, float* x, float* y, float* z,
+                           float* ux, float* uy, float* uz, uint64_t* id, uint64_t* n_out) {
+  B2P_TRY
+  Container& c = C(t, sp);
+  const size_t n = c.n;
+  std::vector<unsigned long long> hid(n);
+  d2h(hid.data(), c.id.p, n);
+  float* dst[6] = { x, y, z, ux, uy, uz };
+  const float* src[6] = { c.x.p, c.y.p, c.z.p, c.ux.p, c.uy.p, c.uz.p };
+  std::vector<float> tmp[6];
+  for (int a = 0; a < 6; ++a) if (dst[a]) { tmp[a].resize(n); d2h(tmp[a].data(), src[a], n); }
+  sync();
+  uint64_t m = 0;
+  for (size_t i = 0; i < n; ++i) {                                               // pic/particle.c++:82-168
+    if (alive_only && hid[i] == DEAD) continue;
+    for (int a = 0; a < 6; ++a) if (dst[a]) dst[a][m] = tmp[a][i];
+    if (id) id[m] = hid[i];
+    ++m;
+  }
+  if (n_out) *n_out = m;
+  B2P_CATCH
+}
+int b2p_tile_push_particles(b2p_tile* t) { B2P_TRY phase_push_particles({ T(t) }); B2P_CATCH }
+int b2p_tile_deposit_current(b2p_tile* t) { B2P_TRY phase_deposit({ T(t) }); B2P_CATCH }
+int b2p_tile_sort_particles(b2p_tile* t) { B2P_TRY phase_sort({ T(t) }); B2P_CATCH }
+int b2p_tile_pack_outgoing_particles(b2p_tile* t) { B2P_TRY phase_pack_outgoing({ T(t) }); B2P_CATCH }
+int b2p_tile_sort_keys(b2p_tile* t, int sp, uint32_t* keys) {
+  B2P_TRY
+  Container& c = C(t, sp);
+  if (c.n) {
+    Scratch& s = scratch();
+    s.keys[0].reserve(c.n);
+    launch_sort_keys(c.view(), t->g, t->origo, s.keys[0].p, nullptr, 0xFFFFFFFFu);
+    d2h(keys, s.keys[0].p, c.n);
+    sync();
+  }
+  B2P_CATCH
+}
+int b2p_tile_get_outgoing(b2p_tile* t, b2p_particle_state* buf, uint64_t cap, uint64_t* ends, uint64_t* n_out) {
+  B2P_TRY
+  T(t);
+  if (n_out) *n_out = t->out_count;
+  if (ends) for (size_t i = 0; i < t->out_ends.size(); ++i) ends[i] = t->out_ends[i];
+  if (buf) {
+    if (cap < t->out_count) throw Error(B2P_ERR_RUNTIME, "outgoing buffer too small");
+    d2h(buf, t->out_buf.p, t->out_count);
+    sync();
+  }
+  B2P_CATCH
+}
+int b2p_tile_kinetic_energy(b2p_tile* t, int sp, double* energy, uint64_t* container_size) {
+  B2P_TRY
+  Container& c = C(t, sp);
+  double h = 0;
+  if (c.n) {
+    Scratch& s = scratch();
+    s.energy.reserve(2);
+    B2P_CUDA(cudaMemsetAsync(s.energy.p, 0, sizeof(double), ctx().stream));
+    launch_kinetic_energy(c.view(), s.energy.p);
+    d2h(&h, s.energy.p, 1);
+    sync();
+  }
+  if (energy) *energy = h;
+  if (container_size) *container_size = c.n;
+  B2P_CATCH
+}
+
+// --------------------------------------------------------------------- grid --
+int b2p_grid_create(const b2p_config* cfg, b2p_grid** out) {
+  B2P_TRY
+  if (!cfg || !out) throw Error(B2P_ERR_RUNTIME, "null argument");
+  validate_config(*cfg);
+  ctx();
+  b2p_grid* g = new b2p_grid;
+  g->cfg = *cfg;
+  g->g = make_geom(*cfg);
+  const size_t nt = size_t(cfg->n_tiles[0]) * cfg->n_tiles[1] * cfg->n_tiles[2];
+  g->slot_of_cid.assign(nt, -1);
+  g->owner.assign(nt, 0);
+  *out = g;
+  B2P_CATCH
+}
+void b2p_grid_destroy(b2p_grid* g) { delete g; }
+int b2p_grid_add_tile(b2p_grid* g, b2p_tile* t) {
+  B2P_TRY
+  G(g); T(t);
+  for (int d = 0; d < 3; ++d)
+    if (t->cfg.n_tiles[d] != g->cfg.n_tiles[d] || t->cfg.n_cells[d] != g->cfg.n_cells[d])
+      throw Error(B2P_ERR_RUNTIME, "tile and grid configurations differ");
+  const int c = g->cid(t->idx[0], t->idx[1], t->idx[2]);
+  if (g->slot_of_cid[c] >= 0) throw Error(B2P_ERR_RUNTIME, "tile already added at this index");
+  t->grid = g; t->slot = int(g->tiles.size());
+  g->slot_of_cid[c] = t->slot;
+  g->tiles.push_back(t);
+  g->table_dirty = g->nbr_dirty = true;
+  B2P_CATCH
+}
+int b2p_grid_local_communication(b2p_grid* g, int mode) { B2P_TRY grid_local_communication(G(g), mode); B2P_CATCH }
+int b2p_grid_push_half_b(b2p_grid* g) { B2P_TRY phase_push_half_b(G(g)->tiles, g->device_table()); B2P_CATCH }
+int b2p_grid_push_e(b2p_grid* g) { B2P_TRY phase_push_e(G(g)->tiles, g->device_table(), false); B2P_CATCH }
+int b2p_grid_add_current(b2p_grid* g) { B2P_TRY phase_add_current(G(g)->tiles, g->device_table()); B2P_CATCH }
+int b2p_grid_filter_current(b2p_grid* g) { B2P_TRY phase_filter(G(g)->tiles); B2P_CATCH }
+int b2p_grid_push_particles(b2p_grid* g) { B2P_TRY phase_push_particles(G(g)->tiles); B2P_CATCH }
+int b2p_grid_pack_outgoing_particles(b2p_grid* g) { B2P_TRY phase_pack_outgoing(G(g)->tiles); B2P_CATCH }
+int b2p_grid_sort_particles(b2p_grid* g) { B2P_TRY phase_sort(G(g)->tiles); B2P_CATCH }
+int b2p_grid_deposit_current(b2p_grid* g) { B2P_TRY phase_deposit(G(g)->tiles); B2P_CATCH }
+
+int b2p_grid_external_communication(b2p_grid* g, int mode);
+
+// projects/pic-turbulence/pic.py:187-221
+int b2p_grid_step_pic(b2p_grid* g, int64_t lap) {
+  B2P_TRY
+  G(g);
+  const bool multi = g->nranks > 1;
+  auto ext = [&](int mode) {
+    if (multi) { const int rc = b2p_grid_external_communication(g, mode); if (rc) throw Error(rc, g_last_error); }
+  };
+  phase_push_half_b(g->tiles, g->device_table());
+  ext(B2P_COMM_EMF_B); grid_local_communication(g, B2P_COMM_EMF_B);
+  phase_push_particles(g->tiles);
+  phase_pack_outgoing(g->tiles);
+  ext(B2P_COMM_PIC_PARTICLE); grid_local_communication(g, B2P_COMM_PIC_PARTICLE);
+  if (lap % 5 == 0) phase_sort(g->tiles);
+  phase_deposit(g->tiles);
+  ext(B2P_COMM_EMF_J); grid_local_communication(g, B2P_COMM_EMF_J_EXCHANGE);
+  ext(B2P_COMM_EMF_J); grid_local_communication(g, B2P_COMM_EMF_J);
+  if (g->cfg.current_filter >= 0) {
+    phase_filter(g->tiles);
+    ext(B2P_COMM_EMF_J); grid_local_communication(g, B2P_COMM_EMF_J);
+    phase_filter(g->tiles);
+    phase_filter(g->tiles);
+  }
+  phase_push_half_b(g->tiles, g->device_table());
+  ext(B2P_COMM_EMF_B); grid_local_communication(g, B2P_COMM_EMF_B);
+  phase_push_e(g->tiles, g->device_table(), true);   // push_e + add_current fused (same roundings)
+  ext(B2P_COMM_EMF_E); grid_local_communication(g, B2P_COMM_EMF_E);
+  B2P_CATCH
+}
+
+// projects/emf-wave/emf.py:48-62
+int b2p_grid_step_emf(b2p_grid* g) {
+  B2P_TRY
+  G(g);
+  const bool multi = g->nranks > 1;
+  auto ext = [&](int mode) {
+    if (multi) { const int rc = b2p_grid_external_communication(g, mode); if (rc) throw Error(rc, g_last_error); }
+  };
+  ext(B2P_COMM_EMF_E); grid_local_communication(g, B2P_COMM_EMF_E);
+  phase_push_half_b(g->tiles, g->device_table());
+  phase_push_half_b(g->tiles, g->device_table());
+  ext(B2P_COMM_EMF_B); grid_local_communication(g, B2P_COMM_EMF_B);
+  phase_push_e(g->tiles, g->device_table(), false);
+  B2P_CATCH
+}
+
+int b2p_grid_energies(b2p_grid* g, double* eB, double* eE, double* kinetic, uint64_t* sizes) {
+  B2P_TRY
+  G(g);
+  const int nt = int(g->tiles.size());
+  const int ns = g->cfg.n_species;
+  Scratch& s = scratch();
+  s.energy.reserve(size_t(2) * std::max(nt, 1) + ns + 1);
+  double* dk = s.energy.p + 2 * size_t(std::max(nt, 1));
+  launch_field_energy(g->device_table(), nt, g->g, s.energy.p);
+  B2P_CUDA(cudaMemsetAsync(dk, 0, sizeof(double) * (ns + 1), ctx().stream));
+  std::vector<uint64_t> hs(ns, 0);
+  for (b2p_tile* t : g->tiles)
+    for (int q = 0; q < ns; ++q) { launch_kinetic_energy(t->sp[q].view(), dk + q); hs[q] += t->sp[q].n; }
+  std::vector<double> h(size_t(2) * nt + ns);
+  d2h(h.data(), s.energy.p, size_t(2) * nt);
+  d2h(h.data() + 2 * size_t(nt), dk, ns);
+  sync();
+  double b = 0, e = 0;
+  for (int i = 0; i < nt; ++i) { b += h[2 * i] / 2.0; e += h[2 * i + 1] / 2.0; }
+  if (eB) *eB = b;
+  if (eE) *eE = e;
+  for (int q = 0; q < ns; ++q) { if (kinetic) kinetic[q] = h[2 * size_t(nt) + q]; if (sizes) sizes[q] = hs[q]; }
+  B2P_CATCH
+}
+
+int b2p_grid_inject_thermal(b2p_grid* g, int ppc, double delgam, uint64_t seed) {
+  B2P_TRY
+  G(g);
+  if (ppc < 0) throw Error(B2P_ERR_RUNTIME, "ppc must be non-negative");
+  for (b2p_tile* t : g->tiles) {
+    const size_t total = size_t(t->g.N[0]) * t->g.N[1] * t->g.N[2] * size_t(ppc);
+    if (total >= (size_t(1) << 32)) throw Error(B2P_ERR_RUNTIME, "particle container exceeds uint32 indexing");
+    const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
+    for (size_t q = 0; q < t->sp.size(); ++q) {
+      Container& c = t->sp[q];
+      if (c.n) throw Error(B2P_ERR_RUNTIME, "inject_thermal requires empty containers");
+      c.reserve(total + total / 16);
+      c.n = unsigned(total);
+      const unsigned long long sp_seed = seed * 0x9E3779B97F4A7C15ull + t->tile_tag * 0xC2B2AE3D27D4EB4Full;
+      launch_inject_thermal(c.view(), t->g, mn, unsigned(ppc), float(delgam), sp_seed, sp_seed ^ (0xA5A5A5A5ull * (q + 1)),
+                            (t->tile_tag << 40) | t->next_ordinal[q]);
+      t->next_ordinal[q] += total;
+      c.P = c.n; c.P_valid = true;
+    }
+  }
+  B2P_CATCH
+}
+
+int b2p_grid_set_uniform_B(b2p_grid* g, float bx, float by, float bz) {
+  B2P_TRY
+  G(g);
+  for (b2p_tile* t : g->tiles) {
+    std::vector<float> h(t->lattice_floats());
+    const float v[3] = { bx, by, bz };
+    for (int c = 0; c < 3; ++c) std::fill(h.begin() + size_t(c) * t->g.Ch, h.begin() + size_t(c + 1) * t->g.Ch, v[c]);
+    h2d(t->B.p, h.data(), h.size());
+    sync();
+  }
+  B2P_CATCH
+}
+
+int b2p_timer_start(void) { B2P_TRY B2P_CUDA(cudaEventRecord(ctx().ev0, ctx().stream)); B2P_CATCH }
+int b2p_timer_stop(float* ms) {
+  B2P_TRY
+  B2P_CUDA(cudaEventRecord(ctx().ev1, ctx().stream));
+  B2P_CUDA(cudaEventSynchronize(ctx().ev1));
+  B2P_CUDA(cudaEventElapsedTime(ms, ctx().ev0, ctx().ev1));
+  B2P_CATCH
+}
+uint64_t b2p_launch_count(void) { return g_ctx_ready ? ctx().launches : 0; }
+
+}  // extern "C"

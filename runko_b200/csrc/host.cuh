@@ -1,0 +1,84 @@
+// host.cuh — host-side objects behind the C-ABI handles (b2p_tile, b2p_grid).
+#pragma once
+#include <array>
+#include <memory>
+
+#include "common.cuh"
+#include "fields.cuh"
+#include "particles.cuh"
+
+namespace b2p {
+
+// One particle container (pic::ParticleContainer, pic/particle.h:55-90) on the device.
+struct Container {
+  DBuf<float> x, y, z, ux, uy, uz;
+  DBuf<unsigned long long> id;
+  unsigned n = 0;             // size, dead or alive
+  double charge = 0, mass = 1;
+  bool P_valid = false;       // P = 1 + last alive slot known on the host
+  unsigned P = 0;
+  Species view() const { return Species{ x.p, y.p, z.p, ux.p, uy.p, uz.p, id.p, n }; }
+  size_t capacity() const { return id.cap; }
+  void reserve(size_t cap);   // keeps the first n slots
+};
+
+struct CommPlan;              // multi-GPU exchange plan (comm.cu)
+
+}  // namespace b2p
+
+struct b2p_tile {
+  b2p_config cfg;
+  int idx[3];
+  double mins[3], maxs[3];
+  float origo[3];             // float(mins) - 3  (pic/tile.c++:329-332)
+  b2p::Geom g;
+  float stencilM[3][3][5];
+  b2p::DBuf<float> E, B, Jbuf[2];
+  int jcur = 0;
+  b2p::DBuf<b2p::FieldPtrs> d_fp;   // 1-entry device tile table for per-tile launches
+  bool fp_dirty = true;
+  std::vector<b2p::Container> sp;
+  unsigned long long tile_tag = 0;
+  std::vector<unsigned long long> next_ordinal;
+  b2p::DBuf<b2p_particle_state> out_buf;      // subregion_particle_buff_ (pic/tile.h:85)
+  std::vector<unsigned long long> out_ends;   // subregion_particle_ends_ (pic/tile.h:84)
+  unsigned long long out_count = 0;
+  b2p_grid* grid = nullptr;
+  int slot = -1;
+
+  float* J() { return Jbuf[jcur].p; }
+  b2p::FieldPtrs ptrs() { return b2p::FieldPtrs{ E.p, B.p, J() }; }
+  const b2p::FieldPtrs* device_entry();       // uploads when dirty
+  size_t lattice_floats() const { return size_t(3) * g.Ch; }
+};
+
+struct b2p_grid {
+  b2p_config cfg;
+  b2p::Geom g;
+  std::vector<b2p_tile*> tiles;               // local tiles, in add order
+  std::vector<int> slot_of_cid;               // cid -> local slot or -1
+  b2p::DBuf<b2p::FieldPtrs> d_tiles;
+  b2p::DBuf<int> d_nbr;
+  bool table_dirty = true, nbr_dirty = true;
+  b2p::CommPlan* comm = nullptr;              // owned; freed in ~b2p_grid (comm.cu)
+  int rank = 0, nranks = 1;
+  std::vector<int> owner;                     // cid -> rank
+
+  ~b2p_grid();
+  const b2p::FieldPtrs* device_table();
+  const int* device_nbr();
+  int cid(int i, int j, int k) const { return i + cfg.n_tiles[0] * (j + cfg.n_tiles[1] * k); }
+};
+
+namespace b2p {
+// phase implementations shared by the per-tile and the batched grid entry points
+void phase_push_half_b(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table);
+void phase_push_e(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table, bool add_current);
+void phase_add_current(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table);
+void phase_filter(const std::vector<b2p_tile*>& tiles);
+void phase_push_particles(const std::vector<b2p_tile*>& tiles);
+void phase_deposit(const std::vector<b2p_tile*>& tiles);
+void phase_sort(const std::vector<b2p_tile*>& tiles);
+void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles);
+void grid_local_communication(b2p_grid* g, int mode);
+}  // namespace b2p

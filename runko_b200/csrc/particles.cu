@@ -1,0 +1,576 @@
+// particles.cu — particle kernels: nodal-mean staging + interpolation + the three
+// relativistic pushers, zigzag current deposition, cell-key sort, leaver
+// detection / migration packing, append with periodic wrap, kinetic energy,
+// synthetic thermal injection.
+//
+// Arithmetic contract: fp32, no FMA contraction (-fmad=false), IEEE div/sqrt
+// (nvcc defaults -prec-div=true -prec-sqrt=true), operation order of the
+// reference (citations per function) => push, keys and migration lists are
+// bit-identical to the reference's unfused CPU build.
+#include "particles.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace b2p {
+
+// ---------------------------------------------------------------- helpers --
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 operator*(const V3 a, const float s) { return { a.x * s, a.y * s, a.z * s }; }
+__device__ __forceinline__ V3 operator*(const float s, const V3 a) { return a * s; }
+__device__ __forceinline__ V3 operator/(const V3 a, const float s) { return { a.x / s, a.y / s, a.z / s }; }
+__device__ __forceinline__ V3 operator+(const V3 a, const V3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+__device__ __forceinline__ V3 operator-(const V3 a, const V3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+// tools/vector.h:248-255: accumulates from 0, left to right
+__device__ __forceinline__ float dot(const V3 a, const V3 b) {
+  float r = 0.0f;
+  r = r + a.x * b.x; r = r + a.y * b.y; r = r + a.z * b.z;
+  return r;
+}
+// tools/vector.h:281-289
+__device__ __forceinline__ V3 cross(const V3 a, const V3 b) {
+  return { a.y * b.z - a.z * b.y, -a.x * b.z + a.z * b.x, a.x * b.y - a.y * b.x };
+}
+__device__ __forceinline__ float lerp1(const float x, const float A, const float B) { return (1.0f - x) * A + x * B; }
+
+// ------------------------------------------------------- nodal field means --
+// The interpolator's per-corner staggered averages
+// (emf/yee_lattice_interpolate_linear_1st.h:91-113) depend only on the lattice
+// node (ii,jj,kk), not on the particle, so they are computed once per tile into
+// a node-major AoS array {Ex,Ey,Ez,Bx | By,Bz,0,0} (32 B/node): a particle then
+// needs 8 corners x 2 LDG.128 instead of 144 scalar gathers.  Same operands and
+// same association (2-term sum /2; 4-term right fold /4) => same bits.
+__global__ void __launch_bounds__(256)
+k_nodal_means(const float* __restrict__ E, const float* __restrict__ B, const Geom g, float4* __restrict__ nod) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int i = blockIdx.z;
+  if (k >= g.Hx[2] || j >= g.Hx[1]) return;
+  const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2], Ch = g.Ch;
+  const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (i >= 1 && j >= 1 && k >= 1) {
+    const float* Ex = E; const float* Ey = E + Ch; const float* Ez = E + 2 * Ch;
+    const float* Bx = B; const float* By = B + Ch; const float* Bz = B + 2 * Ch;
+    a.x = (Ex[n - si] + Ex[n]) / 2.0f;
+    a.y = (Ey[n - sj] + Ey[n]) / 2.0f;
+    a.z = (Ez[n - 1] + Ez[n]) / 2.0f;
+    a.w = (Bx[n] + (Bx[n - sj] + (Bx[n - 1] + Bx[n - sj - 1]))) / 4.0f;
+    b.x = (By[n] + (By[n - si] + (By[n - 1] + By[n - si - 1]))) / 4.0f;
+    b.y = (Bz[n] + (Bz[n - si] + (Bz[n - sj] + Bz[n - si - sj]))) / 4.0f;
+  }
+  nod[2 * n] = a;
+  nod[2 * n + 1] = b;
+}
+
+struct EB { V3 E, B; };
+
+// emf/yee_lattice_interpolate_linear_1st.h:58-138 on top of the nodal means.
+__device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const Geom& g, const float3 origo,
+                                          const float px, const float py, const float pz) {
+  const float lx = px - origo.x, ly = py - origo.y, lz = pz - origo.z;
+  const unsigned i = __float2uint_rz(lx), j = __float2uint_rz(ly), k = __float2uint_rz(lz);
+  const float dx = lx - float(i), dy = ly - float(j), dz = lz - float(k);
+  const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2];
+  const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
+  float4 a[2][2][2], b[2][2][2];
+#pragma unroll
+  for (int ic = 0; ic < 2; ++ic)
+#pragma unroll
+    for (int jc = 0; jc < 2; ++jc)
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        const size_t m = n + ic * si + jc * sj + kc;
+        a[ic][jc][kc] = __ldg(&nod[2 * m]);
+        b[ic][jc][kc] = __ldg(&nod[2 * m + 1]);
+      }
+  // lerp3D (:29-52): along x, then y, then z
+#define LERP3(field, comp)                                                                     \
+  lerp1(dz,                                                                                    \
+        lerp1(dy, lerp1(dx, field[0][0][0].comp, field[1][0][0].comp), lerp1(dx, field[0][1][0].comp, field[1][1][0].comp)), \
+        lerp1(dy, lerp1(dx, field[0][0][1].comp, field[1][0][1].comp), lerp1(dx, field[0][1][1].comp, field[1][1][1].comp)))
+  EB eb;
+  eb.E.x = LERP3(a, x); eb.E.y = LERP3(a, y); eb.E.z = LERP3(a, z);
+  eb.B.x = LERP3(a, w); eb.B.y = LERP3(b, x); eb.B.z = LERP3(b, y);
+#undef LERP3
+  return eb;
+}
+
+// 27-way subregion index of a position relative to the tile box
+// (pic/particle.c++:228-238, communication_common.h:137-147)
+__device__ __forceinline__ int subregion_of(const float x, const float y, const float z, const float3 mn, const float3 mx) {
+  const int i = int(x >= mn.x) - int(x < mx.x);
+  const int j = int(y >= mn.y) - int(y < mx.y);
+  const int k = int(z >= mn.z) - int(z < mx.z);
+  return ((i + 1) * 3 + (j + 1)) * 3 + (k + 1);
+}
+
+// ----------------------------------------------------------------- pushers --
+struct PushArgs {
+  Species s;
+  const float4* nod;
+  Geom g;
+  float3 origo;
+  float cfl;
+  float qm;       // sign(q)/m   (pic/particle_boris.h:26-27)
+};
+
+template <int PUSHER>
+__global__ void __launch_bounds__(256)
+k_push(const PushArgs a) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.s.n) return;
+  if (a.s.id[n] == DEAD) return;                                   // :33
+  const float px = a.s.x[n], py = a.s.y[n], pz = a.s.z[n];
+  const V3 u = { a.s.ux[n], a.s.uy[n], a.s.uz[n] };
+  const EB eb = interpolate(a.nod, a.g, a.origo, px, py, pz);
+  const float cfl = a.cfl, qm = a.qm;
+  V3 vel; float nx, ny, nz;
+  if (PUSHER == B2P_PUSHER_BORIS) {                                // pic/particle_boris.h:37-59
+    const V3 v0 = cfl * u;
+    const V3 E0 = 0.5f * qm * eb.E;
+    const V3 u0 = v0 + E0;
+    const float ginv = cfl / sqrtf(cfl * cfl + dot(u0, u0));
+    const V3 B0 = 0.5f * qm * ginv * eb.B / cfl;
+    const float f = 2.0f / (1.0f + dot(B0, B0));
+    const V3 u1 = f * (u0 + cross(u0, B0));
+    const V3 u2 = u0 + cross(u1, B0) + E0;
+    vel = u2 / cfl;
+    const float ginv2 = cfl / sqrtf(cfl * cfl + dot(u2, u2));
+    nx = px + vel.x * ginv2 * cfl; ny = py + vel.y * ginv2 * cfl; nz = pz + vel.z * ginv2 * cfl;
+  } else if (PUSHER == B2P_PUSHER_HIGUERA_CARY) {                  // pic/particle_higuera_cary.h:26-75
+    const float hqm = 0.5f * qm, cfl2 = cfl * cfl, cinv = 1.0f / cfl, cinv2 = cinv * cinv;
+    const V3 v0 = cfl * u;
+    const V3 E0 = hqm * eb.E;
+    const V3 u0 = v0 + E0;
+    const V3 Bt = hqm * eb.B;
+    const float u0sq = dot(u0, u0), b2 = dot(Bt, Bt), bdotu = dot(Bt, u0);
+    const float gmb = 1.0f + u0sq * cinv2 - b2 * cinv2;
+    const float disc = gmb * gmb + 4.0f * (b2 * cinv2 + bdotu * bdotu * cinv2);
+    const float ginv = 1.0f / sqrtf(0.5f * (gmb + sqrtf(disc)));
+    const float gc = ginv * cinv;
+    const V3 B0 = gc * Bt;
+    const float f = 2.0f / (1.0f + gc * gc * b2);
+    const V3 u1 = f * (u0 + cross(u0, B0));
+    const V3 u2 = u0 + cross(u1, B0) + E0;
+    const float ginv2 = cfl / sqrtf(cfl2 + dot(u2, u2));
+    vel = u2 * cinv;
+    nx = px + u2.x * ginv2; ny = py + u2.y * ginv2; nz = pz + u2.z * ginv2;
+  } else {                                                         // pic/particle_faraday.h:53-107
+    const V3 v0 = cfl * u;
+    const float gcfl = sqrtf(cfl * cfl + dot(v0, v0));
+    const V3 u0 = v0 + 0.5f * qm * eb.E;
+    const float geff_cfl = sqrtf(cfl * cfl + dot(u0, u0));
+    const float kappa = 0.5f * qm / geff_cfl;
+    const V3 eps = kappa * eb.E;
+    const V3 beta = kappa * eb.B;
+    const float w0 = gcfl + dot(eps, v0);
+    const V3 W = v0 + eps * gcfl + cross(v0, beta) + w0 * eps;
+    const float b2 = dot(beta, beta);
+    const float f = 1.0f / (1.0f + b2);
+    const V3 W_rot = f * (W - cross(beta, W) + dot(beta, W) * beta);
+    const float bde = dot(beta, eps);
+    const V3 eps_rot = f * (eps - cross(beta, eps) + bde * beta);
+    const float D = 1.0f - f * (dot(eps, eps) + bde * bde);
+    const V3 u2 = W_rot + eps_rot * (dot(eps, W_rot) / D);
+    vel = u2 / cfl;
+    const float ginv2 = cfl / sqrtf(cfl * cfl + dot(u2, u2));
+    nx = px + vel.x * ginv2 * cfl; ny = py + vel.y * ginv2 * cfl; nz = pz + vel.z * ginv2 * cfl;
+  }
+  a.s.ux[n] = vel.x; a.s.uy[n] = vel.y; a.s.uz[n] = vel.z;
+  a.s.x[n] = nx; a.s.y[n] = ny; a.s.z[n] = nz;
+}
+
+// ---------------------------------------------------------------- deposit --
+struct DepositArgs {
+  Species s;
+  float* J;        // 3*Ch accumulation target (haloed lattice)
+  Geom g;
+  float3 origo;
+  float cfl;
+  float charge;
+};
+
+// pic/particle_current_zigzag_1st.c++:241-336.  One thread per particle; the 24
+// structurally non-zero (node, component) contributions go to J with fp32 RED
+// atomics.  Per-particle values are bit-identical to the reference; only the
+// accumulation order differs.
+__global__ void __launch_bounds__(256)
+k_deposit_zigzag(const DepositArgs a) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.s.n) return;
+  if (a.s.id[n] == DEAD) return;
+  const V3 u = { a.s.ux[n], a.s.uy[n], a.s.uz[n] };
+  const float invgam = 1.0f / sqrtf(1.0f + dot(u, u));
+  const V3 x2 = V3{ a.s.x[n], a.s.y[n], a.s.z[n] } - V3{ a.origo.x, a.origo.y, a.origo.z };
+  const V3 x1 = x2 - a.cfl * invgam * u;
+  const V3 fi1 = { floorf(x1.x), floorf(x1.y), floorf(x1.z) };
+  const V3 fi2 = { floorf(x2.x), floorf(x2.y), floorf(x2.z) };
+  auto relay = [](const float f1, const float f2, const float p1, const float p2) {
+    const float lo = (f1 < f2 ? f1 : f2) + 1.0f;
+    const float b1 = f1 > f2 ? f1 : f2;
+    const float b2 = 0.5f * (p1 + p2);
+    const float b = b1 > b2 ? b1 : b2;
+    return lo < b ? lo : b;
+  };
+  const V3 xr = { relay(fi1.x, fi2.x, x1.x, x2.x), relay(fi1.y, fi2.y, x1.y, x2.y), relay(fi1.z, fi2.z, x1.z, x2.z) };
+  const V3 F1 = a.charge * (xr - x1);
+  const V3 F2 = a.charge * (x2 - xr);
+  const V3 W1 = 0.5f * (x1 + xr) - fi1;
+  const V3 W2 = 0.5f * (x2 + xr) - fi2;
+  const size_t sj = a.g.Hx[2], si = size_t(a.g.Hx[1]) * a.g.Hx[2], Ch = a.g.Ch;
+  const size_t n1 = (size_t(__float2uint_rz(fi1.x)) * a.g.Hx[1] + __float2uint_rz(fi1.y)) * a.g.Hx[2] + __float2uint_rz(fi1.z);
+  const size_t n2 = (size_t(__float2uint_rz(fi2.x)) * a.g.Hx[1] + __float2uint_rz(fi2.y)) * a.g.Hx[2] + __float2uint_rz(fi2.z);
+  float* Jx = a.J; float* Jy = a.J + Ch; float* Jz = a.J + 2 * Ch;
+  const float one = 1.0f;
+#define HALF(nn, F, W)                                                   \
+  {                                                                      \
+    atomicAdd(&Jx[nn], F.x * (one - W.y) * (one - W.z));                 \
+    atomicAdd(&Jy[nn], F.y * (one - W.x) * (one - W.z));                 \
+    atomicAdd(&Jz[nn], F.z * (one - W.x) * (one - W.y));                 \
+    atomicAdd(&Jy[nn + si], F.y * W.x * (one - W.z));                    \
+    atomicAdd(&Jz[nn + si], F.z * W.x * (one - W.y));                    \
+    atomicAdd(&Jx[nn + sj], F.x * W.y * (one - W.z));                    \
+    atomicAdd(&Jz[nn + sj], F.z * (one - W.x) * W.y);                    \
+    atomicAdd(&Jx[nn + 1], F.x * (one - W.y) * W.z);                     \
+    atomicAdd(&Jy[nn + 1], F.y * (one - W.x) * W.z);                     \
+    atomicAdd(&Jx[nn + sj + 1], F.x * W.y * W.z);                        \
+    atomicAdd(&Jy[nn + si + 1], F.y * W.x * W.z);                        \
+    atomicAdd(&Jz[nn + si + sj], F.z * W.x * W.y);                       \
+  }
+  HALF(n1, F1, W1)
+  HALF(n2, F2, W2)
+#undef HALF
+}
+
+// ------------------------------------------------------------------- sort --
+// pic/tile.c++:430-435 + pic/particle.h:607-614: key = layout_right cell index in
+// the haloed lattice (uint32), dead -> UINT32_MAX.
+__global__ void __launch_bounds__(256)
+k_sort_keys(const Species s, const Geom g, const float3 origo, unsigned* __restrict__ keys, unsigned* __restrict__ idx,
+            const unsigned dead_key) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= s.n) return;
+  unsigned key = dead_key;
+  if (s.id[n] != DEAD) {
+    const unsigned i = __float2uint_rz(s.x[n] - origo.x);
+    const unsigned j = __float2uint_rz(s.y[n] - origo.y);
+    const unsigned k = __float2uint_rz(s.z[n] - origo.z);
+    key = (i * unsigned(g.Hx[1]) + j) * unsigned(g.Hx[2]) + k;
+  }
+  keys[n] = key;
+  if (idx) idx[n] = n;
+}
+
+// gather all seven streams through the sort permutation (pic/particle.h:640-701)
+__global__ void __launch_bounds__(256)
+k_gather(const Species src, const Species dst, const unsigned* __restrict__ perm) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= src.n) return;
+  const unsigned p = perm[n];
+  dst.x[n] = src.x[p]; dst.y[n] = src.y[p]; dst.z[n] = src.z[p];
+  dst.ux[n] = src.ux[p]; dst.uy[n] = src.uy[p]; dst.uz[n] = src.uz[p];
+  dst.id[n] = src.id[p];
+}
+
+// -------------------------------------------------------------- migration --
+// Leaver detection (pic/particle.c++:252-262): every alive particle whose
+// position is outside the tile box appends the key
+//   (container << 37) | (subregion << 32) | slot
+// to an unordered list; a radix sort of that list restores the reference's order
+// (species, subregion, container order).  Also records 1 + the largest slot that
+// stays alive (the P of ParticleContainer::append, pic/particle.h:469-488).
+__global__ void __launch_bounds__(256)
+k_detect_leavers(const Species s, const float3 mn, const float3 mx, const unsigned container,
+                 unsigned long long* __restrict__ list, unsigned* __restrict__ list_count, const unsigned list_cap,
+                 unsigned* __restrict__ last_alive, unsigned* __restrict__ cont_count) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  bool leaving = false, staying_alive = false;
+  int sub = 13;
+  if (n < s.n) {
+    const bool alive = s.id[n] != DEAD;
+    sub = subregion_of(s.x[n], s.y[n], s.z[n], mn, mx);
+    leaving = alive && sub != 13;
+    staying_alive = alive && sub == 13;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, leaving);
+  const unsigned lane = threadIdx.x & 31;
+  if (m) {
+    unsigned base = 0;
+    const int leader = __ffs(m) - 1;
+    if (int(lane) == leader) { base = atomicAdd(list_count, __popc(m)); atomicAdd(cont_count, __popc(m)); }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (leaving) {
+      const unsigned pos = base + __popc(m & ((1u << lane) - 1));
+      if (pos < list_cap)
+        list[pos] = (static_cast<unsigned long long>(container) << 37) | (static_cast<unsigned long long>(sub) << 32) | n;
+    }
+  }
+  const unsigned sa = __ballot_sync(0xffffffffu, staying_alive);
+  if (sa && lane == 0) atomicMax(last_alive, (n & ~31u) + (32 - __clz(sa)));
+}
+
+struct OutTile {              // per container: where its leavers go
+  b2p_particle_state* buf;    // tile's outgoing AoS buffer
+  unsigned long long base;    // index of this tile's first entry in the sorted list
+  Species s;
+};
+
+// Sorted leaver list -> AoS ParticleState (pic/particle.c++:268-291) + mark the
+// source slots dead (:304-312) + per-(container, subregion) counts (:336-346).
+__global__ void __launch_bounds__(256)
+k_gather_outgoing(const unsigned long long* __restrict__ sorted, const unsigned total, const OutTile* __restrict__ cont,
+                  unsigned* __restrict__ counts /*[ncont][27]*/) {
+  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const unsigned long long key = sorted[q];
+  const unsigned c = unsigned(key >> 37), sub = unsigned(key >> 32) & 31u, n = unsigned(key);
+  const OutTile t = cont[c];
+  b2p_particle_state st;
+  st.pos[0] = t.s.x[n]; st.pos[1] = t.s.y[n]; st.pos[2] = t.s.z[n];
+  st.vel[0] = t.s.ux[n]; st.vel[1] = t.s.uy[n]; st.vel[2] = t.s.uz[n];
+  st.id = t.s.id[n];
+  t.buf[q - t.base] = st;
+  t.s.id[n] = DEAD;
+  atomicAdd(&counts[c * 27 + sub], 1u);
+}
+
+// Full-pass fallback for P = 1 + last alive slot (pic/particle.h:469-488), used
+// when no detection pass has produced it (inject outside the lap).
+__global__ void __launch_bounds__(256)
+k_last_alive(const unsigned long long* __restrict__ id, const unsigned n_total, unsigned* __restrict__ last_alive) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool alive = n < n_total && id[n] != DEAD;
+  const unsigned m = __ballot_sync(0xffffffffu, alive);
+  if (m && (threadIdx.x & 31) == 0) atomicMax(last_alive, (n & ~31u) + (32 - __clz(m)));
+}
+
+struct AppendJob {            // one incoming span (pic/tile_communication.c++:133-181)
+  const b2p_particle_state* src;
+  unsigned count;
+  unsigned dst_offset;        // P + exclusive scan of span sizes (pic/particle.h:490-509)
+  Species dst;
+};
+
+// ParticleContainer::append (pic/particle.h:511-571): AoS -> SoA after the last
+// alive particle; with `wrap` the global periodic wrap
+// (x<0 ? max : min) + fmodf(x, L) of :534-549.
+__global__ void __launch_bounds__(256)
+k_append(const AppendJob* __restrict__ jobs, const int wrap, const float3 wmin, const float3 wmax) {
+  const AppendJob jb = jobs[blockIdx.y];
+  const float Lx = wmax.x - wmin.x, Ly = wmax.y - wmin.y, Lz = wmax.z - wmin.z;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.count; i += gridDim.x * blockDim.x) {
+    const b2p_particle_state st = jb.src[i];
+    const unsigned j = jb.dst_offset + i;
+    if (wrap) {
+      jb.dst.x[j] = (st.pos[0] < 0 ? wmax.x : wmin.x) + fmodf(st.pos[0], Lx);
+      jb.dst.y[j] = (st.pos[1] < 0 ? wmax.y : wmin.y) + fmodf(st.pos[1], Ly);
+      jb.dst.z[j] = (st.pos[2] < 0 ? wmax.z : wmin.z) + fmodf(st.pos[2], Lz);
+    } else {
+      jb.dst.x[j] = st.pos[0]; jb.dst.y[j] = st.pos[1]; jb.dst.z[j] = st.pos[2];
+    }
+    jb.dst.ux[j] = st.vel[0]; jb.dst.uy[j] = st.vel[1]; jb.dst.uz[j] = st.vel[2];
+    jb.dst.id[j] = st.id;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_dead(unsigned long long* __restrict__ id, const unsigned begin, const unsigned end) {
+  const unsigned n = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < end) id[n] = DEAD;
+}
+
+// pic/particle.c++:352-377: Σ alive (sqrt(1+u·u) − 1), fp32 per particle, fp64 sum.
+__global__ void __launch_bounds__(256)
+k_kinetic_energy(const Species s, double* __restrict__ out) {
+  double acc = 0.0;
+  for (unsigned n = blockIdx.x * blockDim.x + threadIdx.x; n < s.n; n += gridDim.x * blockDim.x) {
+    const V3 v = { s.ux[n], s.uy[n], s.uz[n] };
+    const float e = sqrtf(1.0f + dot(v, v)) - 1.0f;
+    if (s.id[n] != DEAD) acc += double(e);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int q = 0; q < int(blockDim.x >> 5); ++q) t += sh[q];
+    atomicAdd(out, t);
+  }
+}
+
+// ------------------------------------------------- synthetic thermal plasma --
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+struct Rng {
+  unsigned long long state;
+  __device__ float uniform() {   // (0,1)
+    state = mix64(state);
+    return (float(unsigned(state >> 40)) + 0.5f) * (1.0f / 16777216.0f);
+  }
+};
+
+// Bench-only generator (no reference equivalent): slot p = round*Ncells + cell,
+// cells ordered i->j->k like pic::Tile::batch_inject_in_x_stripe (pic/tile.c++:264-275);
+// position = cell corner + U[0,1)^3 (the same position for every species, as in
+// projects/pic-turbulence/pic.py:141-156); momentum = Sobol sampling of a
+// Juttner-Synge distribution for theta > 0.2, Maxwellian below
+// (runko/sample_thermal_distributions.py:58-127, statistically — not bitwise).
+__global__ void __launch_bounds__(256)
+k_inject_thermal(const Species s, const Geom g, const float3 mins, const unsigned ppc, const float theta,
+                 const unsigned long long seed_pos, const unsigned long long seed_vel, const unsigned long long id_base) {
+  const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned ncell = unsigned(g.N[0]) * g.N[1] * g.N[2];
+  if (p >= ncell * ppc) return;
+  const unsigned cell = p % ncell;
+  const unsigned k = cell % g.N[2], j = (cell / g.N[2]) % g.N[1], i = cell / (g.N[2] * g.N[1]);
+  Rng rp{ mix64(seed_pos ^ (static_cast<unsigned long long>(p) * 0xD6E8FEB86659FD93ull)) };
+  s.x[p] = mins.x + float(i) + rp.uniform() * 0.999999f;
+  s.y[p] = mins.y + float(j) + rp.uniform() * 0.999999f;
+  s.z[p] = mins.z + float(k) + rp.uniform() * 0.999999f;
+  Rng rv{ mix64(seed_vel ^ (static_cast<unsigned long long>(p) * 0xD6E8FEB86659FD93ull)) };
+  float umag;
+  if (theta > 0.2f) {
+    for (;;) {
+      const float x4 = rv.uniform(), x5 = rv.uniform(), x6 = rv.uniform(), x7 = rv.uniform();
+      const float uu = -theta * logf(x4 * x5 * x6);
+      const float eta = -theta * logf(x4 * x5 * x6 * x7);
+      if (eta * eta - uu * uu > 1.0f) { umag = uu; break; }
+    }
+    const float mu = 2.0f * rv.uniform() - 1.0f, phi = 6.2831853f * rv.uniform();
+    const float st = sqrtf(fmaxf(0.0f, 1.0f - mu * mu));
+    s.ux[p] = umag * st * cosf(phi); s.uy[p] = umag * st * sinf(phi); s.uz[p] = umag * mu;
+  } else {
+    const float sig = sqrtf(theta);
+    const float r1 = sqrtf(-2.0f * logf(rv.uniform())), a1 = 6.2831853f * rv.uniform();
+    const float r2 = sqrtf(-2.0f * logf(rv.uniform())), a2 = 6.2831853f * rv.uniform();
+    s.ux[p] = sig * r1 * cosf(a1); s.uy[p] = sig * r1 * sinf(a1); s.uz[p] = sig * r2 * cosf(a2);
+  }
+  s.id[p] = id_base + p;
+}
+
+// ---------------------------------------------------------------- launchers --
+static unsigned blocks_for(size_t n) { return unsigned((n + 255) / 256); }
+
+void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* nod) {
+  const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, g.Hx[0]);
+  k_nodal_means<<<grid, dim3(32, 8, 1), 0, ctx().stream>>>(E, B, g, nod);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm) {
+  if (!s.n) return;
+  PushArgs a{ s, nod, g, make_float3(origo[0], origo[1], origo[2]), cfl, qm };
+  const unsigned nb = blocks_for(s.n);
+  switch (pusher) {
+    case B2P_PUSHER_BORIS: k_push<B2P_PUSHER_BORIS><<<nb, 256, 0, ctx().stream>>>(a); break;
+    case B2P_PUSHER_HIGUERA_CARY: k_push<B2P_PUSHER_HIGUERA_CARY><<<nb, 256, 0, ctx().stream>>>(a); break;
+    case B2P_PUSHER_FARADAY: k_push<B2P_PUSHER_FARADAY><<<nb, 256, 0, ctx().stream>>>(a); break;
+    default: throw Error(B2P_ERR_LOGIC, "pic::Tile::push_particles: unkown particle pusher");
+  }
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_deposit(const Species& s, float* J, const Geom& g, const float origo[3], float cfl, float charge) {
+  if (!s.n) return;
+  DepositArgs a{ s, J, g, make_float3(origo[0], origo[1], origo[2]), cfl, charge };
+  k_deposit_zigzag<<<blocks_for(s.n), 256, 0, ctx().stream>>>(a);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_sort_keys(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* idx, unsigned dead_key) {
+  if (!s.n) return;
+  k_sort_keys<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, g, make_float3(origo[0], origo[1], origo[2]), keys, idx, dead_key);
+  B2P_LAUNCH_CHECK();
+}
+
+size_t sort_pairs_temp_bytes(unsigned n, int end_bit) {
+  size_t bytes = 0;
+  cub::DoubleBuffer<unsigned> k(nullptr, nullptr), v(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, int(n), 0, end_bit, ctx().stream);
+  return bytes;
+}
+// stable LSD radix sort of (key, slot) pairs; returns which half of the double
+// buffers holds the result
+int sort_pairs(void* temp, size_t temp_bytes, unsigned* keys[2], unsigned* vals[2], unsigned n, int end_bit) {
+  cub::DoubleBuffer<unsigned> k(keys[0], keys[1]), v(vals[0], vals[1]);
+  B2P_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, int(n), 0, end_bit, ctx().stream));
+  count_launch((end_bit + 7) / 8 + 2);
+  return v.selector;
+}
+size_t sort_keys64_temp_bytes(unsigned n, int end_bit) {
+  size_t bytes = 0;
+  cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
+  cub::DeviceRadixSort::SortKeys(nullptr, bytes, k, int(n), 0, end_bit, ctx().stream);
+  return bytes;
+}
+int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit) {
+  cub::DoubleBuffer<unsigned long long> k(keys[0], keys[1]);
+  B2P_CUDA(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, k, int(n), 0, end_bit, ctx().stream));
+  count_launch((end_bit + 7) / 8 + 2);
+  return k.selector;
+}
+
+void launch_gather(const Species& src, const Species& dst, const unsigned* perm) {
+  if (!src.n) return;
+  k_gather<<<blocks_for(src.n), 256, 0, ctx().stream>>>(src, dst, perm);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_detect_leavers(const Species& s, const float mins[3], const float maxs[3], unsigned container,
+                           unsigned long long* list, unsigned* list_count, unsigned list_cap, unsigned* last_alive,
+                           unsigned* cont_count) {
+  if (!s.n) return;
+  k_detect_leavers<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, make_float3(mins[0], mins[1], mins[2]),
+                                                               make_float3(maxs[0], maxs[1], maxs[2]), container, list,
+                                                               list_count, list_cap, last_alive, cont_count);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_gather_outgoing(const unsigned long long* sorted, unsigned total, const void* out_tiles, unsigned* counts) {
+  if (!total) return;
+  k_gather_outgoing<<<blocks_for(total), 256, 0, ctx().stream>>>(sorted, total, static_cast<const OutTile*>(out_tiles), counts);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_last_alive(const unsigned long long* id, unsigned n, unsigned* last_alive) {
+  if (!n) return;
+  k_last_alive<<<blocks_for(n), 256, 0, ctx().stream>>>(id, n, last_alive);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, const float wmin[3], const float wmax[3]) {
+  if (!njobs || !max_count) return;
+  const unsigned bx = std::min(blocks_for(max_count), 1024u);
+  k_append<<<dim3(bx, njobs), 256, 0, ctx().stream>>>(static_cast<const AppendJob*>(jobs), wrap ? 1 : 0,
+                                                      make_float3(wmin[0], wmin[1], wmin[2]), make_float3(wmax[0], wmax[1], wmax[2]));
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_fill_dead(unsigned long long* id, unsigned begin, unsigned end) {
+  if (end <= begin) return;
+  k_fill_dead<<<blocks_for(end - begin), 256, 0, ctx().stream>>>(id, begin, end);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_kinetic_energy(const Species& s, double* out) {
+  if (!s.n) return;
+  const unsigned nb = std::min(blocks_for(s.n), unsigned(ctx().sm_count) * 8);
+  k_kinetic_energy<<<nb, 256, 0, ctx().stream>>>(s, out);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_inject_thermal(const Species& s, const Geom& g, const float mins[3], unsigned ppc, float theta,
+                           unsigned long long seed_pos, unsigned long long seed_vel, unsigned long long id_base) {
+  const size_t total = size_t(g.N[0]) * g.N[1] * g.N[2] * ppc;
+  if (!total) return;
+  k_inject_thermal<<<blocks_for(total), 256, 0, ctx().stream>>>(s, g, make_float3(mins[0], mins[1], mins[2]), ppc, theta,
+                                                                 seed_pos, seed_vel, id_base);
+  B2P_LAUNCH_CHECK();
+}
+
+}  // namespace b2p

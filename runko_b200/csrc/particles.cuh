@@ -1,0 +1,38 @@
+// particles.cuh — launchers of the particle kernels (particles.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b2p {
+
+struct OutTileHost {          // mirrors particles.cu::OutTile
+  b2p_particle_state* buf;
+  unsigned long long base;
+  Species s;
+};
+struct AppendJobHost {        // mirrors particles.cu::AppendJob
+  const b2p_particle_state* src;
+  unsigned count;
+  unsigned dst_offset;
+  Species dst;
+};
+
+void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* nod);
+void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm);
+void launch_deposit(const Species& s, float* J, const Geom& g, const float origo[3], float cfl, float charge);
+void launch_sort_keys(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* idx, unsigned dead_key);
+size_t sort_pairs_temp_bytes(unsigned n, int end_bit);
+int sort_pairs(void* temp, size_t temp_bytes, unsigned* keys[2], unsigned* vals[2], unsigned n, int end_bit);
+size_t sort_keys64_temp_bytes(unsigned n, int end_bit);
+int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit);
+void launch_gather(const Species& src, const Species& dst, const unsigned* perm);
+void launch_detect_leavers(const Species& s, const float mins[3], const float maxs[3], unsigned container,
+                           unsigned long long* list, unsigned* list_count, unsigned list_cap, unsigned* last_alive,
+                           unsigned* cont_count);
+void launch_gather_outgoing(const unsigned long long* sorted, unsigned total, const void* out_tiles, unsigned* counts);
+void launch_last_alive(const unsigned long long* id, unsigned n, unsigned* last_alive);
+void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, const float wmin[3], const float wmax[3]);
+void launch_fill_dead(unsigned long long* id, unsigned begin, unsigned end);
+void launch_kinetic_energy(const Species& s, double* out);
+void launch_inject_thermal(const Species& s, const Geom& g, const float mins[3], unsigned ppc, float theta,
+                           unsigned long long seed_pos, unsigned long long seed_vel, unsigned long long id_base);
+}  // namespace b2p

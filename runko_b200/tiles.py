@@ -1,0 +1,388 @@
+"""Host-side mirror of the reference's pybind11 tile API for the PIC hot path:
+emf.threeD.Tile (src/runko/bindings/pyemf.c++:214-267), pic.threeD.Tile
+(src/runko/bindings/pypic.c++:92-139) and the slice of pycorgi.threeD.Grid that
+runko/simulation.py drives (external/corgi/pycorgi/pycorgi.c++:79-126,317-374).
+Same method names, argument meaning and error behaviour; every call goes through
+the C-ABI of libb200pic.so (include/b200pic.h).
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _abi
+from ._abi import ConfigError, ParticleState, make_config
+from ._lib import B2PError, B2PLogicError, check, lib
+
+
+class comm_mode(enum.Enum):
+    """runko::comm_mode (src/runko/communication_common.h:30-38, bindings/pytools.c++:23-29)."""
+    emf_J = 0
+    emf_E = 1
+    emf_B = 2
+    pic_particle = 3
+    pic_particle_extra = 4
+    emf_J_exchange = 6
+
+
+_number_of_particles = 5  # not exported by the reference either
+
+
+def _virtual_tile_sync_handshake_mode(mode):
+    """communication_common.h:42-49"""
+    return _number_of_particles if mode == comm_mode.pic_particle else None
+
+
+def _get_gpu_mem_kB():
+    return int(lib().b2p_gpu_mem_kB())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class ParticleStateBatch:
+    """pic::ParticleStateBatch (pic/tile.h:38-43)."""
+
+    def __init__(self, pos, vel):
+        self.pos = tuple(pos)
+        self.vel = tuple(vel)
+
+
+class ParticleStateD:
+    """runko::ParticleState<double> as exposed to Python (bindings/pypic.c++:60-64)."""
+
+    def __init__(self, pos, vel):
+        self.pos = list(pos)
+        self.vel = list(vel)
+
+
+class Tile:
+    """emf::Tile<3> — owns E, B, J on the device (emf/tile.h:36-213)."""
+
+    _need_pic = False
+
+    def __init__(self, tile_grid_idx, config):
+        try:
+            self._cfg = config if isinstance(config, _abi.B2PConfig) else make_config(config, need_pic=self._need_pic)
+        except ConfigError as e:
+            raise B2PError(str(e)) from None
+        idx = (C.c_int32 * 3)(*[int(v) for v in tile_grid_idx])
+        h = C.c_void_p()
+        check(lib().b2p_tile_create(C.byref(self._cfg), C.byref(idx), C.byref(h)))
+        self._h = h
+        self.index = tuple(int(v) for v in tile_grid_idx)
+        mins, maxs = (C.c_double * 3)(), (C.c_double * 3)()
+        check(lib().b2p_tile_bounds(self._h, C.byref(mins), C.byref(maxs)))
+        self.mins, self.maxs = list(mins), list(maxs)
+        self.n_cells = tuple(self._cfg.n_cells)
+        self.cid = self.index[0] + self._cfg.n_tiles[0] * (self.index[1] + self._cfg.n_tiles[1] * self.index[2])
+        self.communication = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().b2p_tile_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @staticmethod
+    def canonical_type():
+        return Tile
+
+    # -- geometry -------------------------------------------------------------
+    def global_coordinate_map(self):
+        """emf/tile.h:215-236: (i,j,k) tile-local (fractional) index -> global coordinates."""
+        mins, maxs, e = self.mins, self.maxs, self.n_cells
+
+        def m(idx):
+            return tuple(mins[d] + (float(idx[d]) / float(e[d])) * (maxs[d] - mins[d]) for d in range(3))
+        return m
+
+    def _lattice_shape(self, with_halo):
+        n = self.n_cells
+        return (3,) + (tuple(v + 6 for v in n) if with_halo else tuple(n))
+
+    # -- field setters / getters ------------------------------------------------
+    def _upload(self, E, B, J, with_halo=False):
+        arrs = []
+        for a in (E, B, J):
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                if a.shape != self._lattice_shape(with_halo):
+                    raise B2PError("Batch field setter returned array with incorrect shape!")
+            arrs.append(a)
+        check(lib().b2p_tile_set_fields(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), int(with_halo)))
+
+    def set_EBJ(self, E, B, J):
+        """emf/tile.c++:184-224: per-point callables evaluated at the Yee-staggered positions."""
+        nx, ny, nz = self.n_cells
+        gm = self.global_coordinate_map()
+        out = np.empty((3, 3, nx, ny, nz), np.float64)
+        for i in range(nx):
+            for j in range(ny):
+                for k in range(nz):
+                    x, y, z = gm((i, j, k))
+                    for f, fn in enumerate((E, B, J)):
+                        if f == 1:
+                            out[f, 0, i, j, k] = fn(x, y + 0.5, z + 0.5)[0]
+                            out[f, 1, i, j, k] = fn(x + 0.5, y, z + 0.5)[1]
+                            out[f, 2, i, j, k] = fn(x + 0.5, y + 0.5, z)[2]
+                        else:
+                            out[f, 0, i, j, k] = fn(x + 0.5, y, z)[0]
+                            out[f, 1, i, j, k] = fn(x, y + 0.5, z)[1]
+                            out[f, 2, i, j, k] = fn(x, y, z + 0.5)[2]
+        self._upload(out[0], out[1], out[2])
+
+    def batch_set_EBJ(self, Ex, Ey, Ez, Bx, By, Bz, Jx, Jy, Jz):
+        """emf/tile.c++:226-335."""
+        nx, ny, nz = self.n_cells
+        gm = self.global_coordinate_map()
+        ii, jj, kk = np.meshgrid(np.arange(nx, dtype=np.float64), np.arange(ny, dtype=np.float64),
+                                 np.arange(nz, dtype=np.float64), indexing="ij")
+        x, y, z = gm((ii, jj, kk))
+        xp5, yp5, zp5 = gm((ii + 0.5, jj + 0.5, kk + 0.5))
+        x, y, z, xp5, yp5, zp5 = (np.ascontiguousarray(a) for a in (x, y, z, xp5, yp5, zp5))
+
+        def shaped(a):
+            a = np.asarray(a, dtype=np.float64)
+            if a.shape != (nx, ny, nz):
+                raise B2PError("Batch field setter returned array with incorrect shape!")
+            return a
+        E = np.stack([shaped(Ex(xp5, y, z)), shaped(Ey(x, yp5, z)), shaped(Ez(x, y, zp5))])
+        B = np.stack([shaped(Bx(x, yp5, zp5)), shaped(By(xp5, y, zp5)), shaped(Bz(xp5, yp5, z))])
+        J = np.stack([shaped(Jx(xp5, y, z)), shaped(Jy(x, yp5, z)), shaped(Jz(x, y, zp5))])
+        self._upload(E, B, J)
+
+    def _download(self, with_halo):
+        E, B, J = (np.empty(self._lattice_shape(with_halo), np.float32) for _ in range(3))
+        check(lib().b2p_tile_get_fields(self._h, _ptr(E), _ptr(B), _ptr(J), int(with_halo)))
+        return E, B, J
+
+    def get_EBJ(self):
+        """bindings/pyemf.c++:32-78: owning float64 copies of the fp32 interior."""
+        E, B, J = self._download(False)
+        return tuple(tuple(np.array(f[c], dtype=np.float64) for c in range(3)) for f in (E, B, J))
+
+    def get_EBJ_with_halo(self):
+        E, B, J = self._download(True)
+        return tuple(tuple(np.array(f[c], dtype=np.float64) for c in range(3)) for f in (E, B, J))
+
+    # raw fp32 access used by the parity tests
+    def get_fields_f32(self, with_halo=True):
+        return self._download(with_halo)
+
+    def set_fields_f32(self, E=None, B=None, J=None, with_halo=True):
+        self._upload(E, B, J, with_halo)
+
+    # -- field solver ----------------------------------------------------------
+    def push_half_b(self):
+        check(lib().b2p_tile_push_half_b(self._h))
+
+    def push_e(self):
+        check(lib().b2p_tile_push_e(self._h))
+
+    def add_current(self):
+        check(lib().b2p_tile_add_current(self._h))
+
+    def filter_current(self):
+        check(lib().b2p_tile_filter_current(self._h))
+
+    def clear_current(self):
+        check(lib().b2p_tile_clear_current(self._h))
+
+    def field_energy(self):
+        b, e = C.c_double(), C.c_double()
+        check(lib().b2p_tile_field_energy(self._h, C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+
+class PicTile(Tile):
+    """pic::Tile<3> (pic/tile.h:52-202)."""
+
+    _need_pic = True
+
+    @staticmethod
+    def canonical_type():
+        return PicTile
+
+    @property
+    def n_species(self):
+        return self._cfg.n_species
+
+    # -- getters ---------------------------------------------------------------
+    def container_size(self, sp):
+        n = C.c_uint64()
+        check(lib().b2p_tile_container_size(self._h, int(sp), C.byref(n)))
+        return n.value
+
+    def get_particles(self, sp, alive_only=True):
+        n = self.container_size(sp)
+        a = [np.empty(n, np.float32) for _ in range(6)]
+        ids = np.empty(n, np.uint64)
+        m = C.c_uint64()
+        check(lib().b2p_tile_get_particles(self._h, int(sp), int(alive_only), *[_ptr(v) for v in a], _ptr(ids), C.byref(m)))
+        return tuple(np.array(v[:m.value]) for v in a) + (np.array(ids[:m.value]),)
+
+    def get_positions(self, sp):
+        p = self.get_particles(sp)
+        return p[0], p[1], p[2]
+
+    def get_velocities(self, sp):
+        p = self.get_particles(sp)
+        return p[3], p[4], p[5]
+
+    def get_ids(self, sp):
+        return self.get_particles(sp)[6]
+
+    # -- injection ---------------------------------------------------------------
+    def _inject_arrays(self, sp, pos, vel):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (*pos, *vel)]
+        for v in a:
+            if v.ndim != 1:
+                raise B2PError("pic::Tile::batch_inject_in_x_stripe: given batch must be one dimensional.")
+            if v.shape[0] != a[0].shape[0]:
+                raise B2PError("pic::Tile::batch_inject_in_x_stripe: batches must have same length.")
+        check(lib().b2p_tile_inject(self._h, int(sp), a[0].shape[0], *[_ptr(v) for v in a]))
+
+    def inject(self, sp, particles):
+        """pic/tile.c++:207-217"""
+        pos = np.array([p.pos for p in particles], dtype=np.float64).reshape(-1, 3)
+        vel = np.array([p.vel for p in particles], dtype=np.float64).reshape(-1, 3)
+        self._inject_arrays(sp, pos.T, vel.T)
+
+    def inject_to_each_cell(self, sp, pgen):
+        """pic/tile.c++:180-205: generator called per cell corner, cells in i->j->k order."""
+        nx, ny, nz = self.n_cells
+        gm = self.global_coordinate_map()
+        out = []
+        for i in range(nx):
+            for j in range(ny):
+                for k in range(nz):
+                    out.extend(pgen(*gm((i, j, k))))
+        self.inject(sp, out)
+
+    def batch_inject_to_cells(self, sp, pgen):
+        self.batch_inject_in_x_stripe(sp, pgen, float(self.mins[0]), float(self.maxs[0]))
+
+    def batch_inject_in_x_stripe(self, sp, pgen, x_left, x_right):
+        """pic/tile.c++:235-322"""
+        xmin, xmax = float(self.mins[0]), float(self.maxs[0])
+        if x_right <= xmin or x_left >= xmax:
+            return
+        nx, ny, nz = self.n_cells
+        dl, dr = x_left - xmin, x_right - xmin
+        i_begin = 0 if dl <= 0.0 else min(nx, int(np.floor(dl)))
+        i_end = nx if dr >= float(nx) else int(np.ceil(dr))
+        if i_begin >= i_end:
+            return
+        gm = self.global_coordinate_map()
+        ii, jj, kk = np.meshgrid(np.arange(i_begin, i_end, dtype=np.float64), np.arange(ny, dtype=np.float64),
+                                 np.arange(nz, dtype=np.float64), indexing="ij")
+        x, y, z = (np.ascontiguousarray(a.reshape(-1)) for a in gm((ii, jj, kk)))
+        batch = pgen(x, y, z)
+        self._inject_arrays(sp, batch.pos, batch.vel)
+
+    def set_particles_raw(self, sp, x, y, z, ux, uy, uz, ids):
+        a = [np.ascontiguousarray(v, dtype=np.float32) for v in (x, y, z, ux, uy, uz)]
+        i = np.ascontiguousarray(ids, dtype=np.uint64)
+        check(lib().b2p_tile_set_particles(self._h, int(sp), len(i), *[_ptr(v) for v in a], _ptr(i)))
+
+    # -- hot path ------------------------------------------------------------------
+    def push_particles(self):
+        check(lib().b2p_tile_push_particles(self._h))
+
+    def deposit_current(self):
+        check(lib().b2p_tile_deposit_current(self._h))
+
+    def sort_particles(self):
+        check(lib().b2p_tile_sort_particles(self._h))
+
+    def pack_outgoing_particles(self):
+        check(lib().b2p_tile_pack_outgoing_particles(self._h))
+
+    def sort_keys(self, sp):
+        k = np.empty(self.container_size(sp), np.uint32)
+        check(lib().b2p_tile_sort_keys(self._h, int(sp), _ptr(k)))
+        return k
+
+    def get_outgoing(self):
+        n = C.c_uint64()
+        ends = np.zeros(27 * self.n_species, np.uint64)
+        check(lib().b2p_tile_get_outgoing(self._h, None, 0, _ptr(ends), C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.dtype([("pos", np.float32, 3), ("vel", np.float32, 3), ("id", np.uint64)]))
+        check(lib().b2p_tile_get_outgoing(self._h, _ptr(buf), n.value, _ptr(ends), C.byref(n)))
+        return buf, ends
+
+    def kinetic_energy(self, sp):
+        e, n = C.c_double(), C.c_uint64()
+        check(lib().b2p_tile_kinetic_energy(self._h, int(sp), C.byref(e), C.byref(n)))
+        return e.value, n.value
+
+
+class Grid:
+    """The slice of corgi::Grid<3> the PIC lap uses, batched per phase on the device."""
+
+    def __init__(self, config):
+        try:
+            self._cfg = config if isinstance(config, _abi.B2PConfig) else make_config(config)
+        except ConfigError as e:
+            raise B2PError(str(e)) from None
+        h = C.c_void_p()
+        check(lib().b2p_grid_create(C.byref(self._cfg), C.byref(h)))
+        self._h = h
+        self._tiles = {}
+        self.n_species = self._cfg.n_species
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().b2p_grid_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def add_tile(self, tile, idx=None):
+        check(lib().b2p_grid_add_tile(self._h, tile._h))
+        self._tiles[tile.index] = tile   # keep_alive<1,2> (pycorgi.c++:333)
+
+    def get_tile(self, i, j, k):
+        return self._tiles[(i, j, k)]
+
+    def get_local_tiles(self):
+        return list(self._tiles.values())
+
+    def local_communication(self, mode):
+        check(lib().b2p_grid_local_communication(self._h, mode.value if isinstance(mode, comm_mode) else int(mode)))
+
+    def external_communication(self, mode):
+        check(lib().b2p_grid_external_communication(self._h, mode.value if isinstance(mode, comm_mode) else int(mode)))
+
+    def phase(self, name):
+        check(getattr(lib(), "b2p_grid_" + name)(self._h))
+
+    def step_pic(self, lap):
+        check(lib().b2p_grid_step_pic(self._h, int(lap)))
+
+    def step_emf(self):
+        check(lib().b2p_grid_step_emf(self._h))
+
+    def energies(self):
+        b, e = C.c_double(), C.c_double()
+        k = np.zeros(max(1, self.n_species), np.float64)
+        s = np.zeros(max(1, self.n_species), np.uint64)
+        check(lib().b2p_grid_energies(self._h, C.byref(b), C.byref(e), _ptr(k), _ptr(s)))
+        return b.value, e.value, k[:self.n_species], s[:self.n_species]
+
+    def inject_thermal(self, ppc, delgam, seed=1):
+        check(lib().b2p_grid_inject_thermal(self._h, int(ppc), float(delgam), int(seed)))
+
+    def set_uniform_B(self, bx, by, bz):
+        check(lib().b2p_grid_set_uniform_B(self._h, bx, by, bz))
+
+
+def sync():
+    check(lib().b2p_sync())
