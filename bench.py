@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — particle-pushes/s per full PIC step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+One "step" = one lap of projects/pic-turbulence/pic.py:187-221 (push_half_b, B halo,
+push, pack+migrate, sort every 5th lap, deposit, J exchange + halo, 3 binomial
+filter passes, push_half_b, push_e + add_current, E halo) over a synthetic
+uniform thermal pair plasma (BASELINE.json configs[4], "projects/scaling"):
+2 species x 16 ppc, theta = 0.3, uniform Bz, tiles of 64^3 cells, a cube of
+--cells^3 cells per GPU, GPUs arranged 1 / 2x1x1 / 2x2x1 / 2x2x2 (weak scaling).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_PARTICLE_PUSH = 56.0      # R pos,vel,id (32) + W pos,vel (24)
+BYTES_PER_PARTICLE_DEPOSIT = 32.0   # R pos,vel,id
+BYTES_PER_PARTICLE_STEP = 88.0      # push + deposit
+BYTES_PER_PARTICLE_SORT = 30.0      # amortised over 5 laps
+BYTES_PER_CELL_STEP = 300.0
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class Conf:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def gpu_blocks(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+def make_conf(args, n_gpus):
+    tpg = args.cells // args.tile            # tiles per GPU per axis
+    gb = gpu_blocks(n_gpus)
+    ppc = args.ppc
+    cfl = 0.45
+    oppc = 2 * ppc
+    q0 = -(cfl ** 2) / (0.5 * oppc * 2.0)    # projects/pic-turbulence/pic.py:49-50 with gamma=c_omp=1, m0=m1=1
+    return Conf(n_tiles=[tpg * gb[0], tpg * gb[1], tpg * gb[2]], n_cells_per_tile=[args.tile] * 3, cfl=cfl,
+                field_propagator="fdtd2", current_filter="binomial2", q0=q0, m0=1.0, q1=abs(q0), m1=1.0,
+                particle_pusher="boris", field_interpolator="linear_1st", current_depositer="zigzag_1st_atomic"), tpg, gb
+
+
+def binit(conf, ppc, delgam=0.3, sigma=10.0):
+    oppc = 2 * ppc
+    m0 = conf.m0 * abs(conf.q0)
+    gammath = 1.0 + 1.5 * delgam
+    return float(np.sqrt(gammath * oppc * m0 * conf.cfl ** 2 * sigma))   # pic.py:64-67
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- reference / CPU arm
+def cpu_reference(args, n_threads, seconds_target=20.0):
+    """The reference's CPU algorithm (oracle port, oracle/pic_oracle.cpp) on the host cores: one
+    worker per core, one tile at a time per worker (the reference's rank-per-core model)."""
+    from oracle.oracle import OracleGrid
+    # bounded sample of the same workload: same physics / ppc / tile-local work, fewer & smaller tiles
+    edge = 32
+    nt = max(1, n_threads)
+    tz = 1
+    while tz * tz * tz < nt:
+        tz += 1
+    tiles = (tz, tz, max(1, -(-nt // (tz * tz))))
+    conf, _, _ = make_conf(argparse.Namespace(cells=edge, tile=edge, ppc=args.ppc), 1)
+    conf.n_tiles = list(tiles)
+    g = OracleGrid(conf)
+    rng = np.random.default_rng(42)
+    ncell = edge ** 3
+    bz = binit(conf, args.ppc)
+    B = np.zeros((3, edge + 6, edge + 6, edge + 6), np.float32)
+    B[2] = bz
+    n_part = 0
+    for t in range(g.num_tiles):
+        i, j, k = t % tiles[0], (t // tiles[0]) % tiles[1], t // (tiles[0] * tiles[1])
+        g.set_fields(t, B=B, with_halo=True)
+        ii, jj, kk = np.meshgrid(np.arange(edge), np.arange(edge), np.arange(edge), indexing="ij")
+        corner = np.stack([ii.ravel() + i * edge, jj.ravel() + j * edge, kk.ravel() + k * edge]).astype(np.float64)
+        for _ in range(args.ppc):
+            pos = corner + rng.random((3, ncell))
+            for sp in range(2):
+                vel = 0.55 * rng.standard_normal((3, ncell))   # ~ theta=0.3 thermal spread
+                g.inject(t, sp, *pos, *vel)
+                n_part += ncell
+    g.step_pic(0, threads=n_threads)   # warm-up lap (includes the lap-0 sort)
+    return g, n_part, tiles, edge
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_threads = os.cpu_count() or 1
+    g, n_part, tiles, edge = cpu_reference(args, n_threads)
+    for w in range(args.warmup):
+        g.step_pic(1 + w, threads=n_threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        g.step_pic(1 + args.warmup + s, threads=n_threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n_part / dt
+    conf, tpg, gb = make_conf(args, args.gpus)
+    sample = f"{tiles[0]}x{tiles[1]}x{tiles[2]} tiles of {edge}^3 cells, 2 species x {args.ppc} ppc = {n_part} particles per step"
+    out = {
+        "impl": "reference", "metric": "particle-pushes/s per full PIC step", "value": value, "unit": "particle-pushes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "particle-pushes/s", "cores": n_threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "particle-pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def workload_config(args, n_gpus):
+    gb = gpu_blocks(n_gpus)
+    return {"workload": "projects/scaling uniform thermal pair plasma (BASELINE configs[4] physics), weak scaling",
+            "cells_per_gpu": f"{args.cells}^3", "tile": f"{args.tile}^3", "species": 2, "ppc_per_species": args.ppc,
+            "particles_per_gpu": 2 * args.ppc * args.cells ** 3, "gpu_blocks": "x".join(map(str, gb)),
+            "lap": "pic-turbulence/pic.py:187-221, sort every 5th lap, fdtd2 + boris + linear_1st + zigzag_1st_atomic + 3x binomial2",
+            "l2": "per-step working set (>= 17 GB) far exceeds the 126 MB L2; no explicit flush"}
+
+
+# --------------------------------------------------------------------------- CUDA arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=256, help="cube edge of cells per GPU")
+    ap.add_argument("--tile", type=int, default=64)
+    ap.add_argument("--ppc", type=int, default=16, help="particles per cell per species")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="per-kernel-class timing table on stderr")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+    n_gpus = world
+
+    import runko_b200 as rb
+    from runko_b200._lib import check
+    L = rb.lib()
+    check(L.b2p_init(local_rank))
+
+    conf, tpg, gb = make_conf(args, n_gpus)
+    grid = rb.Grid(conf)
+    # this rank's block of tiles
+    bi, bj, bk = rank % gb[0], (rank // gb[0]) % gb[1], rank // (gb[0] * gb[1])
+    tiles = []
+    for i in range(tpg):
+        for j in range(tpg):
+            for k in range(tpg):
+                t = rb.PicTile((bi * tpg + i, bj * tpg + j, bk * tpg + k), conf)
+                grid.add_tile(t)
+                tiles.append(t)
+    if world > 1:
+        T = conf.n_tiles
+        owner = np.zeros(T[0] * T[1] * T[2], np.int32)
+        for k in range(T[2]):
+            for j in range(T[1]):
+                for i in range(T[0]):
+                    owner[i + T[0] * (j + T[1] * k)] = (i // tpg) + gb[0] * ((j // tpg) + gb[1] * (k // tpg))
+        uid = np.zeros(128, np.uint8)
+        if rank == 0:
+            check(L.b2p_nccl_unique_id(uid.ctypes.data_as(C.c_void_p)))
+        lst = [uid.tobytes()]
+        dist.broadcast_object_list(lst, src=0)
+        uid = np.frombuffer(lst[0], np.uint8).copy()
+        check(L.b2p_grid_comm_init(grid._h, rank, world, uid.ctypes.data_as(C.c_void_p), owner.ctypes.data_as(C.c_void_p)))
+    grid.set_uniform_B(0.0, 0.0, binit(conf, args.ppc))
+    grid.inject_thermal(args.ppc, 0.3, seed=42)
+    n_part_local = 2 * args.ppc * args.cells ** 3
+    n_cells_local = args.cells ** 3
+    rb.sync()
+
+    def barrier():
+        rb.sync()
+        if dist is not None:
+            dist.barrier()
+
+    # prelude: sync E,B halos (pic.py:177-185)
+    for m in (rb.comm_mode.emf_E, rb.comm_mode.emf_B):
+        if world > 1:
+            grid.external_communication(m)
+        grid.local_communication(m)
+    lap = 0
+    for _ in range(args.warmup):
+        grid.step_pic(lap)
+        lap += 1
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    check(L.b2p_profile_enable(1))
+    launches0 = L.b2p_launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    check(L.b2p_timer_start())
+    for _ in range(args.steps):
+        grid.step_pic(lap)
+        lap += 1
+    ms = C.c_float()
+    check(L.b2p_timer_stop(C.byref(ms)))
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = L.b2p_launch_count() - launches0
+    clocks = sampler.stop()
+    nk = L.b2p_profile_num_classes()
+    pms, pl, pu = np.zeros(nk), np.zeros(nk, np.uint64), np.zeros(nk)
+    check(L.b2p_profile_report(pms.ctypes.data_as(C.c_void_p), pl.ctypes.data_as(C.c_void_p), pu.ctypes.data_as(C.c_void_p)))
+    check(L.b2p_profile_enable(0))
+    names = [L.b2p_profile_class_name(k).decode() for k in range(nk)]
+
+    dev_s = ms.value / 1e3
+    t_max = dev_s
+    if dist is not None:
+        import torch
+        tt = torch.tensor([dev_s], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_max = float(tt[0])
+    per_step = t_max / args.steps
+    value = n_part_local * world / per_step
+
+    # ---- roofline of the dominant kernel class (largest share of the timed region) ----
+    peak, peak_src = read_peaks()
+    bytes_per_unit = {"push": BYTES_PER_PARTICLE_PUSH, "deposit": BYTES_PER_PARTICLE_DEPOSIT, "gather": 64.0,
+                      "detect_leavers": 20.0, "sort_keys": 28.0, "radix_sort": 64.0, "filter": 24.0, "push_b": 36.0,
+                      "push_e": 48.0, "zero": 4.0, "halo_fill": 0.0, "J_exchange": 0.0, "nodal_means": 56.0}
+    top = int(np.argmax(pms))
+    share = {names[k]: round(float(pms[k] / max(pms.sum(), 1e-9)), 4) for k in np.argsort(-pms)[:8] if pms[k] > 0}
+    avg_ms = pms[top] / max(int(pl[top]), 1)
+    units_per_launch = pu[top] / max(int(pl[top]), 1)
+    achieved = bytes_per_unit.get(names[top], 0.0) * units_per_launch / (avg_ms * 1e-3) / 1e9
+    step_bytes = (BYTES_PER_PARTICLE_STEP + BYTES_PER_PARTICLE_SORT) * n_part_local + BYTES_PER_CELL_STEP * n_cells_local
+    roofline = {"bound": "hbm", "kernel": names[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": avg_ms, "launches": int(pl[top]), "bytes_per_unit": bytes_per_unit.get(names[top], 0.0),
+                "units_per_launch": units_per_launch, "share_of_step": share,
+                "step": {"algorithmic_bytes_per_gpu": step_bytes, "achieved_GBs": step_bytes / per_step / 1e9,
+                         "frac_of_peak": step_bytes / per_step / 1e9 / peak, "frac_of_8TBs": step_bytes / per_step / 8e12}}
+    if args.profile and rank == 0:
+        for k in np.argsort(-pms):
+            if pl[k]:
+                print(f"  {names[k]:16s} {pms[k] / args.steps:9.3f} ms/step  {int(pl[k]) // args.steps:6d} launches/step", file=sys.stderr)
+
+    # ---- e2e: whole job through the reference-facing per-tile API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, rb, L, conf, grid, tiles, world, dist)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_threads = os.cpu_count() or 1
+        g, n_part, tl, edge = cpu_reference(args, n_threads)
+        c0 = time.perf_counter()
+        nl = 0
+        while nl < 5 or (time.perf_counter() - c0 < 10.0 and nl < 50):
+            g.step_pic(1 + nl, threads=n_threads)
+            nl += 1
+        cdt = (time.perf_counter() - c0) / nl
+        cpu = {"value": n_part / cdt, "unit": "particle-pushes/s", "cores": n_threads, "kind": "port",
+               "sample": f"{tl[0]}x{tl[1]}x{tl[2]} tiles of {edge}^3 cells, 2 species x {args.ppc} ppc = {n_part} particles, {nl} laps"}
+
+    if rank == 0:
+        out = {"metric": "particle-pushes/s per full PIC step", "value": value, "unit": "particle-pushes/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+               "cell_updates_per_s": n_cells_local * world / per_step, "wall_ms_per_step": wall / args.steps * 1e3,
+               "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+        if e2e is not None:
+            out["e2e"] = e2e
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, rb, L, conf, grid, tiles, world, dist):
+    """Whole-job end to end through the reference-facing tile API (runko_b200.PicTile methods, the
+    calls runko/simulation.py makes per tile) starting and ending in HOST memory: every timed step
+    (i) re-uploads one tile's particle state from pinned-equivalent host arrays through the public
+    setter, (ii) runs the lap tile by tile, (iii) reads the per-lap energy diagnostics and one tile's
+    particle state back to the host.  Bytes are counted by the library (b2p_copy_bytes)."""
+    from runko_b200._lib import check
+    M = rb.comm_mode
+    multi = world > 1
+
+    def ext(m):
+        if multi:
+            grid.external_communication(m)
+
+    def lap_via_tile_api(lap):
+        for t in tiles: t.push_half_b()
+        ext(M.emf_B); grid.local_communication(M.emf_B)
+        for t in tiles: t.push_particles()
+        for t in tiles: t.pack_outgoing_particles()
+        ext(M.pic_particle); grid.local_communication(M.pic_particle)
+        if lap % 5 == 0:
+            for t in tiles: t.sort_particles()
+        for t in tiles: t.deposit_current()
+        ext(M.emf_J); grid.local_communication(M.emf_J_exchange)
+        ext(M.emf_J); grid.local_communication(M.emf_J)
+        for t in tiles: t.filter_current()
+        ext(M.emf_J); grid.local_communication(M.emf_J)
+        for t in tiles: t.filter_current()
+        for t in tiles: t.filter_current()
+        for t in tiles: t.push_half_b()
+        ext(M.emf_B); grid.local_communication(M.emf_B)
+        for t in tiles: t.push_e()
+        for t in tiles: t.add_current()
+        ext(M.emf_E); grid.local_communication(M.emf_E)
+        return grid.energies()                                   # io_average_* (D2H)
+
+    steps = max(2, min(args.steps, 5))
+    h0, d0 = C.c_uint64(), C.c_uint64()
+    rb.sync()
+    if dist is not None:
+        dist.barrier()
+    L.b2p_copy_bytes(C.byref(h0), C.byref(d0))
+    t0 = time.perf_counter()
+    lap = 1000   # keeps lap % 5 phase: laps 1000..: sort on the first
+    for s in range(steps):
+        t = tiles[s % len(tiles)]
+        state = [t.get_particles(sp, alive_only=False) for sp in range(2)]      # D2H of one tile
+        for sp in range(2):
+            t.set_particles_raw(sp, *state[sp])                                   # H2D of one tile
+        lap_via_tile_api(lap + s)
+    rb.sync()
+    if dist is not None:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    h1, d1 = C.c_uint64(), C.c_uint64()
+    L.b2p_copy_bytes(C.byref(h1), C.byref(d1))
+    if dist is not None:
+        import torch
+        tt = torch.tensor([dt], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+    n_part = 2 * args.ppc * args.cells ** 3 * world
+    return {"value": n_part / (dt / steps), "unit": "particle-pushes/s", "steps": steps,
+            "h2d_bytes_per_step": int((h1.value - h0.value) / steps), "d2h_bytes_per_step": int((d1.value - d0.value) / steps),
+            "how": "lap driven tile-by-tile through the PicTile API (as runko/simulation.py does), plus per step one tile's "
+                   "particle state host round trip (get_particles -> set_particles) and the energy diagnostics read-back; wall clock"}
+
+
+if __name__ == "__main__":
+    main()

@@ -202,6 +202,16 @@ int b2p_timer_start(void);
 int b2p_timer_stop(float* ms);
 /* number of kernels this library has launched since process start */
 uint64_t b2p_launch_count(void);
+/* bytes this library has copied host->device / device->host since process start */
+void b2p_copy_bytes(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* Per-kernel-class device timing (CUDA events on the launch stream around every
+ * launch of the class).  enable(1) clears and starts, enable(0) stops; report()
+ * fills arrays of b2p_profile_num_classes() entries: total ms, launches and
+ * processed units (particles or cells) per class. */
+int b2p_profile_enable(int on);
+int b2p_profile_num_classes(void);
+const char* b2p_profile_class_name(int k);
+int b2p_profile_report(double* ms, uint64_t* launches, double* units);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,7 @@ struct orc_grid {
   float stencilM[3][3][5];
   std::vector<Tile> tiles;                         // index = cid
   double gmins[3], gmaxs[3];
+  int threads = 1;   // workers used by orc_local_communication (set by the step drivers)
 };
 
 namespace {
@@ -906,11 +907,22 @@ int orc_tile_interpolate(orc_grid* g, int t, uint64_t n, const float* x, const f
 // external/corgi/src/corgi/corgi.h:1697-1718 with emf/tile.c++:478-542 and
 // pic/tile_communication.c++:100-195. Moore order: cellular_automata.h:48-62.
 int orc_local_communication(orc_grid* g, int mode) {
+  switch (mode) {
+    case B2P_COMM_EMF_E: case B2P_COMM_EMF_B: case B2P_COMM_EMF_J: case B2P_COMM_EMF_J_EXCHANGE: case B2P_COMM_PIC_PARTICLE: break;
+    default: g_err = "local_communication does not support given communication mode"; return B2P_ERR_LOGIC;
+  }
+  if (mode == B2P_COMM_PIC_PARTICLE)
+    for (const Tile& t : g->tiles)
+      if (t.out_ends.size() != 27 * t.sp.size()) { g_err = "pack_outgoing_particles not called"; return 1; }
   const int* T = g->cfg.n_tiles;
-  for (int kr = -1; kr <= 1; ++kr) for (int jr = -1; jr <= 1; ++jr) for (int ir = -1; ir <= 1; ++ir) {
-    if (ir == 0 && jr == 0 && kr == 0) continue;
-    const int dir[3] = { ir, jr, kr };
-    for (Tile& me : g->tiles) {
+  // corgi loops directions outermost and tiles innermost; no tile reads anything another
+  // tile writes within one mode, so tiles can be processed independently (here: one
+  // worker per tile, the reference's one-rank-per-core execution model) as long as each
+  // tile keeps the Moore order kr -> jr -> ir of its own 26 exchanges.
+  parallel_tiles(g, g->threads, [&](Tile& me) {
+    for (int kr = -1; kr <= 1; ++kr) for (int jr = -1; jr <= 1; ++jr) for (int ir = -1; ir <= 1; ++ir) {
+      if (ir == 0 && jr == 0 && kr == 0) continue;
+      const int dir[3] = { ir, jr, kr };
       const int oi = wrap(me.idx[0] + ir, T[0]), oj = wrap(me.idx[1] + jr, T[1]), ok = wrap(me.idx[2] + kr, T[2]);
       Tile& other = g->tiles[oi + T[0] * (oj + T[1] * ok)];
       switch (mode) {
@@ -918,27 +930,24 @@ int orc_local_communication(orc_grid* g, int mode) {
         case B2P_COMM_EMF_B: set_in_subregion(me, me.B, other, other.B, dir); break;
         case B2P_COMM_EMF_J: set_in_subregion(me, me.J, other, other.J, dir); break;
         case B2P_COMM_EMF_J_EXCHANGE: add_to_J_from_subregion(me, other, dir); break;
-        case B2P_COMM_PIC_PARTICLE: {
+        default: {
           const int inv = subregion_index(-ir, -jr, -kr);
           for (size_t s = 0; s < me.sp.size(); ++s) {
             const size_t index = 27 * s + inv;
-            if (other.out_ends.size() != 27 * other.sp.size()) { g_err = "pack_outgoing_particles not called"; return 1; }
             const size_t end = other.out_ends[index];
             const size_t begin = index == 0 ? 0 : other.out_ends[index - 1];
             me.incoming[s].push_back({ other.out_buf.data() + begin, end - begin });
           }
-          break;
         }
-        default: g_err = "local_communication does not support given communication mode"; return B2P_ERR_LOGIC;
       }
     }
-  }
+  });
   if (mode == B2P_COMM_PIC_PARTICLE) {                             // postlude, tile_communication.c++:100-117
     float wmin[3], wmax[3];
     for (int d = 0; d < 3; ++d) { wmin[d] = float(g->gmins[d]); wmax[d] = float(g->gmaxs[d]); }
-    for (Tile& me : g->tiles) {
+    parallel_tiles(g, g->threads, [&](Tile& me) {
       for (size_t s = 0; s < me.sp.size(); ++s) { append_spans(me.sp[s], me.incoming[s], wmin, wmax); me.incoming[s].clear(); }
-    }
+    });
     for (Tile& me : g->tiles) me.out_ends.clear();
   }
   return 0;
@@ -966,6 +975,7 @@ int orc_grid_phase(orc_grid* g, const char* phase, int threads) {
 // no-op in a single process)
 int orc_step_pic(orc_grid* g, int64_t lap, int threads) {
   int rc = 0;
+  g->threads = threads;
 #define DO(x) do { rc = (x); if (rc) return rc; } while (0)
   DO(orc_grid_phase(g, "push_half_b", threads));
   DO(orc_local_communication(g, B2P_COMM_EMF_B));
@@ -993,6 +1003,7 @@ int orc_step_pic(orc_grid* g, int64_t lap, int threads) {
 // projects/emf-wave/emf.py:48-62
 int orc_step_emf(orc_grid* g, int threads) {
   int rc = 0;
+  g->threads = threads;
   DO(orc_local_communication(g, B2P_COMM_EMF_E));
   DO(orc_grid_phase(g, "push_half_b", threads));
   DO(orc_grid_phase(g, "push_half_b", threads));

@@ -36,6 +36,7 @@ struct Context {
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   unsigned long long launches = 0;
+  unsigned long long h2d_bytes = 0, d2h_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 Context& ctx();          // initialises lazily on device 0; throws if no GPU
@@ -45,6 +46,19 @@ void count_launch(int n = 1);
     ::b2p::count_launch();                  \
     B2P_CUDA(cudaGetLastError());           \
   } while (0)
+
+// Optional per-kernel-class timing with CUDA events on the launch stream
+// (bench.py's roofline leg).  Off by default: zero overhead on the hot path.
+enum KernelClass {
+  KC_NODAL, KC_PUSH, KC_DEPOSIT, KC_SORT_KEYS, KC_RADIX_SORT, KC_GATHER, KC_DETECT, KC_GATHER_OUT, KC_APPEND,
+  KC_ZERO, KC_PUSH_B, KC_PUSH_E, KC_ADD_CURRENT, KC_FILTER, KC_HALO, KC_J_EXCHANGE, KC_ENERGY, KC_OTHER, KC_COUNT
+};
+const char* kernel_class_name(int k);
+struct ProfScope {
+  int idx = -1;
+  explicit ProfScope(KernelClass k, double units = 0.0);
+  ~ProfScope();
+};
 
 void* dmalloc(size_t bytes);   // stream-ordered (cudaMallocAsync)
 void dfree(void* p);

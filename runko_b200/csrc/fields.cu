@@ -289,11 +289,13 @@ static dim3 interior_grid(const Geom& g, int ntiles) {
 }
 
 void launch_push_b_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt) {
+  ProfScope prof_(KC_PUSH_B, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
   k_push_b_fdtd2<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
   B2P_LAUNCH_CHECK();
 }
 void launch_push_b_stencil(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, const float M[3][3][5]) {
+  ProfScope prof_(KC_PUSH_B, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
   StencilM c;
   for (int a = 0; a < 3; ++a) for (int r = 0; r < 3; ++r) for (int q = 0; q < 5; ++q) c.M[a][r][q] = M[a][r][q];
@@ -301,17 +303,20 @@ void launch_push_b_stencil(const FieldPtrs* tiles, int ntiles, const Geom& g, fl
   B2P_LAUNCH_CHECK();
 }
 void launch_push_e_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, bool add_current) {
+  ProfScope prof_(KC_PUSH_E, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
   if (add_current) k_push_e_fdtd2<true><<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
   else k_push_e_fdtd2<false><<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
   B2P_LAUNCH_CHECK();
 }
 void launch_add_current(const FieldPtrs* tiles, int ntiles, const Geom& g) {
+  ProfScope prof_(KC_ADD_CURRENT, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
   k_add_current<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g);
   B2P_LAUNCH_CHECK();
 }
 void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unrolled) {
+  ProfScope prof_(KC_FILTER, double(ntiles) * g.Ch);
   if (!ntiles) return;
   const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, unsigned(ntiles) * 3 * g.Hx[0]);
   const FilterTile* ft = static_cast<const FilterTile*>(filter_tiles);
@@ -320,23 +325,27 @@ void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unr
   B2P_LAUNCH_CHECK();
 }
 void launch_zero(float* p, size_t n) {
+  ProfScope prof_(KC_ZERO, double(n));
   if (!n) return;
   const unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, size_t(ctx().sm_count) * 16));
   k_zero<<<blocks, 256, 0, ctx().stream>>>(p, n);
   B2P_LAUNCH_CHECK();
 }
 void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which) {
+  ProfScope prof_(KC_HALO, double(ntiles) * g.Ch);
   if (!ntiles) return;
   const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, unsigned(ntiles) * g.Hx[0]);
   k_halo_fill<<<grid, cell_block(), 0, ctx().stream>>>(tiles, nbr, g, which);
   B2P_LAUNCH_CHECK();
 }
 void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g) {
+  ProfScope prof_(KC_J_EXCHANGE, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
   k_J_exchange<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, nbr, g);
   B2P_LAUNCH_CHECK();
 }
 void launch_field_energy(const FieldPtrs* tiles, int ntiles, const Geom& g, double* out) {
+  ProfScope prof_(KC_ENERGY, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
   B2P_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 2 * ntiles, ctx().stream));
   const size_t Ni = size_t(g.N[0]) * g.N[1] * g.N[2];

@@ -56,10 +56,36 @@ void dfree(void* p) {
 }
 static void sync() { B2P_CUDA(cudaStreamSynchronize(ctx().stream)); }
 template <class T> static void h2d(T* dst, const T* src, size_t n) {
-  if (n) B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+  if (n) { B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx().stream)); g_ctx.h2d_bytes += n * sizeof(T); }
 }
 template <class T> static void d2h(T* dst, const T* src, size_t n) {
-  if (n) B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream));
+  if (n) { B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream)); g_ctx.d2h_bytes += n * sizeof(T); }
+}
+
+// ----------------------------------------------------------------- profiler --
+struct ProfRecord { int kc; cudaEvent_t a, b; double units; };
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; B2P_CUDA(cudaEventCreate(&e)); return e;
+}
+const char* kernel_class_name(int k) {
+  static const char* n[KC_COUNT] = { "nodal_means", "push", "deposit", "sort_keys", "radix_sort", "gather", "detect_leavers",
+                                     "gather_outgoing", "append", "zero", "push_b", "push_e", "add_current", "filter",
+                                     "halo_fill", "J_exchange", "energy", "other" };
+  return (k >= 0 && k < KC_COUNT) ? n[k] : "?";
+}
+ProfScope::ProfScope(KernelClass k, double units) {
+  if (!g_prof_on) return;
+  ProfRecord r{ int(k), take_event(), take_event(), units };
+  cudaEventRecord(r.a, ctx().stream);
+  idx = int(g_prof.size());
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(g_prof[idx].b, ctx().stream);
 }
 
 // process-level scratch shared by all tiles (all work is ordered on one stream)
@@ -863,5 +889,30 @@ int b2p_timer_stop(float* ms) {
   B2P_CATCH
 }
 uint64_t b2p_launch_count(void) { return g_ctx_ready ? ctx().launches : 0; }
+void b2p_copy_bytes(uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+  if (h2d_bytes) *h2d_bytes = g_ctx_ready ? ctx().h2d_bytes : 0;
+  if (d2h_bytes) *d2h_bytes = g_ctx_ready ? ctx().d2h_bytes : 0;
+}
+int b2p_profile_enable(int on) {
+  B2P_TRY
+  sync();
+  for (auto& r : b2p::g_prof) { b2p::g_event_pool.push_back(r.a); b2p::g_event_pool.push_back(r.b); }
+  b2p::g_prof.clear();
+  b2p::g_prof_on = on != 0;
+  B2P_CATCH
+}
+int b2p_profile_num_classes(void) { return b2p::KC_COUNT; }
+const char* b2p_profile_class_name(int k) { return b2p::kernel_class_name(k); }
+int b2p_profile_report(double* ms, uint64_t* launches, double* units) {
+  B2P_TRY
+  sync();
+  for (int k = 0; k < b2p::KC_COUNT; ++k) { ms[k] = 0; launches[k] = 0; units[k] = 0; }
+  for (auto& r : b2p::g_prof) {
+    float t = 0;
+    B2P_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.kc] += t; launches[r.kc] += 1; units[r.kc] += r.units;
+  }
+  B2P_CATCH
+}
 
 }  // extern "C"

@@ -457,12 +457,14 @@ k_inject_thermal(const Species s, const Geom g, const float3 mins, const unsigne
 static unsigned blocks_for(size_t n) { return unsigned((n + 255) / 256); }
 
 void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* nod) {
+  ProfScope prof_(KC_NODAL, double(g.Ch));
   const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, g.Hx[0]);
   k_nodal_means<<<grid, dim3(32, 8, 1), 0, ctx().stream>>>(E, B, g, nod);
   B2P_LAUNCH_CHECK();
 }
 
 void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm) {
+  ProfScope prof_(KC_PUSH, double(s.n));
   if (!s.n) return;
   PushArgs a{ s, nod, g, make_float3(origo[0], origo[1], origo[2]), cfl, qm };
   const unsigned nb = blocks_for(s.n);
@@ -476,6 +478,7 @@ void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g,
 }
 
 void launch_deposit(const Species& s, float* J, const Geom& g, const float origo[3], float cfl, float charge) {
+  ProfScope prof_(KC_DEPOSIT, double(s.n));
   if (!s.n) return;
   DepositArgs a{ s, J, g, make_float3(origo[0], origo[1], origo[2]), cfl, charge };
   k_deposit_zigzag<<<blocks_for(s.n), 256, 0, ctx().stream>>>(a);
@@ -483,6 +486,7 @@ void launch_deposit(const Species& s, float* J, const Geom& g, const float origo
 }
 
 void launch_sort_keys(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* idx, unsigned dead_key) {
+  ProfScope prof_(KC_SORT_KEYS, double(s.n));
   if (!s.n) return;
   k_sort_keys<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, g, make_float3(origo[0], origo[1], origo[2]), keys, idx, dead_key);
   B2P_LAUNCH_CHECK();
@@ -497,6 +501,7 @@ size_t sort_pairs_temp_bytes(unsigned n, int end_bit) {
 // stable LSD radix sort of (key, slot) pairs; returns which half of the double
 // buffers holds the result
 int sort_pairs(void* temp, size_t temp_bytes, unsigned* keys[2], unsigned* vals[2], unsigned n, int end_bit) {
+  ProfScope prof_(KC_RADIX_SORT, double(n));
   cub::DoubleBuffer<unsigned> k(keys[0], keys[1]), v(vals[0], vals[1]);
   B2P_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, int(n), 0, end_bit, ctx().stream));
   count_launch((end_bit + 7) / 8 + 2);
@@ -509,6 +514,7 @@ size_t sort_keys64_temp_bytes(unsigned n, int end_bit) {
   return bytes;
 }
 int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit) {
+  ProfScope prof_(KC_RADIX_SORT, double(n));
   cub::DoubleBuffer<unsigned long long> k(keys[0], keys[1]);
   B2P_CUDA(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, k, int(n), 0, end_bit, ctx().stream));
   count_launch((end_bit + 7) / 8 + 2);
@@ -516,6 +522,7 @@ int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsi
 }
 
 void launch_gather(const Species& src, const Species& dst, const unsigned* perm) {
+  ProfScope prof_(KC_GATHER, double(src.n));
   if (!src.n) return;
   k_gather<<<blocks_for(src.n), 256, 0, ctx().stream>>>(src, dst, perm);
   B2P_LAUNCH_CHECK();
@@ -524,6 +531,7 @@ void launch_gather(const Species& src, const Species& dst, const unsigned* perm)
 void launch_detect_leavers(const Species& s, const float mins[3], const float maxs[3], unsigned container,
                            unsigned long long* list, unsigned* list_count, unsigned list_cap, unsigned* last_alive,
                            unsigned* cont_count) {
+  ProfScope prof_(KC_DETECT, double(s.n));
   if (!s.n) return;
   k_detect_leavers<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, make_float3(mins[0], mins[1], mins[2]),
                                                                make_float3(maxs[0], maxs[1], maxs[2]), container, list,
@@ -532,18 +540,21 @@ void launch_detect_leavers(const Species& s, const float mins[3], const float ma
 }
 
 void launch_gather_outgoing(const unsigned long long* sorted, unsigned total, const void* out_tiles, unsigned* counts) {
+  ProfScope prof_(KC_GATHER_OUT, double(total));
   if (!total) return;
   k_gather_outgoing<<<blocks_for(total), 256, 0, ctx().stream>>>(sorted, total, static_cast<const OutTile*>(out_tiles), counts);
   B2P_LAUNCH_CHECK();
 }
 
 void launch_last_alive(const unsigned long long* id, unsigned n, unsigned* last_alive) {
+  ProfScope prof_(KC_OTHER, double(n));
   if (!n) return;
   k_last_alive<<<blocks_for(n), 256, 0, ctx().stream>>>(id, n, last_alive);
   B2P_LAUNCH_CHECK();
 }
 
 void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, const float wmin[3], const float wmax[3]) {
+  ProfScope prof_(KC_APPEND, double(max_count));
   if (!njobs || !max_count) return;
   const unsigned bx = std::min(blocks_for(max_count), 1024u);
   k_append<<<dim3(bx, njobs), 256, 0, ctx().stream>>>(static_cast<const AppendJob*>(jobs), wrap ? 1 : 0,
@@ -552,12 +563,14 @@ void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, c
 }
 
 void launch_fill_dead(unsigned long long* id, unsigned begin, unsigned end) {
+  ProfScope prof_(KC_OTHER, 0.0);
   if (end <= begin) return;
   k_fill_dead<<<blocks_for(end - begin), 256, 0, ctx().stream>>>(id, begin, end);
   B2P_LAUNCH_CHECK();
 }
 
 void launch_kinetic_energy(const Species& s, double* out) {
+  ProfScope prof_(KC_ENERGY, double(s.n));
   if (!s.n) return;
   const unsigned nb = std::min(blocks_for(s.n), unsigned(ctx().sm_count) * 8);
   k_kinetic_energy<<<nb, 256, 0, ctx().stream>>>(s, out);
@@ -566,6 +579,7 @@ void launch_kinetic_energy(const Species& s, double* out) {
 
 void launch_inject_thermal(const Species& s, const Geom& g, const float mins[3], unsigned ppc, float theta,
                            unsigned long long seed_pos, unsigned long long seed_vel, unsigned long long id_base) {
+  ProfScope prof_(KC_OTHER, 0.0);
   const size_t total = size_t(g.N[0]) * g.N[1] * g.N[2] * ppc;
   if (!total) return;
   k_inject_thermal<<<blocks_for(total), 256, 0, ctx().stream>>>(s, g, make_float3(mins[0], mins[1], mins[2]), ppc, theta,
