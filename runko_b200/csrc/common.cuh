@@ -51,7 +51,7 @@ void count_launch(int n = 1);
 // (bench.py's roofline leg).  Off by default: zero overhead on the hot path.
 enum KernelClass {
   KC_NODAL, KC_PUSH, KC_DEPOSIT, KC_SORT_KEYS, KC_RADIX_SORT, KC_GATHER, KC_DETECT, KC_GATHER_OUT, KC_APPEND,
-  KC_ZERO, KC_PUSH_B, KC_PUSH_E, KC_ADD_CURRENT, KC_FILTER, KC_HALO, KC_J_EXCHANGE, KC_ENERGY, KC_OTHER, KC_COUNT
+  KC_ZERO, KC_PUSH_B, KC_PUSH_E, KC_ADD_CURRENT, KC_FILTER, KC_HALO, KC_J_EXCHANGE, KC_ENERGY, KC_EDGE_GATHER, KC_OTHER, KC_COUNT
 };
 const char* kernel_class_name(int k);
 struct ProfScope {
@@ -82,7 +82,10 @@ struct DBuf {
   // ensure capacity >= n; contents are NOT preserved unless keep > 0 (first `keep` elements)
   void reserve(size_t n, size_t keep = 0) {
     if (n <= cap) return;
-    size_t ncap = n + n / 8 + 64;
+    reserve_exact(n + n / 8 + 64, keep);
+  }
+  void reserve_exact(size_t ncap, size_t keep = 0) {
+    if (ncap <= cap) return;
     T* q = dalloc<T>(ncap);
     if (keep && p) B2P_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, ctx().stream));
     if (p) dfree(p);

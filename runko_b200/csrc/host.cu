@@ -3,6 +3,8 @@
 #include "host.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -74,7 +76,7 @@ static cudaEvent_t take_event() {
 const char* kernel_class_name(int k) {
   static const char* n[KC_COUNT] = { "nodal_means", "push", "deposit", "sort_keys", "radix_sort", "gather", "detect_leavers",
                                      "gather_outgoing", "append", "zero", "push_b", "push_e", "add_current", "filter",
-                                     "halo_fill", "J_exchange", "energy", "other" };
+                                     "halo_fill", "J_exchange", "energy", "edge_gather", "other" };
   return (k >= 0 && k < KC_COUNT) ? n[k] : "?";
 }
 ProfScope::ProfScope(KernelClass k, double units) {
@@ -91,6 +93,7 @@ ProfScope::~ProfScope() {
 // process-level scratch shared by all tiles (all work is ordered on one stream)
 struct Scratch {
   DBuf<float4> nodal;
+  DBuf<float4> edges;             // cell-edge current accumulators of the tile being deposited
   DBuf<unsigned> keys[2], vals[2];
   DBuf<unsigned char> cub_temp;
   DBuf<unsigned long long> list[2];
@@ -102,11 +105,16 @@ struct Scratch {
 static Scratch& scratch() { static Scratch* s = new Scratch; return *s; }
 
 // ---------------------------------------------------------------- container --
-void Container::reserve(size_t cap) {
+void Container::reserve(size_t cap, bool exact) {
   if (cap <= capacity()) return;
-  x.reserve(cap, n); y.reserve(cap, n); z.reserve(cap, n);
-  ux.reserve(cap, n); uy.reserve(cap, n); uz.reserve(cap, n);
-  id.reserve(cap, n);
+  if (!exact)
+  // uniform capacity classes (multiples of 256 Ki slots incl. 1/16 slack): containers of a
+  // uniform plasma end up with identical capacities, so the sort's spare set never reallocates
+  cap = ((cap + cap / 16 + 262143) / 262144) * 262144;
+  if (std::getenv("B2P_TRACE")) std::fprintf(stderr, "[b2p trace] container realloc %zu -> %zu slots (n=%u)\n", capacity(), cap, n);
+  x.reserve_exact(cap, n); y.reserve_exact(cap, n); z.reserve_exact(cap, n);
+  ux.reserve_exact(cap, n); uy.reserve_exact(cap, n); uz.reserve_exact(cap, n);
+  id.reserve_exact(cap, n);
 }
 
 static void swap_storage(Container& a, Container& b) {
@@ -295,29 +303,83 @@ void phase_filter(const std::vector<b2p_tile*>& tiles) {
 // -------------------------------------------------------- particle phases --
 static int sign_of(double v) { return (0.0 < v) - (v < 0.0); }   // tools/math.h:181-183
 
-// pic/tile.c++:326-365
-void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
+// Shared state of the leaver detection: filled either by the fused push of
+// b2p_grid_step_pic or by the standalone detection pass of pack_outgoing_particles.
+struct DetectPlan {
+  std::vector<Container*> conts;
+  std::vector<b2p_tile*> owner;
+  size_t total_slots = 0;
+  bool fused_valid = false;      // the last push already ran the detection for exactly these tiles
+  std::vector<b2p_tile*> tiles;
+};
+static DetectPlan& detect_plan() { static DetectPlan p; return p; }
+
+static void detect_setup(const std::vector<b2p_tile*>& tiles, size_t min_cap) {
   Scratch& s = scratch();
+  DetectPlan& dp = detect_plan();
+  dp.conts.clear(); dp.owner.clear(); dp.total_slots = 0; dp.tiles = tiles; dp.fused_valid = false;
+  for (b2p_tile* t : tiles)
+    for (Container& c : t->sp) { dp.conts.push_back(&c); dp.owner.push_back(t); dp.total_slots += c.n; }
+  const size_t nc = dp.conts.size();
+  if (nc >= (size_t(1) << 26)) throw Error(B2P_ERR_RUNTIME, "too many containers in one pack call");
+  // device counters: [0] list length | [1..nc] P per container | [1+nc..1+2nc) leavers per container | counts[nc][27]
+  const size_t ncounters = 1 + 2 * nc + nc * 27;
+  s.counters.reserve(ncounters);
+  const size_t cap = std::max<size_t>(std::max(min_cap, dp.total_slots / 8 + 65536), s.list[0].cap);
+  s.list[0].reserve(cap); s.list[1].reserve(cap);
+  B2P_CUDA(cudaMemsetAsync(s.counters.p, 0, ncounters * sizeof(unsigned), ctx().stream));
+}
+
+static DetectArgsHost detect_args(size_t c) {
+  Scratch& s = scratch();
+  DetectPlan& dp = detect_plan();
+  const b2p_tile* t = dp.owner[c];
+  const size_t nc = dp.conts.size();
+  DetectArgsHost d;
+  for (int q = 0; q < 3; ++q) { d.mins[q] = float(t->mins[q]); d.maxs[q] = float(t->maxs[q]); }
+  d.container = unsigned(c);
+  d.list = s.list[0].p; d.list_count = s.counters.p;
+  d.list_cap = unsigned(std::min<size_t>(s.list[0].cap, 0xFFFFFFFFu));
+  d.last_alive = s.counters.p + 1 + c;
+  d.cont_count = s.counters.p + 1 + nc + c;
+  return d;
+}
+
+// pic/tile.c++:326-365.  fuse_detect: also run pack_outgoing's leaver detection on the
+// freshly pushed positions (valid only when pack_outgoing_particles is the next call).
+void phase_push_particles(const std::vector<b2p_tile*>& tiles, bool fuse_detect) {
+  Scratch& s = scratch();
+  if (fuse_detect) detect_setup(tiles, 0);
+  size_t cidx = 0;
   for (b2p_tile* t : tiles) {
     bool any = false;
     for (const Container& c : t->sp) any = any || c.n;
-    if (!any) continue;
+    if (!any) { cidx += t->sp.size(); continue; }
     s.nodal.reserve(size_t(2) * t->g.Ch);
     launch_nodal_means(t->E.p, t->B.p, t->g, s.nodal.p);
     for (Container& c : t->sp) {
       const float qm = static_cast<float>(sign_of(c.charge) / c.mass);
-      launch_push(t->cfg.particle_pusher, c.view(), s.nodal.p, t->g, t->origo, static_cast<float>(t->cfg.cfl), qm);
+      DetectArgsHost d;
+      if (fuse_detect) d = detect_args(cidx);
+      launch_push(t->cfg.particle_pusher, c.view(), s.nodal.p, t->g, t->origo, static_cast<float>(t->cfg.cfl), qm,
+                  fuse_detect ? &d : nullptr);
+      c.P_valid = false;
+      ++cidx;
     }
   }
+  if (fuse_detect) detect_plan().fused_valid = true;
 }
 
 // pic/tile.c++:369-415.  clear_current + scratch accumulate + `J += scratch`
 // collapse to "zero J, accumulate into J" (0 + x == x).
 void phase_deposit(const std::vector<b2p_tile*>& tiles) {
+  Scratch& s = scratch();
   for (b2p_tile* t : tiles) {
-    launch_zero(t->J(), t->lattice_floats());
+    s.edges.reserve(size_t(3) * t->g.Ch);
+    launch_zero(reinterpret_cast<float*>(s.edges.p), size_t(12) * t->g.Ch);
     for (Container& c : t->sp)
-      launch_deposit(c.view(), t->J(), t->g, t->origo, static_cast<float>(t->cfg.cfl), static_cast<float>(c.charge));
+      launch_deposit(c.view(), s.edges.p, t->g, t->origo, static_cast<float>(t->cfg.cfl), static_cast<float>(c.charge));
+    launch_edge_gather(s.edges.p, t->J(), t->g);
   }
 }
 
@@ -328,13 +390,19 @@ void phase_sort(const std::vector<b2p_tile*>& tiles) {
     for (Container& c : t->sp) {
       if (c.n < 2) continue;
       for (int b = 0; b < 2; ++b) { s.keys[b].reserve(c.n); s.vals[b].reserve(c.n); }
-      launch_sort_keys(c.view(), t->g, t->origo, s.keys[0].p, s.vals[0].p, 0xFFFFFFFFu);
-      const size_t tb = sort_pairs_temp_bytes(c.n, 32);
+      // Alive keys are < Ch (particles live inside the haloed lattice), so dead slots are keyed
+      // Ch instead of UINT32_MAX and only bits(Ch) key bits are sorted: same stable order,
+      // one radix pass fewer.  (Keys >= Ch — positions outside the lattice, undefined
+      // behaviour in the reference — are clamped to Ch.)
+      int key_bits = 1;
+      while ((1ull << key_bits) <= t->g.Ch) ++key_bits;
+      launch_sort_keys(c.view(), t->g, t->origo, s.keys[0].p, s.vals[0].p, t->g.Ch);
+      const size_t tb = sort_pairs_temp_bytes(c.n, key_bits);
       s.cub_temp.reserve(tb);
       unsigned* k[2] = { s.keys[0].p, s.keys[1].p };
       unsigned* v[2] = { s.vals[0].p, s.vals[1].p };
-      const int sel = sort_pairs(s.cub_temp.p, tb, k, v, c.n, 32);
-      s.spare.reserve(c.capacity());
+      const int sel = sort_pairs(s.cub_temp.p, tb, k, v, c.n, key_bits);
+      s.spare.reserve(c.capacity(), /*exact=*/true);
       s.spare.n = c.n;
       launch_gather(c.view(), s.spare.view(), v[sel]);
       swap_storage(c, s.spare);
@@ -346,36 +414,27 @@ void phase_sort(const std::vector<b2p_tile*>& tiles) {
 void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles) {
   if (tiles.empty()) return;
   Scratch& s = scratch();
-  std::vector<Container*> conts;
-  std::vector<b2p_tile*> owner;
-  size_t total_slots = 0;
-  for (b2p_tile* t : tiles)
-    for (Container& c : t->sp) { conts.push_back(&c); owner.push_back(t); total_slots += c.n; }
-  const size_t nc = conts.size();
+  DetectPlan& dp = detect_plan();
+  const bool fused = dp.fused_valid && dp.tiles == tiles;
+  dp.fused_valid = false;
   for (b2p_tile* t : tiles) { t->out_ends.assign(27 * t->sp.size(), 0); t->out_count = 0; }
-  if (nc == 0) return;
-  if (nc >= (size_t(1) << 26)) throw Error(B2P_ERR_RUNTIME, "too many containers in one pack call");
-  // device counters: [0] list length | [1..nc] P per container | [1+nc..1+2nc) leavers per container | counts[nc][27]
-  const size_t ncounters = 1 + 2 * nc + nc * 27;
-  s.counters.reserve(ncounters);
-  std::vector<unsigned> hc(1 + 2 * nc);
-  size_t cap = std::max<size_t>(total_slots / 8 + 65536, s.list[0].cap);
-  for (;;) {
-    s.list[0].reserve(cap); s.list[1].reserve(cap);
-    B2P_CUDA(cudaMemsetAsync(s.counters.p, 0, ncounters * sizeof(unsigned), ctx().stream));
-    for (size_t c = 0; c < nc; ++c) {
-      const b2p_tile* t = owner[c];
-      const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
-      const float mx[3] = { float(t->maxs[0]), float(t->maxs[1]), float(t->maxs[2]) };
-      launch_detect_leavers(conts[c]->view(), mn, mx, unsigned(c), s.list[0].p, s.counters.p,
-                            unsigned(std::min<size_t>(s.list[0].cap, 0xFFFFFFFFu)), s.counters.p + 1 + c,
-                            s.counters.p + 1 + nc + c);
+  std::vector<unsigned> hc;
+  size_t nc = 0;
+  size_t min_cap = 0;
+  for (int attempt = 0;; ++attempt) {
+    if (!(fused && attempt == 0)) {
+      detect_setup(tiles, min_cap);
+      for (size_t c = 0; c < dp.conts.size(); ++c) launch_detect_leavers(dp.conts[c]->view(), detect_args(c));
     }
+    nc = dp.conts.size();
+    if (nc == 0) return;
+    hc.resize(1 + 2 * nc);
     d2h(hc.data(), s.counters.p, 1 + 2 * nc);
     sync();
     if (hc[0] <= s.list[0].cap) break;
-    cap = hc[0];   // overflow: nothing was modified yet, redo with a larger list
+    min_cap = hc[0];   // overflow: nothing was modified yet, redo the detection with a larger list
   }
+  std::vector<Container*>& conts = dp.conts;
   const unsigned total = hc[0];
   for (size_t c = 0; c < nc; ++c) { conts[c]->P = hc[1 + c]; conts[c]->P_valid = true; }
   if (total == 0) return;
@@ -773,21 +832,40 @@ int b2p_grid_deposit_current(b2p_grid* g) { B2P_TRY phase_deposit(G(g)->tiles); 
 
 int b2p_grid_external_communication(b2p_grid* g, int mode);
 
+struct HostTrace {
+  bool on = std::getenv("B2P_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what, int64_t lap) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (ms > 5.0) std::fprintf(stderr, "[b2p trace] lap %lld %-22s host %.1f ms\n", (long long)lap, what, ms);
+    t0 = t1;
+  }
+};
+
 // projects/pic-turbulence/pic.py:187-221
 int b2p_grid_step_pic(b2p_grid* g, int64_t lap) {
   B2P_TRY
   G(g);
+  HostTrace tr;
   const bool multi = g->nranks > 1;
   auto ext = [&](int mode) {
     if (multi) { const int rc = b2p_grid_external_communication(g, mode); if (rc) throw Error(rc, g_last_error); }
   };
   phase_push_half_b(g->tiles, g->device_table());
   ext(B2P_COMM_EMF_B); grid_local_communication(g, B2P_COMM_EMF_B);
-  phase_push_particles(g->tiles);
+  tr.mark("fields", lap);
+  phase_push_particles(g->tiles, true);   // leaver detection fused into the push
+  tr.mark("push enqueue", lap);
   phase_pack_outgoing(g->tiles);
+  tr.mark("pack", lap);
   ext(B2P_COMM_PIC_PARTICLE); grid_local_communication(g, B2P_COMM_PIC_PARTICLE);
+  tr.mark("particle comm", lap);
   if (lap % 5 == 0) phase_sort(g->tiles);
+  tr.mark("sort enqueue", lap);
   phase_deposit(g->tiles);
+  tr.mark("deposit enqueue", lap);
   ext(B2P_COMM_EMF_J); grid_local_communication(g, B2P_COMM_EMF_J_EXCHANGE);
   ext(B2P_COMM_EMF_J); grid_local_communication(g, B2P_COMM_EMF_J);
   if (g->cfg.current_filter >= 0) {
@@ -800,6 +878,7 @@ int b2p_grid_step_pic(b2p_grid* g, int64_t lap) {
   ext(B2P_COMM_EMF_B); grid_local_communication(g, B2P_COMM_EMF_B);
   phase_push_e(g->tiles, g->device_table(), true);   // push_e + add_current fused (same roundings)
   ext(B2P_COMM_EMF_E); grid_local_communication(g, B2P_COMM_EMF_E);
+  tr.mark("J comm+filter+fields", lap);
   B2P_CATCH
 }
 
@@ -855,7 +934,7 @@ int b2p_grid_inject_thermal(b2p_grid* g, int ppc, double delgam, uint64_t seed) 
     for (size_t q = 0; q < t->sp.size(); ++q) {
       Container& c = t->sp[q];
       if (c.n) throw Error(B2P_ERR_RUNTIME, "inject_thermal requires empty containers");
-      c.reserve(total + total / 16);
+      c.reserve(total);
       c.n = unsigned(total);
       const unsigned long long sp_seed = seed * 0x9E3779B97F4A7C15ull + t->tile_tag * 0xC2B2AE3D27D4EB4Full;
       launch_inject_thermal(c.view(), t->g, mn, unsigned(ppc), float(delgam), sp_seed, sp_seed ^ (0xA5A5A5A5ull * (q + 1)),

@@ -19,7 +19,7 @@ struct Container {
   unsigned P = 0;
   Species view() const { return Species{ x.p, y.p, z.p, ux.p, uy.p, uz.p, id.p, n }; }
   size_t capacity() const { return id.cap; }
-  void reserve(size_t cap);   // keeps the first n slots
+  void reserve(size_t cap, bool exact = false);   // keeps the first n slots; !exact rounds up to a capacity class
 };
 
 struct CommPlan;              // multi-GPU exchange plan (comm.cu)
@@ -76,7 +76,7 @@ void phase_push_half_b(const std::vector<b2p_tile*>& tiles, const FieldPtrs* tab
 void phase_push_e(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table, bool add_current);
 void phase_add_current(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table);
 void phase_filter(const std::vector<b2p_tile*>& tiles);
-void phase_push_particles(const std::vector<b2p_tile*>& tiles);
+void phase_push_particles(const std::vector<b2p_tile*>& tiles, bool fuse_detect = false);
 void phase_deposit(const std::vector<b2p_tile*>& tiles);
 void phase_sort(const std::vector<b2p_tile*>& tiles);
 void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles);

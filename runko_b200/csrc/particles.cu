@@ -104,6 +104,54 @@ __device__ __forceinline__ int subregion_of(const float x, const float y, const 
   return ((i + 1) * 3 + (j + 1)) * 3 + (k + 1);
 }
 
+// Leaver detection shared by the standalone pass and the fused push
+// (pic/particle.c++:252-262): every alive particle whose position is outside the
+// tile box appends the key (container << 37) | (subregion << 32) | slot to an
+// unordered list — one global atomic per block; a radix sort of the list restores
+// the reference's (species, subregion, container order).  Also records
+// P = 1 + the largest slot that stays alive (ParticleContainer::append,
+// pic/particle.h:469-488).  Must be called by every thread of the block.
+struct DetectArgs {
+  float3 mn, mx;
+  unsigned container;
+  unsigned long long* list;
+  unsigned* list_count;
+  unsigned list_cap;
+  unsigned* last_alive;
+  unsigned* cont_count;
+};
+
+__device__ __forceinline__ void block_detect(const bool alive, const float x, const float y, const float z,
+                                             const unsigned n, const DetectArgs& d) {
+  __shared__ unsigned sh_cnt[32];
+  __shared__ unsigned sh_base, sh_last;
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (threadIdx.x == 0) sh_last = 0;
+  int sub = 13;
+  if (alive) sub = subregion_of(x, y, z, d.mn, d.mx);
+  const bool leaving = alive && sub != 13;
+  const bool staying = alive && sub == 13;
+  const unsigned m = __ballot_sync(0xffffffffu, leaving);
+  const unsigned sa = __ballot_sync(0xffffffffu, staying);
+  if (lane == 0) sh_cnt[w] = __popc(m);
+  __syncthreads();
+  if (sa && lane == 0) atomicMax(&sh_last, (n & ~31u) + (32 - __clz(sa)));
+  if (threadIdx.x == 0) {
+    unsigned total = 0;
+    for (unsigned q = 0; q < nw; ++q) { const unsigned c = sh_cnt[q]; sh_cnt[q] = total; total += c; }
+    unsigned base = 0;
+    if (total) { base = atomicAdd(d.list_count, total); atomicAdd(d.cont_count, total); }
+    sh_base = base;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && sh_last) atomicMax(d.last_alive, sh_last);
+  if (leaving) {
+    const unsigned pos = sh_base + sh_cnt[w] + __popc(m & ((1u << lane) - 1));
+    if (pos < d.list_cap)
+      d.list[pos] = (static_cast<unsigned long long>(d.container) << 37) | (static_cast<unsigned long long>(sub) << 32) | n;
+  }
+}
+
 // ----------------------------------------------------------------- pushers --
 struct PushArgs {
   Species s;
@@ -114,17 +162,18 @@ struct PushArgs {
   float qm;       // sign(q)/m   (pic/particle_boris.h:26-27)
 };
 
-template <int PUSHER>
+template <int PUSHER, bool DETECT>
 __global__ void __launch_bounds__(256)
-k_push(const PushArgs a) {
+k_push(const PushArgs a, const DetectArgs d) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= a.s.n) return;
-  if (a.s.id[n] == DEAD) return;                                   // :33
+  const bool alive = n < a.s.n && a.s.id[n] != DEAD;               // :33
+  float nx = 0.f, ny = 0.f, nz = 0.f;
+  if (alive) {
   const float px = a.s.x[n], py = a.s.y[n], pz = a.s.z[n];
   const V3 u = { a.s.ux[n], a.s.uy[n], a.s.uz[n] };
   const EB eb = interpolate(a.nod, a.g, a.origo, px, py, pz);
   const float cfl = a.cfl, qm = a.qm;
-  V3 vel; float nx, ny, nz;
+  V3 vel;
   if (PUSHER == B2P_PUSHER_BORIS) {                                // pic/particle_boris.h:37-59
     const V3 v0 = cfl * u;
     const V3 E0 = 0.5f * qm * eb.E;
@@ -178,22 +227,31 @@ k_push(const PushArgs a) {
   }
   a.s.ux[n] = vel.x; a.s.uy[n] = vel.y; a.s.uz[n] = vel.z;
   a.s.x[n] = nx; a.s.y[n] = ny; a.s.z[n] = nz;
+  }
+  if (DETECT) block_detect(alive, nx, ny, nz, n, d);
 }
 
 // ---------------------------------------------------------------- deposit --
 struct DepositArgs {
   Species s;
-  float* J;        // 3*Ch accumulation target (haloed lattice)
+  float4* Jc;      // cell-edge accumulators: 3 float4 per lattice cell (see below)
   Geom g;
   float3 origo;
   float cfl;
   float charge;
 };
 
-// pic/particle_current_zigzag_1st.c++:241-336.  One thread per particle; the 24
-// structurally non-zero (node, component) contributions go to J with fp32 RED
-// atomics.  Per-particle values are bit-identical to the reference; only the
-// accumulation order differs.
+// pic/particle_current_zigzag_1st.c++:241-336.  One thread per particle.  Each of
+// the two zigzag segments touches the 12 edges of one cell (4 x-edges, 4 y-edges,
+// 4 z-edges), so instead of the reference's 42 scalar atomics per particle the
+// 12 values go to a cell-major scratch of 3 float4 per cell with 3 vector RED.128
+// (6 per particle, 3 when both segments lie in the same cell):
+//   Jc[3c+0] = Jx at nodes c+(0,0,0), c+(0,1,0), c+(0,0,1), c+(0,1,1)
+//   Jc[3c+1] = Jy at nodes c+(0,0,0), c+(1,0,0), c+(0,0,1), c+(1,0,1)
+//   Jc[3c+2] = Jz at nodes c+(0,0,0), c+(1,0,0), c+(0,1,0), c+(1,1,0)
+// k_edge_gather then folds the (up to 4) cell records that share a node into the
+// nodal J.  Per-particle values are bit-identical to the reference; only the
+// accumulation order differs (stated tolerance 1e-5 * max|J|).
 __global__ void __launch_bounds__(256)
 k_deposit_zigzag(const DepositArgs a) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,29 +275,49 @@ k_deposit_zigzag(const DepositArgs a) {
   const V3 F2 = a.charge * (x2 - xr);
   const V3 W1 = 0.5f * (x1 + xr) - fi1;
   const V3 W2 = 0.5f * (x2 + xr) - fi2;
-  const size_t sj = a.g.Hx[2], si = size_t(a.g.Hx[1]) * a.g.Hx[2], Ch = a.g.Ch;
   const size_t n1 = (size_t(__float2uint_rz(fi1.x)) * a.g.Hx[1] + __float2uint_rz(fi1.y)) * a.g.Hx[2] + __float2uint_rz(fi1.z);
   const size_t n2 = (size_t(__float2uint_rz(fi2.x)) * a.g.Hx[1] + __float2uint_rz(fi2.y)) * a.g.Hx[2] + __float2uint_rz(fi2.z);
-  float* Jx = a.J; float* Jy = a.J + Ch; float* Jz = a.J + 2 * Ch;
   const float one = 1.0f;
-#define HALF(nn, F, W)                                                   \
-  {                                                                      \
-    atomicAdd(&Jx[nn], F.x * (one - W.y) * (one - W.z));                 \
-    atomicAdd(&Jy[nn], F.y * (one - W.x) * (one - W.z));                 \
-    atomicAdd(&Jz[nn], F.z * (one - W.x) * (one - W.y));                 \
-    atomicAdd(&Jy[nn + si], F.y * W.x * (one - W.z));                    \
-    atomicAdd(&Jz[nn + si], F.z * W.x * (one - W.y));                    \
-    atomicAdd(&Jx[nn + sj], F.x * W.y * (one - W.z));                    \
-    atomicAdd(&Jz[nn + sj], F.z * (one - W.x) * W.y);                    \
-    atomicAdd(&Jx[nn + 1], F.x * (one - W.y) * W.z);                     \
-    atomicAdd(&Jy[nn + 1], F.y * (one - W.x) * W.z);                     \
-    atomicAdd(&Jx[nn + sj + 1], F.x * W.y * W.z);                        \
-    atomicAdd(&Jy[nn + si + 1], F.y * W.x * W.z);                        \
-    atomicAdd(&Jz[nn + si + sj], F.z * W.x * W.y);                       \
+#define EDGES(F, W, ex, ey, ez)                                                                                \
+  const float4 ex = make_float4(F.x * (one - W.y) * (one - W.z), F.x * W.y * (one - W.z), F.x * (one - W.y) * W.z, F.x * W.y * W.z); \
+  const float4 ey = make_float4(F.y * (one - W.x) * (one - W.z), F.y * W.x * (one - W.z), F.y * (one - W.x) * W.z, F.y * W.x * W.z); \
+  const float4 ez = make_float4(F.z * (one - W.x) * (one - W.y), F.z * W.x * (one - W.y), F.z * (one - W.x) * W.y, F.z * W.x * W.y);
+  EDGES(F1, W1, ax, ay, az)
+  EDGES(F2, W2, bx, by, bz)
+#undef EDGES
+  if (n1 == n2) {
+    atomicAdd(&a.Jc[3 * n1 + 0], make_float4(ax.x + bx.x, ax.y + bx.y, ax.z + bx.z, ax.w + bx.w));
+    atomicAdd(&a.Jc[3 * n1 + 1], make_float4(ay.x + by.x, ay.y + by.y, ay.z + by.z, ay.w + by.w));
+    atomicAdd(&a.Jc[3 * n1 + 2], make_float4(az.x + bz.x, az.y + bz.y, az.z + bz.z, az.w + bz.w));
+  } else {
+    atomicAdd(&a.Jc[3 * n1 + 0], ax); atomicAdd(&a.Jc[3 * n1 + 1], ay); atomicAdd(&a.Jc[3 * n1 + 2], az);
+    atomicAdd(&a.Jc[3 * n2 + 0], bx); atomicAdd(&a.Jc[3 * n2 + 1], by); atomicAdd(&a.Jc[3 * n2 + 2], bz);
   }
-  HALF(n1, F1, W1)
-  HALF(n2, F2, W2)
-#undef HALF
+}
+
+// Fold the cell-edge records into the nodal current and write ALL of J (this is also
+// the reference's clear_current + `J += generated_J`, pic/tile.c++:371,405):
+//   Jx[i,j,k] = c(i,j,k).x0 + c(i,j-1,k).x1 + c(i,j,k-1).x2 + c(i,j-1,k-1).x3   etc.
+__global__ void __launch_bounds__(256)
+k_edge_gather(const float4* __restrict__ Jc, float* __restrict__ J, const Geom g) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int i = blockIdx.z;
+  if (k >= g.Hx[2] || j >= g.Hx[1]) return;
+  const long sj = g.Hx[2], si = long(g.Hx[1]) * g.Hx[2];
+  const long n = (long(i) * g.Hx[1] + j) * g.Hx[2] + k;
+  const bool pi = i > 0, pj = j > 0, pk = k > 0;
+  float jx = Jc[3 * n + 0].x, jy = Jc[3 * n + 1].x, jz = Jc[3 * n + 2].x;
+  if (pj) jx += Jc[3 * (n - sj) + 0].y;
+  if (pk) jx += Jc[3 * (n - 1) + 0].z;
+  if (pj && pk) jx += Jc[3 * (n - sj - 1) + 0].w;
+  if (pi) jy += Jc[3 * (n - si) + 1].y;
+  if (pk) jy += Jc[3 * (n - 1) + 1].z;
+  if (pi && pk) jy += Jc[3 * (n - si - 1) + 1].w;
+  if (pi) jz += Jc[3 * (n - si) + 2].y;
+  if (pj) jz += Jc[3 * (n - sj) + 2].z;
+  if (pi && pj) jz += Jc[3 * (n - si - sj) + 2].w;
+  J[n] = jx; J[size_t(g.Ch) + n] = jy; J[2 * size_t(g.Ch) + n] = jz;
 }
 
 // ------------------------------------------------------------------- sort --
@@ -256,6 +334,7 @@ k_sort_keys(const Species s, const Geom g, const float3 origo, unsigned* __restr
     const unsigned j = __float2uint_rz(s.y[n] - origo.y);
     const unsigned k = __float2uint_rz(s.z[n] - origo.z);
     key = (i * unsigned(g.Hx[1]) + j) * unsigned(g.Hx[2]) + k;
+    if (dead_key != 0xFFFFFFFFu && key > dead_key) key = dead_key;   // sort path: clamp to the dead key (= Ch)
   }
   keys[n] = key;
   if (idx) idx[n] = n;
@@ -273,40 +352,14 @@ k_gather(const Species src, const Species dst, const unsigned* __restrict__ perm
 }
 
 // -------------------------------------------------------------- migration --
-// Leaver detection (pic/particle.c++:252-262): every alive particle whose
-// position is outside the tile box appends the key
-//   (container << 37) | (subregion << 32) | slot
-// to an unordered list; a radix sort of that list restores the reference's order
-// (species, subregion, container order).  Also records 1 + the largest slot that
-// stays alive (the P of ParticleContainer::append, pic/particle.h:469-488).
+// standalone leaver detection (when the push was not fused with it)
 __global__ void __launch_bounds__(256)
-k_detect_leavers(const Species s, const float3 mn, const float3 mx, const unsigned container,
-                 unsigned long long* __restrict__ list, unsigned* __restrict__ list_count, const unsigned list_cap,
-                 unsigned* __restrict__ last_alive, unsigned* __restrict__ cont_count) {
+k_detect_leavers(const Species s, const DetectArgs d) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  bool leaving = false, staying_alive = false;
-  int sub = 13;
-  if (n < s.n) {
-    const bool alive = s.id[n] != DEAD;
-    sub = subregion_of(s.x[n], s.y[n], s.z[n], mn, mx);
-    leaving = alive && sub != 13;
-    staying_alive = alive && sub == 13;
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, leaving);
-  const unsigned lane = threadIdx.x & 31;
-  if (m) {
-    unsigned base = 0;
-    const int leader = __ffs(m) - 1;
-    if (int(lane) == leader) { base = atomicAdd(list_count, __popc(m)); atomicAdd(cont_count, __popc(m)); }
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (leaving) {
-      const unsigned pos = base + __popc(m & ((1u << lane) - 1));
-      if (pos < list_cap)
-        list[pos] = (static_cast<unsigned long long>(container) << 37) | (static_cast<unsigned long long>(sub) << 32) | n;
-    }
-  }
-  const unsigned sa = __ballot_sync(0xffffffffu, staying_alive);
-  if (sa && lane == 0) atomicMax(last_alive, (n & ~31u) + (32 - __clz(sa)));
+  const bool alive = n < s.n && s.id[n] != DEAD;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (alive) { x = s.x[n]; y = s.y[n]; z = s.z[n]; }
+  block_detect(alive, x, y, z, n, d);
 }
 
 struct OutTile {              // per container: where its leavers go
@@ -463,25 +516,42 @@ void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* n
   B2P_LAUNCH_CHECK();
 }
 
-void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm) {
+void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm,
+                 const DetectArgsHost* det) {
   ProfScope prof_(KC_PUSH, double(s.n));
   if (!s.n) return;
   PushArgs a{ s, nod, g, make_float3(origo[0], origo[1], origo[2]), cfl, qm };
+  DetectArgs d{};
+  if (det) d = DetectArgs{ make_float3(det->mins[0], det->mins[1], det->mins[2]), make_float3(det->maxs[0], det->maxs[1], det->maxs[2]),
+                           det->container, det->list, det->list_count, det->list_cap, det->last_alive, det->cont_count };
   const unsigned nb = blocks_for(s.n);
+#define PUSH_CASE(P)                                                                   \
+  case P:                                                                              \
+    if (det) k_push<P, true><<<nb, 256, 0, ctx().stream>>>(a, d);                      \
+    else k_push<P, false><<<nb, 256, 0, ctx().stream>>>(a, d);                         \
+    break;
   switch (pusher) {
-    case B2P_PUSHER_BORIS: k_push<B2P_PUSHER_BORIS><<<nb, 256, 0, ctx().stream>>>(a); break;
-    case B2P_PUSHER_HIGUERA_CARY: k_push<B2P_PUSHER_HIGUERA_CARY><<<nb, 256, 0, ctx().stream>>>(a); break;
-    case B2P_PUSHER_FARADAY: k_push<B2P_PUSHER_FARADAY><<<nb, 256, 0, ctx().stream>>>(a); break;
+    PUSH_CASE(B2P_PUSHER_BORIS)
+    PUSH_CASE(B2P_PUSHER_HIGUERA_CARY)
+    PUSH_CASE(B2P_PUSHER_FARADAY)
     default: throw Error(B2P_ERR_LOGIC, "pic::Tile::push_particles: unkown particle pusher");
   }
+#undef PUSH_CASE
   B2P_LAUNCH_CHECK();
 }
 
-void launch_deposit(const Species& s, float* J, const Geom& g, const float origo[3], float cfl, float charge) {
+void launch_deposit(const Species& s, float4* Jc, const Geom& g, const float origo[3], float cfl, float charge) {
   ProfScope prof_(KC_DEPOSIT, double(s.n));
   if (!s.n) return;
-  DepositArgs a{ s, J, g, make_float3(origo[0], origo[1], origo[2]), cfl, charge };
+  DepositArgs a{ s, Jc, g, make_float3(origo[0], origo[1], origo[2]), cfl, charge };
   k_deposit_zigzag<<<blocks_for(s.n), 256, 0, ctx().stream>>>(a);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_edge_gather(const float4* Jc, float* J, const Geom& g) {
+  ProfScope prof_(KC_EDGE_GATHER, double(g.Ch));
+  const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, g.Hx[0]);
+  k_edge_gather<<<grid, dim3(32, 8, 1), 0, ctx().stream>>>(Jc, J, g);
   B2P_LAUNCH_CHECK();
 }
 
@@ -528,14 +598,12 @@ void launch_gather(const Species& src, const Species& dst, const unsigned* perm)
   B2P_LAUNCH_CHECK();
 }
 
-void launch_detect_leavers(const Species& s, const float mins[3], const float maxs[3], unsigned container,
-                           unsigned long long* list, unsigned* list_count, unsigned list_cap, unsigned* last_alive,
-                           unsigned* cont_count) {
+void launch_detect_leavers(const Species& s, const DetectArgsHost& det) {
   ProfScope prof_(KC_DETECT, double(s.n));
   if (!s.n) return;
-  k_detect_leavers<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, make_float3(mins[0], mins[1], mins[2]),
-                                                               make_float3(maxs[0], maxs[1], maxs[2]), container, list,
-                                                               list_count, list_cap, last_alive, cont_count);
+  const DetectArgs d{ make_float3(det.mins[0], det.mins[1], det.mins[2]), make_float3(det.maxs[0], det.maxs[1], det.maxs[2]),
+                      det.container, det.list, det.list_count, det.list_cap, det.last_alive, det.cont_count };
+  k_detect_leavers<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, d);
   B2P_LAUNCH_CHECK();
 }
 

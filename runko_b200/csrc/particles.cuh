@@ -16,18 +16,29 @@ struct AppendJobHost {        // mirrors particles.cu::AppendJob
   Species dst;
 };
 
+struct DetectArgsHost {       // leaver-detection targets of one container
+  float mins[3], maxs[3];     // tile box (float(mins/maxs), pic/tile_communication.c++:71-79)
+  unsigned container;
+  unsigned long long* list;
+  unsigned* list_count;
+  unsigned list_cap;
+  unsigned* last_alive;
+  unsigned* cont_count;
+};
+
 void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* nod);
-void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm);
-void launch_deposit(const Species& s, float* J, const Geom& g, const float origo[3], float cfl, float charge);
+// det != nullptr fuses the leaver detection of pack_outgoing_particles into the push
+void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm,
+                 const DetectArgsHost* det);
+void launch_deposit(const Species& s, float4* Jc, const Geom& g, const float origo[3], float cfl, float charge);
+void launch_edge_gather(const float4* Jc, float* J, const Geom& g);
 void launch_sort_keys(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* idx, unsigned dead_key);
 size_t sort_pairs_temp_bytes(unsigned n, int end_bit);
 int sort_pairs(void* temp, size_t temp_bytes, unsigned* keys[2], unsigned* vals[2], unsigned n, int end_bit);
 size_t sort_keys64_temp_bytes(unsigned n, int end_bit);
 int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit);
 void launch_gather(const Species& src, const Species& dst, const unsigned* perm);
-void launch_detect_leavers(const Species& s, const float mins[3], const float maxs[3], unsigned container,
-                           unsigned long long* list, unsigned* list_count, unsigned list_cap, unsigned* last_alive,
-                           unsigned* cont_count);
+void launch_detect_leavers(const Species& s, const DetectArgsHost& det);
 void launch_gather_outgoing(const unsigned long long* sorted, unsigned total, const void* out_tiles, unsigned* counts);
 void launch_last_alive(const unsigned long long* id, unsigned n, unsigned* last_alive);
 void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, const float wmin[3], const float wmax[3]);
