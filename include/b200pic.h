@@ -197,6 +197,11 @@ int b2p_grid_comm_init(b2p_grid* g, int rank, int nranks, const void* id128, con
  * including the number_of_particles handshake for B2P_COMM_PIC_PARTICLE. */
 int b2p_grid_external_communication(b2p_grid* g, int mode);
 
+/* Host-only description of rank `rank`'s exchange plan (no GPU, no NCCL; used by the
+ * world_size-2 gloo tests): rows of 7 int64 {peer, my cid, direction index, remote cid,
+ * send_key, recv_key, floats of the interior-edge slab}; returns the row count. */
+int64_t b2p_plan_describe(const b2p_config* cfg, const int32_t* owner, int rank, int64_t* rows, int64_t cap);
+
 /* ---- timing helpers for bench.py (CUDA events on the library's stream) --- */
 int b2p_timer_start(void);
 int b2p_timer_stop(float* ms);

@@ -24,7 +24,7 @@ b2p_grid_create b2p_grid_destroy b2p_grid_add_tile b2p_grid_local_communication
 b2p_grid_push_half_b b2p_grid_push_e b2p_grid_add_current b2p_grid_filter_current
 b2p_grid_push_particles b2p_grid_pack_outgoing_particles b2p_grid_sort_particles b2p_grid_deposit_current
 b2p_grid_step_pic b2p_grid_step_emf b2p_grid_energies b2p_grid_inject_thermal b2p_grid_set_uniform_B
-b2p_nccl_unique_id b2p_grid_comm_init b2p_grid_external_communication
+b2p_nccl_unique_id b2p_grid_comm_init b2p_grid_external_communication b2p_plan_describe
 b2p_timer_start b2p_timer_stop b2p_launch_count b2p_copy_bytes
 b2p_profile_enable b2p_profile_num_classes b2p_profile_class_name b2p_profile_report
 """.split()
@@ -88,6 +88,8 @@ def lib():
     L.b2p_nccl_unique_id.argtypes = [vp]
     L.b2p_grid_comm_init.argtypes = [vp, ci, ci, vp, vp]
     L.b2p_grid_external_communication.argtypes = [vp, ci]
+    L.b2p_plan_describe.argtypes = [C.POINTER(B2PConfig), vp, ci, vp, C.c_int64]
+    L.b2p_plan_describe.restype = C.c_int64
     L.b2p_timer_stop.argtypes = [C.POINTER(C.c_float)]
     L.b2p_copy_bytes.argtypes = [C.POINTER(u64), C.POINTER(u64)]
     L.b2p_copy_bytes.restype = None

@@ -102,6 +102,15 @@ struct Geom {                 // identical for every tile of a grid
 
 struct FieldPtrs { float* E; float* B; float* J; };
 
+// A packed comp-major slab of a lattice region (multi-GPU staging, comm.cu):
+// value(c, ii, jj, kk) = base[c*vol + (ii*dims[1] + jj)*dims[2] + kk]
+struct SlabDesc {
+  float* base;
+  float* field;               // pack only: source lattice (3*Ch)
+  int begin[3];               // pack only: first lattice index of the region
+  int dims[3];
+};
+
 struct Species {              // one particle container on the device
   float* x; float* y; float* z; float* ux; float* uy; float* uz;
   unsigned long long* id;

@@ -189,7 +189,8 @@ __device__ __forceinline__ int dir_of_halo(int a, int N) { return a < H ? -1 : (
 // directions of every tile (emf/yee_lattice.c++:206-239). One thread per lattice
 // cell and component; interior cells exit. `which` selects E/B/J.
 __global__ void __launch_bounds__(256)
-k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, const Geom g, const int which) {
+k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, const Geom g, const int which,
+            const SlabDesc* __restrict__ remote) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int tile = blockIdx.z / g.Hx[0];
@@ -198,10 +199,25 @@ k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, co
   const int di = dir_of_halo(i, g.N[0]), dj = dir_of_halo(j, g.N[1]), dk = dir_of_halo(k, g.N[2]);
   if (di == 0 && dj == 0 && dk == 0) return;
   const int o = nbr[tile * 27 + ((di + 1) * 3 + (dj + 1)) * 3 + (dk + 1)];
-  if (o < 0) return;   // remote neighbour: filled by the external exchange
+  if (o == -1) return;
+  const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
+  if (o < -1) {
+    // remote neighbour: its corresponding_subregion(d) was staged by the external exchange
+    // (emf/yee_lattice.c++:431-472 reads the VirtualTile's hollow grid here)
+    const SlabDesc s = remote[-(o + 2)];
+    const int a[3] = { i, j, k }, dr[3] = { di, dj, dk };
+    int r[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) r[q] = dr[q] == 0 ? a[q] - H : (dr[q] == 1 ? a[q] - (H + g.N[q]) : a[q]);
+    const size_t vol = size_t(s.dims[0]) * s.dims[1] * s.dims[2];
+    const size_t m = (size_t(r[0]) * s.dims[1] + r[1]) * s.dims[2] + r[2];
+    float* dstr = which == 0 ? tiles[tile].E : (which == 1 ? tiles[tile].B : tiles[tile].J);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dstr[size_t(c) * g.Ch + n] = s.base[size_t(c) * vol + m];
+    return;
+  }
   // my halo index a in subregion(d) maps to a - d*N in the neighbour (same formula for d=-1,0,+1)
   const int si_ = i - di * g.N[0], sj_ = j - dj * g.N[1], sk_ = k - dk * g.N[2];
-  const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
   const size_t m = (size_t(si_) * g.Hx[1] + sj_) * g.Hx[2] + sk_;
   const FieldPtrs me = tiles[tile], ot = tiles[o];
   float* dst = which == 0 ? me.E : (which == 1 ? me.B : me.J);
@@ -215,7 +231,8 @@ k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, co
 // corgi cellular_automata.h:48-62), so every cell accumulates its up-to-7
 // contributions in the reference's order. One thread per interior cell/component.
 __global__ void __launch_bounds__(256)
-k_J_exchange(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, const Geom g) {
+k_J_exchange(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, const Geom g,
+             const SlabDesc* __restrict__ remote) {
   INTERIOR_CELL_OR_RETURN();
   (void)sj; (void)si;
   const int a[3] = { i + H, j + H, k + H };
@@ -242,7 +259,20 @@ k_J_exchange(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, c
         }
         if (!in) continue;
         const int o = nbr[tile * 27 + ((ir + 1) * 3 + (jr + 1)) * 3 + (kr + 1)];
-        if (o < 0) continue;
+        if (o == -1) continue;
+        if (o < -1) {
+          // remote neighbour: its halo subregion(-dir) was staged by the external exchange
+          // (emf/yee_lattice.c++:498-524)
+          const SlabDesc sl = remote[-(o + 2)];
+          int r[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) r[d] = dr[d] == 1 ? a[d] - g.N[d] : a[d] - H;
+          const size_t vol = size_t(sl.dims[0]) * sl.dims[1] * sl.dims[2];
+          const size_t mm = (size_t(r[0]) * sl.dims[1] + r[1]) * sl.dims[2] + r[2];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[c] = acc[c] + sl.base[size_t(c) * vol + mm];
+          continue;
+        }
         const float* oJ = tiles[o].J;
         const size_t m = (size_t(s[0]) * g.Hx[1] + s[1]) * g.Hx[2] + s[2];
 #pragma unroll
@@ -331,17 +361,17 @@ void launch_zero(float* p, size_t n) {
   k_zero<<<blocks, 256, 0, ctx().stream>>>(p, n);
   B2P_LAUNCH_CHECK();
 }
-void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which) {
+void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which, const SlabDesc* remote) {
   ProfScope prof_(KC_HALO, double(ntiles) * g.Ch);
   if (!ntiles) return;
   const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, unsigned(ntiles) * g.Hx[0]);
-  k_halo_fill<<<grid, cell_block(), 0, ctx().stream>>>(tiles, nbr, g, which);
+  k_halo_fill<<<grid, cell_block(), 0, ctx().stream>>>(tiles, nbr, g, which, remote);
   B2P_LAUNCH_CHECK();
 }
-void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g) {
+void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, const SlabDesc* remote) {
   ProfScope prof_(KC_J_EXCHANGE, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
-  k_J_exchange<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, nbr, g);
+  k_J_exchange<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, nbr, g, remote);
   B2P_LAUNCH_CHECK();
 }
 void launch_field_energy(const FieldPtrs* tiles, int ntiles, const Geom& g, double* out) {

@@ -11,7 +11,8 @@ void launch_add_current(const FieldPtrs* tiles, int ntiles, const Geom& g);
 void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unrolled);
 void launch_zero(float* p, size_t n);
 // which: 0=E 1=B 2=J; nbr: device int[ntiles][27] (tile-table index of the neighbour, -1 = remote)
-void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which);
-void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g);
+// nbr codes: >= 0 local tile slot; -1 none; <= -2 remote, staged slab remote[-(code+2)] (comm.cu)
+void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which, const SlabDesc* remote);
+void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, const SlabDesc* remote);
 void launch_field_energy(const FieldPtrs* tiles, int ntiles, const Geom& g, double* out);
 }  // namespace b2p

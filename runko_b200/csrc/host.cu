@@ -178,7 +178,11 @@ const int* b2p_grid::device_nbr() {
       for (int ir = -1; ir <= 1; ++ir) for (int jr = -1; jr <= 1; ++jr) for (int kr = -1; kr <= 1; ++kr) {
         const int* T = cfg.n_tiles;
         const int c = cid(wrapi(tiles[t]->idx[0] + ir, T[0]), wrapi(tiles[t]->idx[1] + jr, T[1]), wrapi(tiles[t]->idx[2] + kr, T[2]));
-        h[t * 27 + ((ir + 1) * 3 + (jr + 1)) * 3 + (kr + 1)] = slot_of_cid[c];
+        const int di = ((ir + 1) * 3 + (jr + 1)) * 3 + (kr + 1);
+        int code = slot_of_cid[c];
+        int entry = 0;
+        if (code < 0 && comm_remote_entry(this, int(t), di, &entry)) code = -(2 + entry);
+        h[t * 27 + di] = code;
       }
     d_nbr.reserve(std::max<size_t>(1, h.size()));
     h2d(d_nbr.p, h.data(), h.size());
@@ -517,10 +521,10 @@ void grid_local_communication(b2p_grid* g, int mode) {
   const int nt = int(g->tiles.size());
   if (!nt) return;
   switch (mode) {
-    case B2P_COMM_EMF_E: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 0); return;
-    case B2P_COMM_EMF_B: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 1); return;
-    case B2P_COMM_EMF_J: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 2); return;
-    case B2P_COMM_EMF_J_EXCHANGE: launch_J_exchange(g->device_table(), g->device_nbr(), nt, g->g); return;
+    case B2P_COMM_EMF_E: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 0, static_cast<const SlabDesc*>(comm_remote_table(g, 0))); return;
+    case B2P_COMM_EMF_B: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 1, static_cast<const SlabDesc*>(comm_remote_table(g, 0))); return;
+    case B2P_COMM_EMF_J: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 2, static_cast<const SlabDesc*>(comm_remote_table(g, 0))); return;
+    case B2P_COMM_EMF_J_EXCHANGE: launch_J_exchange(g->device_table(), g->device_nbr(), nt, g->g, static_cast<const SlabDesc*>(comm_remote_table(g, 1))); return;
     case B2P_COMM_PIC_PARTICLE: break;
     default:
       throw Error(B2P_ERR_LOGIC, "local_communication does not support given communication mode: " + std::to_string(mode));
@@ -537,7 +541,18 @@ void grid_local_communication(b2p_grid* g, int mode) {
       if (!ir && !jr && !kr) continue;
       const int oc = g->cid(wrapi(me->idx[0] + ir, T[0]), wrapi(me->idx[1] + jr, T[1]), wrapi(me->idx[2] + kr, T[2]));
       const int os = g->slot_of_cid[oc];
-      if (os < 0) continue;   // remote neighbour: its particles arrive through the external exchange
+      if (os < 0) {
+        // remote neighbour: spans received by the external exchange (the reference reads the
+        // pic::VirtualTile buffer here, pic/tile_communication.c++:166-181)
+        int entry = 0;
+        if (!comm_remote_entry(g, me->slot, ((ir + 1) * 3 + (jr + 1)) * 3 + (kr + 1), &entry)) continue;
+        for (size_t q = 0; q < me->sp.size(); ++q) {
+          const b2p_particle_state* ptr = nullptr; unsigned cnt = 0;
+          comm_particle_span(g, entry, int(q), &ptr, &cnt);
+          spans[base + q].push_back(SpanRef{ ptr, cnt });
+        }
+        continue;
+      }
       b2p_tile* other = g->tiles[os];
       if (other->out_ends.size() != 27 * other->sp.size())
         throw Error(B2P_ERR_LOGIC, "pic_particle communication requires pack_outgoing_particles first");
@@ -554,12 +569,23 @@ void grid_local_communication(b2p_grid* g, int mode) {
   for (int d = 0; d < 3; ++d) { wmin[d] = 0.0f; wmax[d] = static_cast<float>(double(size_t(T[d]) * size_t(g->cfg.n_cells[d]))); }
   append_spans(conts, spans, true, wmin, wmax);
   for (b2p_tile* t : g->tiles) t->out_ends.clear();
+  comm_particles_consumed(g);
 }
 
 }  // namespace b2p
 
 // ==================================================================== C ABI ==
 static thread_local std::string g_last_error;
+namespace b2p {
+void set_last_error(const std::string& s) { g_last_error = s; }
+void Scratch_table_upload(const void* src, size_t bytes) {
+  Scratch& s = scratch();
+  s.table.reserve(bytes);
+  B2P_CUDA(cudaMemcpyAsync(s.table.p, src, bytes, cudaMemcpyHostToDevice, ctx().stream));
+  g_ctx.h2d_bytes += bytes;
+}
+const void* Scratch_table_ptr() { return scratch().table.p; }
+}  // namespace b2p
 #define B2P_TRY try {
 #define B2P_CATCH                                                              \
   }                                                                            \

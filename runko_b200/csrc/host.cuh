@@ -81,4 +81,12 @@ void phase_deposit(const std::vector<b2p_tile*>& tiles);
 void phase_sort(const std::vector<b2p_tile*>& tiles);
 void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles);
 void grid_local_communication(b2p_grid* g, int mode);
+void set_last_error(const std::string& s);
+void Scratch_table_upload(const void* src, size_t bytes);   // host -> the shared device table scratch
+const void* Scratch_table_ptr();
+// multi-GPU plan queries (comm.cu)
+bool comm_remote_entry(b2p_grid* g, int slot, int dir_idx, int* entry);
+const void* comm_remote_table(b2p_grid* g, int kind);        // kind 0: halo-fill slabs, 1: J-exchange slabs
+bool comm_particle_span(b2p_grid* g, int entry, int species, const b2p_particle_state** ptr, unsigned* count);
+void comm_particles_consumed(b2p_grid* g);
 }  // namespace b2p
