@@ -9,11 +9,13 @@
 namespace b2p {
 
 // thread <-> cell mapping shared by the interior sweeps: x->k, y->j, z->(tile,i)
+// grid = (k blocks, j blocks * planes, tiles): blockIdx.y carries (plane, j block)
 #define INTERIOR_CELL_OR_RETURN()                                              \
+  const int jblocks = (g.N[1] + int(blockDim.y) - 1) / int(blockDim.y);        \
   const int k = blockIdx.x * blockDim.x + threadIdx.x;                         \
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;                         \
-  const int tile = blockIdx.z / g.N[0];                                        \
-  const int i = blockIdx.z - tile * g.N[0];                                    \
+  const int i = blockIdx.y / jblocks;                                          \
+  const int j = (blockIdx.y - i * jblocks) * blockDim.y + threadIdx.y;         \
+  const int tile = blockIdx.z;                                                 \
   if (k >= g.N[2] || j >= g.N[1]) return;                                      \
   const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2];                   \
   const size_t n = (size_t(i + H) * g.Hx[1] + (j + H)) * g.Hx[2] + (k + H);    \
@@ -130,10 +132,11 @@ struct FilterTile { const float* src; float* dst; };
 template <bool UNROLLED>
 __global__ void __launch_bounds__(256)
 k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g) {
+  const int jblocks = (g.Hx[1] + int(blockDim.y) - 1) / int(blockDim.y);
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int tile = blockIdx.z / (3 * g.Hx[0]);
-  const int rem = blockIdx.z - tile * 3 * g.Hx[0];
+  const int rem = blockIdx.y / jblocks;            // plane index: component * Hx + i
+  const int j = (blockIdx.y - rem * jblocks) * blockDim.y + threadIdx.y;
+  const int tile = blockIdx.z;
   const int c = rem / g.Hx[0];
   const int i = rem - c * g.Hx[0];
   if (k >= g.Hx[2] || j >= g.Hx[1]) return;
@@ -191,10 +194,11 @@ __device__ __forceinline__ int dir_of_halo(int a, int N) { return a < H ? -1 : (
 __global__ void __launch_bounds__(256)
 k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, const Geom g, const int which,
             const SlabDesc* __restrict__ remote) {
+  const int jblocks = (g.Hx[1] + int(blockDim.y) - 1) / int(blockDim.y);
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int tile = blockIdx.z / g.Hx[0];
-  const int i = blockIdx.z - tile * g.Hx[0];
+  const int i = blockIdx.y / jblocks;
+  const int j = (blockIdx.y - i * jblocks) * blockDim.y + threadIdx.y;
+  const int tile = blockIdx.z;
   if (k >= g.Hx[2] || j >= g.Hx[1]) return;
   const int di = dir_of_halo(i, g.N[0]), dj = dir_of_halo(j, g.N[1]), dk = dir_of_halo(k, g.N[2]);
   if (di == 0 && dj == 0 && dk == 0) return;
@@ -314,19 +318,29 @@ k_field_energy(const FieldPtrs* __restrict__ tiles, const Geom g, double* __rest
 
 // ------------------------------------------------------------------ launchers --
 static dim3 cell_block() { return dim3(32, 8, 1); }
+// grid.z (<= 65535) spans tiles
+constexpr int MAX_TILES_PER_LAUNCH = 65535;
 static dim3 interior_grid(const Geom& g, int ntiles) {
-  return dim3((g.N[2] + 31) / 32, (g.N[1] + 7) / 8, unsigned(ntiles) * g.N[0]);
+  return dim3((g.N[2] + 31) / 32, unsigned((g.N[1] + 7) / 8) * g.N[0], unsigned(ntiles));
+}
+static dim3 haloed_grid(const Geom& g, int ntiles, int planes_per_i) {
+  return dim3((g.Hx[2] + 31) / 32, unsigned((g.Hx[1] + 7) / 8) * g.Hx[0] * planes_per_i, unsigned(ntiles));
+}
+static void check_tiles(int ntiles) {
+  if (ntiles > MAX_TILES_PER_LAUNCH) throw Error(B2P_ERR_RUNTIME, "more than 65535 local tiles per GPU are not supported");
 }
 
 void launch_push_b_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt) {
   ProfScope prof_(KC_PUSH_B, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
+  check_tiles(ntiles);
   k_push_b_fdtd2<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
   B2P_LAUNCH_CHECK();
 }
 void launch_push_b_stencil(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, const float M[3][3][5]) {
   ProfScope prof_(KC_PUSH_B, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
+  check_tiles(ntiles);
   StencilM c;
   for (int a = 0; a < 3; ++a) for (int r = 0; r < 3; ++r) for (int q = 0; q < 5; ++q) c.M[a][r][q] = M[a][r][q];
   k_push_b_stencil<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt, c);
@@ -335,6 +349,7 @@ void launch_push_b_stencil(const FieldPtrs* tiles, int ntiles, const Geom& g, fl
 void launch_push_e_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, bool add_current) {
   ProfScope prof_(KC_PUSH_E, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
+  check_tiles(ntiles);
   if (add_current) k_push_e_fdtd2<true><<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
   else k_push_e_fdtd2<false><<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
   B2P_LAUNCH_CHECK();
@@ -342,13 +357,15 @@ void launch_push_e_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, floa
 void launch_add_current(const FieldPtrs* tiles, int ntiles, const Geom& g) {
   ProfScope prof_(KC_ADD_CURRENT, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
+  check_tiles(ntiles);
   k_add_current<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g);
   B2P_LAUNCH_CHECK();
 }
 void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unrolled) {
   ProfScope prof_(KC_FILTER, double(ntiles) * g.Ch);
   if (!ntiles) return;
-  const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, unsigned(ntiles) * 3 * g.Hx[0]);
+  check_tiles(ntiles);
+  const dim3 grid = haloed_grid(g, ntiles, 3);
   const FilterTile* ft = static_cast<const FilterTile*>(filter_tiles);
   if (unrolled) k_filter_binomial2<true><<<grid, cell_block(), 0, ctx().stream>>>(ft, g);
   else k_filter_binomial2<false><<<grid, cell_block(), 0, ctx().stream>>>(ft, g);
@@ -364,19 +381,22 @@ void launch_zero(float* p, size_t n) {
 void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which, const SlabDesc* remote) {
   ProfScope prof_(KC_HALO, double(ntiles) * g.Ch);
   if (!ntiles) return;
-  const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, unsigned(ntiles) * g.Hx[0]);
+  check_tiles(ntiles);
+  const dim3 grid = haloed_grid(g, ntiles, 1);
   k_halo_fill<<<grid, cell_block(), 0, ctx().stream>>>(tiles, nbr, g, which, remote);
   B2P_LAUNCH_CHECK();
 }
 void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, const SlabDesc* remote) {
   ProfScope prof_(KC_J_EXCHANGE, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
+  check_tiles(ntiles);
   k_J_exchange<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, nbr, g, remote);
   B2P_LAUNCH_CHECK();
 }
 void launch_field_energy(const FieldPtrs* tiles, int ntiles, const Geom& g, double* out) {
   ProfScope prof_(KC_ENERGY, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
+  check_tiles(ntiles);
   B2P_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 2 * ntiles, ctx().stream));
   const size_t Ni = size_t(g.N[0]) * g.N[1] * g.N[2];
   const unsigned bx = unsigned(std::min<size_t>((Ni + 255) / 256, 64));

@@ -329,7 +329,7 @@ static void detect_setup(const std::vector<b2p_tile*>& tiles, size_t min_cap) {
   // device counters: [0] list length | [1..nc] P per container | [1+nc..1+2nc) leavers per container | counts[nc][27]
   const size_t ncounters = 1 + 2 * nc + nc * 27;
   s.counters.reserve(ncounters);
-  const size_t cap = std::max<size_t>(std::max(min_cap, dp.total_slots / 8 + 65536), s.list[0].cap);
+  const size_t cap = std::max<size_t>(std::max(min_cap, dp.total_slots / 24 + 65536), s.list[0].cap);
   s.list[0].reserve(cap); s.list[1].reserve(cap);
   B2P_CUDA(cudaMemsetAsync(s.counters.p, 0, ncounters * sizeof(unsigned), ctx().stream));
 }

@@ -57,40 +57,15 @@ class ParticleStateD:
         self.vel = list(vel)
 
 
-class Tile:
-    """emf::Tile<3> — owns E, B, J on the device (emf/tile.h:36-213)."""
+class EmfTileHost:
+    """Backend-independent host logic of emf::Tile<3> (emf/tile.c++:184-335,
+    bindings/pyemf.c++:32-78): where the Yee-staggered sample points are, what the
+    setters validate and what the getters return.  A backend supplies
+    `_backend_set_fields(E, B, J, with_halo)` / `_backend_get_fields(with_halo)` on
+    fp32 component-major arrays plus `mins`, `maxs`, `n_cells`.  The CUDA backend is
+    `Tile` below; tests/refshim binds the same logic to the CPU oracle."""
 
-    _need_pic = False
-
-    def __init__(self, tile_grid_idx, config):
-        try:
-            self._cfg = config if isinstance(config, _abi.B2PConfig) else make_config(config, need_pic=self._need_pic)
-        except ConfigError as e:
-            raise B2PError(str(e)) from None
-        idx = (C.c_int32 * 3)(*[int(v) for v in tile_grid_idx])
-        h = C.c_void_p()
-        check(lib().b2p_tile_create(C.byref(self._cfg), C.byref(idx), C.byref(h)))
-        self._h = h
-        self.index = tuple(int(v) for v in tile_grid_idx)
-        mins, maxs = (C.c_double * 3)(), (C.c_double * 3)()
-        check(lib().b2p_tile_bounds(self._h, C.byref(mins), C.byref(maxs)))
-        self.mins, self.maxs = list(mins), list(maxs)
-        self.n_cells = tuple(self._cfg.n_cells)
-        self.cid = self.index[0] + self._cfg.n_tiles[0] * (self.index[1] + self._cfg.n_tiles[1] * self.index[2])
-        self.communication = None
-
-    def __del__(self):
-        h = getattr(self, "_h", None)
-        if h:
-            try:
-                lib().b2p_tile_destroy(h)
-            except Exception:
-                pass
-            self._h = None
-
-    @staticmethod
-    def canonical_type():
-        return Tile
+    error_type = B2PError
 
     # -- geometry -------------------------------------------------------------
     def global_coordinate_map(self):
@@ -98,7 +73,7 @@ class Tile:
         mins, maxs, e = self.mins, self.maxs, self.n_cells
 
         def m(idx):
-            return tuple(mins[d] + (float(idx[d]) / float(e[d])) * (maxs[d] - mins[d]) for d in range(3))
+            return tuple(mins[d] + (idx[d] / float(e[d])) * (maxs[d] - mins[d]) for d in range(3))
         return m
 
     def _lattice_shape(self, with_halo):
@@ -112,9 +87,9 @@ class Tile:
             if a is not None:
                 a = np.ascontiguousarray(a, dtype=np.float32)
                 if a.shape != self._lattice_shape(with_halo):
-                    raise B2PError("Batch field setter returned array with incorrect shape!")
+                    raise self.error_type("Batch field setter returned array with incorrect shape!")
             arrs.append(a)
-        check(lib().b2p_tile_set_fields(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), int(with_halo)))
+        self._backend_set_fields(arrs[0], arrs[1], arrs[2], bool(with_halo))
 
     def set_EBJ(self, E, B, J):
         """emf/tile.c++:184-224: per-point callables evaluated at the Yee-staggered positions."""
@@ -149,7 +124,7 @@ class Tile:
         def shaped(a):
             a = np.asarray(a, dtype=np.float64)
             if a.shape != (nx, ny, nz):
-                raise B2PError("Batch field setter returned array with incorrect shape!")
+                raise self.error_type("Batch field setter returned array with incorrect shape!")
             return a
         E = np.stack([shaped(Ex(xp5, y, z)), shaped(Ey(x, yp5, z)), shaped(Ez(x, y, zp5))])
         B = np.stack([shaped(Bx(x, yp5, zp5)), shaped(By(xp5, y, zp5)), shaped(Bz(xp5, yp5, z))])
@@ -157,9 +132,7 @@ class Tile:
         self._upload(E, B, J)
 
     def _download(self, with_halo):
-        E, B, J = (np.empty(self._lattice_shape(with_halo), np.float32) for _ in range(3))
-        check(lib().b2p_tile_get_fields(self._h, _ptr(E), _ptr(B), _ptr(J), int(with_halo)))
-        return E, B, J
+        return self._backend_get_fields(bool(with_halo))
 
     def get_EBJ(self):
         """bindings/pyemf.c++:32-78: owning float64 copies of the fp32 interior."""
@@ -176,6 +149,52 @@ class Tile:
 
     def set_fields_f32(self, E=None, B=None, J=None, with_halo=True):
         self._upload(E, B, J, with_halo)
+
+
+
+class Tile(EmfTileHost):
+    """emf::Tile<3> — owns E, B, J on the device (emf/tile.h:36-213)."""
+
+    _need_pic = False
+
+    def __init__(self, tile_grid_idx, config):
+        try:
+            self._cfg = config if isinstance(config, _abi.B2PConfig) else make_config(config, need_pic=self._need_pic)
+        except ConfigError as e:
+            raise B2PError(str(e)) from None
+        idx = (C.c_int32 * 3)(*[int(v) for v in tile_grid_idx])
+        h = C.c_void_p()
+        check(lib().b2p_tile_create(C.byref(self._cfg), C.byref(idx), C.byref(h)))
+        self._h = h
+        self.index = tuple(int(v) for v in tile_grid_idx)
+        mins, maxs = (C.c_double * 3)(), (C.c_double * 3)()
+        check(lib().b2p_tile_bounds(self._h, C.byref(mins), C.byref(maxs)))
+        self.mins, self.maxs = list(mins), list(maxs)
+        self.n_cells = tuple(self._cfg.n_cells)
+        self.cid = self.index[0] + self._cfg.n_tiles[0] * (self.index[1] + self._cfg.n_tiles[1] * self.index[2])
+        self.communication = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().b2p_tile_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @staticmethod
+    def canonical_type():
+        return Tile
+
+    # -- backend: C-ABI ----------------------------------------------------------
+    def _backend_set_fields(self, E, B, J, with_halo):
+        check(lib().b2p_tile_set_fields(self._h, _ptr(E), _ptr(B), _ptr(J), int(with_halo)))
+
+    def _backend_get_fields(self, with_halo):
+        E, B, J = (np.empty(self._lattice_shape(with_halo), np.float32) for _ in range(3))
+        check(lib().b2p_tile_get_fields(self._h, _ptr(E), _ptr(B), _ptr(J), int(with_halo)))
+        return E, B, J
 
     # -- field solver ----------------------------------------------------------
     def push_half_b(self):
@@ -199,32 +218,10 @@ class Tile:
         return b.value, e.value
 
 
-class PicTile(Tile):
-    """pic::Tile<3> (pic/tile.h:52-202)."""
-
-    _need_pic = True
-
-    @staticmethod
-    def canonical_type():
-        return PicTile
-
-    @property
-    def n_species(self):
-        return self._cfg.n_species
-
-    # -- getters ---------------------------------------------------------------
-    def container_size(self, sp):
-        n = C.c_uint64()
-        check(lib().b2p_tile_container_size(self._h, int(sp), C.byref(n)))
-        return n.value
-
-    def get_particles(self, sp, alive_only=True):
-        n = self.container_size(sp)
-        a = [np.empty(n, np.float32) for _ in range(6)]
-        ids = np.empty(n, np.uint64)
-        m = C.c_uint64()
-        check(lib().b2p_tile_get_particles(self._h, int(sp), int(alive_only), *[_ptr(v) for v in a], _ptr(ids), C.byref(m)))
-        return tuple(np.array(v[:m.value]) for v in a) + (np.array(ids[:m.value]),)
+class PicTileHost:
+    """Backend-independent host logic of pic::Tile<3> (pic/tile.c++:180-322,
+    pic/particle.c++:82-168): injection cell order and validation, getters.  A backend
+    supplies `get_particles(sp, alive_only)` and `_backend_inject(sp, six float64 arrays)`."""
 
     def get_positions(self, sp):
         p = self.get_particles(sp)
@@ -242,10 +239,10 @@ class PicTile(Tile):
         a = [np.ascontiguousarray(v, dtype=np.float64) for v in (*pos, *vel)]
         for v in a:
             if v.ndim != 1:
-                raise B2PError("pic::Tile::batch_inject_in_x_stripe: given batch must be one dimensional.")
+                raise self.error_type("pic::Tile::batch_inject_in_x_stripe: given batch must be one dimensional.")
             if v.shape[0] != a[0].shape[0]:
-                raise B2PError("pic::Tile::batch_inject_in_x_stripe: batches must have same length.")
-        check(lib().b2p_tile_inject(self._h, int(sp), a[0].shape[0], *[_ptr(v) for v in a]))
+                raise self.error_type("pic::Tile::batch_inject_in_x_stripe: batches must have same length.")
+        self._backend_inject(int(sp), a)
 
     def inject(self, sp, particles):
         """pic/tile.c++:207-217"""
@@ -284,6 +281,38 @@ class PicTile(Tile):
         x, y, z = (np.ascontiguousarray(a.reshape(-1)) for a in gm((ii, jj, kk)))
         batch = pgen(x, y, z)
         self._inject_arrays(sp, batch.pos, batch.vel)
+
+
+
+class PicTile(PicTileHost, Tile):
+    """pic::Tile<3> (pic/tile.h:52-202)."""
+
+    _need_pic = True
+
+    @staticmethod
+    def canonical_type():
+        return PicTile
+
+    @property
+    def n_species(self):
+        return self._cfg.n_species
+
+    # -- backend: C-ABI ----------------------------------------------------------
+    def container_size(self, sp):
+        n = C.c_uint64()
+        check(lib().b2p_tile_container_size(self._h, int(sp), C.byref(n)))
+        return n.value
+
+    def get_particles(self, sp, alive_only=True):
+        n = self.container_size(sp)
+        a = [np.empty(n, np.float32) for _ in range(6)]
+        ids = np.empty(n, np.uint64)
+        m = C.c_uint64()
+        check(lib().b2p_tile_get_particles(self._h, int(sp), int(alive_only), *[_ptr(v) for v in a], _ptr(ids), C.byref(m)))
+        return tuple(np.array(v[:m.value]) for v in a) + (np.array(ids[:m.value]),)
+
+    def _backend_inject(self, sp, a):
+        check(lib().b2p_tile_inject(self._h, sp, a[0].shape[0], *[_ptr(v) for v in a]))
 
     def set_particles_raw(self, sp, x, y, z, ux, uy, uz, ids):
         a = [np.ascontiguousarray(v, dtype=np.float32) for v in (x, y, z, ux, uy, uz)]
