@@ -6,15 +6,17 @@
  * cpu_baseline / --impl reference legs.  Nothing under runko_b200/ may import,
  * link or execute it.
  *
- * Parity pin: the reference ships no numeric golden vectors for this path
- * (SURVEY.md §8c); the oracle is pinned against the reference's own
- * known-answer / behavioural tests (tests/py/test_emf_fdtd2.py,
- * test_emf_stencil.py, test_emf_current_filter_binomial2.py,
- * test_pic_particle_pusher.py, test_pic_current_depositer_zigzag_1st*.py,
- * test_pic_particle_sorting.py, tests/py-multirank/test_{emf,pic}_simulation.py),
- * re-expressed in tests/test_oracle_reference_kats.py.  The reference itself
- * cannot be compiled here (needs MPI, kokkos mdspan, rocThrust, GCC>=14 —
- * see DESIGN.md).
+ * Parity pin (two independent ones):
+ *  1. the reference's OWN kernel sources (emf::YeeLattice, pic::ParticleContainer)
+ *     are compiled here from /root/reference into oracle/_ref/libref_kernels.so
+ *     (oracle/Makefile.ref, oracle/ref_harness.cpp) and this oracle must match
+ *     them BIT FOR BIT on seeded inputs for every kernel and for whole laps on
+ *     periodic multi-tile grids: tests/test_oracle_vs_reference_build.py;
+ *  2. the reference's own unit tests (tests/py/test_{emf,pic}*.py, 103 cases) run
+ *     unmodified against this oracle through tests/refshim:
+ *     tests/test_reference_suite.py.
+ * The reference ships no numeric golden vectors for this path;
+ * tests/golden/*.npz freeze the pinned behaviour for the GPU box.
  */
 #ifndef PIC_ORACLE_H
 #define PIC_ORACLE_H
