@@ -91,6 +91,10 @@ const char* b2p_version(void);
  * when no CUDA device is usable — there is no CPU fallback. */
 int b2p_init(int device);
 int b2p_sync(void);
+/* Kernel-variant knob (launch bounds, aggregation strategy; see runko_b200/csrc/common.cuh
+ * Tuning).  Never changes results beyond the stated deposit tolerance.  Also read from the
+ * environment: B2P_OPTS="name=value,...".  No reference equivalent. */
+int b2p_set_option(const char* name, int value);
 /* tools._get_gpu_mem_kB (src/runko/tools/gpu_memory.h:16-28) */
 int64_t b2p_gpu_mem_kB(void);
 

@@ -60,6 +60,16 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// Kernel-variant knobs (b2p_set_option / env B2P_OPTS="name=value,..."): results are identical for
+// every setting, only the launch shape / aggregation strategy changes.
+struct Tuning {
+  int push_minb = 5;      // __launch_bounds__(256, minb) variant of k_push: 5, 6 or 8 resident blocks per SM
+  int deposit_minb = 4;   // same for k_deposit_zigzag: 4, 6 or 8
+  int deposit_agg = 1;    // warp-level run aggregation before the REDs
+  int fuse_deposit = 1;   // deposit the stayers' current inside the push kernel (arrivals deposit on append)
+};
+Tuning& tuning();
+
 void* dmalloc(size_t bytes);   // stream-ordered (cudaMallocAsync)
 void dfree(void* p);
 template <class T> T* dalloc(size_t n) { return static_cast<T*>(dmalloc(n * sizeof(T))); }

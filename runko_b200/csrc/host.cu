@@ -48,6 +48,35 @@ Context& ctx() {
 }
 void count_launch(int n) { g_ctx.launches += n; }
 
+static Tuning g_tuning;
+static bool set_option(const std::string& name, int value) {
+  if (name == "push_minb") g_tuning.push_minb = value;
+  else if (name == "deposit_minb") g_tuning.deposit_minb = value;
+  else if (name == "deposit_agg") g_tuning.deposit_agg = value;
+  else if (name == "fuse_deposit") g_tuning.fuse_deposit = value;
+  else return false;
+  return true;
+}
+Tuning& tuning() {
+  static bool parsed = false;
+  if (!parsed) {
+    parsed = true;
+    if (const char* e = std::getenv("B2P_OPTS")) {       // "name=value,name=value"
+      std::string str(e);
+      size_t pos = 0;
+      while (pos < str.size()) {
+        const size_t end = std::min(str.find(',', pos), str.size());
+        const std::string kv = str.substr(pos, end - pos);
+        const size_t eq = kv.find('=');
+        if (eq != std::string::npos && !set_option(kv.substr(0, eq), std::atoi(kv.c_str() + eq + 1)))
+          std::fprintf(stderr, "[b2p] unknown option in B2P_OPTS: %s\n", kv.c_str());
+        pos = end + 1;
+      }
+    }
+  }
+  return g_tuning;
+}
+
 void* dmalloc(size_t bytes) {
   void* p = nullptr;
   B2P_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, ctx().stream));
@@ -115,6 +144,12 @@ void Container::reserve(size_t cap, bool exact) {
   x.reserve_exact(cap, n); y.reserve_exact(cap, n); z.reserve_exact(cap, n);
   ux.reserve_exact(cap, n); uy.reserve_exact(cap, n); uz.reserve_exact(cap, n);
   id.reserve_exact(cap, n);
+}
+
+uint2* Container::mask_words() {
+  const size_t words = (size_t(n) + 255) / 256 * 8;
+  masks.reserve(std::max<size_t>(words, 8));
+  return masks.p;
 }
 
 static void swap_storage(Container& a, Container& b) {
@@ -301,77 +336,45 @@ void phase_filter(const std::vector<b2p_tile*>& tiles) {
     t->jcur = 1 - t->jcur;
     t->fp_dirty = true;
     if (t->grid) t->grid->table_dirty = true;
+    t->pendJ_valid = false;   // the spare lattice was overwritten
   }
 }
 
 // -------------------------------------------------------- particle phases --
 static int sign_of(double v) { return (0.0 < v) - (v < 0.0); }   // tools/math.h:181-183
 
-// Shared state of the leaver detection: filled either by the fused push of
-// b2p_grid_step_pic or by the standalone detection pass of pack_outgoing_particles.
-struct DetectPlan {
-  std::vector<Container*> conts;
-  std::vector<b2p_tile*> owner;
-  size_t total_slots = 0;
-  bool fused_valid = false;      // the last push already ran the detection for exactly these tiles
-  std::vector<b2p_tile*> tiles;
-};
-static DetectPlan& detect_plan() { static DetectPlan p; return p; }
-
-static void detect_setup(const std::vector<b2p_tile*>& tiles, size_t min_cap) {
+// pic/tile.c++:326-365.  Every push also publishes the leaver/stayer ballots of the pushed
+// positions (Container::masks), which pack_outgoing_particles consumes if nothing touched
+// the container in between.
+void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
-  DetectPlan& dp = detect_plan();
-  dp.conts.clear(); dp.owner.clear(); dp.total_slots = 0; dp.tiles = tiles; dp.fused_valid = false;
-  for (b2p_tile* t : tiles)
-    for (Container& c : t->sp) { dp.conts.push_back(&c); dp.owner.push_back(t); dp.total_slots += c.n; }
-  const size_t nc = dp.conts.size();
-  if (nc >= (size_t(1) << 26)) throw Error(B2P_ERR_RUNTIME, "too many containers in one pack call");
-  // device counters: [0] list length | [1..nc] P per container | [1+nc..1+2nc) leavers per container | counts[nc][27]
-  const size_t ncounters = 1 + 2 * nc + nc * 27;
-  s.counters.reserve(ncounters);
-  const size_t cap = std::max<size_t>(std::max(min_cap, dp.total_slots / 24 + 65536), s.list[0].cap);
-  s.list[0].reserve(cap); s.list[1].reserve(cap);
-  B2P_CUDA(cudaMemsetAsync(s.counters.p, 0, ncounters * sizeof(unsigned), ctx().stream));
-}
-
-static DetectArgsHost detect_args(size_t c) {
-  Scratch& s = scratch();
-  DetectPlan& dp = detect_plan();
-  const b2p_tile* t = dp.owner[c];
-  const size_t nc = dp.conts.size();
-  DetectArgsHost d;
-  for (int q = 0; q < 3; ++q) { d.mins[q] = float(t->mins[q]); d.maxs[q] = float(t->maxs[q]); }
-  d.container = unsigned(c);
-  d.list = s.list[0].p; d.list_count = s.counters.p;
-  d.list_cap = unsigned(std::min<size_t>(s.list[0].cap, 0xFFFFFFFFu));
-  d.last_alive = s.counters.p + 1 + c;
-  d.cont_count = s.counters.p + 1 + nc + c;
-  return d;
-}
-
-// pic/tile.c++:326-365.  fuse_detect: also run pack_outgoing's leaver detection on the
-// freshly pushed positions (valid only when pack_outgoing_particles is the next call).
-void phase_push_particles(const std::vector<b2p_tile*>& tiles, bool fuse_detect) {
-  Scratch& s = scratch();
-  if (fuse_detect) detect_setup(tiles, 0);
-  size_t cidx = 0;
+  const bool fuse = tuning().fuse_deposit != 0;
   for (b2p_tile* t : tiles) {
+    t->pendJ_valid = t->pend_packed = false;
     bool any = false;
     for (const Container& c : t->sp) any = any || c.n;
-    if (!any) { cidx += t->sp.size(); continue; }
+    if (!any) continue;
     s.nodal.reserve(size_t(2) * t->g.Ch);
     launch_nodal_means(t->E.p, t->B.p, t->g, s.nodal.p);
+    if (fuse) {
+      s.edges.reserve(size_t(3) * t->g.Ch);
+      launch_zero(reinterpret_cast<float*>(s.edges.p), size_t(12) * t->g.Ch);
+    }
+    const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
+    const float mx[3] = { float(t->maxs[0]), float(t->maxs[1]), float(t->maxs[2]) };
     for (Container& c : t->sp) {
+      if (!c.n) continue;
       const float qm = static_cast<float>(sign_of(c.charge) / c.mass);
-      DetectArgsHost d;
-      if (fuse_detect) d = detect_args(cidx);
       launch_push(t->cfg.particle_pusher, c.view(), s.nodal.p, t->g, t->origo, static_cast<float>(t->cfg.cfl), qm,
-                  fuse_detect ? &d : nullptr);
-      c.P_valid = false;
-      ++cidx;
+                  c.mask_words(), mn, mx, fuse ? s.edges.p : nullptr, static_cast<float>(c.charge));
+      c.touch();
+      c.masks_valid = true;
+    }
+    if (fuse) {
+      launch_edge_gather(s.edges.p, t->Jbuf[1 - t->jcur].p, t->g);
+      t->pendJ_valid = true;
     }
   }
-  if (fuse_detect) detect_plan().fused_valid = true;
 }
 
 // pic/tile.c++:369-415.  clear_current + scratch accumulate + `J += scratch`
@@ -379,6 +382,16 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles, bool fuse_detect)
 void phase_deposit(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
   for (b2p_tile* t : tiles) {
+    if (t->pendJ_valid && t->pend_packed) {
+      // the fused push (stayers) and the particle exchange (arrivals) already accumulated this
+      // lap's current in the spare lattice: adopt it
+      t->jcur = 1 - t->jcur;
+      t->fp_dirty = true;
+      if (t->grid) t->grid->table_dirty = true;
+      t->pendJ_valid = t->pend_packed = false;
+      continue;
+    }
+    t->pendJ_valid = t->pend_packed = false;
     s.edges.reserve(size_t(3) * t->g.Ch);
     launch_zero(reinterpret_cast<float*>(s.edges.p), size_t(12) * t->g.Ch);
     for (Container& c : t->sp)
@@ -410,7 +423,7 @@ void phase_sort(const std::vector<b2p_tile*>& tiles) {
       s.spare.n = c.n;
       launch_gather(c.view(), s.spare.view(), v[sel]);
       swap_storage(c, s.spare);
-      c.P_valid = false;
+      c.touch();
     }
 }
 
@@ -418,30 +431,50 @@ void phase_sort(const std::vector<b2p_tile*>& tiles) {
 void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles) {
   if (tiles.empty()) return;
   Scratch& s = scratch();
-  DetectPlan& dp = detect_plan();
-  const bool fused = dp.fused_valid && dp.tiles == tiles;
-  dp.fused_valid = false;
   for (b2p_tile* t : tiles) { t->out_ends.assign(27 * t->sp.size(), 0); t->out_count = 0; }
-  std::vector<unsigned> hc;
-  size_t nc = 0;
-  size_t min_cap = 0;
-  for (int attempt = 0;; ++attempt) {
-    if (!(fused && attempt == 0)) {
-      detect_setup(tiles, min_cap);
-      for (size_t c = 0; c < dp.conts.size(); ++c) launch_detect_leavers(dp.conts[c]->view(), detect_args(c));
+  std::vector<Container*> conts;
+  std::vector<CollectJobHost> jobs;
+  size_t total_slots = 0;
+  unsigned max_words = 0;
+  for (b2p_tile* t : tiles) {
+    const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
+    const float mx[3] = { float(t->maxs[0]), float(t->maxs[1]), float(t->maxs[2]) };
+    for (Container& c : t->sp) {
+      uint2* words = c.mask_words();
+      if (!c.masks_valid) {                                            // not pushed since the last change
+        launch_make_masks(c.view(), words, mn, mx);
+        t->pendJ_valid = false;
+      }
+      const unsigned nwords = unsigned((size_t(c.n) + 31) / 32);
+      jobs.push_back(CollectJobHost{ words, nwords, c.view(), make_float3(mn[0], mn[1], mn[2]), make_float3(mx[0], mx[1], mx[2]) });
+      conts.push_back(&c);
+      total_slots += c.n;
+      max_words = std::max(max_words, nwords);
     }
-    nc = dp.conts.size();
-    if (nc == 0) return;
-    hc.resize(1 + 2 * nc);
+  }
+  const size_t nc = conts.size();
+  if (nc == 0) return;
+  if (nc >= (size_t(1) << 26)) throw Error(B2P_ERR_RUNTIME, "too many containers in one pack call");
+  // device counters: [0] list length | [1..nc] P per container | [1+nc..1+2nc) leavers per container | counts[nc][27]
+  const size_t ncounters = 1 + 2 * nc + nc * 27;
+  s.counters.reserve(ncounters);
+  s.table.reserve(nc * sizeof(CollectJobHost));
+  h2d(reinterpret_cast<CollectJobHost*>(s.table.p), jobs.data(), nc);
+  std::vector<unsigned> hc(1 + 2 * nc);
+  size_t cap = std::max<size_t>(total_slots / 24 + 65536, s.list[0].cap);
+  for (;;) {
+    s.list[0].reserve(cap); s.list[1].reserve(cap);
+    B2P_CUDA(cudaMemsetAsync(s.counters.p, 0, ncounters * sizeof(unsigned), ctx().stream));
+    launch_collect_leavers(s.table.p, unsigned(nc), max_words, s.list[0].p, s.counters.p,
+                           unsigned(std::min<size_t>(s.list[0].cap, 0xFFFFFFFFu)), s.counters.p + 1, s.counters.p + 1 + nc);
     d2h(hc.data(), s.counters.p, 1 + 2 * nc);
     sync();
     if (hc[0] <= s.list[0].cap) break;
-    min_cap = hc[0];   // overflow: nothing was modified yet, redo the detection with a larger list
+    cap = hc[0];   // overflow: nothing was modified yet, collect again into a larger list
   }
-  std::vector<Container*>& conts = dp.conts;
   const unsigned total = hc[0];
   for (size_t c = 0; c < nc; ++c) { conts[c]->P = hc[1 + c]; conts[c]->P_valid = true; }
-  if (total == 0) return;
+  if (total == 0) { for (b2p_tile* t : tiles) t->pend_packed = t->pendJ_valid; return; }
   // restore the reference's (species, subregion, container order) order
   int cbits = 1;
   while ((size_t(1) << cbits) < nc) ++cbits;
@@ -467,6 +500,8 @@ void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles) {
   h2d(reinterpret_cast<OutTileHost*>(s.table.p), ot.data(), nc);
   unsigned* counts = s.counters.p + 1 + 2 * nc;
   launch_gather_outgoing(k[sel], total, s.table.p, counts);
+  for (Container* ct : conts) ct->masks_valid = false;              // leavers are dead now
+  for (b2p_tile* t : tiles) t->pend_packed = t->pendJ_valid;
   std::vector<unsigned> hcounts(nc * 27);
   d2h(hcounts.data(), counts, nc * 27);
   sync();
@@ -484,8 +519,8 @@ void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles) {
 // ---------------------------------------------------------- communication --
 struct SpanRef { const b2p_particle_state* p; unsigned n; };
 
-static void append_spans(std::vector<Container*>& conts, std::vector<std::vector<SpanRef>>& spans, bool wrap,
-                         const float wmin[3], const float wmax[3]) {
+static void append_spans(std::vector<Container*>& conts, std::vector<b2p_tile*>& owners, std::vector<std::vector<SpanRef>>& spans,
+                         bool wrap, const float wmin[3], const float wmax[3]) {
   // pic/particle.h:454-572 for many containers at once
   std::vector<AppendJobHost> jobs;
   unsigned max_count = 0;
@@ -501,10 +536,17 @@ static void append_spans(std::vector<Container*>& conts, std::vector<std::vector
     ct.n = unsigned(P + total);
     unsigned off = P;
     for (const SpanRef& sr : spans[c]) {
-      if (sr.n) { jobs.push_back(AppendJobHost{ sr.p, sr.n, off, ct.view() }); max_count = std::max(max_count, sr.n); }
+      if (sr.n) {
+        b2p_tile* t = owners[c];
+        float* jp = (t->pendJ_valid && t->pend_packed) ? t->Jbuf[1 - t->jcur].p : nullptr;   // arrivals join the fused deposit
+        jobs.push_back(AppendJobHost{ sr.p, sr.n, off, ct.view(), jp, make_float3(t->origo[0], t->origo[1], t->origo[2]),
+                                      static_cast<float>(ct.charge) });
+        max_count = std::max(max_count, sr.n);
+      }
       off += sr.n;
     }
     ct.P = ct.n; ct.P_valid = true;   // either the last appended slot is alive, or n == P
+    ct.masks_valid = false;
   }
   if (jobs.empty()) return;
   Scratch& s = scratch();
@@ -512,7 +554,8 @@ static void append_spans(std::vector<Container*>& conts, std::vector<std::vector
   h2d(reinterpret_cast<AppendJobHost*>(s.table.p), jobs.data(), jobs.size());
   for (size_t b = 0; b < jobs.size(); b += 65535) {
     const int nj = int(std::min<size_t>(65535, jobs.size() - b));
-    launch_append(reinterpret_cast<AppendJobHost*>(s.table.p) + b, nj, max_count, wrap, wmin, wmax);
+    launch_append(reinterpret_cast<AppendJobHost*>(s.table.p) + b, nj, max_count, wrap, wmin, wmax, owners[0]->g,
+                  static_cast<float>(owners[0]->cfg.cfl));
   }
 }
 
@@ -532,11 +575,12 @@ void grid_local_communication(b2p_grid* g, int mode) {
   // pic/tile_communication.c++:121-195: for every Moore direction (kr, jr, ir order) take
   // the neighbour's span for the inverted direction; then the postlude appends (:100-117)
   std::vector<Container*> conts;
+  std::vector<b2p_tile*> owners;
   std::vector<std::vector<SpanRef>> spans;
   const int* T = g->cfg.n_tiles;
   for (b2p_tile* me : g->tiles) {
     const size_t base = conts.size();
-    for (Container& c : me->sp) { conts.push_back(&c); spans.emplace_back(); }
+    for (Container& c : me->sp) { conts.push_back(&c); owners.push_back(me); spans.emplace_back(); }
     for (int kr = -1; kr <= 1; ++kr) for (int jr = -1; jr <= 1; ++jr) for (int ir = -1; ir <= 1; ++ir) {
       if (!ir && !jr && !kr) continue;
       const int oc = g->cid(wrapi(me->idx[0] + ir, T[0]), wrapi(me->idx[1] + jr, T[1]), wrapi(me->idx[2] + kr, T[2]));
@@ -567,7 +611,7 @@ void grid_local_communication(b2p_grid* g, int mode) {
   }
   float wmin[3], wmax[3];
   for (int d = 0; d < 3; ++d) { wmin[d] = 0.0f; wmax[d] = static_cast<float>(double(size_t(T[d]) * size_t(g->cfg.n_cells[d]))); }
-  append_spans(conts, spans, true, wmin, wmax);
+  append_spans(conts, owners, spans, true, wmin, wmax);
   for (b2p_tile* t : g->tiles) t->out_ends.clear();
   comm_particles_consumed(g);
 }
@@ -607,6 +651,12 @@ const char* b2p_last_error(void) { return g_last_error.c_str(); }
 const char* b2p_version(void) { return "b200pic 0.1 (sm_100a)"; }
 int b2p_init(int device) { B2P_TRY b2p::init(device); B2P_CATCH }
 int b2p_sync(void) { B2P_TRY sync(); B2P_CATCH }
+int b2p_set_option(const char* name, int value) {
+  B2P_TRY
+  b2p::tuning();
+  if (!name || !b2p::set_option(name, value)) throw Error(B2P_ERR_RUNTIME, std::string("unknown option: ") + (name ? name : "(null)"));
+  B2P_CATCH
+}
 int64_t b2p_gpu_mem_kB(void) {
   size_t fr = 0, tot = 0;
   if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return -1;
@@ -706,6 +756,7 @@ int b2p_tile_inject(b2p_tile* t, int sp, uint64_t n, const double* x, const doub
                     const double* ux, const double* uy, const double* uz) {
   B2P_TRY
   Container& c = C(t, sp);
+  t->pendJ_valid = false;
   // pic/tile.c++:207-217 + pic/particle.h:258-287: narrow, assign ids, append after the last alive slot
   const unsigned P = find_P(c);
   if (size_t(P) + n >= (size_t(1) << 32)) throw Error(B2P_ERR_RUNTIME, "particle container exceeds uint32 indexing");
@@ -729,7 +780,7 @@ int b2p_tile_inject(b2p_tile* t, int sp, uint64_t n, const double* x, const doub
     h2d(c.id.p + P, ids.data(), n);
     sync();
   }
-  c.P = c.n; c.P_valid = true;
+  c.P = c.n; c.P_valid = true; c.masks_valid = false;
   B2P_CATCH
 }
 
@@ -737,6 +788,7 @@ int b2p_tile_set_particles(b2p_tile* t, int sp, uint64_t n, const float* x, cons
                            const float* ux, const float* uy, const float* uz, const uint64_t* id) {
   B2P_TRY
   Container& c = C(t, sp);
+  t->pendJ_valid = false;
   if (n >= (1ull << 32)) throw Error(B2P_ERR_RUNTIME, "particle container exceeds uint32 indexing");
   c.n = 0;
   c.reserve(n);
@@ -745,7 +797,7 @@ int b2p_tile_set_particles(b2p_tile* t, int sp, uint64_t n, const float* x, cons
   h2d(c.ux.p, ux, n); h2d(c.uy.p, uy, n); h2d(c.uz.p, uz, n);
   h2d(c.id.p, reinterpret_cast<const unsigned long long*>(id), n);
   sync();
-  c.P_valid = false;
+  c.touch();
   B2P_CATCH
 }
 int b2p_tile_container_size(b2p_tile* t, int sp, uint64_t* n) { B2P_TRY *n = C(t, sp).n; B2P_CATCH }
@@ -882,7 +934,7 @@ int b2p_grid_step_pic(b2p_grid* g, int64_t lap) {
   phase_push_half_b(g->tiles, g->device_table());
   ext(B2P_COMM_EMF_B); grid_local_communication(g, B2P_COMM_EMF_B);
   tr.mark("fields", lap);
-  phase_push_particles(g->tiles, true);   // leaver detection fused into the push
+  phase_push_particles(g->tiles);         // also publishes the leaver masks pack_outgoing consumes
   tr.mark("push enqueue", lap);
   phase_pack_outgoing(g->tiles);
   tr.mark("pack", lap);
@@ -957,6 +1009,7 @@ int b2p_grid_inject_thermal(b2p_grid* g, int ppc, double delgam, uint64_t seed) 
     const size_t total = size_t(t->g.N[0]) * t->g.N[1] * t->g.N[2] * size_t(ppc);
     if (total >= (size_t(1) << 32)) throw Error(B2P_ERR_RUNTIME, "particle container exceeds uint32 indexing");
     const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
+    t->pendJ_valid = false;
     for (size_t q = 0; q < t->sp.size(); ++q) {
       Container& c = t->sp[q];
       if (c.n) throw Error(B2P_ERR_RUNTIME, "inject_thermal requires empty containers");
@@ -966,7 +1019,7 @@ int b2p_grid_inject_thermal(b2p_grid* g, int ppc, double delgam, uint64_t seed) 
       launch_inject_thermal(c.view(), t->g, mn, unsigned(ppc), float(delgam), sp_seed, sp_seed ^ (0xA5A5A5A5ull * (q + 1)),
                             (t->tile_tag << 40) | t->next_ordinal[q]);
       t->next_ordinal[q] += total;
-      c.P = c.n; c.P_valid = true;
+      c.P = c.n; c.P_valid = true; c.masks_valid = false;
     }
   }
   B2P_CATCH

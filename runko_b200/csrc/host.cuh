@@ -17,6 +17,10 @@ struct Container {
   double charge = 0, mass = 1;
   bool P_valid = false;       // P = 1 + last alive slot known on the host
   unsigned P = 0;
+  DBuf<uint2> masks;          // per 32 slots: {leaving, staying} ballots of the tile box test (particles.cu)
+  bool masks_valid = false;   // masks describe the current container contents
+  void touch() { P_valid = false; masks_valid = false; }   // contents changed
+  uint2* mask_words();        // sized for the current n (whole blocks of 256 slots)
   Species view() const { return Species{ x.p, y.p, z.p, ux.p, uy.p, uz.p, id.p, n }; }
   size_t capacity() const { return id.cap; }
   void reserve(size_t cap, bool exact = false);   // keeps the first n slots; !exact rounds up to a capacity class
@@ -35,6 +39,10 @@ struct b2p_tile {
   float stencilM[3][3][5];
   b2p::DBuf<float> E, B, Jbuf[2];
   int jcur = 0;
+  // fused push+deposit: Jbuf[1 - jcur] holds the current of the particles that stayed in the tile
+  // (plus, after the particle exchange, of the arrivals); deposit_current adopts it when the
+  // leavers of that same push were removed by pack_outgoing_particles, else it deposits afresh
+  bool pendJ_valid = false, pend_packed = false;
   b2p::DBuf<b2p::FieldPtrs> d_fp;   // 1-entry device tile table for per-tile launches
   bool fp_dirty = true;
   std::vector<b2p::Container> sp;
@@ -76,7 +84,7 @@ void phase_push_half_b(const std::vector<b2p_tile*>& tiles, const FieldPtrs* tab
 void phase_push_e(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table, bool add_current);
 void phase_add_current(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table);
 void phase_filter(const std::vector<b2p_tile*>& tiles);
-void phase_push_particles(const std::vector<b2p_tile*>& tiles, bool fuse_detect = false);
+void phase_push_particles(const std::vector<b2p_tile*>& tiles);
 void phase_deposit(const std::vector<b2p_tile*>& tiles);
 void phase_sort(const std::vector<b2p_tile*>& tiles);
 void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles);

@@ -65,13 +65,17 @@ k_nodal_means(const float* __restrict__ E, const float* __restrict__ B, const Ge
 struct EB { V3 E, B; };
 
 // emf/yee_lattice_interpolate_linear_1st.h:58-138 on top of the nodal means.
+// Node indices fit 32 bits (Ch < 2^31 is checked at tile creation), so all index
+// arithmetic is 32-bit; only the four row base addresses are widened.
 __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const Geom& g, const float3 origo,
                                           const float px, const float py, const float pz) {
   const float lx = px - origo.x, ly = py - origo.y, lz = pz - origo.z;
   const unsigned i = __float2uint_rz(lx), j = __float2uint_rz(ly), k = __float2uint_rz(lz);
   const float dx = lx - float(i), dy = ly - float(j), dz = lz - float(k);
-  const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2];
-  const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
+  const unsigned sj = unsigned(g.Hx[2]), si = unsigned(g.Hx[1]) * unsigned(g.Hx[2]);
+  const unsigned n = (i * unsigned(g.Hx[1]) + j) * sj + k;
+  const float4* __restrict__ row[2][2] = { { nod + 2u * size_t(n), nod + 2u * size_t(n + sj) },
+                                           { nod + 2u * size_t(n + si), nod + 2u * size_t(n + si + sj) } };
   float4 a[2][2][2], b[2][2][2];
 #pragma unroll
   for (int ic = 0; ic < 2; ++ic)
@@ -79,9 +83,8 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
     for (int jc = 0; jc < 2; ++jc)
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        const size_t m = n + ic * si + jc * sj + kc;
-        a[ic][jc][kc] = __ldg(&nod[2 * m]);
-        b[ic][jc][kc] = __ldg(&nod[2 * m + 1]);
+        a[ic][jc][kc] = __ldg(row[ic][jc] + 2 * kc);
+        b[ic][jc][kc] = __ldg(row[ic][jc] + 2 * kc + 1);
       }
   // lerp3D (:29-52): along x, then y, then z
 #define LERP3(field, comp)                                                                     \
@@ -104,52 +107,163 @@ __device__ __forceinline__ int subregion_of(const float x, const float y, const 
   return ((i + 1) * 3 + (j + 1)) * 3 + (k + 1);
 }
 
-// Leaver detection shared by the standalone pass and the fused push
-// (pic/particle.c++:252-262): every alive particle whose position is outside the
-// tile box appends the key (container << 37) | (subregion << 32) | slot to an
-// unordered list — one global atomic per block; a radix sort of the list restores
-// the reference's (species, subregion, container order).  Also records
-// P = 1 + the largest slot that stays alive (ParticleContainer::append,
-// pic/particle.h:469-488).  Must be called by every thread of the block.
-struct DetectArgs {
-  float3 mn, mx;
-  unsigned container;
-  unsigned long long* list;
-  unsigned* list_count;
-  unsigned list_cap;
-  unsigned* last_alive;
-  unsigned* cont_count;
+// Leaver detection (pic/particle.c++:228-262), shared by the push and the standalone
+// pass.  Every warp publishes two 32-bit ballots for its 32 slots — `leaving` (alive and
+// outside the tile box) and `staying` (alive and inside) — as one uint2 per warp: no
+// atomics, no shared memory and no barrier in the particle sweep.  k_collect_leavers
+// turns the words of all containers into the unordered (container, subregion, slot) key
+// list; a radix sort of that short list restores the reference's order.
+// A particle stays iff per axis (x >= min) == (x < max)  [direction 0 of :228-238].
+__device__ __forceinline__ bool inside_box(const float x, const float y, const float z, const float3 mn, const float3 mx) {
+  return ((x >= mn.x) == (x < mx.x)) & ((y >= mn.y) == (y < mx.y)) & ((z >= mn.z) == (z < mx.z));
+}
+__device__ __forceinline__ void publish_masks(const bool alive, const bool inside, const unsigned n, uint2* __restrict__ masks) {
+  const unsigned lm = __ballot_sync(0xffffffffu, alive && !inside);
+  const unsigned sm = __ballot_sync(0xffffffffu, alive && inside);
+  if ((threadIdx.x & 31) == 0) masks[n >> 5] = make_uint2(lm, sm);
+}
+
+// ---------------------------------------------------------------- deposit --
+struct DepositArgs {
+  Species s;
+  float4* Jc;      // cell-edge accumulators: 3 float4 per lattice cell (see below)
+  Geom g;
+  float3 origo;
+  float cfl;
+  float charge;
 };
 
-__device__ __forceinline__ void block_detect(const bool alive, const float x, const float y, const float z,
-                                             const unsigned n, const DetectArgs& d) {
-  __shared__ unsigned sh_cnt[32];
-  __shared__ unsigned sh_base, sh_last;
-  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  if (threadIdx.x == 0) sh_last = 0;
-  int sub = 13;
-  if (alive) sub = subregion_of(x, y, z, d.mn, d.mx);
-  const bool leaving = alive && sub != 13;
-  const bool staying = alive && sub == 13;
-  const unsigned m = __ballot_sync(0xffffffffu, leaving);
-  const unsigned sa = __ballot_sync(0xffffffffu, staying);
-  if (lane == 0) sh_cnt[w] = __popc(m);
-  __syncthreads();
-  if (sa && lane == 0) atomicMax(&sh_last, (n & ~31u) + (32 - __clz(sa)));
-  if (threadIdx.x == 0) {
-    unsigned total = 0;
-    for (unsigned q = 0; q < nw; ++q) { const unsigned c = sh_cnt[q]; sh_cnt[q] = total; total += c; }
-    unsigned base = 0;
-    if (total) { base = atomicAdd(d.list_count, total); atomicAdd(d.cont_count, total); }
-    sh_base = base;
+// Warp-level pre-aggregation of one segment set before the global REDs.  Lanes whose
+// segment lies in the same cell form contiguous runs whenever the container is (nearly)
+// cell-sorted: the sort every 5th lap orders by the cell of x2, and one lap later the cell of
+// x1 is that same cell.  A segmented shuffle reduction over runs (steps 1, 2, 4; each skipped
+// warp-uniformly when no run is that long) leaves partial sums at every 8th lane of a run,
+// and only those lanes issue the three RED.128 — up to 8x fewer atomics leave the SM, which
+// is what bounds this kernel (~1.3 cycles per RED lane per SM).  Unsorted input degenerates
+// to the plain per-lane REDs at the cost of one ballot.  Summation order differs from the
+// reference's serial loop: covered by the stated deposit tolerance.
+template <int AGG>
+__device__ __forceinline__ void reduce_runs_and_red(const unsigned key, float4 ex, float4 ey, float4 ez, float4* __restrict__ Jc) {
+  const unsigned lane = threadIdx.x & 31;
+  bool issue = key != 0xFFFFFFFFu;
+  if (AGG) {
+    const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || key != prev;
+    const unsigned hm = __ballot_sync(0xffffffffu, head);
+    const unsigned above = lane == 31 ? 0u : (hm >> (lane + 1));
+    const unsigned rem = above ? unsigned(__ffs(above)) : 32u - lane;   // lanes [lane, lane + rem) share my key
+    const unsigned start = 31u - __clz(hm & (0xFFFFFFFFu >> (31u - lane)));
+#pragma unroll
+    for (int d = 1; d <= 4; d <<= 1) {
+      if (__any_sync(0xffffffffu, rem > unsigned(d))) {
+        const bool take = rem > unsigned(d);
+#define B2P_STEP(v) { const float t_ = __shfl_down_sync(0xffffffffu, v, d); if (take) v += t_; }
+        B2P_STEP(ex.x) B2P_STEP(ex.y) B2P_STEP(ex.z) B2P_STEP(ex.w)
+        B2P_STEP(ey.x) B2P_STEP(ey.y) B2P_STEP(ey.z) B2P_STEP(ey.w)
+        B2P_STEP(ez.x) B2P_STEP(ez.y) B2P_STEP(ez.z) B2P_STEP(ez.w)
+#undef B2P_STEP
+      }
+    }
+    issue = issue && (((lane - start) & 7u) == 0u);
   }
-  __syncthreads();
-  if (threadIdx.x == 0 && sh_last) atomicMax(d.last_alive, sh_last);
-  if (leaving) {
-    const unsigned pos = sh_base + sh_cnt[w] + __popc(m & ((1u << lane) - 1));
-    if (pos < d.list_cap)
-      d.list[pos] = (static_cast<unsigned long long>(d.container) << 37) | (static_cast<unsigned long long>(sub) << 32) | n;
+  if (issue) {
+    atomicAdd(&Jc[3 * size_t(key) + 0], ex);
+    atomicAdd(&Jc[3 * size_t(key) + 1], ey);
+    atomicAdd(&Jc[3 * size_t(key) + 2], ez);
   }
+}
+
+// Layout of the deposit scratch (pic/particle_current_zigzag_1st.c++:241-336).  Each of
+// the two zigzag segments touches the 12 edges of one cell (4 x-edges, 4 y-edges,
+// 4 z-edges), so instead of the reference's 42 scalar atomics per particle the
+// 12 values go to a cell-major scratch of 3 float4 per cell with 3 vector RED.128:
+//   Jc[3c+0] = Jx at nodes c+(0,0,0), c+(0,1,0), c+(0,0,1), c+(0,1,1)
+//   Jc[3c+1] = Jy at nodes c+(0,0,0), c+(1,0,0), c+(0,0,1), c+(1,0,1)
+//   Jc[3c+2] = Jz at nodes c+(0,0,0), c+(1,0,0), c+(0,1,0), c+(1,1,0)
+// k_edge_gather then folds the (up to 4) cell records that share a node into the
+// nodal J.  Per-particle values are bit-identical to the reference; only the
+// accumulation order differs (stated tolerance 1e-5 * max|J|).
+// The zigzag split of one particle (pic/particle_current_zigzag_1st.c++:241-336): cells n1, n2 of
+// the two segments and their 12 edge currents each.  `pos`/`u` are the stored fp32 values.
+struct Zigzag {
+  unsigned n1, n2;
+  float4 ax, ay, az, bx, by, bz;
+};
+__device__ __forceinline__ Zigzag zigzag_split(const V3 pos, const V3 u, const float3 origo, const float cfl, const float charge,
+                                               const Geom& g) {
+  Zigzag r;
+  const float invgam = 1.0f / sqrtf(1.0f + dot(u, u));
+  const V3 x2 = pos - V3{ origo.x, origo.y, origo.z };
+  const V3 x1 = x2 - cfl * invgam * u;
+  const V3 fi1 = { floorf(x1.x), floorf(x1.y), floorf(x1.z) };
+  const V3 fi2 = { floorf(x2.x), floorf(x2.y), floorf(x2.z) };
+  auto relay = [](const float f1, const float f2, const float p1, const float p2) {
+    const float lo = (f1 < f2 ? f1 : f2) + 1.0f;
+    const float b1 = f1 > f2 ? f1 : f2;
+    const float b2 = 0.5f * (p1 + p2);
+    const float b = b1 > b2 ? b1 : b2;
+    return lo < b ? lo : b;
+  };
+  const V3 xr = { relay(fi1.x, fi2.x, x1.x, x2.x), relay(fi1.y, fi2.y, x1.y, x2.y), relay(fi1.z, fi2.z, x1.z, x2.z) };
+  const V3 F1 = charge * (xr - x1);
+  const V3 F2 = charge * (x2 - xr);
+  const V3 W1 = 0.5f * (x1 + xr) - fi1;
+  const V3 W2 = 0.5f * (x2 + xr) - fi2;
+  const unsigned Hy = unsigned(g.Hx[1]), Hz = unsigned(g.Hx[2]);
+  r.n1 = (__float2uint_rz(fi1.x) * Hy + __float2uint_rz(fi1.y)) * Hz + __float2uint_rz(fi1.z);
+  r.n2 = (__float2uint_rz(fi2.x) * Hy + __float2uint_rz(fi2.y)) * Hz + __float2uint_rz(fi2.z);
+  const float one = 1.0f;
+#define EDGES(F, W, ex, ey, ez)                                                                                \
+  ex = make_float4(F.x * (one - W.y) * (one - W.z), F.x * W.y * (one - W.z), F.x * (one - W.y) * W.z, F.x * W.y * W.z); \
+  ey = make_float4(F.y * (one - W.x) * (one - W.z), F.y * W.x * (one - W.z), F.y * (one - W.x) * W.z, F.y * W.x * W.z); \
+  ez = make_float4(F.z * (one - W.x) * (one - W.y), F.z * W.x * (one - W.y), F.z * (one - W.x) * W.y, F.z * W.x * W.y);
+  EDGES(F1, W1, r.ax, r.ay, r.az)
+  EDGES(F2, W2, r.bx, r.by, r.bz)
+#undef EDGES
+  return r;
+}
+
+// Accumulate one particle's split into the cell-edge scratch (all 32 lanes must call).
+template <int AGG>
+__device__ __forceinline__ void deposit_split(const bool active, Zigzag z, float4* __restrict__ Jc) {
+  if (!active) {
+    z.n1 = z.n2 = 0xFFFFFFFFu;
+    z.ax = z.ay = z.az = z.bx = z.by = z.bz = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (z.n1 == z.n2) {   // both segments in one cell (about half of a thermal plasma): one record
+    z.bx.x += z.ax.x; z.bx.y += z.ax.y; z.bx.z += z.ax.z; z.bx.w += z.ax.w;
+    z.by.x += z.ay.x; z.by.y += z.ay.y; z.by.z += z.ay.z; z.by.w += z.ay.w;
+    z.bz.x += z.az.x; z.bz.y += z.az.y; z.bz.z += z.az.z; z.bz.w += z.az.w;
+    z.n1 = 0xFFFFFFFFu;
+  }
+  if (__any_sync(0xffffffffu, z.n1 != 0xFFFFFFFFu)) reduce_runs_and_red<AGG>(z.n1, z.ax, z.ay, z.az, Jc);
+  reduce_runs_and_red<AGG>(z.n2, z.bx, z.by, z.bz, Jc);
+}
+
+// Standalone deposit of a whole container: one thread per particle.
+template <int AGG, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_deposit_zigzag(const DepositArgs a) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool alive = n < a.s.n && a.s.id[n] != DEAD;
+  Zigzag z;
+  if (alive)
+    z = zigzag_split(V3{ a.s.x[n], a.s.y[n], a.s.z[n] }, V3{ a.s.ux[n], a.s.uy[n], a.s.uz[n] }, a.origo, a.cfl, a.charge, a.g);
+  deposit_split<AGG>(alive, z, a.Jc);
+}
+
+// Scalar nodal scatter of one particle's split (arrivals of the migration: ~1% of the particles).
+// Same node pattern as k_edge_gather's fold of the cell-edge records.
+__device__ __forceinline__ void deposit_split_nodal(const Zigzag& z, float* __restrict__ J, const Geom& g) {
+  const size_t Ch = g.Ch;
+  const unsigned sj = unsigned(g.Hx[2]), si = unsigned(g.Hx[1]) * unsigned(g.Hx[2]);
+  auto put = [&](const unsigned c, const float4 ex, const float4 ey, const float4 ez) {
+    float* Jx = J; float* Jy = J + Ch; float* Jz = J + 2 * Ch;
+    atomicAdd(Jx + c, ex.x); atomicAdd(Jx + c + sj, ex.y); atomicAdd(Jx + c + 1, ex.z); atomicAdd(Jx + c + sj + 1, ex.w);
+    atomicAdd(Jy + c, ey.x); atomicAdd(Jy + c + si, ey.y); atomicAdd(Jy + c + 1, ey.z); atomicAdd(Jy + c + si + 1, ey.w);
+    atomicAdd(Jz + c, ez.x); atomicAdd(Jz + c + si, ez.y); atomicAdd(Jz + c + sj, ez.z); atomicAdd(Jz + c + si + sj, ez.w);
+  };
+  put(z.n1, z.ax, z.ay, z.az);
+  put(z.n2, z.bx, z.by, z.bz);
 }
 
 // ----------------------------------------------------------------- pushers --
@@ -162,18 +276,23 @@ struct PushArgs {
   float qm;       // sign(q)/m   (pic/particle_boris.h:26-27)
 };
 
-template <int PUSHER, bool DETECT>
-__global__ void __launch_bounds__(256)
-k_push(const PushArgs a, const DetectArgs d) {
+// One thread per slot.  `masks` has one uint2 per 32 slots (rounded up to the block).
+// FUSE: the zigzag current of every particle that STAYS in the tile box is deposited right here
+// from the registers (cell-edge scratch Jc, charge); particles that leave are deposited when they
+// arrive in their new tile (k_append), so every tile's J still receives exactly the particles that
+// reside in it after migration — the reference's deposit_current, minus one pass over HBM.
+template <int PUSHER, int MINB, int FUSE>
+__global__ void __launch_bounds__(256, MINB)
+k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float3 mx, float4* __restrict__ Jc, const float charge) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
   const bool alive = n < a.s.n && a.s.id[n] != DEAD;               // :33
   float nx = 0.f, ny = 0.f, nz = 0.f;
+  V3 vel = { 0.f, 0.f, 0.f };
   if (alive) {
   const float px = a.s.x[n], py = a.s.y[n], pz = a.s.z[n];
   const V3 u = { a.s.ux[n], a.s.uy[n], a.s.uz[n] };
   const EB eb = interpolate(a.nod, a.g, a.origo, px, py, pz);
   const float cfl = a.cfl, qm = a.qm;
-  V3 vel;
   if (PUSHER == B2P_PUSHER_BORIS) {                                // pic/particle_boris.h:37-59
     const V3 v0 = cfl * u;
     const V3 E0 = 0.5f * qm * eb.E;
@@ -228,73 +347,17 @@ k_push(const PushArgs a, const DetectArgs d) {
   a.s.ux[n] = vel.x; a.s.uy[n] = vel.y; a.s.uz[n] = vel.z;
   a.s.x[n] = nx; a.s.y[n] = ny; a.s.z[n] = nz;
   }
-  if (DETECT) block_detect(alive, nx, ny, nz, n, d);
-}
-
-// ---------------------------------------------------------------- deposit --
-struct DepositArgs {
-  Species s;
-  float4* Jc;      // cell-edge accumulators: 3 float4 per lattice cell (see below)
-  Geom g;
-  float3 origo;
-  float cfl;
-  float charge;
-};
-
-// pic/particle_current_zigzag_1st.c++:241-336.  One thread per particle.  Each of
-// the two zigzag segments touches the 12 edges of one cell (4 x-edges, 4 y-edges,
-// 4 z-edges), so instead of the reference's 42 scalar atomics per particle the
-// 12 values go to a cell-major scratch of 3 float4 per cell with 3 vector RED.128
-// (6 per particle, 3 when both segments lie in the same cell):
-//   Jc[3c+0] = Jx at nodes c+(0,0,0), c+(0,1,0), c+(0,0,1), c+(0,1,1)
-//   Jc[3c+1] = Jy at nodes c+(0,0,0), c+(1,0,0), c+(0,0,1), c+(1,0,1)
-//   Jc[3c+2] = Jz at nodes c+(0,0,0), c+(1,0,0), c+(0,1,0), c+(1,1,0)
-// k_edge_gather then folds the (up to 4) cell records that share a node into the
-// nodal J.  Per-particle values are bit-identical to the reference; only the
-// accumulation order differs (stated tolerance 1e-5 * max|J|).
-__global__ void __launch_bounds__(256)
-k_deposit_zigzag(const DepositArgs a) {
-  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= a.s.n) return;
-  if (a.s.id[n] == DEAD) return;
-  const V3 u = { a.s.ux[n], a.s.uy[n], a.s.uz[n] };
-  const float invgam = 1.0f / sqrtf(1.0f + dot(u, u));
-  const V3 x2 = V3{ a.s.x[n], a.s.y[n], a.s.z[n] } - V3{ a.origo.x, a.origo.y, a.origo.z };
-  const V3 x1 = x2 - a.cfl * invgam * u;
-  const V3 fi1 = { floorf(x1.x), floorf(x1.y), floorf(x1.z) };
-  const V3 fi2 = { floorf(x2.x), floorf(x2.y), floorf(x2.z) };
-  auto relay = [](const float f1, const float f2, const float p1, const float p2) {
-    const float lo = (f1 < f2 ? f1 : f2) + 1.0f;
-    const float b1 = f1 > f2 ? f1 : f2;
-    const float b2 = 0.5f * (p1 + p2);
-    const float b = b1 > b2 ? b1 : b2;
-    return lo < b ? lo : b;
-  };
-  const V3 xr = { relay(fi1.x, fi2.x, x1.x, x2.x), relay(fi1.y, fi2.y, x1.y, x2.y), relay(fi1.z, fi2.z, x1.z, x2.z) };
-  const V3 F1 = a.charge * (xr - x1);
-  const V3 F2 = a.charge * (x2 - xr);
-  const V3 W1 = 0.5f * (x1 + xr) - fi1;
-  const V3 W2 = 0.5f * (x2 + xr) - fi2;
-  const size_t n1 = (size_t(__float2uint_rz(fi1.x)) * a.g.Hx[1] + __float2uint_rz(fi1.y)) * a.g.Hx[2] + __float2uint_rz(fi1.z);
-  const size_t n2 = (size_t(__float2uint_rz(fi2.x)) * a.g.Hx[1] + __float2uint_rz(fi2.y)) * a.g.Hx[2] + __float2uint_rz(fi2.z);
-  const float one = 1.0f;
-#define EDGES(F, W, ex, ey, ez)                                                                                \
-  const float4 ex = make_float4(F.x * (one - W.y) * (one - W.z), F.x * W.y * (one - W.z), F.x * (one - W.y) * W.z, F.x * W.y * W.z); \
-  const float4 ey = make_float4(F.y * (one - W.x) * (one - W.z), F.y * W.x * (one - W.z), F.y * (one - W.x) * W.z, F.y * W.x * W.z); \
-  const float4 ez = make_float4(F.z * (one - W.x) * (one - W.y), F.z * W.x * (one - W.y), F.z * (one - W.x) * W.y, F.z * W.x * W.y);
-  EDGES(F1, W1, ax, ay, az)
-  EDGES(F2, W2, bx, by, bz)
-#undef EDGES
-  if (n1 == n2) {
-    atomicAdd(&a.Jc[3 * n1 + 0], make_float4(ax.x + bx.x, ax.y + bx.y, ax.z + bx.z, ax.w + bx.w));
-    atomicAdd(&a.Jc[3 * n1 + 1], make_float4(ay.x + by.x, ay.y + by.y, ay.z + by.z, ay.w + by.w));
-    atomicAdd(&a.Jc[3 * n1 + 2], make_float4(az.x + bz.x, az.y + bz.y, az.z + bz.z, az.w + bz.w));
-  } else {
-    atomicAdd(&a.Jc[3 * n1 + 0], ax); atomicAdd(&a.Jc[3 * n1 + 1], ay); atomicAdd(&a.Jc[3 * n1 + 2], az);
-    atomicAdd(&a.Jc[3 * n2 + 0], bx); atomicAdd(&a.Jc[3 * n2 + 1], by); atomicAdd(&a.Jc[3 * n2 + 2], bz);
+  const bool inside = inside_box(nx, ny, nz, mn, mx);
+  publish_masks(alive, inside, n, masks);
+  if (FUSE) {
+    const bool stays = alive && inside;
+    Zigzag z;
+    if (stays) z = zigzag_split(V3{ nx, ny, nz }, vel, a.origo, a.cfl, charge, a.g);
+    deposit_split<(FUSE > 1)>(stays, z, Jc);
   }
 }
 
+// ------------------------------------------------------------ edge gather --
 // Fold the cell-edge records into the nodal current and write ALL of J (this is also
 // the reference's clear_current + `J += generated_J`, pic/tile.c++:371,405):
 //   Jx[i,j,k] = c(i,j,k).x0 + c(i,j-1,k).x1 + c(i,j,k-1).x2 + c(i,j-1,k-1).x3   etc.
@@ -352,14 +415,73 @@ k_gather(const Species src, const Species dst, const unsigned* __restrict__ perm
 }
 
 // -------------------------------------------------------------- migration --
-// standalone leaver detection (when the push was not fused with it)
+// standalone mask pass (containers whose masks are stale: injected / uploaded / appended)
 __global__ void __launch_bounds__(256)
-k_detect_leavers(const Species s, const DetectArgs d) {
+k_make_masks(const Species s, uint2* __restrict__ masks, const float3 mn, const float3 mx) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
   const bool alive = n < s.n && s.id[n] != DEAD;
   float x = 0.f, y = 0.f, z = 0.f;
   if (alive) { x = s.x[n]; y = s.y[n]; z = s.z[n]; }
-  block_detect(alive, x, y, z, n, d);
+  publish_masks(alive, inside_box(x, y, z, mn, mx), n, masks);
+}
+
+struct CollectJob {           // one container
+  const uint2* masks;
+  unsigned nwords;
+  Species s;
+  float3 mn, mx;
+};
+
+// Mask words of all containers -> key list (container << 37) | (subregion << 32) | slot,
+// per-container leaver counts and P = 1 + the largest slot that stays alive
+// (ParticleContainer::append, pic/particle.h:469-488).  One thread per mask word, one
+// list-position atomic per block.  blockIdx.y = container.
+__global__ void __launch_bounds__(256)
+k_collect_leavers(const CollectJob* __restrict__ jobs, const unsigned first_container, unsigned long long* __restrict__ list,
+                  unsigned* __restrict__ list_count, const unsigned list_cap, unsigned* __restrict__ last_alive,
+                  unsigned* __restrict__ cont_count) {
+  const unsigned c = first_container + blockIdx.y;
+  const CollectJob jb = jobs[c];
+  __shared__ unsigned sh_cnt[8], sh_base, sh_last;
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (unsigned w0 = blockIdx.x * blockDim.x; w0 < jb.nwords; w0 += gridDim.x * blockDim.x) {
+    const unsigned w = w0 + threadIdx.x;
+    uint2 m = make_uint2(0u, 0u);
+    if (w < jb.nwords) m = jb.masks[w];
+    const unsigned cnt = __popc(m.x);
+    // exclusive scan of cnt over the block
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= unsigned(o)) incl += t; }
+    unsigned last = m.y ? w * 32u + (32u - __clz(m.y)) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    if (threadIdx.x == 0) sh_last = 0;
+    if (lane == 31) sh_cnt[wid] = incl;
+    __syncthreads();
+    if (lane == 0 && last) atomicMax(&sh_last, last);
+    if (threadIdx.x == 0) {
+      unsigned total = 0;
+      for (int q = 0; q < 8; ++q) { const unsigned v = sh_cnt[q]; sh_cnt[q] = total; total += v; }
+      unsigned base = 0;
+      if (total) { base = atomicAdd(list_count, total); atomicAdd(&cont_count[c], total); }
+      sh_base = base;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && sh_last) atomicMax(&last_alive[c], sh_last);
+    unsigned pos = sh_base + sh_cnt[wid] + incl - cnt;
+    unsigned bits = m.x;
+    while (bits) {
+      const unsigned b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const unsigned n = w * 32u + b;
+      const int sub = subregion_of(jb.s.x[n], jb.s.y[n], jb.s.z[n], jb.mn, jb.mx);
+      if (pos < list_cap)
+        list[pos] = (static_cast<unsigned long long>(c) << 37) | (static_cast<unsigned long long>(sub) << 32) | n;
+      ++pos;
+    }
+    __syncthreads();
+  }
 }
 
 struct OutTile {              // per container: where its leavers go
@@ -402,27 +524,34 @@ struct AppendJob {            // one incoming span (pic/tile_communication.c++:1
   unsigned count;
   unsigned dst_offset;        // P + exclusive scan of span sizes (pic/particle.h:490-509)
   Species dst;
+  float* Jpend;               // != nullptr: the destination tile's pending nodal J (fused push+deposit)
+  float3 origo;
+  float charge;
 };
 
 // ParticleContainer::append (pic/particle.h:511-571): AoS -> SoA after the last
 // alive particle; with `wrap` the global periodic wrap
 // (x<0 ? max : min) + fmodf(x, L) of :534-549.
+// Arrivals of a tile whose stayers were deposited by the fused push add their zigzag current
+// to that tile's pending J here (scalar atomics: arrivals are ~1% of the particles).
 __global__ void __launch_bounds__(256)
-k_append(const AppendJob* __restrict__ jobs, const int wrap, const float3 wmin, const float3 wmax) {
+k_append(const AppendJob* __restrict__ jobs, const int wrap, const float3 wmin, const float3 wmax, const Geom g, const float cfl) {
   const AppendJob jb = jobs[blockIdx.y];
   const float Lx = wmax.x - wmin.x, Ly = wmax.y - wmin.y, Lz = wmax.z - wmin.z;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.count; i += gridDim.x * blockDim.x) {
     const b2p_particle_state st = jb.src[i];
     const unsigned j = jb.dst_offset + i;
+    V3 p = { st.pos[0], st.pos[1], st.pos[2] };
     if (wrap) {
-      jb.dst.x[j] = (st.pos[0] < 0 ? wmax.x : wmin.x) + fmodf(st.pos[0], Lx);
-      jb.dst.y[j] = (st.pos[1] < 0 ? wmax.y : wmin.y) + fmodf(st.pos[1], Ly);
-      jb.dst.z[j] = (st.pos[2] < 0 ? wmax.z : wmin.z) + fmodf(st.pos[2], Lz);
-    } else {
-      jb.dst.x[j] = st.pos[0]; jb.dst.y[j] = st.pos[1]; jb.dst.z[j] = st.pos[2];
+      p.x = (st.pos[0] < 0 ? wmax.x : wmin.x) + fmodf(st.pos[0], Lx);
+      p.y = (st.pos[1] < 0 ? wmax.y : wmin.y) + fmodf(st.pos[1], Ly);
+      p.z = (st.pos[2] < 0 ? wmax.z : wmin.z) + fmodf(st.pos[2], Lz);
     }
+    jb.dst.x[j] = p.x; jb.dst.y[j] = p.y; jb.dst.z[j] = p.z;
     jb.dst.ux[j] = st.vel[0]; jb.dst.uy[j] = st.vel[1]; jb.dst.uz[j] = st.vel[2];
     jb.dst.id[j] = st.id;
+    if (jb.Jpend && st.id != DEAD)
+      deposit_split_nodal(zigzag_split(p, V3{ st.vel[0], st.vel[1], st.vel[2] }, jb.origo, cfl, jb.charge, g), jb.Jpend, g);
   }
 }
 
@@ -517,18 +646,20 @@ void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* n
 }
 
 void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm,
-                 const DetectArgsHost* det) {
+                 uint2* masks, const float mins[3], const float maxs[3], float4* Jc, float charge) {
   ProfScope prof_(KC_PUSH, double(s.n));
   if (!s.n) return;
   PushArgs a{ s, nod, g, make_float3(origo[0], origo[1], origo[2]), cfl, qm };
-  DetectArgs d{};
-  if (det) d = DetectArgs{ make_float3(det->mins[0], det->mins[1], det->mins[2]), make_float3(det->maxs[0], det->maxs[1], det->maxs[2]),
-                           det->container, det->list, det->list_count, det->list_cap, det->last_alive, det->cont_count };
+  const float3 mn = make_float3(mins[0], mins[1], mins[2]), mx = make_float3(maxs[0], maxs[1], maxs[2]);
   const unsigned nb = blocks_for(s.n);
-#define PUSH_CASE(P)                                                                   \
-  case P:                                                                              \
-    if (det) k_push<P, true><<<nb, 256, 0, ctx().stream>>>(a, d);                      \
-    else k_push<P, false><<<nb, 256, 0, ctx().stream>>>(a, d);                         \
+  const int minb = tuning().push_minb;
+  const int fuse = Jc ? (tuning().deposit_agg ? 2 : 1) : 0;
+#define PUSH_LAUNCH(P, M, F) k_push<P, M, F><<<nb, 256, 0, ctx().stream>>>(a, masks, mn, mx, Jc, charge)
+#define PUSH_CASE(P)                                                                                   \
+  case P:                                                                                              \
+    if (fuse == 2) { if (minb >= 6) PUSH_LAUNCH(P, 6, 2); else if (minb >= 5) PUSH_LAUNCH(P, 5, 2); else PUSH_LAUNCH(P, 4, 2); } \
+    else if (fuse == 1) { if (minb >= 6) PUSH_LAUNCH(P, 6, 1); else if (minb >= 5) PUSH_LAUNCH(P, 5, 1); else PUSH_LAUNCH(P, 4, 1); } \
+    else { if (minb >= 8) PUSH_LAUNCH(P, 8, 0); else if (minb >= 6) PUSH_LAUNCH(P, 6, 0); else PUSH_LAUNCH(P, 5, 0); } \
     break;
   switch (pusher) {
     PUSH_CASE(B2P_PUSHER_BORIS)
@@ -537,6 +668,7 @@ void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g,
     default: throw Error(B2P_ERR_LOGIC, "pic::Tile::push_particles: unkown particle pusher");
   }
 #undef PUSH_CASE
+#undef PUSH_LAUNCH
   B2P_LAUNCH_CHECK();
 }
 
@@ -544,7 +676,17 @@ void launch_deposit(const Species& s, float4* Jc, const Geom& g, const float ori
   ProfScope prof_(KC_DEPOSIT, double(s.n));
   if (!s.n) return;
   DepositArgs a{ s, Jc, g, make_float3(origo[0], origo[1], origo[2]), cfl, charge };
-  k_deposit_zigzag<<<blocks_for(s.n), 256, 0, ctx().stream>>>(a);
+  const unsigned nb = blocks_for(s.n);
+  const int minb = tuning().deposit_minb, agg = tuning().deposit_agg;
+  if (agg) {
+    if (minb >= 8) k_deposit_zigzag<1, 8><<<nb, 256, 0, ctx().stream>>>(a);
+    else if (minb >= 6) k_deposit_zigzag<1, 6><<<nb, 256, 0, ctx().stream>>>(a);
+    else k_deposit_zigzag<1, 4><<<nb, 256, 0, ctx().stream>>>(a);
+  } else {
+    if (minb >= 8) k_deposit_zigzag<0, 8><<<nb, 256, 0, ctx().stream>>>(a);
+    else if (minb >= 6) k_deposit_zigzag<0, 6><<<nb, 256, 0, ctx().stream>>>(a);
+    else k_deposit_zigzag<0, 4><<<nb, 256, 0, ctx().stream>>>(a);
+  }
   B2P_LAUNCH_CHECK();
 }
 
@@ -598,13 +740,25 @@ void launch_gather(const Species& src, const Species& dst, const unsigned* perm)
   B2P_LAUNCH_CHECK();
 }
 
-void launch_detect_leavers(const Species& s, const DetectArgsHost& det) {
+void launch_make_masks(const Species& s, uint2* masks, const float mins[3], const float maxs[3]) {
   ProfScope prof_(KC_DETECT, double(s.n));
   if (!s.n) return;
-  const DetectArgs d{ make_float3(det.mins[0], det.mins[1], det.mins[2]), make_float3(det.maxs[0], det.maxs[1], det.maxs[2]),
-                      det.container, det.list, det.list_count, det.list_cap, det.last_alive, det.cont_count };
-  k_detect_leavers<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, d);
+  k_make_masks<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, masks, make_float3(mins[0], mins[1], mins[2]),
+                                                         make_float3(maxs[0], maxs[1], maxs[2]));
   B2P_LAUNCH_CHECK();
+}
+
+void launch_collect_leavers(const void* jobs, unsigned ncont, unsigned max_words, unsigned long long* list, unsigned* list_count,
+                            unsigned list_cap, unsigned* last_alive, unsigned* cont_count) {
+  ProfScope prof_(KC_DETECT, double(max_words) * 32.0 * ncont);
+  if (!ncont || !max_words) return;
+  const unsigned bx = std::min(blocks_for(max_words), 2048u);
+  for (unsigned c0 = 0; c0 < ncont; c0 += 65535u) {
+    const unsigned nc = std::min(65535u, ncont - c0);
+    k_collect_leavers<<<dim3(bx, nc), 256, 0, ctx().stream>>>(static_cast<const CollectJob*>(jobs), c0, list, list_count, list_cap,
+                                                              last_alive, cont_count);
+    B2P_LAUNCH_CHECK();
+  }
 }
 
 void launch_gather_outgoing(const unsigned long long* sorted, unsigned total, const void* out_tiles, unsigned* counts) {
@@ -621,12 +775,14 @@ void launch_last_alive(const unsigned long long* id, unsigned n, unsigned* last_
   B2P_LAUNCH_CHECK();
 }
 
-void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, const float wmin[3], const float wmax[3]) {
+void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, const float wmin[3], const float wmax[3],
+                   const Geom& g, float cfl) {
   ProfScope prof_(KC_APPEND, double(max_count));
   if (!njobs || !max_count) return;
   const unsigned bx = std::min(blocks_for(max_count), 1024u);
   k_append<<<dim3(bx, njobs), 256, 0, ctx().stream>>>(static_cast<const AppendJob*>(jobs), wrap ? 1 : 0,
-                                                      make_float3(wmin[0], wmin[1], wmin[2]), make_float3(wmax[0], wmax[1], wmax[2]));
+                                                      make_float3(wmin[0], wmin[1], wmin[2]), make_float3(wmax[0], wmax[1], wmax[2]),
+                                                      g, cfl);
   B2P_LAUNCH_CHECK();
 }
 

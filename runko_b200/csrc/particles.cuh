@@ -14,22 +14,24 @@ struct AppendJobHost {        // mirrors particles.cu::AppendJob
   unsigned count;
   unsigned dst_offset;
   Species dst;
+  float* Jpend;               // destination tile's pending nodal J, or nullptr
+  float3 origo;
+  float charge;
 };
 
-struct DetectArgsHost {       // leaver-detection targets of one container
-  float mins[3], maxs[3];     // tile box (float(mins/maxs), pic/tile_communication.c++:71-79)
-  unsigned container;
-  unsigned long long* list;
-  unsigned* list_count;
-  unsigned list_cap;
-  unsigned* last_alive;
-  unsigned* cont_count;
+struct CollectJobHost {       // mirrors particles.cu::CollectJob: leaver masks of one container
+  const uint2* masks;
+  unsigned nwords;
+  Species s;
+  float3 mn, mx;              // tile box (float(mins/maxs), pic/tile_communication.c++:71-79)
 };
 
 void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* nod);
-// det != nullptr fuses the leaver detection of pack_outgoing_particles into the push
+// the push also publishes the leaver / stayer ballots of every warp (masks: one uint2 per 32 slots,
+// rounded up to whole blocks of 256 slots) for pack_outgoing_particles
 void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm,
-                 const DetectArgsHost* det);
+                 uint2* masks, const float mins[3], const float maxs[3], float4* Jc, float charge);
+// Jc != nullptr: fused push + deposit of the particles that stay inside the tile box
 void launch_deposit(const Species& s, float4* Jc, const Geom& g, const float origo[3], float cfl, float charge);
 void launch_edge_gather(const float4* Jc, float* J, const Geom& g);
 void launch_sort_keys(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* idx, unsigned dead_key);
@@ -38,10 +40,13 @@ int sort_pairs(void* temp, size_t temp_bytes, unsigned* keys[2], unsigned* vals[
 size_t sort_keys64_temp_bytes(unsigned n, int end_bit);
 int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit);
 void launch_gather(const Species& src, const Species& dst, const unsigned* perm);
-void launch_detect_leavers(const Species& s, const DetectArgsHost& det);
+void launch_make_masks(const Species& s, uint2* masks, const float mins[3], const float maxs[3]);
+void launch_collect_leavers(const void* jobs, unsigned ncont, unsigned max_words, unsigned long long* list, unsigned* list_count,
+                            unsigned list_cap, unsigned* last_alive, unsigned* cont_count);
 void launch_gather_outgoing(const unsigned long long* sorted, unsigned total, const void* out_tiles, unsigned* counts);
 void launch_last_alive(const unsigned long long* id, unsigned n, unsigned* last_alive);
-void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, const float wmin[3], const float wmax[3]);
+void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, const float wmin[3], const float wmax[3],
+                   const Geom& g, float cfl);
 void launch_fill_dead(unsigned long long* id, unsigned begin, unsigned end);
 void launch_kinetic_energy(const Species& s, double* out);
 void launch_inject_thermal(const Species& s, const Geom& g, const float mins[3], unsigned ppc, float theta,

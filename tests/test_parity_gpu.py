@@ -377,3 +377,35 @@ def test_multigpu_parity_two_ranks():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "run_multigpu_parity.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("fuse", [1, 0])
+@pytest.mark.parametrize("sequence", ["push-pack-comm-sort-deposit", "push-deposit", "push-pack-deposit", "push-push-pack-comm-deposit"])
+def test_deposit_after_push_matches_reference_per_tile(fuse, sequence):
+    """The fused push+deposit (stayers deposited in the push, arrivals on append) must give every
+    tile the J the reference's deposit_current gives it — including halo contributions — and fall
+    back to a fresh deposit whenever the leavers of that push were not removed."""
+    from runko_b200._lib import check
+    check(rb.lib().b2p_set_option(b"fuse_deposit", fuse))
+    try:
+        rng = np.random.default_rng(21)
+        conf = pic_conf(n_tiles=(2, 2, 2), n_cells=(5, 6, 7), q0=-0.7, q1=0.4)
+        org, grid, tiles = build_grids(conf, rng, ppc=6, u_scale=2.0)
+        for step in sequence.split("-"):
+            if step == "comm":
+                org.local_communication(rb.comm_mode.pic_particle.value)
+                grid.local_communication(rb.comm_mode.pic_particle)
+            else:
+                name = {"push": "push_particles", "pack": "pack_outgoing_particles", "sort": "sort_particles",
+                        "deposit": "deposit_current"}[step]
+                org.phase(name)
+                grid.phase(name)
+        for (i, j, k), tile in tiles.items():
+            oJ = org.get_fields(org.cid(i, j, k), with_halo=True)[2]
+            gJ = tile.get_fields_f32(with_halo=True)[2]
+            assert np.max(np.abs(oJ)) > 0
+            assert np.max(np.abs(gJ - oJ)) <= 1e-5 * np.max(np.abs(oJ)), (sequence, (i, j, k))
+            if "comm" in sequence:
+                compare_particles(org, tile, t=org.cid(i, j, k))
+    finally:
+        check(rb.lib().b2p_set_option(b"fuse_deposit", 1))

@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log )
+tail -n 5 gpurun_out/pytest_gpu.log
+( B2P_OPTS="deposit_agg=0,push_minb=8,deposit_minb=8" timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -x -q > gpurun_out/pytest_gpu_b.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_b.log )
+tail -n 3 gpurun_out/pytest_gpu_b.log
+timeout 900 python tools/microbench.py --cells 128 --out gpurun_out/micro4.json \
+  "push_minb=5,deposit_minb=4,deposit_agg=0" "push_minb=6" "push_minb=8" "push_minb=5,deposit_minb=6" "deposit_minb=8" \
+  "deposit_minb=4,deposit_agg=1" "deposit_minb=6,deposit_agg=1" "deposit_minb=8,deposit_agg=1" 2>&1 | tee gpurun_out/micro4.log
