@@ -9,7 +9,8 @@ push, pack+migrate, sort every 5th lap, deposit, J exchange + halo, 3 binomial
 filter passes, push_half_b, push_e + add_current, E halo) over a synthetic
 uniform thermal pair plasma (BASELINE.json configs[4], "projects/scaling"):
 2 species x 16 ppc, theta = 0.3, uniform Bz, tiles of 64^3 cells, a cube of
---cells^3 cells per GPU, GPUs arranged 1 / 2x1x1 / 2x2x1 / 2x2x2 (weak scaling).
+--cells^3 cells per GPU (default 512^3 = 4.29e9 particles = 137 GB per GPU, the size the
+metric is quoted on), GPUs arranged 1 / 2x1x1 / 2x2x1 / 2x2x2 (weak scaling).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -111,39 +112,75 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- reference / CPU arm
-def cpu_reference(args, n_threads, seconds_target=20.0):
-    """The reference's CPU algorithm (oracle port, oracle/pic_oracle.cpp) on the host cores: one
-    worker per core, one tile at a time per worker (the reference's rank-per-core model)."""
-    from oracle.oracle import OracleGrid
-    # bounded sample of the same workload: same physics / ppc / tile-local work, fewer & smaller tiles
-    edge = 32
-    nt = max(1, n_threads)
-    tz = 1
-    while tz * tz * tz < nt:
-        tz += 1
-    tiles = (tz, tz, max(1, -(-nt // (tz * tz))))
-    conf, _, _ = make_conf(argparse.Namespace(cells=edge, tile=edge, ppc=args.ppc), 1)
-    conf.n_tiles = list(tiles)
-    g = OracleGrid(conf)
-    rng = np.random.default_rng(42)
-    ncell = edge ** 3
-    bz = binit(conf, args.ppc)
-    B = np.zeros((3, edge + 6, edge + 6, edge + 6), np.float32)
-    B[2] = bz
-    n_part = 0
-    for t in range(g.num_tiles):
-        i, j, k = t % tiles[0], (t // tiles[0]) % tiles[1], t // (tiles[0] * tiles[1])
-        g.set_fields(t, B=B, with_halo=True)
+class CpuArm:
+    """The reference's CPU implementation of the lap on the host cores, one tile per worker at a time
+    (the reference's rank-per-core model: serial inside a tile, `OMP_NUM_THREADS=1`).
+
+    kind "reference": the reference's OWN kernel sources (emf::YeeLattice, pic::ParticleContainer)
+    compiled from /root/reference into oracle/_ref/libref_kernels.so (-O3 -mavx2 -fopenmp-simd), driven
+    tile by tile in corgi's order.  kind "port": the oracle restatement, when that build is absent."""
+
+    def __init__(self, args, n_threads):
+        from oracle import reference_build as rbuild
+        edge = 32
+        nt = max(1, n_threads)
+        tz = 1
+        while tz * tz * tz < nt:
+            tz += 1
+        self.tiles = (tz, tz, max(1, -(-nt // (tz * tz))))
+        self.edge, self.n_threads = edge, nt
+        conf, _, _ = make_conf(argparse.Namespace(cells=edge, tile=edge, ppc=args.ppc), 1)
+        conf.n_tiles = list(self.tiles)
+        use_ref = rbuild.available() and rbuild.cpu_ok()
+        self.kind = "reference" if use_ref else "port"
+        rng = np.random.default_rng(42)
+        ncell = edge ** 3
+        B = np.zeros((3, edge + 6, edge + 6, edge + 6), np.float32)
+        B[2] = binit(conf, args.ppc)
+        self.n_part = 0
+        if use_ref:
+            from concurrent.futures import ThreadPoolExecutor
+            self.g = rbuild.RefGrid(conf)
+            pool = ThreadPoolExecutor(nt)
+            tiles = list(self.g.tiles.values())
+            self.g.phase = lambda name: list(pool.map(lambda t: t.op(name), tiles))    # ctypes releases the GIL
+            items = [(idx, t) for idx, t in self.g.tiles.items()]
+        else:
+            from oracle.oracle import OracleGrid
+            self.g = OracleGrid(conf)
+            T = self.tiles
+            items = [((t % T[0], (t // T[0]) % T[1], t // (T[0] * T[1])), t) for t in range(self.g.num_tiles)]
         ii, jj, kk = np.meshgrid(np.arange(edge), np.arange(edge), np.arange(edge), indexing="ij")
-        corner = np.stack([ii.ravel() + i * edge, jj.ravel() + j * edge, kk.ravel() + k * edge]).astype(np.float64)
-        for _ in range(args.ppc):
-            pos = corner + rng.random((3, ncell))
+        for (i, j, k), t in items:
+            corner = np.stack([ii.ravel() + i * edge, jj.ravel() + j * edge, kk.ravel() + k * edge]).astype(np.float64)
+            pos = np.concatenate([corner + rng.random((3, ncell)) for _ in range(args.ppc)], axis=1)
+            n = pos.shape[1]
             for sp in range(2):
-                vel = 0.55 * rng.standard_normal((3, ncell))   # ~ theta=0.3 thermal spread
-                g.inject(t, sp, *pos, *vel)
-                n_part += ncell
-    g.step_pic(0, threads=n_threads)   # warm-up lap (includes the lap-0 sort)
-    return g, n_part, tiles, edge
+                vel = 0.55 * rng.standard_normal((3, n))       # ~ theta = 0.3 thermal spread
+                if use_ref:
+                    ids = (np.uint64(sp + 1) << np.uint64(40)) + np.arange(n, dtype=np.uint64)
+                    t.set_particles(sp, *pos.astype(np.float32), *vel.astype(np.float32), ids)
+                else:
+                    self.g.inject(t, sp, *pos, *vel)
+                self.n_part += n
+            if use_ref:
+                t.set_fields(B=B)
+            else:
+                self.g.set_fields(t, B=B, with_halo=True)
+        self.lap = 0
+        self.step()                                            # warm-up lap (includes the lap-0 sort)
+
+    def step(self):
+        if self.kind == "reference":
+            self.g.step_pic(self.lap)
+        else:
+            self.g.step_pic(self.lap, threads=self.n_threads)
+        self.lap += 1
+
+    def sample(self, laps):
+        t = self.tiles
+        return (f"{t[0]}x{t[1]}x{t[2]} tiles of {self.edge}^3 cells, 2 species x 16 ppc = {self.n_part} particles per lap, "
+                f"{laps} laps, one tile per worker")
 
 
 def run_reference(args):
@@ -151,22 +188,21 @@ def run_reference(args):
     if rank != 0:
         return
     n_threads = os.cpu_count() or 1
-    g, n_part, tiles, edge = cpu_reference(args, n_threads)
-    for w in range(args.warmup):
-        g.step_pic(1 + w, threads=n_threads)
+    arm = CpuArm(args, n_threads)
+    for _ in range(args.warmup):
+        arm.step()
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        g.step_pic(1 + args.warmup + s, threads=n_threads)
+    for _ in range(args.steps):
+        arm.step()
     dt = (time.perf_counter() - t0) / args.steps
-    value = n_part / dt
-    conf, tpg, gb = make_conf(args, args.gpus)
-    sample = f"{tiles[0]}x{tiles[1]}x{tiles[2]} tiles of {edge}^3 cells, 2 species x {args.ppc} ppc = {n_part} particles per step"
+    value = arm.n_part / dt
     out = {
         "impl": "reference", "metric": "particle-pushes/s per full PIC step", "value": value, "unit": "particle-pushes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "particle-pushes/s", "cores": n_threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "particle-pushes/s", "cores": n_threads, "kind": arm.kind,
+                         "sample": arm.sample(args.steps)},
         "e2e": {"value": value, "unit": "particle-pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
@@ -178,7 +214,7 @@ def workload_config(args, n_gpus):
             "cells_per_gpu": f"{args.cells}^3", "tile": f"{args.tile}^3", "species": 2, "ppc_per_species": args.ppc,
             "particles_per_gpu": 2 * args.ppc * args.cells ** 3, "gpu_blocks": "x".join(map(str, gb)),
             "lap": "pic-turbulence/pic.py:187-221, sort every 5th lap, fdtd2 + boris + linear_1st + zigzag_1st_atomic + 3x binomial2",
-            "l2": "per-step working set (>= 17 GB) far exceeds the 126 MB L2; no explicit flush"}
+            "l2": "per-step working set (32 B x particles >= 17 GB) far exceeds the 126 MB L2; no explicit flush"}
 
 
 # --------------------------------------------------------------------------- CUDA arm
@@ -188,7 +224,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cells", type=int, default=256, help="cube edge of cells per GPU")
+    ap.add_argument("--cells", type=int, default=512, help="cube edge of cells per GPU")
     ap.add_argument("--tile", type=int, default=64)
     ap.add_argument("--ppc", type=int, default=16, help="particles per cell per species")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -298,7 +334,8 @@ def main():
 
     # ---- roofline of the dominant kernel class (largest share of the timed region) ----
     peak, peak_src = read_peaks()
-    bytes_per_unit = {"push": BYTES_PER_PARTICLE_PUSH, "deposit": BYTES_PER_PARTICLE_DEPOSIT, "gather": 64.0,
+    fused = pl[names.index("deposit")] == 0      # push + deposit fused: credited with both phases' algorithmic bytes
+    bytes_per_unit = {"push": BYTES_PER_PARTICLE_STEP if fused else BYTES_PER_PARTICLE_PUSH, "deposit": BYTES_PER_PARTICLE_DEPOSIT, "gather": 64.0,
                       "detect_leavers": 20.0, "sort_keys": 28.0, "radix_sort": 64.0, "filter": 24.0, "push_b": 36.0,
                       "push_e": 48.0, "zero": 4.0, "halo_fill": 0.0, "J_exchange": 0.0, "nodal_means": 56.0}
     top = int(np.argmax(pms))
@@ -307,7 +344,8 @@ def main():
     units_per_launch = pu[top] / max(int(pl[top]), 1)
     achieved = bytes_per_unit.get(names[top], 0.0) * units_per_launch / (avg_ms * 1e-3) / 1e9
     step_bytes = (BYTES_PER_PARTICLE_STEP + BYTES_PER_PARTICLE_SORT) * n_part_local + BYTES_PER_CELL_STEP * n_cells_local
-    roofline = {"bound": "hbm", "kernel": names[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kname = "push+deposit (fused k_push)" if (fused and names[top] == "push") else names[top]
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": avg_ms, "launches": int(pl[top]), "bytes_per_unit": bytes_per_unit.get(names[top], 0.0),
                 "units_per_launch": units_per_launch, "share_of_step": share,
@@ -327,15 +365,14 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_threads = os.cpu_count() or 1
-        g, n_part, tl, edge = cpu_reference(args, n_threads)
+        arm = CpuArm(args, n_threads)
         c0 = time.perf_counter()
         nl = 0
-        while nl < 5 or (time.perf_counter() - c0 < 10.0 and nl < 50):
-            g.step_pic(1 + nl, threads=n_threads)
+        while nl < 3 or (time.perf_counter() - c0 < 12.0 and nl < 50):
+            arm.step()
             nl += 1
         cdt = (time.perf_counter() - c0) / nl
-        cpu = {"value": n_part / cdt, "unit": "particle-pushes/s", "cores": n_threads, "kind": "port",
-               "sample": f"{tl[0]}x{tl[1]}x{tl[2]} tiles of {edge}^3 cells, 2 species x {args.ppc} ppc = {n_part} particles, {nl} laps"}
+        cpu = {"value": arm.n_part / cdt, "unit": "particle-pushes/s", "cores": n_threads, "kind": arm.kind, "sample": arm.sample(nl)}
 
     if rank == 0:
         out = {"metric": "particle-pushes/s per full PIC step", "value": value, "unit": "particle-pushes/s", "n_gpus": world,
@@ -391,6 +428,12 @@ def run_e2e(args, rb, L, conf, grid, tiles, world, dist):
         return grid.energies()                                   # io_average_* (D2H)
 
     steps = max(2, min(args.steps, 5))
+    # page-locked host buffers for the particle round trip (registered once, outside the timed region)
+    cap = max(t.container_size(sp) for t in tiles[:steps] for sp in range(2)) + (1 << 20)
+    host = [[np.empty(cap, np.float32) for _ in range(6)] + [np.empty(cap, np.uint64)] for _ in range(2)]
+    for sp in range(2):
+        for a in host[sp]:
+            check(L.b2p_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes))
     h0, d0 = C.c_uint64(), C.c_uint64()
     rb.sync()
     if dist is not None:
@@ -400,7 +443,7 @@ def run_e2e(args, rb, L, conf, grid, tiles, world, dist):
     lap = 1000   # keeps lap % 5 phase: laps 1000..: sort on the first
     for s in range(steps):
         t = tiles[s % len(tiles)]
-        state = [t.get_particles(sp, alive_only=False) for sp in range(2)]      # D2H of one tile
+        state = [t.get_particles(sp, alive_only=False, out=host[sp]) for sp in range(2)]   # D2H of one tile
         for sp in range(2):
             t.set_particles_raw(sp, *state[sp])                                   # H2D of one tile
         lap_via_tile_api(lap + s)
@@ -410,6 +453,9 @@ def run_e2e(args, rb, L, conf, grid, tiles, world, dist):
     dt = time.perf_counter() - t0
     h1, d1 = C.c_uint64(), C.c_uint64()
     L.b2p_copy_bytes(C.byref(h1), C.byref(d1))
+    for sp in range(2):
+        for a in host[sp]:
+            L.b2p_host_unregister(a.ctypes.data_as(C.c_void_p))
     if dist is not None:
         import torch
         tt = torch.tensor([dt], dtype=torch.float64)
@@ -418,8 +464,9 @@ def run_e2e(args, rb, L, conf, grid, tiles, world, dist):
     n_part = 2 * args.ppc * args.cells ** 3 * world
     return {"value": n_part / (dt / steps), "unit": "particle-pushes/s", "steps": steps,
             "h2d_bytes_per_step": int((h1.value - h0.value) / steps), "d2h_bytes_per_step": int((d1.value - d0.value) / steps),
-            "how": "lap driven tile-by-tile through the PicTile API (as runko/simulation.py does), plus per step one tile's "
-                   "particle state host round trip (get_particles -> set_particles) and the energy diagnostics read-back; wall clock"}
+            "how": "lap driven tile-by-tile through the PicTile API (as runko/simulation.py does); every step one tile's whole "
+                   "particle state makes a host round trip through page-locked buffers (get_particles -> set_particles) and the "
+                   "energy diagnostics are read back; wall clock, max over ranks"}
 
 
 if __name__ == "__main__":

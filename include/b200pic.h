@@ -95,6 +95,10 @@ int b2p_sync(void);
  * Tuning).  Never changes results beyond the stated deposit tolerance.  Also read from the
  * environment: B2P_OPTS="name=value,...".  No reference equivalent. */
 int b2p_set_option(const char* name, int value);
+/* Page-lock / unlock a caller-owned host buffer (cudaHostRegister) so that the getters and
+ * setters below move it at full PCIe speed.  Optional; no reference equivalent. */
+int b2p_host_register(void* ptr, size_t bytes);
+int b2p_host_unregister(void* ptr);
 /* tools._get_gpu_mem_kB (src/runko/tools/gpu_memory.h:16-28) */
 int64_t b2p_gpu_mem_kB(void);
 

@@ -19,7 +19,16 @@ REF = "/root/reference"
 
 
 def available():
-    return os.path.exists(SO)
+    return os.path.exists(SO) and cpu_ok()
+
+
+def cpu_ok():
+    """libref_kernels.so is compiled with -mavx2 (oracle/Makefile.ref)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " avx2 " in f.read().replace("\n", " ")
+    except OSError:
+        return False
 
 
 def build():

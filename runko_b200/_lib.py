@@ -13,7 +13,7 @@ SO_PATH = os.path.join(_HERE, "libb200pic.so")
 
 # every symbol include/b200pic.h declares (checked by tests/test_abi.py)
 SYMBOLS = """
-b2p_last_error b2p_version b2p_init b2p_sync b2p_set_option b2p_gpu_mem_kB
+b2p_last_error b2p_version b2p_init b2p_sync b2p_set_option b2p_host_register b2p_host_unregister b2p_gpu_mem_kB
 b2p_tile_create b2p_tile_destroy b2p_tile_bounds
 b2p_tile_set_fields b2p_tile_get_fields b2p_tile_push_half_b b2p_tile_push_e b2p_tile_add_current
 b2p_tile_filter_current b2p_tile_clear_current b2p_tile_field_energy
@@ -57,6 +57,8 @@ def lib():
     L.b2p_launch_count.restype = C.c_uint64
     L.b2p_init.argtypes = [ci]
     L.b2p_set_option.argtypes = [C.c_char_p, ci]
+    L.b2p_host_register.argtypes = [vp, C.c_size_t]
+    L.b2p_host_unregister.argtypes = [vp]
     L.b2p_tile_create.argtypes = [C.POINTER(B2PConfig), C.POINTER(C.c_int32 * 3), C.POINTER(vp)]
     L.b2p_tile_destroy.argtypes = [vp]
     L.b2p_tile_destroy.restype = None

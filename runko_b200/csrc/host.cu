@@ -657,6 +657,13 @@ int b2p_set_option(const char* name, int value) {
   if (!name || !b2p::set_option(name, value)) throw Error(B2P_ERR_RUNTIME, std::string("unknown option: ") + (name ? name : "(null)"));
   B2P_CATCH
 }
+int b2p_host_register(void* ptr, size_t bytes) {
+  B2P_TRY
+  ctx();
+  B2P_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  B2P_CATCH
+}
+int b2p_host_unregister(void* ptr) { B2P_TRY B2P_CUDA(cudaHostUnregister(ptr)); B2P_CATCH }
 int64_t b2p_gpu_mem_kB(void) {
   size_t fr = 0, tot = 0;
   if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return -1;
@@ -806,16 +813,23 @@ int b2p_tile_get_particles(b2p_tile* t, int sp, int alive_only, float* x, float*
   B2P_TRY
   Container& c = C(t, sp);
   const size_t n = c.n;
-  std::vector<unsigned long long> hid(n);
-  d2h(hid.data(), c.id.p, n);
   float* dst[6] = { x, y, z, ux, uy, uz };
   const float* src[6] = { c.x.p, c.y.p, c.z.p, c.ux.p, c.uy.p, c.uz.p };
+  if (!alive_only) {                                                              // raw container: straight copies
+    for (int a = 0; a < 6; ++a) if (dst[a]) d2h(dst[a], src[a], n);
+    if (id) d2h(reinterpret_cast<unsigned long long*>(id), c.id.p, n);
+    sync();
+    if (n_out) *n_out = n;
+    return B2P_OK;
+  }
+  std::vector<unsigned long long> hid(n);
+  d2h(hid.data(), c.id.p, n);
   std::vector<float> tmp[6];
   for (int a = 0; a < 6; ++a) if (dst[a]) { tmp[a].resize(n); d2h(tmp[a].data(), src[a], n); }
   sync();
   uint64_t m = 0;
   for (size_t i = 0; i < n; ++i) {                                               // pic/particle.c++:82-168
-    if (alive_only && hid[i] == DEAD) continue;
+    if (hid[i] == DEAD) continue;
     for (int a = 0; a < 6; ++a) if (dst[a]) dst[a][m] = tmp[a][i];
     if (id) id[m] = hid[i];
     ++m;

@@ -303,12 +303,19 @@ class PicTile(PicTileHost, Tile):
         check(lib().b2p_tile_container_size(self._h, int(sp), C.byref(n)))
         return n.value
 
-    def get_particles(self, sp, alive_only=True):
+    def get_particles(self, sp, alive_only=True, out=None):
+        """Seven arrays x,y,z,ux,uy,uz,id.  `out` (raw container only): caller-owned arrays of at least
+        container_size entries — e.g. page-locked with lib().b2p_host_register — filled in place."""
         n = self.container_size(sp)
-        a = [np.empty(n, np.float32) for _ in range(6)]
-        ids = np.empty(n, np.uint64)
+        if out is not None:
+            a, ids = list(out[:6]), out[6]
+        else:
+            a = [np.empty(n, np.float32) for _ in range(6)]
+            ids = np.empty(n, np.uint64)
         m = C.c_uint64()
         check(lib().b2p_tile_get_particles(self._h, int(sp), int(alive_only), *[_ptr(v) for v in a], _ptr(ids), C.byref(m)))
+        if out is not None:
+            return tuple(v[:m.value] for v in a) + (ids[:m.value],)
         return tuple(np.array(v[:m.value]) for v in a) + (np.array(ids[:m.value]),)
 
     def _backend_inject(self, sp, a):
