@@ -129,57 +129,79 @@ k_push_b_stencil(const FieldPtrs* __restrict__ tiles, const Geom g, const float 
 // filters in place, :139-156).
 struct FilterTile { const float* src; float* dst; };
 
+// One thread per (j,k) column marching along i with the three contributing planes kept in
+// registers (27 values, or three separable partial sums): 9 loads per output instead of 27,
+// every load coalesced along k.  grid = ((Hy*Hz)/256, i chunks, tiles*3 components).
 template <bool UNROLLED>
 __global__ void __launch_bounds__(256)
-k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g) {
-  const int jblocks = (g.Hx[1] + int(blockDim.y) - 1) / int(blockDim.y);
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int rem = blockIdx.y / jblocks;            // plane index: component * Hx + i
-  const int j = (blockIdx.y - rem * jblocks) * blockDim.y + threadIdx.y;
-  const int tile = blockIdx.z;
-  const int c = rem / g.Hx[0];
-  const int i = rem - c * g.Hx[0];
-  if (k >= g.Hx[2] || j >= g.Hx[1]) return;
-  const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2];
-  const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
+k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g, const int chunk) {
+  const int HyHz = g.Hx[1] * g.Hx[2];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= HyHz) return;
+  const int j = q / g.Hx[2], k = q - j * g.Hx[2];
+  const int tile = blockIdx.z / 3, c = blockIdx.z - 3 * tile;
+  const int ibeg = blockIdx.y * chunk, iend = min(ibeg + chunk, g.Hx[0]);
   const float* __restrict__ J = tiles[tile].src + size_t(c) * g.Ch;
   float* __restrict__ out = tiles[tile].dst + size_t(c) * g.Ch;
-  const bool edge = (i == 0) | (j == 0) | (k == 0) | (i == g.Hx[0] - 1) | (j == g.Hx[1] - 1) | (k == g.Hx[2] - 1);
-  if (edge) { out[n] = UNROLLED ? J[n] : 0.0f; return; }
+  const int Hz = g.Hx[2];
+  if (j == 0 || j == g.Hx[1] - 1 || k == 0 || k == Hz - 1) {      // outermost layer: 0 / unchanged
+    for (int i = ibeg; i < iend; ++i) { const size_t n = size_t(i) * HyHz + q; out[n] = UNROLLED ? J[n] : 0.0f; }
+    return;
+  }
+  int i = ibeg;
+  if (i == 0) { out[q] = UNROLLED ? J[q] : 0.0f; i = 1; }
   if (UNROLLED) {
-    // separable z, y, x passes (..._binomial2.c++:118-156) evaluated on the fly;
-    // same products and the same left-associated 3-term sums per pass.
-    float t2[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
+    // separable z, y, x passes (..._binomial2.c++:118-156): t2(plane) = y-pass of the z-pass;
+    // same products and the same left-associated 3-term sums per pass
+    auto t2_of = [&](const int ii) {
+      const float* p = J + size_t(ii) * HyHz + q;
       float t1[3];
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
-        const float* p = J + n + (a - 1) * long(si) + (b - 1) * long(sj);
-        t1[b] = 0.25f * p[-1] + 0.5f * p[0] + 0.25f * p[1];
+        const float* r = p + (b - 1) * Hz;
+        t1[b] = 0.25f * r[-1] + 0.5f * r[0] + 0.25f * r[1];
       }
-      t2[a] = 0.25f * t1[0] + 0.5f * t1[1] + 0.25f * t1[2];
+      return 0.25f * t1[0] + 0.5f * t1[1] + 0.25f * t1[2];
+    };
+    float a0 = t2_of(i - 1), a1 = t2_of(i);
+    for (; i < iend; ++i) {
+      const size_t n = size_t(i) * HyHz + q;
+      if (i == g.Hx[0] - 1) { out[n] = J[n]; break; }
+      const float a2 = t2_of(i + 1);
+      out[n] = 0.25f * a0 + 0.5f * a1 + 0.25f * a2;
+      a0 = a1; a1 = a2;
     }
-    out[n] = 0.25f * t2[0] + 0.5f * t2[1] + 0.25f * t2[2];
   } else {
     // 27-point sum accumulated from 0 in index_space order, a slowest (:58-73)
-    float acc = 0.0f;
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
+    float P[3][9];
+    auto load = [&](float (&dst)[9], const int ii) {
+      const float* p = J + size_t(ii) * HyHz + q;
 #pragma unroll
       for (int b = 0; b < 3; ++b)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float w = ((a == 1) ? 2.f : 1.f) * ((b == 1) ? 2.f : 1.f) * ((d == 1) ? 2.f : 1.f) / 64.f;
-          acc = acc + w * J[n + (a - 1) * long(si) + (b - 1) * long(sj) + (d - 1)];
-        }
-    out[n] = acc;
+        for (int d = 0; d < 3; ++d) dst[b * 3 + d] = p[(b - 1) * Hz + (d - 1)];
+    };
+    load(P[0], i - 1);
+    load(P[1], i);
+    for (; i < iend; ++i) {
+      const size_t n = size_t(i) * HyHz + q;
+      if (i == g.Hx[0] - 1) { out[n] = 0.0f; break; }
+      load(P[2], i + 1);
+      float acc = 0.0f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const float w = ((a == 1) ? 2.f : 1.f) * ((b == 1) ? 2.f : 1.f) * ((d == 1) ? 2.f : 1.f) / 64.f;
+            acc = acc + w * P[a][b * 3 + d];
+          }
+      out[n] = acc;
+#pragma unroll
+      for (int m = 0; m < 9; ++m) { P[0][m] = P[1][m]; P[1][m] = P[2][m]; }
+    }
   }
-}
-
-__global__ void __launch_bounds__(256)
-k_zero(float* __restrict__ p, const size_t n) {
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = 0.0f;
 }
 
 // ---- halo fill / J exchange (corgi local_communication, Moore order) ----------
@@ -194,14 +216,41 @@ __device__ __forceinline__ int dir_of_halo(int a, int N) { return a < H ? -1 : (
 __global__ void __launch_bounds__(256)
 k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, const Geom g, const int which,
             const SlabDesc* __restrict__ remote) {
-  const int jblocks = (g.Hx[1] + int(blockDim.y) - 1) / int(blockDim.y);
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y / jblocks;
-  const int j = (blockIdx.y - i * jblocks) * blockDim.y + threadIdx.y;
+  // Only halo cells get a thread.  They are enumerated as three groups (k fastest in each):
+  //   A: the six full (j,k) planes with i in the halo        6 * Hy * Hz
+  //   B: for interior i, the six halo rows in j              Nx * 6 * Hz
+  //   C: for interior i and j, the six halo cells in k       Nx * Ny * 6
+  const int Hy = g.Hx[1], Hz = g.Hx[2];
+  const int nA = 2 * H * Hy * Hz, nB = g.N[0] * 2 * H * Hz, nC = g.N[0] * g.N[1] * 2 * H;
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int tile = blockIdx.z;
-  if (k >= g.Hx[2] || j >= g.Hx[1]) return;
+  if (q >= nA + nB + nC) return;
+  int i, j, k;
+  if (q < nA) {
+    const int p = q / (Hy * Hz);
+    q -= p * Hy * Hz;
+    i = p < H ? p : g.N[0] + p;                     // 0,1,2, N+3,N+4,N+5
+    j = q / Hz;
+    k = q - j * Hz;
+  } else if (q < nA + nB) {
+    q -= nA;
+    const int ii = q / (2 * H * Hz);
+    q -= ii * 2 * H * Hz;
+    const int p = q / Hz;
+    i = ii + H;
+    j = p < H ? p : g.N[1] + p;
+    k = q - p * Hz;
+  } else {
+    q -= nA + nB;
+    const int ii = q / (g.N[1] * 2 * H);
+    q -= ii * g.N[1] * 2 * H;
+    const int jj = q / (2 * H);
+    const int p = q - jj * 2 * H;
+    i = ii + H;
+    j = jj + H;
+    k = p < H ? p : g.N[2] + p;
+  }
   const int di = dir_of_halo(i, g.N[0]), dj = dir_of_halo(j, g.N[1]), dk = dir_of_halo(k, g.N[2]);
-  if (di == 0 && dj == 0 && dk == 0) return;
   const int o = nbr[tile * 27 + ((di + 1) * 3 + (dj + 1)) * 3 + (dk + 1)];
   if (o == -1) return;
   const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
@@ -212,7 +261,7 @@ k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, co
     const int a[3] = { i, j, k }, dr[3] = { di, dj, dk };
     int r[3];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) r[q] = dr[q] == 0 ? a[q] - H : (dr[q] == 1 ? a[q] - (H + g.N[q]) : a[q]);
+    for (int q2 = 0; q2 < 3; ++q2) r[q2] = dr[q2] == 0 ? a[q2] - H : (dr[q2] == 1 ? a[q2] - (H + g.N[q2]) : a[q2]);
     const size_t vol = size_t(s.dims[0]) * s.dims[1] * s.dims[2];
     const size_t m = (size_t(r[0]) * s.dims[1] + r[1]) * s.dims[2] + r[2];
     float* dstr = which == 0 ? tiles[tile].E : (which == 1 ? tiles[tile].B : tiles[tile].J);
@@ -323,9 +372,6 @@ constexpr int MAX_TILES_PER_LAUNCH = 65535;
 static dim3 interior_grid(const Geom& g, int ntiles) {
   return dim3((g.N[2] + 31) / 32, unsigned((g.N[1] + 7) / 8) * g.N[0], unsigned(ntiles));
 }
-static dim3 haloed_grid(const Geom& g, int ntiles, int planes_per_i) {
-  return dim3((g.Hx[2] + 31) / 32, unsigned((g.Hx[1] + 7) / 8) * g.Hx[0] * planes_per_i, unsigned(ntiles));
-}
 static void check_tiles(int ntiles) {
   if (ntiles > MAX_TILES_PER_LAUNCH) throw Error(B2P_ERR_RUNTIME, "more than 65535 local tiles per GPU are not supported");
 }
@@ -365,25 +411,26 @@ void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unr
   ProfScope prof_(KC_FILTER, double(ntiles) * g.Ch);
   if (!ntiles) return;
   check_tiles(ntiles);
-  const dim3 grid = haloed_grid(g, ntiles, 3);
+  if (ntiles * 3 > MAX_TILES_PER_LAUNCH) throw Error(B2P_ERR_RUNTIME, "more than 21845 local tiles per GPU are not supported");
+  const int chunk = tuning().filter_chunk > 0 ? tuning().filter_chunk : 35;
+  const dim3 grid((g.Hx[1] * g.Hx[2] + 255) / 256, (g.Hx[0] + chunk - 1) / chunk, unsigned(ntiles) * 3);
   const FilterTile* ft = static_cast<const FilterTile*>(filter_tiles);
-  if (unrolled) k_filter_binomial2<true><<<grid, cell_block(), 0, ctx().stream>>>(ft, g);
-  else k_filter_binomial2<false><<<grid, cell_block(), 0, ctx().stream>>>(ft, g);
+  if (unrolled) k_filter_binomial2<true><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk);
+  else k_filter_binomial2<false><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk);
   B2P_LAUNCH_CHECK();
 }
 void launch_zero(float* p, size_t n) {
   ProfScope prof_(KC_ZERO, double(n));
   if (!n) return;
-  const unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, size_t(ctx().sm_count) * 16));
-  k_zero<<<blocks, 256, 0, ctx().stream>>>(p, n);
-  B2P_LAUNCH_CHECK();
+  B2P_CUDA(cudaMemsetAsync(p, 0, n * sizeof(float), ctx().stream));   // +0.0f is all-zero bits
+  count_launch();
 }
 void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which, const SlabDesc* remote) {
   ProfScope prof_(KC_HALO, double(ntiles) * g.Ch);
   if (!ntiles) return;
   check_tiles(ntiles);
-  const dim3 grid = haloed_grid(g, ntiles, 1);
-  k_halo_fill<<<grid, cell_block(), 0, ctx().stream>>>(tiles, nbr, g, which, remote);
+  const int nhalo = 2 * H * g.Hx[1] * g.Hx[2] + g.N[0] * 2 * H * g.Hx[2] + g.N[0] * g.N[1] * 2 * H;
+  k_halo_fill<<<dim3((nhalo + 255) / 256, 1, unsigned(ntiles)), 256, 0, ctx().stream>>>(tiles, nbr, g, which, remote);
   B2P_LAUNCH_CHECK();
 }
 void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, const SlabDesc* remote) {

@@ -54,6 +54,9 @@ static bool set_option(const std::string& name, int value) {
   else if (name == "deposit_minb") g_tuning.deposit_minb = value;
   else if (name == "deposit_agg") g_tuning.deposit_agg = value;
   else if (name == "fuse_deposit") g_tuning.fuse_deposit = value;
+  else if (name == "filter_chunk") g_tuning.filter_chunk = value;
+  else if (name == "push_streams") g_tuning.push_streams = value;
+  else if (name == "sort_streams") g_tuning.sort_streams = value;
   else return false;
   return true;
 }
@@ -120,18 +123,48 @@ ProfScope::~ProfScope() {
 }
 
 // process-level scratch shared by all tiles (all work is ordered on one stream)
+constexpr int MAX_WORKERS = 4;
 struct Scratch {
-  DBuf<float4> nodal;
-  DBuf<float4> edges;             // cell-edge current accumulators of the tile being deposited
-  DBuf<unsigned> keys[2], vals[2];
-  DBuf<unsigned char> cub_temp;
+  DBuf<float4> nodal_w[MAX_WORKERS];   // per worker stream: nodal field means of the tile being pushed
+  DBuf<float4> edges_w[MAX_WORKERS];   // per worker stream: cell-edge current accumulators
+  DBuf<float4>& nodal = nodal_w[0];
+  DBuf<float4>& edges = edges_w[0];
+  DBuf<unsigned> keys_w[MAX_WORKERS][2], vals_w[MAX_WORKERS][2];   // per worker stream: sort keys / permutation
+  DBuf<unsigned char> cub_temp_w[MAX_WORKERS];
+  DBuf<unsigned> (&keys)[2] = keys_w[0];
+  DBuf<unsigned char>& cub_temp = cub_temp_w[0];
   DBuf<unsigned long long> list[2];
   DBuf<unsigned> counters;        // [0]=list count, then per-container last_alive, then counts[ncont][27]
   DBuf<unsigned char> table;      // device staging for job / out-tile tables
   DBuf<double> energy;
-  Container spare;                // gather target of the sort (swapped with the container)
+  Container spare_w[MAX_WORKERS]; // per worker stream: gather target of the sort (swapped with the container)
 };
 static Scratch& scratch() { static Scratch* s = new Scratch; return *s; }
+
+// Worker streams: the per-tile particle phase (nodal means -> zero -> push per species -> edge
+// gather) is round-robined over a few streams so that one tile's small kernels and launch gaps
+// hide behind another tile's push.  Forked from / joined to the library stream with events, so
+// the library stays stream-ordered for the caller.
+struct Workers {
+  cudaStream_t s[MAX_WORKERS] = {};
+  cudaEvent_t fork = nullptr, join[MAX_WORKERS] = {};
+  bool ready = false;
+  void init() {
+    if (ready) return;
+    for (int w = 0; w < MAX_WORKERS; ++w) {
+      B2P_CUDA(cudaStreamCreateWithFlags(&s[w], cudaStreamNonBlocking));
+      B2P_CUDA(cudaEventCreateWithFlags(&join[w], cudaEventDisableTiming));
+    }
+    B2P_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    ready = true;
+  }
+};
+static Workers& workers() { static Workers w; return w; }
+struct StreamScope {          // makes `st` the stream every launcher / ProfScope / DBuf uses
+  cudaStream_t saved;
+  explicit StreamScope(cudaStream_t st) : saved(g_ctx.stream) { g_ctx.stream = st; }
+  ~StreamScope() { g_ctx.stream = saved; }
+};
 
 // ---------------------------------------------------------------- container --
 void Container::reserve(size_t cap, bool exact) {
@@ -349,32 +382,48 @@ static int sign_of(double v) { return (0.0 < v) - (v < 0.0); }   // tools/math.h
 void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
   const bool fuse = tuning().fuse_deposit != 0;
+  const int nw = std::max(1, std::min({ tuning().push_streams, MAX_WORKERS, int(tiles.size()) }));
+  Workers& wk = workers();
+  cudaStream_t main_stream = ctx().stream;
+  if (nw > 1) {
+    wk.init();
+    B2P_CUDA(cudaEventRecord(wk.fork, main_stream));
+    for (int w = 0; w < nw; ++w) B2P_CUDA(cudaStreamWaitEvent(wk.s[w], wk.fork, 0));
+  }
+  size_t ti = 0;
   for (b2p_tile* t : tiles) {
+    const int w = int(ti++ % size_t(nw));
+    StreamScope on(nw > 1 ? wk.s[w] : main_stream);
     t->pendJ_valid = t->pend_packed = false;
     bool any = false;
     for (const Container& c : t->sp) any = any || c.n;
     if (!any) continue;
-    s.nodal.reserve(size_t(2) * t->g.Ch);
-    launch_nodal_means(t->E.p, t->B.p, t->g, s.nodal.p);
+    s.nodal_w[w].reserve(size_t(2) * t->g.Ch);
+    launch_nodal_means(t->E.p, t->B.p, t->g, s.nodal_w[w].p);
     if (fuse) {
-      s.edges.reserve(size_t(3) * t->g.Ch);
-      launch_zero(reinterpret_cast<float*>(s.edges.p), size_t(12) * t->g.Ch);
+      s.edges_w[w].reserve(size_t(3) * t->g.Ch);
+      launch_zero(reinterpret_cast<float*>(s.edges_w[w].p), size_t(12) * t->g.Ch);
     }
     const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
     const float mx[3] = { float(t->maxs[0]), float(t->maxs[1]), float(t->maxs[2]) };
     for (Container& c : t->sp) {
       if (!c.n) continue;
       const float qm = static_cast<float>(sign_of(c.charge) / c.mass);
-      launch_push(t->cfg.particle_pusher, c.view(), s.nodal.p, t->g, t->origo, static_cast<float>(t->cfg.cfl), qm,
-                  c.mask_words(), mn, mx, fuse ? s.edges.p : nullptr, static_cast<float>(c.charge));
+      launch_push(t->cfg.particle_pusher, c.view(), s.nodal_w[w].p, t->g, t->origo, static_cast<float>(t->cfg.cfl), qm,
+                  c.mask_words(), mn, mx, fuse ? s.edges_w[w].p : nullptr, static_cast<float>(c.charge));
       c.touch();
       c.masks_valid = true;
     }
     if (fuse) {
-      launch_edge_gather(s.edges.p, t->Jbuf[1 - t->jcur].p, t->g);
+      launch_edge_gather(s.edges_w[w].p, t->Jbuf[1 - t->jcur].p, t->g);
       t->pendJ_valid = true;
     }
   }
+  if (nw > 1)
+    for (int w = 0; w < nw; ++w) {
+      B2P_CUDA(cudaEventRecord(wk.join[w], wk.s[w]));
+      B2P_CUDA(cudaStreamWaitEvent(main_stream, wk.join[w], 0));
+    }
 }
 
 // pic/tile.c++:369-415.  clear_current + scratch accumulate + `J += scratch`
@@ -403,27 +452,46 @@ void phase_deposit(const std::vector<b2p_tile*>& tiles) {
 // pic/tile.c++:419-438 + pic/particle.h:575-703: stable sort by cell key, dead last
 void phase_sort(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
+  size_t ncont = 0;
+  for (b2p_tile* t : tiles) ncont += t->sp.size();
+  const int nw = std::max(1, std::min({ tuning().sort_streams, MAX_WORKERS, int(ncont) }));
+  Workers& wk = workers();
+  cudaStream_t main_stream = ctx().stream;
+  if (nw > 1) {
+    wk.init();
+    B2P_CUDA(cudaEventRecord(wk.fork, main_stream));
+    for (int w = 0; w < nw; ++w) B2P_CUDA(cudaStreamWaitEvent(wk.s[w], wk.fork, 0));
+  }
+  size_t ci = 0;
   for (b2p_tile* t : tiles)
     for (Container& c : t->sp) {
+      const int w = int(ci++ % size_t(nw));
       if (c.n < 2) continue;
-      for (int b = 0; b < 2; ++b) { s.keys[b].reserve(c.n); s.vals[b].reserve(c.n); }
+      StreamScope on(nw > 1 ? wk.s[w] : main_stream);
+      for (int b = 0; b < 2; ++b) { s.keys_w[w][b].reserve(c.n); s.vals_w[w][b].reserve(c.n); }
       // Alive keys are < Ch (particles live inside the haloed lattice), so dead slots are keyed
       // Ch instead of UINT32_MAX and only bits(Ch) key bits are sorted: same stable order,
       // one radix pass fewer.  (Keys >= Ch — positions outside the lattice, undefined
       // behaviour in the reference — are clamped to Ch.)
       int key_bits = 1;
       while ((1ull << key_bits) <= t->g.Ch) ++key_bits;
-      launch_sort_keys(c.view(), t->g, t->origo, s.keys[0].p, s.vals[0].p, t->g.Ch);
+      launch_sort_keys(c.view(), t->g, t->origo, s.keys_w[w][0].p, s.vals_w[w][0].p, t->g.Ch);
       const size_t tb = sort_pairs_temp_bytes(c.n, key_bits);
-      s.cub_temp.reserve(tb);
-      unsigned* k[2] = { s.keys[0].p, s.keys[1].p };
-      unsigned* v[2] = { s.vals[0].p, s.vals[1].p };
-      const int sel = sort_pairs(s.cub_temp.p, tb, k, v, c.n, key_bits);
-      s.spare.reserve(c.capacity(), /*exact=*/true);
-      s.spare.n = c.n;
-      launch_gather(c.view(), s.spare.view(), v[sel]);
-      swap_storage(c, s.spare);
+      s.cub_temp_w[w].reserve(tb);
+      unsigned* k[2] = { s.keys_w[w][0].p, s.keys_w[w][1].p };
+      unsigned* v[2] = { s.vals_w[w][0].p, s.vals_w[w][1].p };
+      const int sel = sort_pairs(s.cub_temp_w[w].p, tb, k, v, c.n, key_bits);
+      Container& spare = s.spare_w[w];
+      spare.reserve(c.capacity(), /*exact=*/true);
+      spare.n = c.n;
+      launch_gather(c.view(), spare.view(), v[sel]);
+      swap_storage(c, spare);
       c.touch();
+    }
+  if (nw > 1)
+    for (int w = 0; w < nw; ++w) {
+      B2P_CUDA(cudaEventRecord(wk.join[w], wk.s[w]));
+      B2P_CUDA(cudaStreamWaitEvent(main_stream, wk.join[w], 0));
     }
 }
 

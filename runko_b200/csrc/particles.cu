@@ -506,7 +506,10 @@ k_gather_outgoing(const unsigned long long* __restrict__ sorted, const unsigned 
   st.id = t.s.id[n];
   t.buf[q - t.base] = st;
   t.s.id[n] = DEAD;
-  atomicAdd(&counts[c * 27 + sub], 1u);
+  // the list is sorted by (container, subregion): one count atomic per run inside the warp
+  const unsigned grp = unsigned(key >> 32);
+  const unsigned peers = __match_any_sync(__activemask(), grp);
+  if ((threadIdx.x & 31) == unsigned(__ffs(peers) - 1)) atomicAdd(&counts[c * 27 + sub], unsigned(__popc(peers)));
 }
 
 // Full-pass fallback for P = 1 + last alive slot (pic/particle.h:469-488), used
