@@ -226,6 +226,13 @@ int b2p_profile_num_classes(void);
 const char* b2p_profile_class_name(int k);
 int b2p_profile_report(double* ms, uint64_t* launches, double* units);
 
+
+/* ---- self-checks of arithmetic building blocks (tests only) -------------- */
+/* out[i] = x[i] / c computed by the pushers' constant-divisor division (particles.cu: DivC),
+ * ref[i] = x[i] / c by the IEEE division; host pointers. The parity tests require out == ref
+ * bit for bit (pic/particle_boris.h:46,53 divide by cfl). */
+int b2p_selfcheck_const_division(const float* x, uint64_t n, float c, float* out, float* ref);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@ b2p_grid_step_pic b2p_grid_step_emf b2p_grid_energies b2p_grid_inject_thermal b2
 b2p_nccl_unique_id b2p_grid_comm_init b2p_grid_external_communication b2p_plan_describe
 b2p_timer_start b2p_timer_stop b2p_launch_count b2p_copy_bytes
 b2p_profile_enable b2p_profile_num_classes b2p_profile_class_name b2p_profile_report
+b2p_selfcheck_const_division
 """.split()
 
 
@@ -100,6 +101,7 @@ def lib():
     L.b2p_profile_class_name.argtypes = [ci]
     L.b2p_profile_class_name.restype = C.c_char_p
     L.b2p_profile_report.argtypes = [vp, vp, vp]
+    L.b2p_selfcheck_const_division.argtypes = [vp, u64, C.c_float, vp, vp]
     _lib = L
     return L
 

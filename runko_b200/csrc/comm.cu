@@ -377,7 +377,8 @@ void comm_particles_consumed(b2p_grid* g) { if (g->comm) g->comm->pspan_valid = 
 static thread_local std::string g_comm_error;
 extern "C" const char* b2p_last_error(void);
 namespace b2p { void set_last_error(const std::string& s); }
-#define COMM_TRY try {
+namespace b2p { void flush_deferred(); }
+#define COMM_TRY try { b2p::flush_deferred();
 #define COMM_CATCH                                                                 \
   }                                                                                \
   catch (const b2p::Error& e) { b2p::set_last_error(e.what()); return e.code; }    \

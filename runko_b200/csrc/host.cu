@@ -53,10 +53,13 @@ static bool set_option(const std::string& name, int value) {
   if (name == "push_minb") g_tuning.push_minb = value;
   else if (name == "deposit_minb") g_tuning.deposit_minb = value;
   else if (name == "deposit_agg") g_tuning.deposit_agg = value;
+  else if (name == "agg_min") g_tuning.agg_min = value;
   else if (name == "fuse_deposit") g_tuning.fuse_deposit = value;
   else if (name == "filter_chunk") g_tuning.filter_chunk = value;
   else if (name == "push_streams") g_tuning.push_streams = value;
   else if (name == "sort_streams") g_tuning.sort_streams = value;
+  else if (name == "sort_counting") g_tuning.sort_counting = value;
+  else if (name == "defer_tile_calls") g_tuning.defer_tile_calls = value;
   else return false;
   return true;
 }
@@ -124,7 +127,14 @@ ProfScope::~ProfScope() {
 
 // process-level scratch shared by all tiles (all work is ordered on one stream)
 constexpr int MAX_WORKERS = 4;
+constexpr int SORT_SLOTS = 2 * MAX_WORKERS;
+struct SortSet {                // scratch of one container in flight in the counting sort
+  DBuf<unsigned> keys, rank, members, cnt, offs;
+  DBuf<unsigned char> temp;
+};
 struct Scratch {
+  SortSet sort_set[SORT_SLOTS];
+  DBuf<unsigned> sort_maxpop;
   DBuf<float4> nodal_w[MAX_WORKERS];   // per worker stream: nodal field means of the tile being pushed
   DBuf<float4> edges_w[MAX_WORKERS];   // per worker stream: cell-edge current accumulators
   DBuf<float4>& nodal = nodal_w[0];
@@ -449,50 +459,101 @@ void phase_deposit(const std::vector<b2p_tile*>& tiles) {
   }
 }
 
-// pic/tile.c++:419-438 + pic/particle.h:575-703: stable sort by cell key, dead last
+// pic/tile.c++:419-438 + pic/particle.h:575-703: stable sort by cell key, dead last.
+// Fast path: counting sort by cell (particles.cu, "counting sort"); containers are processed in
+// batches of SORT_SLOTS so that one host read of the batch's largest cell populations decides, per
+// container, between the counting placement and the general radix sort (crowded cells).
+static void sort_radix(b2p_tile* t, Container& c, int w) {
+  Scratch& s = scratch();
+  for (int b = 0; b < 2; ++b) { s.keys_w[w][b].reserve(c.n); s.vals_w[w][b].reserve(c.n); }
+  // Alive keys are < Ch (particles live inside the haloed lattice), so dead slots are keyed
+  // Ch instead of UINT32_MAX and only bits(Ch) key bits are sorted: same stable order,
+  // one radix pass fewer.  (Keys >= Ch — positions outside the lattice, undefined
+  // behaviour in the reference — are clamped to Ch.)
+  int key_bits = 1;
+  while ((1ull << key_bits) <= t->g.Ch) ++key_bits;
+  launch_sort_keys(c.view(), t->g, t->origo, s.keys_w[w][0].p, s.vals_w[w][0].p, t->g.Ch);
+  const size_t tb = sort_pairs_temp_bytes(c.n, key_bits);
+  s.cub_temp_w[w].reserve(tb);
+  unsigned* k[2] = { s.keys_w[w][0].p, s.keys_w[w][1].p };
+  unsigned* v[2] = { s.vals_w[w][0].p, s.vals_w[w][1].p };
+  const int sel = sort_pairs(s.cub_temp_w[w].p, tb, k, v, c.n, key_bits);
+  Container& spare = s.spare_w[w];
+  spare.reserve(c.capacity(), /*exact=*/true);
+  spare.n = c.n;
+  launch_gather(c.view(), spare.view(), v[sel]);
+  swap_storage(c, spare);
+  c.touch();
+}
+
 void phase_sort(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
-  size_t ncont = 0;
-  for (b2p_tile* t : tiles) ncont += t->sp.size();
-  const int nw = std::max(1, std::min({ tuning().sort_streams, MAX_WORKERS, int(ncont) }));
+  struct Item { b2p_tile* t; Container* c; };
+  std::vector<Item> items;
+  for (b2p_tile* t : tiles)
+    for (Container& c : t->sp)
+      if (c.n >= 2) items.push_back(Item{ t, &c });
+  if (items.empty()) return;
+  const int nw = std::max(1, std::min({ tuning().sort_streams, MAX_WORKERS, int(items.size()) }));
+  const bool counting = tuning().sort_counting != 0;
   Workers& wk = workers();
   cudaStream_t main_stream = ctx().stream;
-  if (nw > 1) {
-    wk.init();
+  if (nw > 1) wk.init();
+  auto fork = [&]() {
+    if (nw == 1) return;
     B2P_CUDA(cudaEventRecord(wk.fork, main_stream));
     for (int w = 0; w < nw; ++w) B2P_CUDA(cudaStreamWaitEvent(wk.s[w], wk.fork, 0));
-  }
-  size_t ci = 0;
-  for (b2p_tile* t : tiles)
-    for (Container& c : t->sp) {
-      const int w = int(ci++ % size_t(nw));
-      if (c.n < 2) continue;
-      StreamScope on(nw > 1 ? wk.s[w] : main_stream);
-      for (int b = 0; b < 2; ++b) { s.keys_w[w][b].reserve(c.n); s.vals_w[w][b].reserve(c.n); }
-      // Alive keys are < Ch (particles live inside the haloed lattice), so dead slots are keyed
-      // Ch instead of UINT32_MAX and only bits(Ch) key bits are sorted: same stable order,
-      // one radix pass fewer.  (Keys >= Ch — positions outside the lattice, undefined
-      // behaviour in the reference — are clamped to Ch.)
-      int key_bits = 1;
-      while ((1ull << key_bits) <= t->g.Ch) ++key_bits;
-      launch_sort_keys(c.view(), t->g, t->origo, s.keys_w[w][0].p, s.vals_w[w][0].p, t->g.Ch);
-      const size_t tb = sort_pairs_temp_bytes(c.n, key_bits);
-      s.cub_temp_w[w].reserve(tb);
-      unsigned* k[2] = { s.keys_w[w][0].p, s.keys_w[w][1].p };
-      unsigned* v[2] = { s.vals_w[w][0].p, s.vals_w[w][1].p };
-      const int sel = sort_pairs(s.cub_temp_w[w].p, tb, k, v, c.n, key_bits);
-      Container& spare = s.spare_w[w];
-      spare.reserve(c.capacity(), /*exact=*/true);
-      spare.n = c.n;
-      launch_gather(c.view(), spare.view(), v[sel]);
-      swap_storage(c, spare);
-      c.touch();
-    }
-  if (nw > 1)
+  };
+  auto join = [&]() {
+    if (nw == 1) return;
     for (int w = 0; w < nw; ++w) {
       B2P_CUDA(cudaEventRecord(wk.join[w], wk.s[w]));
       B2P_CUDA(cudaStreamWaitEvent(main_stream, wk.join[w], 0));
     }
+  };
+  s.sort_maxpop.reserve(SORT_SLOTS);
+  const int batch = std::min(SORT_SLOTS, 2 * nw);
+  for (size_t b0 = 0; b0 < items.size(); b0 += size_t(batch)) {
+    const int nb = int(std::min<size_t>(size_t(batch), items.size() - b0));
+    unsigned maxpop[SORT_SLOTS] = {};
+    if (counting) {
+      fork();
+      for (int q = 0; q < nb; ++q) {
+        const Item& it = items[b0 + q];
+        StreamScope on(nw > 1 ? wk.s[q % nw] : main_stream);
+        SortSet& ss = s.sort_set[q];
+        const unsigned nkeys = it.t->g.Ch;
+        ss.keys.reserve(it.c->n); ss.rank.reserve(it.c->n); ss.members.reserve(it.c->n);
+        ss.cnt.reserve(size_t(nkeys) + 2); ss.offs.reserve(size_t(nkeys) + 2);
+        const size_t tb = scan_temp_bytes(nkeys + 2);
+        ss.temp.reserve(tb);
+        launch_sort_count_scan(it.c->view(), it.t->g, it.t->origo, ss.keys.p, ss.rank.p, ss.cnt.p, ss.offs.p, nkeys, ss.temp.p, tb,
+                               s.sort_maxpop.p + q);
+      }
+      join();
+      d2h(maxpop, s.sort_maxpop.p, size_t(nb));
+      sync();
+    }
+    fork();
+    for (int q = 0; q < nb; ++q) {
+      const Item& it = items[b0 + q];
+      const int w = q % nw;
+      StreamScope on(nw > 1 ? wk.s[w] : main_stream);
+      if (counting && maxpop[q] <= SORT_MAX_CELL_POP) {
+        SortSet& ss = s.sort_set[q];
+        Container& c = *it.c;
+        Container& spare = s.spare_w[w];
+        spare.reserve(c.capacity(), /*exact=*/true);
+        spare.n = c.n;
+        launch_sort_scatter_place(c.view(), spare.view(), ss.keys.p, ss.rank.p, ss.offs.p, ss.members.p, it.t->g.Ch);
+        swap_storage(c, spare);
+        c.touch();
+      } else {
+        sort_radix(it.t, *it.c, w);
+      }
+    }
+    join();
+  }
 }
 
 // pic/tile_communication.c++:68-96 + pic/particle.c++:199-348, batched over tiles
@@ -686,6 +747,68 @@ void grid_local_communication(b2p_grid* g, int mode) {
 
 }  // namespace b2p
 
+// -------------------------------------------------- deferred per-tile calls --
+// runko/simulation.py drives a lap as `for tile in tiles: tile.<op>()`.  Tile-local operations of
+// the same kind on different tiles are independent, so consecutive per-tile calls of one kind are
+// collected and executed as ONE batched phase (one launch over all collected tiles for the field
+// kernels; worker streams, one exchange of counters, ... for the particle phases) as soon as any
+// other entry point is called — every C-ABI entry flushes first, so callers observe exactly the
+// synchronous semantics of the reference.
+namespace b2p {
+enum DeferKind { DK_NONE, DK_PUSH_HALF_B, DK_PUSH_E, DK_ADD_CURRENT, DK_FILTER, DK_PUSH, DK_PACK, DK_SORT, DK_DEPOSIT };
+static int g_defer_kind = DK_NONE;
+static std::vector<b2p_tile*> g_defer_tiles;
+static DBuf<FieldPtrs>& defer_table() { static DBuf<FieldPtrs>* t = new DBuf<FieldPtrs>; return *t; }
+
+static const FieldPtrs* table_for(const std::vector<b2p_tile*>& tiles) {
+  b2p_grid* g = tiles[0]->grid;
+  if (g && g->tiles == tiles) return g->device_table();
+  if (tiles.size() == 1) return tiles[0]->device_entry();
+  std::vector<FieldPtrs> h(tiles.size());
+  for (size_t i = 0; i < tiles.size(); ++i) h[i] = tiles[i]->ptrs();
+  defer_table().reserve(h.size());
+  h2d(defer_table().p, h.data(), h.size());
+  sync();                                   // `h` is pageable host memory about to go out of scope
+  return defer_table().p;
+}
+
+void flush_deferred() {
+  if (g_defer_kind == DK_NONE) return;
+  const int kind = g_defer_kind;
+  std::vector<b2p_tile*> tiles;
+  tiles.swap(g_defer_tiles);
+  g_defer_kind = DK_NONE;
+  for (b2p_tile* t : tiles) t->deferred = false;
+  switch (kind) {
+    case DK_PUSH_HALF_B: phase_push_half_b(tiles, table_for(tiles)); break;
+    case DK_PUSH_E: phase_push_e(tiles, table_for(tiles), false); break;
+    case DK_ADD_CURRENT: phase_add_current(tiles, table_for(tiles)); break;
+    case DK_FILTER: phase_filter(tiles); break;
+    case DK_PUSH: phase_push_particles(tiles); break;
+    case DK_PACK: phase_pack_outgoing(tiles); break;
+    case DK_SORT: phase_sort(tiles); break;
+    case DK_DEPOSIT: phase_deposit(tiles); break;
+    default: break;
+  }
+}
+
+static void defer(int kind, b2p_tile* t) {
+  ctx();                                    // no usable device: fail at the call, not at the flush
+  if (!tuning().defer_tile_calls) {
+    flush_deferred();
+    g_defer_kind = kind; g_defer_tiles.assign(1, t);
+    flush_deferred();
+    return;
+  }
+  if (g_defer_kind != kind || t->deferred || (!g_defer_tiles.empty() && g_defer_tiles[0]->grid != t->grid) ||
+      (!g_defer_tiles.empty() && std::memcmp(&g_defer_tiles[0]->g, &t->g, sizeof(Geom)) != 0))
+    flush_deferred();
+  g_defer_kind = kind;
+  g_defer_tiles.push_back(t);
+  t->deferred = true;
+}
+}  // namespace b2p
+
 // ==================================================================== C ABI ==
 static thread_local std::string g_last_error;
 namespace b2p {
@@ -698,7 +821,8 @@ void Scratch_table_upload(const void* src, size_t bytes) {
 }
 const void* Scratch_table_ptr() { return scratch().table.p; }
 }  // namespace b2p
-#define B2P_TRY try {
+#define B2P_TRY try { b2p::flush_deferred();
+#define B2P_TRY_DEFER try {
 #define B2P_CATCH                                                              \
   }                                                                            \
   catch (const b2p::Error& e) { g_last_error = e.what(); return e.code; }     \
@@ -746,6 +870,7 @@ int b2p_tile_create(const b2p_config* cfg, const int32_t idx[3], b2p_tile** out)
 }
 void b2p_tile_destroy(b2p_tile* t) {
   if (!t) return;
+  try { b2p::flush_deferred(); } catch (...) {}
   if (t->grid) {
     b2p_grid* g = t->grid;
     auto it = std::find(g->tiles.begin(), g->tiles.end(), t);
@@ -808,10 +933,17 @@ int b2p_tile_get_fields(b2p_tile* t, float* E, float* B, float* J, int with_halo
   download_field(t, t->E.p, E, with_halo); download_field(t, t->B.p, B, with_halo); download_field(t, t->J(), J, with_halo);
   B2P_CATCH
 }
-int b2p_tile_push_half_b(b2p_tile* t) { B2P_TRY phase_push_half_b({ T(t) }, t->device_entry()); B2P_CATCH }
-int b2p_tile_push_e(b2p_tile* t) { B2P_TRY phase_push_e({ T(t) }, t->device_entry(), false); B2P_CATCH }
-int b2p_tile_add_current(b2p_tile* t) { B2P_TRY phase_add_current({ T(t) }, t->device_entry()); B2P_CATCH }
-int b2p_tile_filter_current(b2p_tile* t) { B2P_TRY phase_filter({ T(t) }); B2P_CATCH }
+int b2p_tile_push_half_b(b2p_tile* t) { B2P_TRY_DEFER defer(DK_PUSH_HALF_B, T(t)); B2P_CATCH }
+int b2p_tile_push_e(b2p_tile* t) { B2P_TRY_DEFER defer(DK_PUSH_E, T(t)); B2P_CATCH }
+int b2p_tile_add_current(b2p_tile* t) { B2P_TRY_DEFER defer(DK_ADD_CURRENT, T(t)); B2P_CATCH }
+int b2p_tile_filter_current(b2p_tile* t) {
+  B2P_TRY_DEFER
+  const int cf = T(t)->cfg.current_filter;                                        // emf/tile.c++:407-411
+  if (cf != B2P_FILTER_BINOMIAL2 && cf != B2P_FILTER_BINOMIAL2_UNROLLED)
+    throw Error(B2P_ERR_LOGIC, "Trying to filter current without specifying `current_filter`!");
+  defer(DK_FILTER, t);
+  B2P_CATCH
+}
 int b2p_tile_clear_current(b2p_tile* t) { B2P_TRY launch_zero(T(t)->J(), t->lattice_floats()); B2P_CATCH }
 int b2p_tile_field_energy(b2p_tile* t, double* eB, double* eE) {
   B2P_TRY
@@ -905,10 +1037,17 @@ int b2p_tile_get_particles(b2p_tile* t, int sp, int alive_only, float* x, float*
   if (n_out) *n_out = m;
   B2P_CATCH
 }
-int b2p_tile_push_particles(b2p_tile* t) { B2P_TRY phase_push_particles({ T(t) }); B2P_CATCH }
-int b2p_tile_deposit_current(b2p_tile* t) { B2P_TRY phase_deposit({ T(t) }); B2P_CATCH }
-int b2p_tile_sort_particles(b2p_tile* t) { B2P_TRY phase_sort({ T(t) }); B2P_CATCH }
-int b2p_tile_pack_outgoing_particles(b2p_tile* t) { B2P_TRY phase_pack_outgoing({ T(t) }); B2P_CATCH }
+int b2p_tile_push_particles(b2p_tile* t) {
+  B2P_TRY_DEFER
+  const int pp = T(t)->cfg.particle_pusher;
+  if (pp != B2P_PUSHER_BORIS && pp != B2P_PUSHER_HIGUERA_CARY && pp != B2P_PUSHER_FARADAY)
+    throw Error(B2P_ERR_LOGIC, "pic::Tile::push_particles: unkown particle pusher");
+  defer(DK_PUSH, t);
+  B2P_CATCH
+}
+int b2p_tile_deposit_current(b2p_tile* t) { B2P_TRY_DEFER defer(DK_DEPOSIT, T(t)); B2P_CATCH }
+int b2p_tile_sort_particles(b2p_tile* t) { B2P_TRY_DEFER defer(DK_SORT, T(t)); B2P_CATCH }
+int b2p_tile_pack_outgoing_particles(b2p_tile* t) { B2P_TRY_DEFER defer(DK_PACK, T(t)); B2P_CATCH }
 int b2p_tile_sort_keys(b2p_tile* t, int sp, uint32_t* keys) {
   B2P_TRY
   Container& c = C(t, sp);
@@ -965,7 +1104,10 @@ int b2p_grid_create(const b2p_config* cfg, b2p_grid** out) {
   *out = g;
   B2P_CATCH
 }
-void b2p_grid_destroy(b2p_grid* g) { delete g; }
+void b2p_grid_destroy(b2p_grid* g) {
+  try { b2p::flush_deferred(); } catch (...) {}
+  delete g;
+}
 int b2p_grid_add_tile(b2p_grid* g, b2p_tile* t) {
   B2P_TRY
   G(g); T(t);
@@ -1128,7 +1270,10 @@ int b2p_timer_stop(float* ms) {
   B2P_CUDA(cudaEventElapsedTime(ms, ctx().ev0, ctx().ev1));
   B2P_CATCH
 }
-uint64_t b2p_launch_count(void) { return g_ctx_ready ? ctx().launches : 0; }
+uint64_t b2p_launch_count(void) {
+  try { b2p::flush_deferred(); } catch (...) {}
+  return g_ctx_ready ? ctx().launches : 0;
+}
 void b2p_copy_bytes(uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
   if (h2d_bytes) *h2d_bytes = g_ctx_ready ? ctx().h2d_bytes : 0;
   if (d2h_bytes) *d2h_bytes = g_ctx_ready ? ctx().d2h_bytes : 0;
@@ -1143,6 +1288,17 @@ int b2p_profile_enable(int on) {
 }
 int b2p_profile_num_classes(void) { return b2p::KC_COUNT; }
 const char* b2p_profile_class_name(int k) { return b2p::kernel_class_name(k); }
+int b2p_selfcheck_const_division(const float* x, uint64_t n, float c, float* out, float* ref) {
+  B2P_TRY
+  if (!x || !out || !ref) throw Error(B2P_ERR_RUNTIME, "null argument");
+  DBuf<float> dx, dout, dref;
+  dx.reserve_exact(n + 1); dout.reserve_exact(n + 1); dref.reserve_exact(n + 1);
+  h2d(dx.p, x, n);
+  launch_selfcheck_divc(dx.p, n, c, dout.p, dref.p);
+  d2h(out, dout.p, n); d2h(ref, dref.p, n);
+  sync();
+  B2P_CATCH
+}
 int b2p_profile_report(double* ms, uint64_t* launches, double* units) {
   B2P_TRY
   sync();

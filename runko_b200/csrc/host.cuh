@@ -53,6 +53,7 @@ struct b2p_tile {
   unsigned long long out_count = 0;
   b2p_grid* grid = nullptr;
   int slot = -1;
+  bool deferred = false;                      // queued in the pending batch of per-tile calls (host.cu)
 
   float* J() { return Jbuf[jcur].p; }
   b2p::FieldPtrs ptrs() { return b2p::FieldPtrs{ E.p, B.p, J() }; }
@@ -89,6 +90,7 @@ void phase_deposit(const std::vector<b2p_tile*>& tiles);
 void phase_sort(const std::vector<b2p_tile*>& tiles);
 void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles);
 void grid_local_communication(b2p_grid* g, int mode);
+void flush_deferred();                      // executes the pending batch of per-tile calls (host.cu)
 void set_last_error(const std::string& s);
 void Scratch_table_upload(const void* src, size_t bytes);   // host -> the shared device table scratch
 const void* Scratch_table_ptr();

@@ -10,6 +10,9 @@
 #include "particles.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
 
 namespace b2p {
 
@@ -32,22 +35,54 @@ __device__ __forceinline__ V3 cross(const V3 a, const V3 b) {
 }
 __device__ __forceinline__ float lerp1(const float x, const float A, const float B) { return (1.0f - x) * A + x * B; }
 
+// Correctly rounded v / c for a warp-uniform divisor (the pushers divide six values per particle by
+// cfl).  It is the fast path of the IEEE division nvcc emits — MUFU.RCP, one Newton step on the
+// reciprocal, q = x*rc, the exact residual r = x - q*c (FMA) and the correction q + r*rc — with the
+// reciprocal hoisted out of the six divisions and the per-operand FCHK replaced by one range test
+// per vector: for c in [2^-20, 2^20] and |x| in [2^-100, 2^100] no intermediate under- or overflows
+// (r is a multiple of 2^(e_x - 47) >= 2^-147), which is the regime in which that fast path is
+// exact.  Everything else (zeros and their signs, denormals, huge values, inf) takes the plain
+// division.  tests/test_parity_gpu.py::test_const_division_bit_exact checks it against `/`.
+struct DivC {
+  float c, rc, hi;
+  __device__ __forceinline__ explicit DivC(const float c_) : c(c_) {
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(c_));
+    rc = fmaf(r0, fmaf(-c_, r0, 1.0f), r0);
+    hi = (fabsf(c_) >= 0x1p-20f && fabsf(c_) <= 0x1p20f) ? 0x1p100f : -1.0f;
+  }
+  __device__ __forceinline__ float fast(const float x) const {
+    const float q = x * rc;
+    return fmaf(fmaf(-c, q, x), rc, q);
+  }
+  __device__ __forceinline__ V3 operator()(const V3 v) const {
+    const float lo = fminf(fminf(fabsf(v.x), fabsf(v.y)), fabsf(v.z));
+    const float mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fabsf(v.z));
+    if (lo >= 0x1p-100f && mx <= hi) return { fast(v.x), fast(v.y), fast(v.z) };
+    return v / c;
+  }
+};
+
 // ------------------------------------------------------- nodal field means --
 // The interpolator's per-corner staggered averages
 // (emf/yee_lattice_interpolate_linear_1st.h:91-113) depend only on the lattice
 // node (ii,jj,kk), not on the particle, so they are computed once per tile into
-// a node-major AoS array {Ex,Ey,Ez,Bx | By,Bz,0,0} (32 B/node): a particle then
-// needs 8 corners x 2 LDG.128 instead of 144 scalar gathers.  Same operands and
-// same association (2-term sum /2; 4-term right fold /4) => same bits.
+// two node-major arrays, nodA[n] = {Ex,Ey,Ez,Bx} (float4) and nodB[n] = {By,Bz} (float2, stored
+// right behind nodA: 24 B/node): a particle then needs 8 corners x (LDG.128 + LDG.64) instead of
+// 144 scalar gathers, and the L1 data pipe — the unit that bounds the push — returns 192 B per
+// lane instead of 256.  Same operands and same association (2-term sum /2; 4-term right fold /4)
+// => same bits.
 __global__ void __launch_bounds__(256)
 k_nodal_means(const float* __restrict__ E, const float* __restrict__ B, const Geom g, float4* __restrict__ nod) {
+  float2* __restrict__ nodB = reinterpret_cast<float2*>(nod + g.Ch);
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int i = blockIdx.z;
   if (k >= g.Hx[2] || j >= g.Hx[1]) return;
   const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2], Ch = g.Ch;
   const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 b = make_float2(0.f, 0.f);
   if (i >= 1 && j >= 1 && k >= 1) {
     const float* Ex = E; const float* Ey = E + Ch; const float* Ez = E + 2 * Ch;
     const float* Bx = B; const float* By = B + Ch; const float* Bz = B + 2 * Ch;
@@ -58,8 +93,8 @@ k_nodal_means(const float* __restrict__ E, const float* __restrict__ B, const Ge
     b.x = (By[n] + (By[n - si] + (By[n - 1] + By[n - si - 1]))) / 4.0f;
     b.y = (Bz[n] + (Bz[n - si] + (Bz[n - sj] + Bz[n - si - sj]))) / 4.0f;
   }
-  nod[2 * n] = a;
-  nod[2 * n + 1] = b;
+  nod[n] = a;
+  nodB[n] = b;
 }
 
 struct EB { V3 E, B; };
@@ -74,17 +109,18 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
   const float dx = lx - float(i), dy = ly - float(j), dz = lz - float(k);
   const unsigned sj = unsigned(g.Hx[2]), si = unsigned(g.Hx[1]) * unsigned(g.Hx[2]);
   const unsigned n = (i * unsigned(g.Hx[1]) + j) * sj + k;
-  const float4* __restrict__ row[2][2] = { { nod + 2u * size_t(n), nod + 2u * size_t(n + sj) },
-                                           { nod + 2u * size_t(n + si), nod + 2u * size_t(n + si + sj) } };
-  float4 a[2][2][2], b[2][2][2];
+  const float2* __restrict__ nodB = reinterpret_cast<const float2*>(nod + g.Ch);
+  const unsigned off[2][2] = { { n, n + sj }, { n + si, n + si + sj } };
+  float4 a[2][2][2];
+  float2 b[2][2][2];
 #pragma unroll
   for (int ic = 0; ic < 2; ++ic)
 #pragma unroll
     for (int jc = 0; jc < 2; ++jc)
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        a[ic][jc][kc] = __ldg(row[ic][jc] + 2 * kc);
-        b[ic][jc][kc] = __ldg(row[ic][jc] + 2 * kc + 1);
+        a[ic][jc][kc] = __ldg(nod + off[ic][jc] + kc);
+        b[ic][jc][kc] = __ldg(nodB + off[ic][jc] + kc);
       }
   // lerp3D (:29-52): along x, then y, then z
 #define LERP3(field, comp)                                                                     \
@@ -125,6 +161,7 @@ __device__ __forceinline__ void publish_masks(const bool alive, const bool insid
 
 // ---------------------------------------------------------------- deposit --
 struct DepositArgs {
+  int agg_min;     // fewest folding lanes for which a warp aggregation step pays (reduce_runs_and_red)
   Species s;
   float4* Jc;      // cell-edge accumulators: 3 float4 per lattice cell (see below)
   Geom g;
@@ -136,35 +173,42 @@ struct DepositArgs {
 // Warp-level pre-aggregation of one segment set before the global REDs.  Lanes whose
 // segment lies in the same cell form contiguous runs whenever the container is (nearly)
 // cell-sorted: the sort every 5th lap orders by the cell of x2, and one lap later the cell of
-// x1 is that same cell.  A segmented shuffle reduction over runs (steps 1, 2, 4; each skipped
-// warp-uniformly when no run is that long) leaves partial sums at every 8th lane of a run,
-// and only those lanes issue the three RED.128 — up to 8x fewer atomics leave the SM, which
-// is what bounds this kernel (~1.3 cycles per RED lane per SM).  Unsorted input degenerates
-// to the plain per-lane REDs at the cost of one ballot.  Summation order differs from the
+// x1 is that same cell.  A segmented shuffle reduction over runs (steps 1, 2, 4) leaves partial
+// sums at every 2nd/4th/8th lane of a run, and only those lanes issue the three RED.128 — up to
+// 8x fewer atomics enter the L1 data pipe, the unit that bounds this kernel (ncu: one wavefront
+// per RED lane).  Unsorted input degenerates to the plain per-lane REDs at the cost of two ballots.  Summation order differs from the
 // reference's serial loop: covered by the stated deposit tolerance.
 template <int AGG>
-__device__ __forceinline__ void reduce_runs_and_red(const unsigned key, float4 ex, float4 ey, float4 ez, float4* __restrict__ Jc) {
+__device__ __forceinline__ void reduce_runs_and_red(const unsigned key, float4 ex, float4 ey, float4 ez, float4* __restrict__ Jc,
+                                                    const int agg_min) {
   const unsigned lane = threadIdx.x & 31;
-  bool issue = key != 0xFFFFFFFFu;
+  const bool valid = key != 0xFFFFFFFFu;
+  bool issue = valid;
   if (AGG) {
     const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
     const bool head = lane == 0 || key != prev;
     const unsigned hm = __ballot_sync(0xffffffffu, head);
     const unsigned above = lane == 31 ? 0u : (hm >> (lane + 1));
     const unsigned rem = above ? unsigned(__ffs(above)) : 32u - lane;   // lanes [lane, lane + rem) share my key
-    const unsigned start = 31u - __clz(hm & (0xFFFFFFFFu >> (31u - lane)));
+    const unsigned off = lane - (31u - __clz(hm & (0xFFFFFFFFu >> (31u - lane))));   // my offset inside the run
+    // A step of width d folds the lanes at run offset d (mod 2d) into the lane d below: every folded
+    // lane saves three RED.128 (one L1 wavefront each) and the step costs twelve shuffles (one
+    // wavefront each) plus the adds, so a step — and every wider one after it — is only taken
+    // when at least `agg_min` lanes of the warp fold (warp-uniform decision).
+    unsigned stride = 1;
 #pragma unroll
     for (int d = 1; d <= 4; d <<= 1) {
-      if (__any_sync(0xffffffffu, rem > unsigned(d))) {
-        const bool take = rem > unsigned(d);
+      const unsigned folded = __ballot_sync(0xffffffffu, valid && (off & unsigned(2 * d - 1)) == unsigned(d));
+      if (int(__popc(folded)) < agg_min) break;
+      const bool take = rem > unsigned(d);
 #define B2P_STEP(v) { const float t_ = __shfl_down_sync(0xffffffffu, v, d); if (take) v += t_; }
-        B2P_STEP(ex.x) B2P_STEP(ex.y) B2P_STEP(ex.z) B2P_STEP(ex.w)
-        B2P_STEP(ey.x) B2P_STEP(ey.y) B2P_STEP(ey.z) B2P_STEP(ey.w)
-        B2P_STEP(ez.x) B2P_STEP(ez.y) B2P_STEP(ez.z) B2P_STEP(ez.w)
+      B2P_STEP(ex.x) B2P_STEP(ex.y) B2P_STEP(ex.z) B2P_STEP(ex.w)
+      B2P_STEP(ey.x) B2P_STEP(ey.y) B2P_STEP(ey.z) B2P_STEP(ey.w)
+      B2P_STEP(ez.x) B2P_STEP(ez.y) B2P_STEP(ez.z) B2P_STEP(ez.w)
 #undef B2P_STEP
-      }
+      stride = unsigned(2 * d);
     }
-    issue = issue && (((lane - start) & 7u) == 0u);
+    issue = issue && ((off & (stride - 1u)) == 0u);
   }
   if (issue) {
     atomicAdd(&Jc[3 * size_t(key) + 0], ex);
@@ -225,7 +269,7 @@ __device__ __forceinline__ Zigzag zigzag_split(const V3 pos, const V3 u, const f
 
 // Accumulate one particle's split into the cell-edge scratch (all 32 lanes must call).
 template <int AGG>
-__device__ __forceinline__ void deposit_split(const bool active, Zigzag z, float4* __restrict__ Jc) {
+__device__ __forceinline__ void deposit_split(const bool active, Zigzag z, float4* __restrict__ Jc, const int agg_min) {
   if (!active) {
     z.n1 = z.n2 = 0xFFFFFFFFu;
     z.ax = z.ay = z.az = z.bx = z.by = z.bz = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -235,8 +279,8 @@ __device__ __forceinline__ void deposit_split(const bool active, Zigzag z, float
     z.bz.x += z.az.x; z.bz.y += z.az.y; z.bz.z += z.az.z; z.bz.w += z.az.w;
     z.n1 = 0xFFFFFFFFu;
   }
-  if (__any_sync(0xffffffffu, z.n1 != 0xFFFFFFFFu)) reduce_runs_and_red<AGG>(z.n1, z.ax, z.ay, z.az, Jc);
-  reduce_runs_and_red<AGG>(z.n2, z.bx, z.by, z.bz, Jc);
+  if (__any_sync(0xffffffffu, z.n1 != 0xFFFFFFFFu)) reduce_runs_and_red<AGG>(z.n1, z.ax, z.ay, z.az, Jc, agg_min);
+  reduce_runs_and_red<AGG>(z.n2, z.bx, z.by, z.bz, Jc, agg_min);
 }
 
 // Standalone deposit of a whole container: one thread per particle.
@@ -248,7 +292,7 @@ k_deposit_zigzag(const DepositArgs a) {
   Zigzag z;
   if (alive)
     z = zigzag_split(V3{ a.s.x[n], a.s.y[n], a.s.z[n] }, V3{ a.s.ux[n], a.s.uy[n], a.s.uz[n] }, a.origo, a.cfl, a.charge, a.g);
-  deposit_split<AGG>(alive, z, a.Jc);
+  deposit_split<AGG>(alive, z, a.Jc, a.agg_min);
 }
 
 // Scalar nodal scatter of one particle's split (arrivals of the migration: ~1% of the particles).
@@ -268,6 +312,7 @@ __device__ __forceinline__ void deposit_split_nodal(const Zigzag& z, float* __re
 
 // ----------------------------------------------------------------- pushers --
 struct PushArgs {
+  int agg_min;    // see DepositArgs
   Species s;
   const float4* nod;
   Geom g;
@@ -293,16 +338,17 @@ k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float
   const V3 u = { a.s.ux[n], a.s.uy[n], a.s.uz[n] };
   const EB eb = interpolate(a.nod, a.g, a.origo, px, py, pz);
   const float cfl = a.cfl, qm = a.qm;
+  const DivC div_cfl(cfl);
   if (PUSHER == B2P_PUSHER_BORIS) {                                // pic/particle_boris.h:37-59
     const V3 v0 = cfl * u;
     const V3 E0 = 0.5f * qm * eb.E;
     const V3 u0 = v0 + E0;
     const float ginv = cfl / sqrtf(cfl * cfl + dot(u0, u0));
-    const V3 B0 = 0.5f * qm * ginv * eb.B / cfl;
+    const V3 B0 = div_cfl(0.5f * qm * ginv * eb.B);
     const float f = 2.0f / (1.0f + dot(B0, B0));
     const V3 u1 = f * (u0 + cross(u0, B0));
     const V3 u2 = u0 + cross(u1, B0) + E0;
-    vel = u2 / cfl;
+    vel = div_cfl(u2);
     const float ginv2 = cfl / sqrtf(cfl * cfl + dot(u2, u2));
     nx = px + vel.x * ginv2 * cfl; ny = py + vel.y * ginv2 * cfl; nz = pz + vel.z * ginv2 * cfl;
   } else if (PUSHER == B2P_PUSHER_HIGUERA_CARY) {                  // pic/particle_higuera_cary.h:26-75
@@ -340,7 +386,7 @@ k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float
     const V3 eps_rot = f * (eps - cross(beta, eps) + bde * beta);
     const float D = 1.0f - f * (dot(eps, eps) + bde * bde);
     const V3 u2 = W_rot + eps_rot * (dot(eps, W_rot) / D);
-    vel = u2 / cfl;
+    vel = div_cfl(u2);
     const float ginv2 = cfl / sqrtf(cfl * cfl + dot(u2, u2));
     nx = px + vel.x * ginv2 * cfl; ny = py + vel.y * ginv2 * cfl; nz = pz + vel.z * ginv2 * cfl;
   }
@@ -353,7 +399,7 @@ k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float
     const bool stays = alive && inside;
     Zigzag z;
     if (stays) z = zigzag_split(V3{ nx, ny, nz }, vel, a.origo, a.cfl, charge, a.g);
-    deposit_split<(FUSE > 1)>(stays, z, Jc);
+    deposit_split<(FUSE > 1)>(stays, z, Jc, a.agg_min);
   }
 }
 
@@ -412,6 +458,85 @@ k_gather(const Species src, const Species dst, const unsigned* __restrict__ perm
   dst.x[n] = src.x[p]; dst.y[n] = src.y[p]; dst.z[n] = src.z[p];
   dst.ux[n] = src.ux[p]; dst.uy[n] = src.uy[p]; dst.uz[n] = src.uz[p];
   dst.id[n] = src.id[p];
+}
+
+// ------------------------------------------------------- counting sort (fast path) --
+// The contract of ParticleContainer::sort is "stable sort by cell key, dead slots last"
+// (pic/particle.h:575-703).  Keys are lattice cell indices < Ch with a few tens of particles per
+// key, so instead of a general radix sort of (key, slot) pairs the container is sorted by counting:
+//   1. k_sort_count   key[n], rank[n] = arrival order among the particles of that key (warp-
+//                     aggregated atomics on cnt[key]; NOT in slot order yet)
+//   2. exclusive scan of cnt -> offs (CUB DeviceScan over Ch + 2 counters) and the largest
+//                     population of a cell
+//   3. k_sort_scatter members[offs[key] + rank] = n: the slots of every cell, in arrival order
+//   4. k_sort_place   the stable rank of slot n inside its cell is the number of members with a
+//                     smaller slot index (a scan of the cell's short member list); the seven
+//                     streams are moved straight to dst[offs[key] + stable rank].
+// Result: exactly the stable order.  Dead slots (key Ch, clamped like the radix path) keep their
+// arrival order — the contents of dead slots are unspecified in the reference.  Step 4 is
+// quadratic in the population of a cell, so the host takes this path only when no cell holds more
+// than SORT_MAX_CELL_POP particles and falls back to the radix sort otherwise.
+__global__ void __launch_bounds__(256)
+k_sort_count(const Species s, const Geom g, const float3 origo, unsigned* __restrict__ keys, unsigned* __restrict__ rank,
+             unsigned* __restrict__ cnt, const unsigned dead_key) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= s.n) return;
+  unsigned key = dead_key;
+  if (s.id[n] != DEAD) {
+    const unsigned i = __float2uint_rz(s.x[n] - origo.x);
+    const unsigned j = __float2uint_rz(s.y[n] - origo.y);
+    const unsigned k = __float2uint_rz(s.z[n] - origo.z);
+    key = (i * unsigned(g.Hx[1]) + j) * unsigned(g.Hx[2]) + k;
+    if (key > dead_key) key = dead_key;
+  }
+  // one atomic per distinct key of the warp (long runs of equal keys after a sort / in the dead tail)
+  const unsigned peers = __match_any_sync(__activemask(), key);
+  const unsigned lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  unsigned base = 0;
+  if (int(lane) == leader) base = atomicAdd(&cnt[key], unsigned(__popc(peers)));
+  base = __shfl_sync(peers, base, leader);
+  keys[n] = key;
+  rank[n] = base + __popc(peers & ((1u << lane) - 1u));
+}
+
+// largest population among the alive keys [0, nkeys)
+__global__ void __launch_bounds__(256)
+k_max_count(const unsigned* __restrict__ cnt, const unsigned nkeys, unsigned* __restrict__ out) {
+  unsigned m = 0;
+  for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < nkeys; c += gridDim.x * blockDim.x) m = max(m, cnt[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+__global__ void __launch_bounds__(256)
+k_sort_scatter(const unsigned* __restrict__ keys, const unsigned* __restrict__ rank, const unsigned* __restrict__ offs,
+               unsigned* __restrict__ members, const unsigned n_total) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_total) return;
+  members[offs[keys[n]] + rank[n]] = n;
+}
+
+__global__ void __launch_bounds__(256)
+k_sort_place(const Species src, const Species dst, const unsigned* __restrict__ keys, const unsigned* __restrict__ rank,
+             const unsigned* __restrict__ offs, const unsigned* __restrict__ members, const unsigned dead_key) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= src.n) return;
+  const unsigned key = keys[n];
+  const unsigned lo = offs[key];
+  unsigned to;
+  if (key == dead_key) {
+    to = lo + rank[n];
+  } else {
+    const unsigned hi = offs[key + 1];
+    unsigned before = 0;
+    for (unsigned t = lo; t < hi; ++t) before += unsigned(__ldg(members + t) < n);
+    to = lo + before;
+  }
+  dst.x[to] = src.x[n]; dst.y[to] = src.y[n]; dst.z[to] = src.z[n];
+  dst.ux[to] = src.ux[n]; dst.uy[to] = src.uy[n]; dst.uz[to] = src.uz[n];
+  dst.id[to] = src.id[n];
 }
 
 // -------------------------------------------------------------- migration --
@@ -638,6 +763,23 @@ k_inject_thermal(const Species s, const Geom g, const float3 mins, const unsigne
   s.id[p] = id_base + p;
 }
 
+__global__ void __launch_bounds__(256)
+k_selfcheck_divc(const float* __restrict__ x, const unsigned long long n, const float c, float* __restrict__ out, float* __restrict__ ref) {
+  const DivC d(c);
+  for (unsigned long long i = (blockIdx.x * blockDim.x + threadIdx.x) * 3ull; i < n; i += gridDim.x * blockDim.x * 3ull) {
+    const V3 v = { x[i], i + 1 < n ? x[i + 1] : 1.0f, i + 2 < n ? x[i + 2] : 1.0f };
+    const V3 q = d(v);
+    const V3 r = v / c;
+    out[i] = q.x; ref[i] = r.x;
+    if (i + 1 < n) { out[i + 1] = q.y; ref[i + 1] = r.y; }
+    if (i + 2 < n) { out[i + 2] = q.z; ref[i + 2] = r.z; }
+  }
+}
+void launch_selfcheck_divc(const float* x, unsigned long long n, float c, float* out, float* ref) {
+  k_selfcheck_divc<<<1184, 256, 0, ctx().stream>>>(x, n, c, out, ref);
+  B2P_LAUNCH_CHECK();
+}
+
 // ---------------------------------------------------------------- launchers --
 static unsigned blocks_for(size_t n) { return unsigned((n + 255) / 256); }
 
@@ -652,7 +794,7 @@ void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g,
                  uint2* masks, const float mins[3], const float maxs[3], float4* Jc, float charge) {
   ProfScope prof_(KC_PUSH, double(s.n));
   if (!s.n) return;
-  PushArgs a{ s, nod, g, make_float3(origo[0], origo[1], origo[2]), cfl, qm };
+  PushArgs a{ tuning().agg_min, s, nod, g, make_float3(origo[0], origo[1], origo[2]), cfl, qm };
   const float3 mn = make_float3(mins[0], mins[1], mins[2]), mx = make_float3(maxs[0], maxs[1], maxs[2]);
   const unsigned nb = blocks_for(s.n);
   const int minb = tuning().push_minb;
@@ -678,7 +820,7 @@ void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g,
 void launch_deposit(const Species& s, float4* Jc, const Geom& g, const float origo[3], float cfl, float charge) {
   ProfScope prof_(KC_DEPOSIT, double(s.n));
   if (!s.n) return;
-  DepositArgs a{ s, Jc, g, make_float3(origo[0], origo[1], origo[2]), cfl, charge };
+  DepositArgs a{ tuning().agg_min, s, Jc, g, make_float3(origo[0], origo[1], origo[2]), cfl, charge };
   const unsigned nb = blocks_for(s.n);
   const int minb = tuning().deposit_minb, agg = tuning().deposit_agg;
   if (agg) {
@@ -734,6 +876,43 @@ int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsi
   B2P_CUDA(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, k, int(n), 0, end_bit, ctx().stream));
   count_launch((end_bit + 7) / 8 + 2);
   return k.selector;
+}
+
+size_t scan_temp_bytes(unsigned n) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, static_cast<unsigned*>(nullptr), static_cast<unsigned*>(nullptr), int(n), ctx().stream);
+  return bytes;
+}
+// steps 1-2 of the counting sort: keys, arrival ranks, offs = exclusive scan of the per-key
+// populations (nkeys alive keys + the dead key + one pad entry), *max_pop = largest alive population
+void launch_sort_count_scan(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* rank, unsigned* cnt,
+                            unsigned* offs, unsigned nkeys, void* temp, size_t temp_bytes, unsigned* max_pop) {
+  if (!s.n) return;
+  {
+    ProfScope prof_(KC_SORT_KEYS, double(s.n));
+    B2P_CUDA(cudaMemsetAsync(cnt, 0, (size_t(nkeys) + 2) * sizeof(unsigned), ctx().stream));
+    B2P_CUDA(cudaMemsetAsync(max_pop, 0, sizeof(unsigned), ctx().stream));
+    k_sort_count<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, g, make_float3(origo[0], origo[1], origo[2]), keys, rank, cnt, nkeys);
+    B2P_LAUNCH_CHECK();
+  }
+  ProfScope prof_(KC_RADIX_SORT, double(s.n));
+  B2P_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, cnt, offs, int(nkeys + 2), ctx().stream));
+  count_launch(1);
+  k_max_count<<<std::min(blocks_for(nkeys), 296u), 256, 0, ctx().stream>>>(cnt, nkeys, max_pop);
+  B2P_LAUNCH_CHECK();
+}
+// steps 3-4
+void launch_sort_scatter_place(const Species& src, const Species& dst, const unsigned* keys, const unsigned* rank,
+                               const unsigned* offs, unsigned* members, unsigned dead_key) {
+  if (!src.n) return;
+  {
+    ProfScope prof_(KC_RADIX_SORT, double(src.n));
+    k_sort_scatter<<<blocks_for(src.n), 256, 0, ctx().stream>>>(keys, rank, offs, members, src.n);
+    B2P_LAUNCH_CHECK();
+  }
+  ProfScope prof_(KC_GATHER, double(src.n));
+  k_sort_place<<<blocks_for(src.n), 256, 0, ctx().stream>>>(src, dst, keys, rank, offs, members, dead_key);
+  B2P_LAUNCH_CHECK();
 }
 
 void launch_gather(const Species& src, const Species& dst, const unsigned* perm) {

@@ -40,6 +40,13 @@ int sort_pairs(void* temp, size_t temp_bytes, unsigned* keys[2], unsigned* vals[
 size_t sort_keys64_temp_bytes(unsigned n, int end_bit);
 int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit);
 void launch_gather(const Species& src, const Species& dst, const unsigned* perm);
+// counting sort by cell key (fast path of sort_particles; particles.cu)
+constexpr unsigned SORT_MAX_CELL_POP = 512;   // largest cell population the quadratic placement step is used for
+size_t scan_temp_bytes(unsigned n);
+void launch_sort_count_scan(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* rank, unsigned* cnt,
+                            unsigned* offs, unsigned nkeys, void* temp, size_t temp_bytes, unsigned* max_pop);
+void launch_sort_scatter_place(const Species& src, const Species& dst, const unsigned* keys, const unsigned* rank,
+                               const unsigned* offs, unsigned* members, unsigned dead_key);
 void launch_make_masks(const Species& s, uint2* masks, const float mins[3], const float maxs[3]);
 void launch_collect_leavers(const void* jobs, unsigned ncont, unsigned max_words, unsigned long long* list, unsigned* list_count,
                             unsigned list_cap, unsigned* last_alive, unsigned* cont_count);
@@ -47,6 +54,7 @@ void launch_gather_outgoing(const unsigned long long* sorted, unsigned total, co
 void launch_last_alive(const unsigned long long* id, unsigned n, unsigned* last_alive);
 void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, const float wmin[3], const float wmax[3],
                    const Geom& g, float cfl);
+void launch_selfcheck_divc(const float* x, unsigned long long n, float c, float* out, float* ref);
 void launch_fill_dead(unsigned long long* id, unsigned begin, unsigned end);
 void launch_kinetic_energy(const Species& s, double* out);
 void launch_inject_thermal(const Species& s, const Geom& g, const float mins[3], unsigned ppc, float theta,

@@ -142,6 +142,74 @@ def test_sort_bit_exact():
     assert np.all(np.diff(k.astype(np.int64)) >= 0)
 
 
+@pytest.mark.parametrize("case", ["uniform-200k", "nearly-sorted", "crowded-cell", "radix-path"])
+def test_sort_bit_exact_cases(case):
+    """Counting sort (uniform / nearly sorted input), its fallback to the radix sort when one cell is
+    crowded, and the radix path forced by option: all must give the oracle's stable order."""
+    import ctypes as C
+    from runko_b200._lib import check
+    rng = np.random.default_rng(55)
+    n_cells = (12, 9, 14)
+    conf = pic_conf(n_cells=n_cells)
+    org, tile = make_pair(conf)
+    L = rb.lib()
+    if case == "radix-path":
+        check(L.b2p_set_option(b"sort_counting", 0))
+    try:
+        n = 200000 if case != "crowded-cell" else 60000
+        load_particles(rng, org, tile, conf, n, dead_frac=0.07)
+        if case == "crowded-cell":
+            # 3000 particles in one cell: over SORT_MAX_CELL_POP -> radix fallback for that container
+            for sp in range(2):
+                x, y, z, ux, uy, uz, ids = org.get_particles(0, sp, alive_only=False)
+                x[1000:4000] = 5.25 + 0.5 * rng.random(3000).astype(np.float32)
+                y[1000:4000] = 4.25
+                z[1000:4000] = 7.5
+                org.set_particles(0, sp, x, y, z, ux, uy, uz, ids)
+                tile.set_particles_raw(sp, x, y, z, ux, uy, uz, ids)
+        rounds = 3 if case == "nearly-sorted" else 1
+        for r in range(rounds):
+            org.tile_op(0, "sort_particles")
+            tile.sort_particles()
+            compare_particles(org, tile)
+            if r + 1 < rounds:                       # drift a little, kill a few, sort again
+                for _ in range(2):
+                    org.tile_op(0, "push_particles")
+                    tile.push_particles()
+                compare_particles(org, tile)
+        k = tile.sort_keys(1)
+        assert np.all(np.diff(k.astype(np.int64)) >= 0)
+    finally:
+        check(L.b2p_set_option(b"sort_counting", 1))
+
+
+def test_const_division_bit_exact():
+    """The pushers' constant-divisor division (particles.cu: DivC) equals the IEEE quotient bit for bit:
+    random mantissas over the whole exponent range, values around the range-test thresholds, zeros of
+    both signs, denormals, inf/nan, for several divisors incl. ones outside the fast-path range."""
+    import ctypes as C
+    from runko_b200._lib import check
+    rng = np.random.default_rng(77)
+    L = rb.lib()
+    n = 1 << 22
+    bits = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    x = bits.view(np.float32).copy()
+    special = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-38, 2.0 ** -100, np.nextafter(np.float32(2.0 ** -100), np.float32(0)),
+                        2.0 ** 100, np.nextafter(np.float32(2.0 ** 100), np.float32(np.inf)), np.inf, -np.inf, np.nan, 3.4e38],
+                       np.float32)
+    x[:special.size] = special
+    x[100:100 + (1 << 20)] = (rng.standard_normal(1 << 20) * 0.7).astype(np.float32)     # the physical range
+    for c in (0.45, 0.45 / 2, 1.0, 0.999999, 3.0, 1.9999999, 1e-3, 7.7e5, 1e-7, 1e9, float(np.float32(1) / np.float32(3))):
+        out, ref = np.empty(n, np.float32), np.empty(n, np.float32)
+        check(L.b2p_selfcheck_const_division(x.ctypes.data_as(C.c_void_p), n, C.c_float(c), out.ctypes.data_as(C.c_void_p),
+                                             ref.ctypes.data_as(C.c_void_p)))
+        host = x / np.float32(c)
+        same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
+        assert same.all(), f"c={c}: {np.count_nonzero(~same)} mismatches vs device IEEE division, e.g. x={x[~same][:4]}"
+        ok_host = (ref.view(np.uint32) == host.view(np.uint32)) | (np.isnan(ref) & np.isnan(host))
+        assert ok_host.all(), f"c={c}: device IEEE division differs from numpy"
+
+
 def test_sort_empty_and_single():
     conf = pic_conf()
     tile = rb.PicTile((0, 0, 0), conf)

@@ -1,0 +1,13 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+( timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log )
+tail -n 15 gpurun_out/pytest_gpu.log
+timeout 900 python tools/microbench.py --cells 256 --laps 5 --out gpurun_out/micro15.json \
+  "push_streams=1,sort_streams=1,agg_min=6" "agg_min=1" "agg_min=4" "agg_min=8" "agg_min=12" "agg_min=33" "agg_min=6,sort_counting=0" "sort_counting=1,push_streams=4,sort_streams=4" 2>&1 | grep -v "^ *per lap"
+python - <<'PY'
+import json
+for r in json.load(open('gpurun_out/micro15.json')):
+    print(r['setting'], {k:round(v,3) for k,v in r['ms_per_lap_by_class'].items()})
+    print('   ', [ (q['lap_mod5'], q['ms'], q['push_us']) for q in r['per_lap']])
+PY
