@@ -127,7 +127,7 @@ ProfScope::~ProfScope() {
 
 // process-level scratch shared by all tiles (all work is ordered on one stream)
 constexpr int MAX_WORKERS = 4;
-constexpr int SORT_SLOTS = 2 * MAX_WORKERS;
+constexpr int SORT_SLOTS = MAX_WORKERS;
 struct SortSet {                // scratch of one container in flight in the counting sort
   DBuf<unsigned> keys, rank, members, cnt, offs;
   DBuf<unsigned char> temp;
@@ -486,6 +486,29 @@ static void sort_radix(b2p_tile* t, Container& c, int w) {
   c.touch();
 }
 
+// Largest cell population seen by the previous counting sort of a container, copied to page-locked
+// host memory without a synchronisation.  It only steers the choice between the counting sort
+// (correct for any input, quadratic in the cell population) and the radix sort, so a value that is
+// one sort old — or has not landed yet — is as good as a fresh one.
+struct PopHints {
+  static constexpr unsigned CHUNK = 4096, UNKNOWN = 0xFFFFFFFFu;
+  std::vector<unsigned*> chunks;
+  unsigned used = 0;
+  unsigned* slot(int& idx) {
+    if (idx < 0) {
+      if (used % CHUNK == 0) {
+        unsigned* c = nullptr;
+        B2P_CUDA(cudaMallocHost(&c, CHUNK * sizeof(unsigned)));
+        for (unsigned q = 0; q < CHUNK; ++q) c[q] = UNKNOWN;
+        chunks.push_back(c);
+      }
+      idx = int(used++);
+    }
+    return chunks[size_t(idx) / CHUNK] + size_t(idx) % CHUNK;
+  }
+};
+static PopHints& pop_hints() { static PopHints* h = new PopHints; return *h; }
+
 void phase_sort(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
   struct Item { b2p_tile* t; Container* c; };
@@ -498,62 +521,52 @@ void phase_sort(const std::vector<b2p_tile*>& tiles) {
   const bool counting = tuning().sort_counting != 0;
   Workers& wk = workers();
   cudaStream_t main_stream = ctx().stream;
-  if (nw > 1) wk.init();
-  auto fork = [&]() {
-    if (nw == 1) return;
+  if (nw > 1) {
+    wk.init();
     B2P_CUDA(cudaEventRecord(wk.fork, main_stream));
     for (int w = 0; w < nw; ++w) B2P_CUDA(cudaStreamWaitEvent(wk.s[w], wk.fork, 0));
-  };
-  auto join = [&]() {
-    if (nw == 1) return;
+  }
+  s.sort_maxpop.reserve(MAX_WORKERS);
+  for (size_t q = 0; q < items.size(); ++q) {
+    const Item& it = items[q];
+    const int w = int(q % size_t(nw));
+    StreamScope on(nw > 1 ? wk.s[w] : main_stream);
+    Container& c = *it.c;
+    volatile unsigned* hint = pop_hints().slot(c.pop_hint_slot);
+    if (!counting || (*hint != PopHints::UNKNOWN && *hint > SORT_RADIX_POP)) {
+      sort_radix(it.t, c, w);
+      // let a crowded container return to the counting sort once it has thinned out: probe again
+      // every few sorts (the probe itself is the cheap first half of the counting sort)
+      if (counting && ++c.radix_sorts_since_probe >= 8) { c.radix_sorts_since_probe = 0; *hint = PopHints::UNKNOWN; }
+      continue;
+    }
+    SortSet& ss = s.sort_set[w];
+    const unsigned nkeys = it.t->g.Ch;
+    ss.keys.reserve(c.n); ss.rank.reserve(c.n); ss.members.reserve(c.n);
+    ss.cnt.reserve(size_t(nkeys) + 2); ss.offs.reserve(size_t(nkeys) + 2);
+    const size_t tb = scan_temp_bytes(nkeys + 2);
+    ss.temp.reserve(tb);
+    launch_sort_count_scan(c.view(), it.t->g, it.t->origo, ss.keys.p, ss.rank.p, ss.cnt.p, ss.offs.p, nkeys, ss.temp.p, tb,
+                           s.sort_maxpop.p + w);
+    const bool first = *hint == PopHints::UNKNOWN;
+    B2P_CUDA(cudaMemcpyAsync(const_cast<unsigned*>(hint), s.sort_maxpop.p + w, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
+    if (first) {
+      // no history for this container: wait for its population once
+      B2P_CUDA(cudaStreamSynchronize(ctx().stream));
+      if (*hint > SORT_RADIX_POP) { sort_radix(it.t, c, w); continue; }
+    }
+    Container& spare = s.spare_w[w];
+    spare.reserve(c.capacity(), /*exact=*/true);
+    spare.n = c.n;
+    launch_sort_scatter_place(c.view(), spare.view(), ss.keys.p, ss.rank.p, ss.offs.p, ss.members.p, ss.cnt.p, nkeys);
+    swap_storage(c, spare);
+    c.touch();
+  }
+  if (nw > 1)
     for (int w = 0; w < nw; ++w) {
       B2P_CUDA(cudaEventRecord(wk.join[w], wk.s[w]));
       B2P_CUDA(cudaStreamWaitEvent(main_stream, wk.join[w], 0));
     }
-  };
-  s.sort_maxpop.reserve(SORT_SLOTS);
-  const int batch = std::min(SORT_SLOTS, 2 * nw);
-  for (size_t b0 = 0; b0 < items.size(); b0 += size_t(batch)) {
-    const int nb = int(std::min<size_t>(size_t(batch), items.size() - b0));
-    unsigned maxpop[SORT_SLOTS] = {};
-    if (counting) {
-      fork();
-      for (int q = 0; q < nb; ++q) {
-        const Item& it = items[b0 + q];
-        StreamScope on(nw > 1 ? wk.s[q % nw] : main_stream);
-        SortSet& ss = s.sort_set[q];
-        const unsigned nkeys = it.t->g.Ch;
-        ss.keys.reserve(it.c->n); ss.rank.reserve(it.c->n); ss.members.reserve(it.c->n);
-        ss.cnt.reserve(size_t(nkeys) + 2); ss.offs.reserve(size_t(nkeys) + 2);
-        const size_t tb = scan_temp_bytes(nkeys + 2);
-        ss.temp.reserve(tb);
-        launch_sort_count_scan(it.c->view(), it.t->g, it.t->origo, ss.keys.p, ss.rank.p, ss.cnt.p, ss.offs.p, nkeys, ss.temp.p, tb,
-                               s.sort_maxpop.p + q);
-      }
-      join();
-      d2h(maxpop, s.sort_maxpop.p, size_t(nb));
-      sync();
-    }
-    fork();
-    for (int q = 0; q < nb; ++q) {
-      const Item& it = items[b0 + q];
-      const int w = q % nw;
-      StreamScope on(nw > 1 ? wk.s[w] : main_stream);
-      if (counting && maxpop[q] <= SORT_MAX_CELL_POP) {
-        SortSet& ss = s.sort_set[q];
-        Container& c = *it.c;
-        Container& spare = s.spare_w[w];
-        spare.reserve(c.capacity(), /*exact=*/true);
-        spare.n = c.n;
-        launch_sort_scatter_place(c.view(), spare.view(), ss.keys.p, ss.rank.p, ss.offs.p, ss.members.p, it.t->g.Ch);
-        swap_storage(c, spare);
-        c.touch();
-      } else {
-        sort_radix(it.t, *it.c, w);
-      }
-    }
-    join();
-  }
 }
 
 // pic/tile_communication.c++:68-96 + pic/particle.c++:199-348, batched over tiles

@@ -19,6 +19,8 @@ struct Container {
   unsigned P = 0;
   DBuf<uint2> masks;          // per 32 slots: {leaving, staying} ballots of the tile box test (particles.cu)
   bool masks_valid = false;   // masks describe the current container contents
+  int pop_hint_slot = -1;     // page-locked slot with the largest cell population of the last counting sort (host.cu)
+  int radix_sorts_since_probe = 0;
   void touch() { P_valid = false; masks_valid = false; }   // contents changed
   uint2* mask_words();        // sized for the current n (whole blocks of 256 slots)
   Species view() const { return Species{ x.p, y.p, z.p, ux.p, uy.p, uz.p, id.p, n }; }

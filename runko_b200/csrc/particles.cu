@@ -311,6 +311,41 @@ __device__ __forceinline__ void deposit_split_nodal(const Zigzag& z, float* __re
 }
 
 // ----------------------------------------------------------------- pushers --
+// Loads the compiler may neither drop nor move into a conditional block.
+__device__ __forceinline__ float ld_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_pinned(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+// L2 prefetch of the 256 slots block `blk` will read (8 KB over the seven streams: 64 lines of
+// 128 B, one per thread of the first two warps).  Blocks run roughly in index order, so asking for
+// the block PREFETCH_BLOCKS ahead (more than one wave of resident blocks) turns that block's
+// DRAM latency at its head into an L2 hit.
+constexpr unsigned PREFETCH_BLOCKS = 1024;
+__device__ __forceinline__ void prefetch_streams(const Species& s, const unsigned blk) {
+  const unsigned t = threadIdx.x;
+  if (t >= 64) return;
+  const size_t base = size_t(blk) * 256;
+  const void* p;
+  if (t < 48) {
+    const unsigned which = t >> 3;
+    const float* f = which == 0 ? s.x : which == 1 ? s.y : which == 2 ? s.z : which == 3 ? s.ux : which == 4 ? s.uy : s.uz;
+    const size_t e = base + (t & 7u) * 32u;
+    if (e >= s.n) return;
+    p = f + e;
+  } else {
+    const size_t e = base + (t - 48u) * 16u;
+    if (e >= s.n) return;
+    p = s.id + e;
+  }
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
 struct PushArgs {
   int agg_min;    // see DepositArgs
   Species s;
@@ -330,12 +365,22 @@ template <int PUSHER, int MINB, int FUSE>
 __global__ void __launch_bounds__(256, MINB)
 k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float3 mx, float4* __restrict__ Jc, const float charge) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool alive = n < a.s.n && a.s.id[n] != DEAD;               // :33
+  prefetch_streams(a.s, blockIdx.x + PREFETCH_BLOCKS);
+  // All seven streams are requested before the id is looked at (pinned loads: the compiler must
+  // not sink the six value loads below the dead-slot test, which would put two DRAM round trips
+  // in series); dead slots hold unspecified but readable values.
+  unsigned long long id = DEAD;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  V3 u = { 0.f, 0.f, 0.f };
+  if (n < a.s.n) {
+    id = ld_pinned(a.s.id + n);
+    px = ld_pinned(a.s.x + n); py = ld_pinned(a.s.y + n); pz = ld_pinned(a.s.z + n);
+    u.x = ld_pinned(a.s.ux + n); u.y = ld_pinned(a.s.uy + n); u.z = ld_pinned(a.s.uz + n);
+  }
+  const bool alive = id != DEAD;                                   // :33
   float nx = 0.f, ny = 0.f, nz = 0.f;
   V3 vel = { 0.f, 0.f, 0.f };
   if (alive) {
-  const float px = a.s.x[n], py = a.s.y[n], pz = a.s.z[n];
-  const V3 u = { a.s.ux[n], a.s.uy[n], a.s.uz[n] };
   const EB eb = interpolate(a.nod, a.g, a.origo, px, py, pz);
   const float cfl = a.cfl, qm = a.qm;
   const DivC div_cfl(cfl);
@@ -464,40 +509,52 @@ k_gather(const Species src, const Species dst, const unsigned* __restrict__ perm
 // The contract of ParticleContainer::sort is "stable sort by cell key, dead slots last"
 // (pic/particle.h:575-703).  Keys are lattice cell indices < Ch with a few tens of particles per
 // key, so instead of a general radix sort of (key, slot) pairs the container is sorted by counting:
-//   1. k_sort_count   key[n], rank[n] = arrival order among the particles of that key (warp-
-//                     aggregated atomics on cnt[key]; NOT in slot order yet)
+//   1. k_sort_count   key[n], rank[n] = arrival order among the particles of that key (one atomic
+//                     on cnt[key] per run of equal keys inside a warp; NOT in slot order yet)
 //   2. exclusive scan of cnt -> offs (CUB DeviceScan over Ch + 2 counters) and the largest
-//                     population of a cell
+//                     population of a cell (a hint for the NEXT sort of this container)
 //   3. k_sort_scatter members[offs[key] + rank] = n: the slots of every cell, in arrival order
-//   4. k_sort_place   the stable rank of slot n inside its cell is the number of members with a
-//                     smaller slot index (a scan of the cell's short member list); the seven
-//                     streams are moved straight to dst[offs[key] + stable rank].
-// Result: exactly the stable order.  Dead slots (key Ch, clamped like the radix path) keep their
-// arrival order — the contents of dead slots are unspecified in the reference.  Step 4 is
-// quadratic in the population of a cell, so the host takes this path only when no cell holds more
-// than SORT_MAX_CELL_POP particles and falls back to the radix sort otherwise.
+//   4. k_sort_fix     one thread per cell puts its (short, almost ordered) member list into
+//                     ascending slot order by insertion; cells with more than SORT_THREAD_POP
+//                     members are queued for k_sort_fix_big (one block per cell, rank by counting)
+//   5. k_gather       dst[p] = src[members[p]]: coalesced writes, reads within a few hundred slots
+//                     of p for a container that was sorted a few laps ago.
+// Result: exactly the stable order for any input.  Dead slots (key Ch, clamped like the radix
+// path) keep their arrival order — the contents of dead slots are unspecified in the reference.
+// Step 4 is quadratic in the population of a cell, so the host routes containers whose last known
+// largest cell population exceeds SORT_RADIX_POP to the general radix sort instead.
 __global__ void __launch_bounds__(256)
 k_sort_count(const Species s, const Geom g, const float3 origo, unsigned* __restrict__ keys, unsigned* __restrict__ rank,
              unsigned* __restrict__ cnt, const unsigned dead_key) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= s.n) return;
+  const bool in = n < s.n;
   unsigned key = dead_key;
-  if (s.id[n] != DEAD) {
-    const unsigned i = __float2uint_rz(s.x[n] - origo.x);
-    const unsigned j = __float2uint_rz(s.y[n] - origo.y);
-    const unsigned k = __float2uint_rz(s.z[n] - origo.z);
+  unsigned long long id = DEAD;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  if (in) { id = ld_pinned(s.id + n); px = ld_pinned(s.x + n); py = ld_pinned(s.y + n); pz = ld_pinned(s.z + n); }
+  if (id != DEAD) {
+    const unsigned i = __float2uint_rz(px - origo.x);
+    const unsigned j = __float2uint_rz(py - origo.y);
+    const unsigned k = __float2uint_rz(pz - origo.z);
     key = (i * unsigned(g.Hx[1]) + j) * unsigned(g.Hx[2]) + k;
     if (key > dead_key) key = dead_key;
   }
-  // one atomic per distinct key of the warp (long runs of equal keys after a sort / in the dead tail)
-  const unsigned peers = __match_any_sync(__activemask(), key);
+  // one atomic per run of equal keys in the warp (a container sorted a few laps ago is made of such runs)
   const unsigned lane = threadIdx.x & 31;
-  const int leader = __ffs(peers) - 1;
+  const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = lane == 0 || key != prev || !in;
+  const unsigned hm = __ballot_sync(0xffffffffu, head);
+  const unsigned start = 31u - __clz(hm & (0xFFFFFFFFu >> (31u - lane)));     // my run's first lane
+  const unsigned above = lane == 31 ? 0u : (hm >> (lane + 1));
+  const unsigned len = above ? unsigned(__ffs(above)) : 32u - lane;            // for a head: length of its run
+  // Dead slots are not ranked: they end up behind the alive particles in any order (k_sort_gather).
   unsigned base = 0;
-  if (int(lane) == leader) base = atomicAdd(&cnt[key], unsigned(__popc(peers)));
-  base = __shfl_sync(peers, base, leader);
-  keys[n] = key;
-  rank[n] = base + __popc(peers & ((1u << lane) - 1u));
+  if (head && key != dead_key) base = atomicAdd(&cnt[key], len);
+  base = __shfl_sync(0xffffffffu, base, start);
+  if (in) {
+    keys[n] = key;
+    rank[n] = base + (lane - start);
+  }
 }
 
 // largest population among the alive keys [0, nkeys)
@@ -512,31 +569,122 @@ k_max_count(const unsigned* __restrict__ cnt, const unsigned nkeys, unsigned* __
 
 __global__ void __launch_bounds__(256)
 k_sort_scatter(const unsigned* __restrict__ keys, const unsigned* __restrict__ rank, const unsigned* __restrict__ offs,
-               unsigned* __restrict__ members, const unsigned n_total) {
+               unsigned* __restrict__ members, const unsigned n_total, const unsigned dead_key) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_total) return;
-  members[offs[keys[n]] + rank[n]] = n;
+  const unsigned key = keys[n];
+  if (key != dead_key) members[offs[key] + rank[n]] = n;
 }
 
+// Step 5: dst[p] = src[members[p]] for the offs[dead_key] alive particles; the slots behind them are
+// dead.  Two slots per thread (256 apart) keep fourteen independent gathers in flight.
 __global__ void __launch_bounds__(256)
-k_sort_place(const Species src, const Species dst, const unsigned* __restrict__ keys, const unsigned* __restrict__ rank,
-             const unsigned* __restrict__ offs, const unsigned* __restrict__ members, const unsigned dead_key) {
-  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= src.n) return;
-  const unsigned key = keys[n];
-  const unsigned lo = offs[key];
-  unsigned to;
-  if (key == dead_key) {
-    to = lo + rank[n];
-  } else {
-    const unsigned hi = offs[key + 1];
-    unsigned before = 0;
-    for (unsigned t = lo; t < hi; ++t) before += unsigned(__ldg(members + t) < n);
-    to = lo + before;
+k_sort_gather(const Species src, const Species dst, const unsigned* __restrict__ members, const unsigned* __restrict__ n_alive) {
+  const unsigned n0 = blockIdx.x * 512u + threadIdx.x, n1 = n0 + 256u;
+  const unsigned na = *n_alive;
+  const bool a0 = n0 < na, a1 = n1 < na;
+  const unsigned p0 = a0 ? members[n0] : 0u, p1 = a1 ? members[n1] : 0u;
+  float f0[6], f1[6];
+  unsigned long long i0 = DEAD, i1 = DEAD;
+  if (a0) { f0[0] = src.x[p0]; f0[1] = src.y[p0]; f0[2] = src.z[p0]; f0[3] = src.ux[p0]; f0[4] = src.uy[p0]; f0[5] = src.uz[p0]; i0 = src.id[p0]; }
+  if (a1) { f1[0] = src.x[p1]; f1[1] = src.y[p1]; f1[2] = src.z[p1]; f1[3] = src.ux[p1]; f1[4] = src.uy[p1]; f1[5] = src.uz[p1]; i1 = src.id[p1]; }
+  if (a0) { dst.x[n0] = f0[0]; dst.y[n0] = f0[1]; dst.z[n0] = f0[2]; dst.ux[n0] = f0[3]; dst.uy[n0] = f0[4]; dst.uz[n0] = f0[5]; }
+  if (a1) { dst.x[n1] = f1[0]; dst.y[n1] = f1[1]; dst.z[n1] = f1[2]; dst.ux[n1] = f1[3]; dst.uy[n1] = f1[4]; dst.uz[n1] = f1[5]; }
+  if (n0 < src.n) dst.id[n0] = i0;
+  if (n1 < src.n) dst.id[n1] = i1;
+}
+
+// Step 4: ascending slot order inside every alive cell.  A block takes blockDim.x (<= 256)
+// consecutive cells — one contiguous piece of `members` — and stages the piece and the cells'
+// offsets in shared memory with coalesced loads.  One thread per cell labels its members with the
+// cell's local index; then one thread per MEMBER flags its cell if it sits behind a larger slot
+// index, and the members of flagged cells count the members of their cell with a smaller slot
+// index (the lanes of a warp read at most a few distinct shared-memory words per step:
+// broadcasts) and write themselves to their stable position.  Cells with more than
+// SORT_THREAD_POP members, and all cells of a piece that does not fit the staging buffer, are
+// queued in `big` = {count, cells...} for k_sort_fix_big.
+constexpr unsigned SORT_FIX_STAGE = 8192;   // entries (32 KB + 8 KB of labels)
+__global__ void __launch_bounds__(256)
+k_sort_fix(const unsigned* __restrict__ offs, unsigned* __restrict__ members, const unsigned nkeys, unsigned* __restrict__ big) {
+  __shared__ unsigned sm[SORT_FIX_STAGE];
+  __shared__ unsigned char cellof[SORT_FIX_STAGE];
+  __shared__ unsigned so[257];
+  __shared__ unsigned char unsorted[256];
+  const unsigned c0 = blockIdx.x * blockDim.x, nc = min(blockDim.x, nkeys - c0);
+  for (unsigned t = threadIdx.x; t <= nc; t += blockDim.x) so[t] = offs[c0 + t];
+  unsorted[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned lo0 = so[0], total = so[nc] - lo0;
+  const bool staged = total <= SORT_FIX_STAGE;
+  if (threadIdx.x < nc) {
+    const unsigned lo = so[threadIdx.x] - lo0, hi = so[threadIdx.x + 1] - lo0;
+    if (hi - lo >= 2 && (!staged || hi - lo > SORT_THREAD_POP)) big[1 + atomicAdd(big, 1u)] = c0 + threadIdx.x;
+    if (staged)
+      for (unsigned t = lo; t < hi; ++t) cellof[t] = static_cast<unsigned char>(threadIdx.x);
   }
-  dst.x[to] = src.x[n]; dst.y[to] = src.y[n]; dst.z[to] = src.z[n];
-  dst.ux[to] = src.ux[n]; dst.uy[to] = src.uy[n]; dst.uz[to] = src.uz[n];
-  dst.id[to] = src.id[n];
+  if (!staged) return;
+  for (unsigned t = threadIdx.x; t < total; t += blockDim.x) sm[t] = members[lo0 + t];
+  __syncthreads();
+  for (unsigned e = threadIdx.x; e < total; e += blockDim.x) {
+    const unsigned a = cellof[e];
+    if (e > so[a] - lo0 && sm[e - 1] > sm[e]) unsorted[a] = 1;
+  }
+  __syncthreads();
+  for (unsigned e = threadIdx.x; e < total; e += blockDim.x) {
+    const unsigned a = cellof[e];
+    if (!unsorted[a]) continue;
+    const unsigned lo = so[a] - lo0, hi = so[a + 1] - lo0;
+    if (hi - lo > SORT_THREAD_POP) continue;
+    const unsigned v = sm[e];
+    unsigned before = 0;
+    for (unsigned q = lo; q < hi; ++q) before += unsigned(sm[q] < v);
+    if (lo + before != e) members[lo0 + lo + before] = v;
+  }
+}
+
+// Queued cells: one warp per cell, rank by counting.  Up to 32 members sit one per lane and are
+// ranked over shuffles; up to 128 sit four per lane and are ranked against the list re-read
+// through L1 (warp-uniform addresses); larger cells go through `tmp` (>= container size; the
+// arrival ranks are no longer needed).  All ranks are known before the first member is rewritten.
+__global__ void __launch_bounds__(256)
+k_sort_fix_big(const unsigned* __restrict__ offs, unsigned* __restrict__ members, unsigned* __restrict__ tmp,
+               const unsigned* __restrict__ big) {
+  const unsigned nbig = big[0];
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < nbig; e += nwarps) {
+    const unsigned c = big[1 + e];
+    const unsigned lo = offs[c], pop = offs[c + 1] - lo;
+    if (pop <= 32) {
+      const unsigned v = lane < pop ? members[lo + lane] : 0xFFFFFFFFu;
+      unsigned before = 0;
+      for (unsigned q = 0; q < pop; ++q) before += unsigned(__shfl_sync(0xffffffffu, v, int(q)) < v);
+      if (lane < pop && before != lane) members[lo + before] = v;
+    } else if (pop <= 128) {
+      unsigned v[4], before[4] = { 0u, 0u, 0u, 0u };
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[r] = lane + 32u * r < pop ? members[lo + lane + 32u * r] : 0xFFFFFFFFu;
+      for (unsigned q = 0; q < pop; ++q) {
+        const unsigned w = members[lo + q];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) before[r] += unsigned(w < v[r]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (lane + 32u * r < pop) members[lo + before[r]] = v[r];
+    } else {
+      for (unsigned t = lane; t < pop; t += 32) {
+        const unsigned v = members[lo + t];
+        unsigned before = 0;
+        for (unsigned q = 0; q < pop; ++q) before += unsigned(members[lo + q] < v);
+        tmp[lo + before] = v;
+      }
+      __syncwarp();
+      for (unsigned t = lane; t < pop; t += 32) members[lo + t] = tmp[lo + t];
+    }
+    __syncwarp();
+  }
 }
 
 // -------------------------------------------------------------- migration --
@@ -901,17 +1049,27 @@ void launch_sort_count_scan(const Species& s, const Geom& g, const float origo[3
   k_max_count<<<std::min(blocks_for(nkeys), 296u), 256, 0, ctx().stream>>>(cnt, nkeys, max_pop);
   B2P_LAUNCH_CHECK();
 }
-// steps 3-4
-void launch_sort_scatter_place(const Species& src, const Species& dst, const unsigned* keys, const unsigned* rank,
-                               const unsigned* offs, unsigned* members, unsigned dead_key) {
+// steps 3-5.  `cnt` (nkeys + 2 counters, free after the scan) becomes the queue of crowded cells,
+// `rank` (free after the scatter) the scratch of k_sort_fix_big.
+void launch_sort_scatter_place(const Species& src, const Species& dst, const unsigned* keys, unsigned* rank,
+                               const unsigned* offs, unsigned* members, unsigned* cnt, unsigned nkeys) {
   if (!src.n) return;
   {
     ProfScope prof_(KC_RADIX_SORT, double(src.n));
-    k_sort_scatter<<<blocks_for(src.n), 256, 0, ctx().stream>>>(keys, rank, offs, members, src.n);
+    k_sort_scatter<<<blocks_for(src.n), 256, 0, ctx().stream>>>(keys, rank, offs, members, src.n, nkeys);
+    B2P_LAUNCH_CHECK();
+    B2P_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned), ctx().stream));
+    // cells per block: about half the staging buffer at the container's mean population
+    const unsigned mean = std::max(1u, src.n / std::max(1u, nkeys));
+    unsigned cells = 256;
+    while (cells > 32 && cells * mean > SORT_FIX_STAGE / 2) cells >>= 1;
+    k_sort_fix<<<(nkeys + cells - 1) / cells, cells, 0, ctx().stream>>>(offs, members, nkeys, cnt);
+    B2P_LAUNCH_CHECK();
+    k_sort_fix_big<<<592, 256, 0, ctx().stream>>>(offs, members, rank, cnt);
     B2P_LAUNCH_CHECK();
   }
   ProfScope prof_(KC_GATHER, double(src.n));
-  k_sort_place<<<blocks_for(src.n), 256, 0, ctx().stream>>>(src, dst, keys, rank, offs, members, dead_key);
+  k_sort_gather<<<(src.n + 511) / 512, 256, 0, ctx().stream>>>(src, dst, members, offs + nkeys);
   B2P_LAUNCH_CHECK();
 }
 

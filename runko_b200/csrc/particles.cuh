@@ -41,12 +41,13 @@ size_t sort_keys64_temp_bytes(unsigned n, int end_bit);
 int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit);
 void launch_gather(const Species& src, const Species& dst, const unsigned* perm);
 // counting sort by cell key (fast path of sort_particles; particles.cu)
-constexpr unsigned SORT_MAX_CELL_POP = 512;   // largest cell population the quadratic placement step is used for
+constexpr unsigned SORT_THREAD_POP = 128;    // largest cell whose member list one thread orders by insertion
+constexpr unsigned SORT_RADIX_POP = 4096;    // containers whose last known largest cell exceeds this take the radix sort
 size_t scan_temp_bytes(unsigned n);
 void launch_sort_count_scan(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* rank, unsigned* cnt,
                             unsigned* offs, unsigned nkeys, void* temp, size_t temp_bytes, unsigned* max_pop);
-void launch_sort_scatter_place(const Species& src, const Species& dst, const unsigned* keys, const unsigned* rank,
-                               const unsigned* offs, unsigned* members, unsigned dead_key);
+void launch_sort_scatter_place(const Species& src, const Species& dst, const unsigned* keys, unsigned* rank,
+                               const unsigned* offs, unsigned* members, unsigned* cnt, unsigned nkeys);
 void launch_make_masks(const Species& s, uint2* masks, const float mins[3], const float maxs[3]);
 void launch_collect_leavers(const void* jobs, unsigned ncont, unsigned max_words, unsigned long long* list, unsigned* list_count,
                             unsigned list_cap, unsigned* last_alive, unsigned* cont_count);

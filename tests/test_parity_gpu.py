@@ -142,10 +142,12 @@ def test_sort_bit_exact():
     assert np.all(np.diff(k.astype(np.int64)) >= 0)
 
 
-@pytest.mark.parametrize("case", ["uniform-200k", "nearly-sorted", "crowded-cell", "radix-path"])
+@pytest.mark.parametrize("case", ["uniform-200k", "nearly-sorted", "crowded-cell", "very-crowded-cell", "radix-path"])
 def test_sort_bit_exact_cases(case):
-    """Counting sort (uniform / nearly sorted input), its fallback to the radix sort when one cell is
-    crowded, and the radix path forced by option: all must give the oracle's stable order."""
+    """Counting sort (uniform / nearly sorted input; a crowded cell whose member list is ordered by the
+    block-per-cell kernel), its hand-over to the radix sort when the largest cell exceeds SORT_RADIX_POP
+    (decided from the first probe, then from the previous sort's hint), and the radix path forced by
+    option: all must give the oracle's stable order."""
     import ctypes as C
     from runko_b200._lib import check
     rng = np.random.default_rng(55)
@@ -156,18 +158,20 @@ def test_sort_bit_exact_cases(case):
     if case == "radix-path":
         check(L.b2p_set_option(b"sort_counting", 0))
     try:
-        n = 200000 if case != "crowded-cell" else 60000
+        n = 200000 if "crowded" not in case else 60000
         load_particles(rng, org, tile, conf, n, dead_frac=0.07)
-        if case == "crowded-cell":
-            # 3000 particles in one cell: over SORT_MAX_CELL_POP -> radix fallback for that container
+        if "crowded" in case:
+            # 3000 particles in one cell: over SORT_THREAD_POP -> k_sort_fix_big for that cell;
+            # 9000: over SORT_RADIX_POP -> radix sort for that container
+            m = 3000 if case == "crowded-cell" else 9000
             for sp in range(2):
                 x, y, z, ux, uy, uz, ids = org.get_particles(0, sp, alive_only=False)
-                x[1000:4000] = 5.25 + 0.5 * rng.random(3000).astype(np.float32)
-                y[1000:4000] = 4.25
-                z[1000:4000] = 7.5
+                x[1000:1000 + m] = 5.25 + 0.5 * rng.random(m).astype(np.float32)
+                y[1000:1000 + m] = 4.25
+                z[1000:1000 + m] = 7.5
                 org.set_particles(0, sp, x, y, z, ux, uy, uz, ids)
                 tile.set_particles_raw(sp, x, y, z, ux, uy, uz, ids)
-        rounds = 3 if case == "nearly-sorted" else 1
+        rounds = 1 if case in ("uniform-200k", "radix-path") else 3
         for r in range(rounds):
             org.tile_op(0, "sort_particles")
             tile.sort_particles()
