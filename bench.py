@@ -25,6 +25,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version / debug lines go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 BYTES_PER_PARTICLE_PUSH = 56.0      # R pos,vel,id (32) + W pos,vel (24)
 BYTES_PER_PARTICLE_DEPOSIT = 32.0   # R pos,vel,id

@@ -63,13 +63,14 @@ struct ProfScope {
 // Kernel-variant knobs (b2p_set_option / env B2P_OPTS="name=value,..."): results are identical for
 // every setting, only the launch shape / aggregation strategy changes.
 struct Tuning {
-  int push_minb = 5;      // __launch_bounds__(256, minb) variant of k_push: 5, 6 or 8 resident blocks per SM
+  int push_minb = 6;      // __launch_bounds__(256, minb) variant of k_push: 5, 6 or 8 resident blocks per SM
   int deposit_minb = 4;   // same for k_deposit_zigzag: 4, 6 or 8
   int deposit_agg = 1;    // warp-level run aggregation before the REDs
   int agg_min = 6;        // ... a step is taken when at least this many lanes of the warp fold
   int filter_chunk = 35;  // i-planes per thread column of k_filter_binomial2
   int push_streams = 4;   // worker streams the per-tile particle phase is round-robined over (1 = library stream only)
   int sort_streams = 4;   // worker streams the per-container sort is round-robined over
+  int push_group = 8;     // tiles per launch of the small kernels around the pushes (nodal means, scratch clear, edge gather)
   int sort_counting = 1;  // counting sort by cell (0: always the general radix sort)
   int defer_tile_calls = 1;   // batch consecutive per-tile calls of one kind (host.cu: deferred per-tile calls)
   int fuse_deposit = 1;   // deposit the stayers' current inside the push kernel (arrivals deposit on append)

@@ -58,6 +58,7 @@ static bool set_option(const std::string& name, int value) {
   else if (name == "filter_chunk") g_tuning.filter_chunk = value;
   else if (name == "push_streams") g_tuning.push_streams = value;
   else if (name == "sort_streams") g_tuning.sort_streams = value;
+  else if (name == "push_group") g_tuning.push_group = value;
   else if (name == "sort_counting") g_tuning.sort_counting = value;
   else if (name == "defer_tile_calls") g_tuning.defer_tile_calls = value;
   else return false;
@@ -392,7 +393,23 @@ static int sign_of(double v) { return (0.0 < v) - (v < 0.0); }   // tools/math.h
 void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
   const bool fuse = tuning().fuse_deposit != 0;
-  const int nw = std::max(1, std::min({ tuning().push_streams, MAX_WORKERS, int(tiles.size()) }));
+  // Tiles that hold particles, in groups of up to `push_group` tiles of one geometry: the small
+  // per-tile kernels around the pushes (nodal means, clearing the cell-edge scratch, edge gather)
+  // run once per group, as launches large enough to fill the GPU.
+  const int gmax = std::max(1, std::min(tuning().push_group, PUSH_GROUP_MAX));
+  std::vector<std::vector<b2p_tile*>> groups;
+  for (b2p_tile* t : tiles) {
+    t->pendJ_valid = t->pend_packed = false;
+    bool any = false;
+    for (const Container& c : t->sp) any = any || c.n;
+    if (!any) continue;
+    if (groups.empty() || int(groups.back().size()) >= gmax || groups.back().front()->g.Ch != t->g.Ch ||
+        std::memcmp(groups.back().front()->g.Hx, t->g.Hx, sizeof(t->g.Hx)) != 0)
+      groups.emplace_back();
+    groups.back().push_back(t);
+  }
+  if (groups.empty()) return;
+  const int nw = std::max(1, std::min({ tuning().push_streams, MAX_WORKERS, int(groups.size()) }));
   Workers& wk = workers();
   cudaStream_t main_stream = ctx().stream;
   if (nw > 1) {
@@ -400,33 +417,45 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
     B2P_CUDA(cudaEventRecord(wk.fork, main_stream));
     for (int w = 0; w < nw; ++w) B2P_CUDA(cudaStreamWaitEvent(wk.s[w], wk.fork, 0));
   }
-  size_t ti = 0;
-  for (b2p_tile* t : tiles) {
-    const int w = int(ti++ % size_t(nw));
+  size_t gi = 0;
+  for (const std::vector<b2p_tile*>& grp : groups) {
+    const int w = int(gi++ % size_t(nw));
     StreamScope on(nw > 1 ? wk.s[w] : main_stream);
-    t->pendJ_valid = t->pend_packed = false;
-    bool any = false;
-    for (const Container& c : t->sp) any = any || c.n;
-    if (!any) continue;
-    s.nodal_w[w].reserve(size_t(2) * t->g.Ch);
-    launch_nodal_means(t->E.p, t->B.p, t->g, s.nodal_w[w].p);
-    if (fuse) {
-      s.edges_w[w].reserve(size_t(3) * t->g.Ch);
-      launch_zero(reinterpret_cast<float*>(s.edges_w[w].p), size_t(12) * t->g.Ch);
+    const Geom& g = grp.front()->g;
+    const size_t nod_stride = size_t(2) * g.Ch, edge_stride = size_t(3) * g.Ch;   // float4 per tile
+    s.nodal_w[w].reserve(nod_stride * grp.size());
+    NodalBatch nb{};
+    EdgeBatch eb{};
+    for (size_t q = 0; q < grp.size(); ++q) {
+      nb.E[q] = grp[q]->E.p; nb.B[q] = grp[q]->B.p; nb.nod[q] = s.nodal_w[w].p + q * nod_stride;
     }
-    const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
-    const float mx[3] = { float(t->maxs[0]), float(t->maxs[1]), float(t->maxs[2]) };
-    for (Container& c : t->sp) {
-      if (!c.n) continue;
-      const float qm = static_cast<float>(sign_of(c.charge) / c.mass);
-      launch_push(t->cfg.particle_pusher, c.view(), s.nodal_w[w].p, t->g, t->origo, static_cast<float>(t->cfg.cfl), qm,
-                  c.mask_words(), mn, mx, fuse ? s.edges_w[w].p : nullptr, static_cast<float>(c.charge));
-      c.touch();
-      c.masks_valid = true;
+    nb.n = int(grp.size());
+    launch_nodal_means(nb, g);
+    if (fuse) {
+      s.edges_w[w].reserve(edge_stride * grp.size());
+      launch_zero(reinterpret_cast<float*>(s.edges_w[w].p), size_t(4) * edge_stride * grp.size());
+    }
+    for (size_t q = 0; q < grp.size(); ++q) {
+      b2p_tile* t = grp[q];
+      const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
+      const float mx[3] = { float(t->maxs[0]), float(t->maxs[1]), float(t->maxs[2]) };
+      float4* Jc = fuse ? s.edges_w[w].p + q * edge_stride : nullptr;
+      for (Container& c : t->sp) {
+        if (!c.n) continue;
+        const float qm = static_cast<float>(sign_of(c.charge) / c.mass);
+        launch_push(t->cfg.particle_pusher, c.view(), nb.nod[q], t->g, t->origo, static_cast<float>(t->cfg.cfl), qm,
+                    c.mask_words(), mn, mx, Jc, static_cast<float>(c.charge));
+        c.touch();
+        c.masks_valid = true;
+      }
+      if (fuse) {
+        eb.Jc[q] = Jc; eb.J[q] = t->Jbuf[1 - t->jcur].p;
+        t->pendJ_valid = true;
+      }
     }
     if (fuse) {
-      launch_edge_gather(s.edges_w[w].p, t->Jbuf[1 - t->jcur].p, t->g);
-      t->pendJ_valid = true;
+      eb.n = int(grp.size());
+      launch_edge_gather(eb, g);
     }
   }
   if (nw > 1)
@@ -546,19 +575,21 @@ void phase_sort(const std::vector<b2p_tile*>& tiles) {
     ss.cnt.reserve(size_t(nkeys) + 2); ss.offs.reserve(size_t(nkeys) + 2);
     const size_t tb = scan_temp_bytes(nkeys + 2);
     ss.temp.reserve(tb);
-    launch_sort_count_scan(c.view(), it.t->g, it.t->origo, ss.keys.p, ss.rank.p, ss.cnt.p, ss.offs.p, nkeys, ss.temp.p, tb,
-                           s.sort_maxpop.p + w);
     const bool first = *hint == PopHints::UNKNOWN;
-    B2P_CUDA(cudaMemcpyAsync(const_cast<unsigned*>(hint), s.sort_maxpop.p + w, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
+    launch_sort_count_scan(c.view(), it.t->g, it.t->origo, ss.keys.p, ss.rank.p, ss.cnt.p, ss.offs.p, nkeys, ss.temp.p, tb,
+                           s.sort_maxpop.p + w, first);
     if (first) {
       // no history for this container: wait for its population once
+      B2P_CUDA(cudaMemcpyAsync(const_cast<unsigned*>(hint), s.sort_maxpop.p + w, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
       B2P_CUDA(cudaStreamSynchronize(ctx().stream));
       if (*hint > SORT_RADIX_POP) { sort_radix(it.t, c, w); continue; }
     }
     Container& spare = s.spare_w[w];
     spare.reserve(c.capacity(), /*exact=*/true);
     spare.n = c.n;
-    launch_sort_scatter_place(c.view(), spare.view(), ss.keys.p, ss.rank.p, ss.offs.p, ss.members.p, ss.cnt.p, nkeys);
+    launch_sort_scatter_place(c.view(), spare.view(), ss.keys.p, ss.rank.p, ss.offs.p, ss.members.p, ss.cnt.p, nkeys,
+                              s.sort_maxpop.p + w);
+    B2P_CUDA(cudaMemcpyAsync(const_cast<unsigned*>(hint), s.sort_maxpop.p + w, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
     swap_storage(c, spare);
     c.touch();
   }

@@ -73,12 +73,17 @@ struct DivC {
 // lane instead of 256.  Same operands and same association (2-term sum /2; 4-term right fold /4)
 // => same bits.
 __global__ void __launch_bounds__(256)
-k_nodal_means(const float* __restrict__ E, const float* __restrict__ B, const Geom g, float4* __restrict__ nod) {
+k_nodal_means(const NodalBatch bt, const Geom g) {
+  const int tile = blockIdx.y;
+  const float* __restrict__ E = bt.E[tile];
+  const float* __restrict__ B = bt.B[tile];
+  float4* __restrict__ nod = bt.nod[tile];
   float2* __restrict__ nodB = reinterpret_cast<float2*>(nod + g.Ch);
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int i = blockIdx.z;
+  const int kblocks = (g.Hx[2] + 31) / 32;
+  const int k = (blockIdx.x % kblocks) * blockDim.x + threadIdx.x;
+  const int j = (blockIdx.x / kblocks) * blockDim.y + threadIdx.y;
   if (k >= g.Hx[2] || j >= g.Hx[1]) return;
+  for (int i = blockIdx.z; i < g.Hx[0]; i += gridDim.z) {
   const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2], Ch = g.Ch;
   const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -95,6 +100,7 @@ k_nodal_means(const float* __restrict__ E, const float* __restrict__ B, const Ge
   }
   nod[n] = a;
   nodB[n] = b;
+  }
 }
 
 struct EB { V3 E, B; };
@@ -453,11 +459,15 @@ k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float
 // the reference's clear_current + `J += generated_J`, pic/tile.c++:371,405):
 //   Jx[i,j,k] = c(i,j,k).x0 + c(i,j-1,k).x1 + c(i,j,k-1).x2 + c(i,j-1,k-1).x3   etc.
 __global__ void __launch_bounds__(256)
-k_edge_gather(const float4* __restrict__ Jc, float* __restrict__ J, const Geom g) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int i = blockIdx.z;
+k_edge_gather(const EdgeBatch bt, const Geom g) {
+  const int tile = blockIdx.y;
+  const float4* __restrict__ Jc = bt.Jc[tile];
+  float* __restrict__ J = bt.J[tile];
+  const int kblocks = (g.Hx[2] + 31) / 32;
+  const int k = (blockIdx.x % kblocks) * blockDim.x + threadIdx.x;
+  const int j = (blockIdx.x / kblocks) * blockDim.y + threadIdx.y;
   if (k >= g.Hx[2] || j >= g.Hx[1]) return;
+  for (int i = blockIdx.z; i < g.Hx[0]; i += gridDim.z) {
   const long sj = g.Hx[2], si = long(g.Hx[1]) * g.Hx[2];
   const long n = (long(i) * g.Hx[1] + j) * g.Hx[2] + k;
   const bool pi = i > 0, pj = j > 0, pk = k > 0;
@@ -472,6 +482,7 @@ k_edge_gather(const float4* __restrict__ Jc, float* __restrict__ J, const Geom g
   if (pj) jz += Jc[3 * (n - sj) + 2].z;
   if (pi && pj) jz += Jc[3 * (n - si - sj) + 2].w;
   J[n] = jx; J[size_t(g.Ch) + n] = jy; J[2 * size_t(g.Ch) + n] = jz;
+  }
 }
 
 // ------------------------------------------------------------------- sort --
@@ -605,7 +616,8 @@ k_sort_gather(const Species src, const Species dst, const unsigned* __restrict__
 // queued in `big` = {count, cells...} for k_sort_fix_big.
 constexpr unsigned SORT_FIX_STAGE = 8192;   // entries (32 KB + 8 KB of labels)
 __global__ void __launch_bounds__(256)
-k_sort_fix(const unsigned* __restrict__ offs, unsigned* __restrict__ members, const unsigned nkeys, unsigned* __restrict__ big) {
+k_sort_fix(const unsigned* __restrict__ offs, unsigned* __restrict__ members, const unsigned nkeys, unsigned* __restrict__ big,
+           unsigned* __restrict__ max_pop) {
   __shared__ unsigned sm[SORT_FIX_STAGE];
   __shared__ unsigned char cellof[SORT_FIX_STAGE];
   __shared__ unsigned so[257];
@@ -616,6 +628,12 @@ k_sort_fix(const unsigned* __restrict__ offs, unsigned* __restrict__ members, co
   __syncthreads();
   const unsigned lo0 = so[0], total = so[nc] - lo0;
   const bool staged = total <= SORT_FIX_STAGE;
+  {   // largest cell population of the container (the hint for its next sort)
+    unsigned m = threadIdx.x < nc ? so[threadIdx.x + 1] - so[threadIdx.x] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 1) atomicMax(max_pop, m);
+  }
   if (threadIdx.x < nc) {
     const unsigned lo = so[threadIdx.x] - lo0, hi = so[threadIdx.x + 1] - lo0;
     if (hi - lo >= 2 && (!staged || hi - lo > SORT_THREAD_POP)) big[1 + atomicAdd(big, 1u)] = c0 + threadIdx.x;
@@ -931,11 +949,17 @@ void launch_selfcheck_divc(const float* x, unsigned long long n, float c, float*
 // ---------------------------------------------------------------- launchers --
 static unsigned blocks_for(size_t n) { return unsigned((n + 255) / 256); }
 
-void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* nod) {
-  ProfScope prof_(KC_NODAL, double(g.Ch));
-  const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, g.Hx[0]);
-  k_nodal_means<<<grid, dim3(32, 8, 1), 0, ctx().stream>>>(E, B, g, nod);
+void launch_nodal_means(const NodalBatch& bt, const Geom& g) {
+  ProfScope prof_(KC_NODAL, double(g.Ch) * bt.n);
+  if (!bt.n) return;
+  const dim3 grid(((g.Hx[2] + 31) / 32) * ((g.Hx[1] + 7) / 8), bt.n, std::min(g.Hx[0], 32768));
+  k_nodal_means<<<grid, dim3(32, 8, 1), 0, ctx().stream>>>(bt, g);
   B2P_LAUNCH_CHECK();
+}
+void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* nod) {
+  NodalBatch bt{};
+  bt.E[0] = E; bt.B[0] = B; bt.nod[0] = nod; bt.n = 1;
+  launch_nodal_means(bt, g);
 }
 
 void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm,
@@ -983,11 +1007,17 @@ void launch_deposit(const Species& s, float4* Jc, const Geom& g, const float ori
   B2P_LAUNCH_CHECK();
 }
 
-void launch_edge_gather(const float4* Jc, float* J, const Geom& g) {
-  ProfScope prof_(KC_EDGE_GATHER, double(g.Ch));
-  const dim3 grid((g.Hx[2] + 31) / 32, (g.Hx[1] + 7) / 8, g.Hx[0]);
-  k_edge_gather<<<grid, dim3(32, 8, 1), 0, ctx().stream>>>(Jc, J, g);
+void launch_edge_gather(const EdgeBatch& bt, const Geom& g) {
+  ProfScope prof_(KC_EDGE_GATHER, double(g.Ch) * bt.n);
+  if (!bt.n) return;
+  const dim3 grid(((g.Hx[2] + 31) / 32) * ((g.Hx[1] + 7) / 8), bt.n, std::min(g.Hx[0], 32768));
+  k_edge_gather<<<grid, dim3(32, 8, 1), 0, ctx().stream>>>(bt, g);
   B2P_LAUNCH_CHECK();
+}
+void launch_edge_gather(const float4* Jc, float* J, const Geom& g) {
+  EdgeBatch bt{};
+  bt.Jc[0] = Jc; bt.J[0] = J; bt.n = 1;
+  launch_edge_gather(bt, g);
 }
 
 void launch_sort_keys(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* idx, unsigned dead_key) {
@@ -1034,7 +1064,7 @@ size_t scan_temp_bytes(unsigned n) {
 // steps 1-2 of the counting sort: keys, arrival ranks, offs = exclusive scan of the per-key
 // populations (nkeys alive keys + the dead key + one pad entry), *max_pop = largest alive population
 void launch_sort_count_scan(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* rank, unsigned* cnt,
-                            unsigned* offs, unsigned nkeys, void* temp, size_t temp_bytes, unsigned* max_pop) {
+                            unsigned* offs, unsigned nkeys, void* temp, size_t temp_bytes, unsigned* max_pop, bool with_max) {
   if (!s.n) return;
   {
     ProfScope prof_(KC_SORT_KEYS, double(s.n));
@@ -1046,13 +1076,15 @@ void launch_sort_count_scan(const Species& s, const Geom& g, const float origo[3
   ProfScope prof_(KC_RADIX_SORT, double(s.n));
   B2P_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, cnt, offs, int(nkeys + 2), ctx().stream));
   count_launch(1);
-  k_max_count<<<std::min(blocks_for(nkeys), 296u), 256, 0, ctx().stream>>>(cnt, nkeys, max_pop);
-  B2P_LAUNCH_CHECK();
+  if (with_max) {
+    k_max_count<<<std::min(blocks_for(nkeys), 296u), 256, 0, ctx().stream>>>(cnt, nkeys, max_pop);
+    B2P_LAUNCH_CHECK();
+  }
 }
 // steps 3-5.  `cnt` (nkeys + 2 counters, free after the scan) becomes the queue of crowded cells,
 // `rank` (free after the scatter) the scratch of k_sort_fix_big.
 void launch_sort_scatter_place(const Species& src, const Species& dst, const unsigned* keys, unsigned* rank,
-                               const unsigned* offs, unsigned* members, unsigned* cnt, unsigned nkeys) {
+                               const unsigned* offs, unsigned* members, unsigned* cnt, unsigned nkeys, unsigned* max_pop) {
   if (!src.n) return;
   {
     ProfScope prof_(KC_RADIX_SORT, double(src.n));
@@ -1063,7 +1095,7 @@ void launch_sort_scatter_place(const Species& src, const Species& dst, const uns
     const unsigned mean = std::max(1u, src.n / std::max(1u, nkeys));
     unsigned cells = 256;
     while (cells > 32 && cells * mean > SORT_FIX_STAGE / 2) cells >>= 1;
-    k_sort_fix<<<(nkeys + cells - 1) / cells, cells, 0, ctx().stream>>>(offs, members, nkeys, cnt);
+    k_sort_fix<<<(nkeys + cells - 1) / cells, cells, 0, ctx().stream>>>(offs, members, nkeys, cnt, max_pop);
     B2P_LAUNCH_CHECK();
     k_sort_fix_big<<<592, 256, 0, ctx().stream>>>(offs, members, rank, cnt);
     B2P_LAUNCH_CHECK();

@@ -26,6 +26,13 @@ struct CollectJobHost {       // mirrors particles.cu::CollectJob: leaver masks 
   float3 mn, mx;              // tile box (float(mins/maxs), pic/tile_communication.c++:71-79)
 };
 
+// groups of tiles of one geometry handled by one launch of the small per-tile kernels of the
+// particle phase (tables passed by value as kernel arguments)
+constexpr int PUSH_GROUP_MAX = 8;
+struct NodalBatch { const float* E[PUSH_GROUP_MAX]; const float* B[PUSH_GROUP_MAX]; float4* nod[PUSH_GROUP_MAX]; int n; };
+struct EdgeBatch { const float4* Jc[PUSH_GROUP_MAX]; float* J[PUSH_GROUP_MAX]; int n; };
+void launch_nodal_means(const NodalBatch& bt, const Geom& g);
+void launch_edge_gather(const EdgeBatch& bt, const Geom& g);
 void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* nod);
 // the push also publishes the leaver / stayer ballots of every warp (masks: one uint2 per 32 slots,
 // rounded up to whole blocks of 256 slots) for pack_outgoing_particles
@@ -45,9 +52,9 @@ constexpr unsigned SORT_THREAD_POP = 128;    // largest cell whose member list o
 constexpr unsigned SORT_RADIX_POP = 4096;    // containers whose last known largest cell exceeds this take the radix sort
 size_t scan_temp_bytes(unsigned n);
 void launch_sort_count_scan(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* rank, unsigned* cnt,
-                            unsigned* offs, unsigned nkeys, void* temp, size_t temp_bytes, unsigned* max_pop);
+                            unsigned* offs, unsigned nkeys, void* temp, size_t temp_bytes, unsigned* max_pop, bool with_max);
 void launch_sort_scatter_place(const Species& src, const Species& dst, const unsigned* keys, unsigned* rank,
-                               const unsigned* offs, unsigned* members, unsigned* cnt, unsigned nkeys);
+                               const unsigned* offs, unsigned* members, unsigned* cnt, unsigned nkeys, unsigned* max_pop);
 void launch_make_masks(const Species& s, uint2* masks, const float mins[3], const float maxs[3]);
 void launch_collect_leavers(const void* jobs, unsigned ncont, unsigned max_words, unsigned long long* list, unsigned* list_count,
                             unsigned list_cap, unsigned* last_alive, unsigned* cont_count);
