@@ -159,6 +159,40 @@ int b2p_tile_get_outgoing(b2p_tile* t, b2p_particle_state* buf, uint64_t cap,
 /* ParticleContainer::total_kinetic_energy (pic/particle.c++:352-377). */
 int b2p_tile_kinetic_energy(b2p_tile* t, int sp, double* energy, uint64_t* container_size);
 
+/* ---- pic-shock boundary pieces (BASELINE configs[3]) ---------- */
+/* emf::edge_bc (src/runko/emf/edge_bc.h:25-40): sets field components in the part of the
+ * tile left (side 0) / right (side 1) of a global coordinate along `direction`. */
+typedef struct b2p_edge_bc {
+  uint8_t direction;            /* 0=x, 1=y, 2=z */
+  uint8_t side;                 /* 0 = left of position, 1 = right of position */
+  float   position;             /* global coordinate */
+  float   E[3], B[3], J[3];     /* values written */
+  uint8_t E_components, B_components, J_components;   /* bit 0=x, 1=y, 2=z */
+} b2p_edge_bc;
+/* pic::reflector_wall (src/runko/pic/reflector_wall.h:14-25): conducting piston in the yz-plane. */
+typedef struct b2p_reflector_wall {
+  float walloc;                 /* wall x in global coordinates */
+  float betawall;               /* wall velocity / c */
+  float gammawall;              /* wall Lorentz factor */
+} b2p_reflector_wall;
+
+/* emf::Tile::register_edge_bc / apply_edge_bcs / apply_edge_bc (emf/tile.c++:808-847,
+ * emf/yee_lattice.c++:263-306).  `mode` is B2P_COMM_EMF_{E,B,J}; anything else fails like the
+ * reference's std::runtime_error. */
+int b2p_tile_register_edge_bc(b2p_tile* t, const b2p_edge_bc* bc);
+int b2p_tile_apply_edge_bcs(b2p_tile* t, int mode);
+int b2p_tile_apply_edge_bc(b2p_tile* t, const b2p_edge_bc* bc, int mode);
+/* pic::Tile::register_reflector_wall / reflect_particles / advance_reflector_walls
+ * (pic/reflector_wall.c++:226-297) and ParticleContainer::reflect_at_wall (:126-222): particles
+ * behind a registered wall are reflected (or parked = marked dead), the +q / -q correction
+ * currents go to a per-tile correction lattice that deposit_current adds to J
+ * (pic/tile.c++:411-414). */
+int b2p_tile_register_reflector_wall(b2p_tile* t, const b2p_reflector_wall* wall);
+int b2p_tile_reflect_particles(b2p_tile* t);
+int b2p_tile_advance_reflector_walls(b2p_tile* t);
+/* Current state of the registered walls (no reference getter; used by the tests and the injector). */
+int b2p_tile_reflector_walls(b2p_tile* t, b2p_reflector_wall* out, uint64_t cap, uint64_t* n);
+
 /* ---- grid (corgi::Grid surface used by runko/simulation.py) -------------- */
 int  b2p_grid_create(const b2p_config* cfg, b2p_grid** out);
 void b2p_grid_destroy(b2p_grid* g);
@@ -178,6 +212,11 @@ int b2p_grid_push_particles(b2p_grid* g);
 int b2p_grid_pack_outgoing_particles(b2p_grid* g);
 int b2p_grid_sort_particles(b2p_grid* g);
 int b2p_grid_deposit_current(b2p_grid* g);
+/* grid_apply_edge_bcs / prtcl_reflect_particles / prtcl_advance_reflector_walls over all local
+ * tiles (runko/simulation.py lap functions used by projects/pic-shock/pic.py:232-279). */
+int b2p_grid_apply_edge_bcs(b2p_grid* g, int mode);
+int b2p_grid_reflect_particles(b2p_grid* g);
+int b2p_grid_advance_reflector_walls(b2p_grid* g);
 /* One lap of projects/pic-turbulence/pic.py:187-221 (diagnostics/IO excluded);
  * sort when lap % 5 == 0. */
 int b2p_grid_step_pic(b2p_grid* g, int64_t lap);

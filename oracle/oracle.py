@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from runko_b200._abi import B2PConfig, ParticleState, make_config  # struct layouts only
+from runko_b200._abi import B2PConfig, EdgeBC, ParticleState, ReflectorWall, make_config  # struct layouts only
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libpic_oracle.so")
@@ -41,7 +41,8 @@ def lib():
         L.orc_tile_cid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         vp, ci = C.c_void_p, C.c_int
         for name in ("push_half_b", "push_e", "add_current", "filter_current", "clear_current",
-                     "push_particles", "deposit_current", "sort_particles", "pack_outgoing_particles"):
+                     "push_particles", "deposit_current", "sort_particles", "pack_outgoing_particles",
+                     "reflect_particles", "advance_reflector_walls"):
             getattr(L, "orc_tile_" + name).argtypes = [vp, ci]
         L.orc_tile_set_fields.argtypes = [vp, ci, vp, vp, vp, ci]
         L.orc_tile_get_fields.argtypes = [vp, ci, vp, vp, vp, ci]
@@ -54,6 +55,11 @@ def lib():
         L.orc_tile_get_outgoing.argtypes = [vp, ci, vp, C.c_uint64, vp, C.POINTER(C.c_uint64)]
         L.orc_tile_kinetic_energy.argtypes = [vp, ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.orc_tile_interpolate.argtypes = [vp, ci, C.c_uint64, vp, vp, vp, vp]
+        L.orc_tile_register_edge_bc.argtypes = [vp, ci, C.POINTER(EdgeBC)]
+        L.orc_tile_apply_edge_bcs.argtypes = [vp, ci, ci]
+        L.orc_tile_apply_edge_bc.argtypes = [vp, ci, C.POINTER(EdgeBC), ci]
+        L.orc_tile_register_reflector_wall.argtypes = [vp, ci, C.POINTER(ReflectorWall)]
+        L.orc_tile_reflector_walls.argtypes = [vp, ci, vp, C.c_uint64, C.POINTER(C.c_uint64)]
         L.orc_local_communication.argtypes = [vp, ci]
         L.orc_grid_phase.argtypes = [vp, C.c_char_p, ci]
         L.orc_step_pic.argtypes = [vp, C.c_int64, ci]
@@ -173,6 +179,25 @@ class OracleGrid:
         out = np.empty((len(a[0]), 6), np.float32)
         self._ck(self._L.orc_tile_interpolate(self._g, t, len(a[0]), *[_p(v) for v in a], _p(out)))
         return out
+
+    # pic-shock boundary pieces ---------------------------------------------------
+    def register_edge_bc(self, t, bc):
+        self._ck(self._L.orc_tile_register_edge_bc(self._g, t, C.byref(bc)))
+
+    def apply_edge_bcs(self, t, mode):
+        self._ck(self._L.orc_tile_apply_edge_bcs(self._g, t, int(mode)))
+
+    def apply_edge_bc(self, t, bc, mode):
+        self._ck(self._L.orc_tile_apply_edge_bc(self._g, t, C.byref(bc), int(mode)))
+
+    def register_reflector_wall(self, t, wall):
+        self._ck(self._L.orc_tile_register_reflector_wall(self._g, t, C.byref(wall)))
+
+    def reflector_walls(self, t):
+        n = C.c_uint64()
+        out = (ReflectorWall * 16)()
+        self._ck(self._L.orc_tile_reflector_walls(self._g, t, out, 16, C.byref(n)))
+        return [(w.walloc, w.betawall, w.gammawall) for w in out[:n.value]]
 
     # grid -------------------------------------------------------------------
     def local_communication(self, mode):

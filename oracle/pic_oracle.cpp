@@ -53,6 +53,10 @@ struct Tile {
   std::vector<b2p_particle_state> out_buf;         // subregion_particle_buff_
   std::vector<size_t> out_ends;                    // subregion_particle_ends_
   std::vector<std::vector<Span>> incoming;         // incoming_subregion_particles_
+  std::vector<b2p_edge_bc> edge_bcs;               // emf/tile.h:51
+  std::vector<b2p_reflector_wall> walls;           // pic/tile.h:71
+  std::vector<float> corrJ;                        // reflector_correction_J_ (pic/tile.h:72)
+  bool corr_pending = false;                       // reflector_correction_pending_ (pic/tile.h:73)
   size_t lin(size_t i, size_t j, size_t k) const { return (i * Hx[1] + j) * Hx[2] + k; }
 };
 
@@ -526,6 +530,168 @@ void deposit_current(Tile& t, const b2p_config& cfg) {
       }
     }
   }
+  if (t.corr_pending) {                                            // pic/tile.c++:411-414
+    for (size_t n = 0; n < 3 * t.Ch; ++n) t.J[n] = t.J[n] + t.corrJ[n];   // emf/yee_lattice.c++:361-375
+    t.corr_pending = false;
+  }
+}
+
+// ------------------------------------------------- pic-shock boundary pieces --
+// emf/tile.c++:808-827: how many interior cells of the tile the edge region covers
+bool edge_bc_width(const Tile& t, const b2p_edge_bc& bc, size_t* width) {
+  const int d = bc.direction;
+  const float tile_min = static_cast<float>(t.mins[d]);
+  const float tile_max = static_cast<float>(t.maxs[d]);
+  const size_t Nd = size_t(t.N[d]);
+  if (bc.side == 0) {
+    if (bc.position <= tile_min) return false;
+    if (bc.position >= tile_max) { *width = Nd; return true; }
+    *width = static_cast<size_t>(bc.position - tile_min) + 1;
+    return true;
+  }
+  if (bc.position >= tile_max) return false;
+  if (bc.position <= tile_min) { *width = Nd; return true; }
+  *width = Nd - static_cast<size_t>(bc.position - tile_min);
+  return true;
+}
+
+// emf/yee_lattice.c++:263-306
+int apply_edge_bc(Tile& t, const b2p_edge_bc& bc, int mode) {
+  size_t width = 0;
+  if (!edge_bc_width(t, bc, &width)) return 0;                     // emf/tile.c++:835-840
+  if (width == 0) return 0;
+  const int d = bc.direction;
+  const size_t Nd = size_t(t.N[d]);
+  const size_t w = std::min(width, Nd);
+  size_t lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    if (a != d) { lo[a] = 0; hi[a] = size_t(t.Hx[a]); }
+    else if (bc.side == 0) { lo[a] = 0; hi[a] = size_t(H) + w; }
+    else { lo[a] = size_t(H) + Nd - w; hi[a] = size_t(t.Hx[a]); }
+  }
+  std::vector<float>* f;
+  uint8_t mask;
+  const float* v;
+  switch (mode) {
+    case B2P_COMM_EMF_E: f = &t.E; mask = bc.E_components; v = bc.E; break;
+    case B2P_COMM_EMF_B: f = &t.B; mask = bc.B_components; v = bc.B; break;
+    case B2P_COMM_EMF_J: f = &t.J; mask = bc.J_components; v = bc.J; break;
+    default:
+      g_err = "YeeLattice::apply_edge_bc does not support given communication mode: " + std::to_string(mode);
+      return B2P_ERR_RUNTIME;
+  }
+  for (size_t i = lo[0]; i < hi[0]; ++i)
+    for (size_t j = lo[1]; j < hi[1]; ++j)
+      for (size_t k = lo[2]; k < hi[2]; ++k)
+        for (int c = 0; c < 3; ++c)
+          if (mask & (1u << c)) (*f)[c * t.Ch + t.lin(i, j, k)] = v[c];
+  return 0;
+}
+
+// pic/reflector_wall.c++:35-118: atomic zigzag deposit of ONE sub-trajectory x1 -> x2 (lattice-local
+// coordinates): 14 nodes x 3 components, explicit zeros included, in source order.
+void zigzag_deposit_single(Tile& t, std::vector<float>& J, const V3 x1, const V3 x2, const float charge) {
+  const V3 fi1{ { std::floor(x1[0]), std::floor(x1[1]), std::floor(x1[2]) } };
+  const V3 fi2{ { std::floor(x2[0]), std::floor(x2[1]), std::floor(x2[2]) } };
+  auto relay = [&](int j) {
+    const float a = (fi1[j] < fi2[j] ? fi1[j] : fi2[j]) + 1.0f;
+    const float m = fi1[j] > fi2[j] ? fi1[j] : fi2[j];
+    const float h = 0.5f * (x1[j] + x2[j]);
+    const float b = m > h ? m : h;
+    return a < b ? a : b;
+  };
+  const V3 xr{ { relay(0), relay(1), relay(2) } };
+  const V3 F1 = charge * (xr - x1);
+  const V3 F2 = charge * (x2 - xr);
+  const uint32_t i1[3] = { uint32_t(fi1[0]), uint32_t(fi1[1]), uint32_t(fi1[2]) };
+  const uint32_t i2[3] = { uint32_t(fi2[0]), uint32_t(fi2[1]), uint32_t(fi2[2]) };
+  const V3 W1 = 0.5f * (x1 + xr) - fi1;
+  const V3 W2 = 0.5f * (x2 + xr) - fi2;
+  const float Fx1 = F1[0], Fy1 = F1[1], Fz1 = F1[2], Fx2 = F2[0], Fy2 = F2[1], Fz2 = F2[2];
+  const float Wx1 = W1[0], Wy1 = W1[1], Wz1 = W1[2], Wx2 = W2[0], Wy2 = W2[1], Wz2 = W2[2];
+  const float one = 1.0f;
+  auto store = [&](const uint32_t b[3], int di, int dj, int dk, float jx, float jy, float jz) {
+    const size_t l = t.lin(b[0] + di, b[1] + dj, b[2] + dk);
+    J[0 * t.Ch + l] += jx; J[1 * t.Ch + l] += jy; J[2 * t.Ch + l] += jz;
+  };
+  store(i1, 0, 0, 0, Fx1 * (one - Wy1) * (one - Wz1), Fy1 * (one - Wx1) * (one - Wz1), Fz1 * (one - Wx1) * (one - Wy1));
+  store(i2, 0, 0, 0, Fx2 * (one - Wy2) * (one - Wz2), Fy2 * (one - Wx2) * (one - Wz2), Fz2 * (one - Wx2) * (one - Wy2));
+  store(i1, 1, 0, 0, 0, Fy1 * Wx1 * (one - Wz1), Fz1 * Wx1 * (one - Wy1));
+  store(i2, 1, 0, 0, 0, Fy2 * Wx2 * (one - Wz2), Fz2 * Wx2 * (one - Wy2));
+  store(i1, 0, 1, 0, Fx1 * Wy1 * (one - Wz1), 0, Fz1 * (one - Wx1) * Wy1);
+  store(i2, 0, 1, 0, Fx2 * Wy2 * (one - Wz2), 0, Fz2 * (one - Wx2) * Wy2);
+  store(i1, 0, 0, 1, Fx1 * (one - Wy1) * Wz1, Fy1 * (one - Wx1) * Wz1, 0);
+  store(i2, 0, 0, 1, Fx2 * (one - Wy2) * Wz2, Fy2 * (one - Wx2) * Wz2, 0);
+  store(i1, 0, 1, 1, Fx1 * Wy1 * Wz1, 0, 0);
+  store(i2, 0, 1, 1, Fx2 * Wy2 * Wz2, 0, 0);
+  store(i1, 1, 0, 1, 0, Fy1 * Wx1 * Wz1, 0);
+  store(i2, 1, 0, 1, 0, Fy2 * Wx2 * Wz2, 0);
+  store(i1, 1, 1, 0, 0, 0, Fz1 * Wx1 * Wy1);
+  store(i2, 1, 1, 0, 0, 0, Fz2 * Wx2 * Wy2);
+}
+
+// ParticleContainer::reflect_at_wall, pic/reflector_wall.c++:126-222 (branch-free float masks)
+void reflect_at_wall(Tile& t, Container& cont, const b2p_reflector_wall& wall, const float origo_[3], const double cfl) {
+  const float EPS = 1e-10f;                                          // :23
+  const float walloc = wall.walloc, betawall = wall.betawall, gammawall = wall.gammawall;
+  const float charge = static_cast<float>(cont.charge);
+  const float c = static_cast<float>(cfl);
+  const float walloc0 = walloc - betawall * c;                       // previous wall location
+  const V3 origo{ { origo_[0], origo_[1], origo_[2] } };
+  for (size_t n = 0; n < cont.size(); ++n) {
+    if (cont.id[n] == DEAD) continue;
+    const V3 pos_1{ { cont.x[n], cont.y[n], cont.z[n] } };
+    const V3 u{ { cont.ux[n], cont.uy[n], cont.uz[n] } };
+    const float gam = std::sqrt(1.0f + dot(u, u));
+    const float invgam = 1.0f / gam;
+    const V3 pos_0 = pos_1 - c * invgam * u;
+    const float mask_skip = (pos_1[0] >= walloc) ? 1.0f : 0.0f;
+    const float mask_close = (walloc0 - pos_0[0] <= c) ? 1.0f : 0.0f;
+    const float denom = betawall * c - c * u[0] * invgam;
+    const float dt = std::fabs((pos_0[0] - walloc0) / (denom + EPS));
+    const float mask_crossed = (dt <= 1.0f) ? 1.0f : 0.0f;
+    const float mask_refl = (1.0f - mask_skip) * mask_close * mask_crossed;
+    const float mask_park = (1.0f - mask_skip) - mask_refl;
+    const V3 pos_col = pos_0 + c * dt * invgam * u;
+    const float ux_new = gammawall * gammawall * gam * (2.0f * betawall - u[0] * invgam * (1.0f + betawall * betawall));
+    const V3 u_new{ { ux_new, u[1], u[2] } };
+    const float gam_new = std::sqrt(1.0f + dot(u_new, u_new));
+    const float invgam_new = 1.0f / gam_new;
+    const float ratio = std::fabs((pos_1[0] - pos_col[0]) / (pos_1[0] - pos_0[0] + EPS));
+    const float dt_refl = 1.0f < ratio ? 1.0f : ratio;               // sstd::min(1.0f, ratio)
+    const V3 pos_refl = pos_col + c * dt_refl * invgam_new * u_new;
+    const V3 p1l = pos_1 - origo;
+    const V3 dep_fwd_from = p1l + mask_refl * (pos_0 - pos_1);
+    const V3 dep_fwd_to = p1l + mask_refl * (pos_col - pos_1);
+    zigzag_deposit_single(t, t.corrJ, dep_fwd_from, dep_fwd_to, mask_refl * charge);
+    const V3 x1_deposit = pos_refl - c * invgam_new * u_new;
+    const V3 dep_rev_from = p1l + mask_refl * (x1_deposit - pos_1);
+    const V3 dep_rev_to = p1l + mask_refl * (pos_col - pos_1);
+    zigzag_deposit_single(t, t.corrJ, dep_rev_from, dep_rev_to, mask_refl * (-charge));
+    cont.x[n] = (1.0f - mask_refl) * pos_1[0] + mask_refl * pos_refl[0];
+    cont.y[n] = (1.0f - mask_refl) * pos_1[1] + mask_refl * pos_refl[1];
+    cont.z[n] = (1.0f - mask_refl) * pos_1[2] + mask_refl * pos_refl[2];
+    cont.ux[n] = (1.0f - mask_refl) * u[0] + mask_refl * ux_new;
+    if (mask_park > 0.5f) cont.id[n] = DEAD;
+  }
+}
+
+// pic::Tile::reflect_particles, pic/reflector_wall.c++:241-284
+void reflect_particles(Tile& t, const b2p_config& cfg) {
+  if (t.walls.empty()) return;
+  auto wall_is_in_tile = [&](const b2p_reflector_wall& w) {
+    return w.walloc >= float(t.mins[0]) - float(cfg.cfl) && w.walloc <= float(t.maxs[0]);
+  };
+  bool any = false;
+  for (const b2p_reflector_wall& w : t.walls) any = any || wall_is_in_tile(w);
+  if (!any) return;
+  t.corr_pending = true;
+  t.corrJ.assign(3 * t.Ch, 0.0f);
+  float origo[3]; tile_origo(t, origo);
+  for (const b2p_reflector_wall& w : t.walls) {
+    if (!wall_is_in_tile(w)) continue;
+    for (Container& c : t.sp) reflect_at_wall(t, c, w, origo, cfg.cfl);
+  }
 }
 
 // ------------------------------------------------------------------- sort --
@@ -894,6 +1060,42 @@ int orc_tile_kinetic_energy(orc_grid* g, int t, int sp, double* energy, uint64_t
   if (container_size) *container_size = c->size();
   return 0;
 }
+int orc_tile_register_edge_bc(orc_grid* g, int t, const b2p_edge_bc* bc) {
+  Tile* tl = get_tile(g, t); if (!tl) return 1;
+  tl->edge_bcs.push_back(*bc);                                       // emf/tile.c++:829-833
+  return 0;
+}
+int orc_tile_apply_edge_bc(orc_grid* g, int t, const b2p_edge_bc* bc, int mode) {
+  Tile* tl = get_tile(g, t); if (!tl) return 1;
+  return apply_edge_bc(*tl, *bc, mode);
+}
+int orc_tile_apply_edge_bcs(orc_grid* g, int t, int mode) {         // emf/tile.c++:842-847
+  Tile* tl = get_tile(g, t); if (!tl) return 1;
+  for (const b2p_edge_bc& bc : tl->edge_bcs) { const int rc = apply_edge_bc(*tl, bc, mode); if (rc) return rc; }
+  return 0;
+}
+int orc_tile_register_reflector_wall(orc_grid* g, int t, const b2p_reflector_wall* wall) {
+  Tile* tl = get_tile(g, t); if (!tl) return 1;
+  tl->walls.push_back(*wall);                                        // pic/reflector_wall.c++:226-233
+  return 0;
+}
+int orc_tile_reflect_particles(orc_grid* g, int t) {
+  Tile* tl = get_tile(g, t); if (!tl) return 1;
+  reflect_particles(*tl, g->cfg);
+  return 0;
+}
+int orc_tile_advance_reflector_walls(orc_grid* g, int t) {          // pic/reflector_wall.c++:286-297
+  Tile* tl = get_tile(g, t); if (!tl) return 1;
+  for (b2p_reflector_wall& w : tl->walls) w.walloc += w.betawall * float(g->cfg.cfl);
+  return 0;
+}
+int orc_tile_reflector_walls(orc_grid* g, int t, b2p_reflector_wall* out, uint64_t cap, uint64_t* n) {
+  Tile* tl = get_tile(g, t); if (!tl) return 1;
+  *n = tl->walls.size();
+  for (size_t q = 0; q < tl->walls.size() && q < cap; ++q) out[q] = tl->walls[q];
+  return 0;
+}
+
 int orc_tile_interpolate(orc_grid* g, int t, uint64_t n, const float* x, const float* y, const float* z, float* out) {
   Tile* tl = get_tile(g, t); if (!tl) return 1;
   float origo[3]; tile_origo(*tl, origo);
@@ -967,6 +1169,13 @@ int orc_grid_phase(orc_grid* g, const char* phase, int threads) {
   else if (p == "pack_outgoing_particles") parallel_tiles(g, threads, [&](Tile& t) { pack_outgoing(t); });
   else if (p == "sort_particles") parallel_tiles(g, threads, [&](Tile& t) { for (Container& c : t.sp) sort_particles(t, c); });
   else if (p == "deposit_current") parallel_tiles(g, threads, [&](Tile& t) { deposit_current(t, g->cfg); });
+  else if (p == "reflect_particles") parallel_tiles(g, threads, [&](Tile& t) { reflect_particles(t, g->cfg); });
+  else if (p == "advance_reflector_walls")
+    parallel_tiles(g, threads, [&](Tile& t) { for (b2p_reflector_wall& w : t.walls) w.walloc += w.betawall * float(g->cfg.cfl); });
+  else if (p == "apply_edge_bcs_E" || p == "apply_edge_bcs_B" || p == "apply_edge_bcs_J") {
+    const int mode = p.back() == 'E' ? B2P_COMM_EMF_E : p.back() == 'B' ? B2P_COMM_EMF_B : B2P_COMM_EMF_J;
+    parallel_tiles(g, threads, [&](Tile& t) { for (const b2p_edge_bc& bc : t.edge_bcs) apply_edge_bc(t, bc, mode); });
+  }
   else { g_err = "unknown phase " + p; rc = 1; }
   return rc;
 }

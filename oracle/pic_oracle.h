@@ -66,6 +66,15 @@ int orc_tile_get_outgoing(orc_grid* g, int t, b2p_particle_state* buf, uint64_t 
                           uint64_t* ends, uint64_t* n_out);
 int orc_tile_kinetic_energy(orc_grid* g, int t, int sp, double* energy, uint64_t* container_size);
 /* Interpolated E,B at n positions (global coordinates) on tile t: out is [n][6]. */
+/* pic-shock boundary pieces: emf/tile.c++:808-847 + emf/yee_lattice.c++:263-306; pic/reflector_wall.c++ */
+int orc_tile_register_edge_bc(orc_grid* g, int t, const b2p_edge_bc* bc);
+int orc_tile_apply_edge_bcs(orc_grid* g, int t, int mode);
+int orc_tile_apply_edge_bc(orc_grid* g, int t, const b2p_edge_bc* bc, int mode);
+int orc_tile_register_reflector_wall(orc_grid* g, int t, const b2p_reflector_wall* wall);
+int orc_tile_reflect_particles(orc_grid* g, int t);
+int orc_tile_advance_reflector_walls(orc_grid* g, int t);
+int orc_tile_reflector_walls(orc_grid* g, int t, b2p_reflector_wall* out, uint64_t cap, uint64_t* n);
+
 int orc_tile_interpolate(orc_grid* g, int t, uint64_t n, const float* x, const float* y,
                          const float* z, float* out);
 

@@ -26,9 +26,11 @@
 #include <string>
 #include <vector>
 
+#include "runko/emf/edge_bc.h"
 #include "runko/emf/stencil_coefficients.h"
 #include "runko/emf/yee_lattice.h"
 #include "runko/pic/particle.h"
+#include "runko/pic/tile.h"   // oracle/ref_shim stand-in: declarations only (see that file)
 
 #include "../include/b200pic.h"
 
@@ -46,6 +48,21 @@ struct RefTile {
   thrust::device_vector<runko::ParticleState<float>> out_buf;            // subregion_particle_buff_
   std::vector<std::size_t> out_ends;                                     // subregion_particle_ends_
   emf::StencilCoeffs stencil;
+  // pic-shock pieces: the reference's Tile<3>::{register_reflector_wall, reflect_particles,
+  // advance_reflector_walls} (compiled from pic/reflector_wall.c++) run on this object; the
+  // containers are moved into it for the duration of reflect_particles
+  std::unique_ptr<pic::Tile<3>> shock;
+  std::vector<emf::edge_bc> edge_bcs;                                                 // emf/tile.h:51
+
+  pic::Tile<3>& shock_tile() {
+    if (!shock) {
+      shock = std::make_unique<pic::Tile<3>>(
+        emf::YeeLatticeCtorArgs{ std::size_t(cfg.n_cells[0]), std::size_t(cfg.n_cells[1]), std::size_t(cfg.n_cells[2]) });
+      for (int d = 0; d < 3; ++d) { shock->mins[d] = mins[d]; shock->maxs[d] = maxs[d]; }
+      shock->cfl_ = cfg.cfl;
+    }
+    return *shock;
+  }
 
   RefTile(const b2p_config& c, const int i[3])
       : cfg(c), lattice(emf::YeeLatticeCtorArgs{ std::size_t(c.n_cells[0]), std::size_t(c.n_cells[1]), std::size_t(c.n_cells[2]) }) {
@@ -210,6 +227,21 @@ int ref_tile_op(void* tp, const char* name) {
       for (const auto& c : t.sp) c.current_zigzag_1st(gJ, t.origo(), t.cfg.cfl);
       t.lattice.deposit_current(gJ);
     }
+    if (t.shock && t.shock->reflector_correction_pending_) {                          // pic/tile.c++:411-414
+      t.lattice.deposit_current(t.shock->reflector_correction_J_.value());
+      t.shock->reflector_correction_pending_ = false;
+    }
+  } else if (op == "reflect_particles") {                                             // pic/reflector_wall.c++:241-284
+    pic::Tile<3>& st = t.shock_tile();
+    for (std::size_t i = 0; i < t.sp.size(); ++i) st.particle_buffs_.insert_or_assign(i, std::move(t.sp[i]));
+    try { st.reflect_particles(); } catch (...) {
+      for (std::size_t i = 0; i < t.sp.size(); ++i) t.sp[i] = std::move(st.particle_buffs_.at(i));
+      throw;
+    }
+    for (std::size_t i = 0; i < t.sp.size(); ++i) t.sp[i] = std::move(st.particle_buffs_.at(i));
+    st.particle_buffs_.clear();
+  } else if (op == "advance_reflector_walls") {                                       // pic/reflector_wall.c++:286-297
+    t.shock_tile().advance_reflector_walls();
   } else if (op == "sort_particles") {                                                // pic/tile.c++:419-438
     const auto m = t.lattice.grid_mapping_with_halo();
     using M      = decltype(m);
@@ -236,6 +268,59 @@ int ref_tile_op(void* tp, const char* name) {
   } else {
     throw std::runtime_error("ref_tile_op: unknown op " + op);
   }
+  REF_CATCH
+}
+
+// emf::Tile::edge_bc_width (emf/tile.c++:808-827; emf/tile.c++ itself needs corgi and is not
+// compiled) + YeeLattice::apply_edge_bc, the reference's own (emf/yee_lattice.c++:263-306)
+static void apply_one_edge_bc(RefTile& t, const emf::edge_bc& bc, int mode) {
+  const auto d        = bc.direction;
+  const auto tile_min = static_cast<emf::edge_bc::value_type>(t.mins[d]);
+  const auto tile_max = static_cast<emf::edge_bc::value_type>(t.maxs[d]);
+  const auto Nd       = t.lattice.extents_wout_halo()[d];
+  std::optional<std::size_t> w;
+  if (bc.side == 0) {
+    if (bc.position <= tile_min) w = std::nullopt;
+    else if (bc.position >= tile_max) w = Nd;
+    else w = static_cast<std::size_t>(bc.position - tile_min) + 1;
+  } else {
+    if (bc.position >= tile_max) w = std::nullopt;
+    else if (bc.position <= tile_min) w = Nd;
+    else w = Nd - static_cast<std::size_t>(bc.position - tile_min);
+  }
+  if (w) t.lattice.apply_edge_bc(bc, *w, mode);
+}
+static emf::edge_bc to_ref(const b2p_edge_bc& b) {
+  return emf::edge_bc{ b.direction, b.side, b.position, b.E[0], b.E[1], b.E[2], b.B[0], b.B[1], b.B[2],
+                       b.J[0], b.J[1], b.J[2], b.E_components, b.B_components, b.J_components };
+}
+int ref_tile_register_edge_bc(void* tp, const b2p_edge_bc* bc) {
+  REF_TRY
+  static_cast<RefTile*>(tp)->edge_bcs.push_back(to_ref(*bc));
+  REF_CATCH
+}
+int ref_tile_apply_edge_bc(void* tp, const b2p_edge_bc* bc, int mode) {
+  REF_TRY
+  apply_one_edge_bc(*static_cast<RefTile*>(tp), to_ref(*bc), mode);
+  REF_CATCH
+}
+int ref_tile_apply_edge_bcs(void* tp, int mode) {                                     // emf/tile.c++:842-847
+  REF_TRY
+  RefTile& t = *static_cast<RefTile*>(tp);
+  for (const auto& bc : t.edge_bcs) apply_one_edge_bc(t, bc, mode);
+  REF_CATCH
+}
+int ref_tile_register_reflector_wall(void* tp, const b2p_reflector_wall* w) {
+  REF_TRY
+  static_cast<RefTile*>(tp)->shock_tile().register_reflector_wall(
+    pic::reflector_wall{ .walloc = w->walloc, .betawall = w->betawall, .gammawall = w->gammawall });
+  REF_CATCH
+}
+int ref_tile_reflector_walls(void* tp, b2p_reflector_wall* out, uint64_t cap, uint64_t* n) {
+  REF_TRY
+  const auto& walls = static_cast<RefTile*>(tp)->shock_tile().reflector_walls_;
+  *n = walls.size();
+  for (std::size_t q = 0; q < walls.size() && q < cap; ++q) out[q] = b2p_reflector_wall{ walls[q].walloc, walls[q].betawall, walls[q].gammawall };
   REF_CATCH
 }
 

@@ -11,7 +11,7 @@ import subprocess
 
 import numpy as np
 
-from runko_b200._abi import B2PConfig, make_config
+from runko_b200._abi import B2PConfig, EdgeBC, ReflectorWall, make_config
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "libref_kernels.so")
@@ -62,6 +62,11 @@ def lib():
         L.ref_tile_append.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
         L.ref_tile_halo.argtypes = [vp, vp, C.POINTER(C.c_int32 * 3), C.c_int]
         L.ref_tile_energies.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
+        L.ref_tile_register_edge_bc.argtypes = [vp, C.POINTER(EdgeBC)]
+        L.ref_tile_apply_edge_bc.argtypes = [vp, C.POINTER(EdgeBC), C.c_int]
+        L.ref_tile_apply_edge_bcs.argtypes = [vp, C.c_int]
+        L.ref_tile_register_reflector_wall.argtypes = [vp, C.POINTER(ReflectorWall)]
+        L.ref_tile_reflector_walls.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -156,6 +161,24 @@ class RefTile:
         else:
             lo, hi = (np.asarray(v, np.float32) for v in wrap)
             self._ck(self.L.ref_tile_append(self.h, sp, len(spans), ptrs, _p(counts), 1, _p(lo), _p(hi)))
+
+    def register_edge_bc(self, bc):
+        self._ck(self.L.ref_tile_register_edge_bc(self.h, C.byref(bc)))
+
+    def apply_edge_bc(self, bc, mode):
+        self._ck(self.L.ref_tile_apply_edge_bc(self.h, C.byref(bc), int(mode)))
+
+    def apply_edge_bcs(self, mode):
+        self._ck(self.L.ref_tile_apply_edge_bcs(self.h, int(mode)))
+
+    def register_reflector_wall(self, wall):
+        self._ck(self.L.ref_tile_register_reflector_wall(self.h, C.byref(wall)))
+
+    def reflector_walls(self):
+        n = C.c_uint64()
+        out = (ReflectorWall * 16)()
+        self._ck(self.L.ref_tile_reflector_walls(self.h, out, 16, C.byref(n)))
+        return [(w.walloc, w.betawall, w.gammawall) for w in out[:n.value]]
 
     def energies(self):
         b, e = C.c_double(), C.c_double()

@@ -49,6 +49,18 @@ class ParticleState(C.Structure):
 assert C.sizeof(ParticleState) == 32
 
 
+class EdgeBC(C.Structure):
+    """b2p_edge_bc == emf::edge_bc (src/runko/emf/edge_bc.h:25-40)"""
+    _fields_ = [("direction", C.c_uint8), ("side", C.c_uint8), ("position", C.c_float),
+                ("E", C.c_float * 3), ("B", C.c_float * 3), ("J", C.c_float * 3),
+                ("E_components", C.c_uint8), ("B_components", C.c_uint8), ("J_components", C.c_uint8)]
+
+
+class ReflectorWall(C.Structure):
+    """b2p_reflector_wall == pic::reflector_wall (src/runko/pic/reflector_wall.h:14-25)"""
+    _fields_ = [("walloc", C.c_float), ("betawall", C.c_float), ("gammawall", C.c_float)]
+
+
 class ConfigError(RuntimeError):
     pass
 

@@ -6,7 +6,7 @@ usable when compute is requested, this raises.
 import ctypes as C
 import os
 
-from ._abi import B2PConfig, ParticleState
+from ._abi import B2PConfig, EdgeBC, ParticleState, ReflectorWall
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libb200pic.so")
@@ -20,6 +20,9 @@ b2p_tile_filter_current b2p_tile_clear_current b2p_tile_field_energy
 b2p_tile_inject b2p_tile_set_particles b2p_tile_container_size b2p_tile_get_particles
 b2p_tile_push_particles b2p_tile_deposit_current b2p_tile_sort_particles b2p_tile_pack_outgoing_particles
 b2p_tile_sort_keys b2p_tile_get_outgoing b2p_tile_kinetic_energy
+b2p_tile_register_edge_bc b2p_tile_apply_edge_bcs b2p_tile_apply_edge_bc
+b2p_tile_register_reflector_wall b2p_tile_reflect_particles b2p_tile_advance_reflector_walls b2p_tile_reflector_walls
+b2p_grid_apply_edge_bcs b2p_grid_reflect_particles b2p_grid_advance_reflector_walls
 b2p_grid_create b2p_grid_destroy b2p_grid_add_tile b2p_grid_local_communication
 b2p_grid_push_half_b b2p_grid_push_e b2p_grid_add_current b2p_grid_filter_current
 b2p_grid_push_particles b2p_grid_pack_outgoing_particles b2p_grid_sort_particles b2p_grid_deposit_current
@@ -77,6 +80,16 @@ def lib():
     L.b2p_tile_sort_keys.argtypes = [vp, ci, vp]
     L.b2p_tile_get_outgoing.argtypes = [vp, vp, u64, vp, C.POINTER(u64)]
     L.b2p_tile_kinetic_energy.argtypes = [vp, ci, dp, C.POINTER(u64)]
+    L.b2p_tile_register_edge_bc.argtypes = [vp, C.POINTER(EdgeBC)]
+    L.b2p_tile_apply_edge_bcs.argtypes = [vp, ci]
+    L.b2p_tile_apply_edge_bc.argtypes = [vp, C.POINTER(EdgeBC), ci]
+    L.b2p_tile_register_reflector_wall.argtypes = [vp, C.POINTER(ReflectorWall)]
+    L.b2p_tile_reflect_particles.argtypes = [vp]
+    L.b2p_tile_advance_reflector_walls.argtypes = [vp]
+    L.b2p_tile_reflector_walls.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.b2p_grid_apply_edge_bcs.argtypes = [vp, ci]
+    L.b2p_grid_reflect_particles.argtypes = [vp]
+    L.b2p_grid_advance_reflector_walls.argtypes = [vp]
     L.b2p_grid_create.argtypes = [C.POINTER(B2PConfig), C.POINTER(vp)]
     L.b2p_grid_destroy.argtypes = [vp]
     L.b2p_grid_destroy.restype = None

@@ -122,6 +122,26 @@ k_push_b_stencil(const FieldPtrs* __restrict__ tiles, const Geom g, const float 
   f.B[2 * Ch + n] = f.B[2 * Ch + n] + dt * (DyEx - DxEy);
 }
 
+// ---- edge boundary condition (emf/yee_lattice.c++:263-306) ---------------------
+// writes the masked components of one field over the box [lo, hi) of the haloed lattice
+__global__ void __launch_bounds__(256)
+k_edge_bc(float* __restrict__ f, const Geom g, const int3 lo, const int3 hi, const unsigned mask, const float3 v) {
+  const size_t q = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t ny = size_t(hi.y - lo.y), nz = size_t(hi.z - lo.z);
+  if (q >= size_t(hi.x - lo.x) * ny * nz) return;
+  const size_t i = lo.x + q / (ny * nz), j = lo.y + (q / nz) % ny, k = lo.z + q % nz;
+  const size_t n = (i * g.Hx[1] + j) * g.Hx[2] + k;
+  if (mask & 1u) f[n] = v.x;
+  if (mask & 2u) f[size_t(g.Ch) + n] = v.y;
+  if (mask & 4u) f[2 * size_t(g.Ch) + n] = v.z;
+}
+// J = J + add over whole haloed lattices (emf/yee_lattice.c++:361-375)
+__global__ void __launch_bounds__(256)
+k_add_lattice(float* __restrict__ J, const float* __restrict__ add, const size_t n) {
+  const size_t q = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q < n) J[q] = J[q] + add[q];
+}
+
 // ---- binomial current filter --------------------------------------------------
 // Both variants write every cell of dst: the region [1,H-1)^3 gets the filtered
 // value, the outermost layer gets 0 (binomial2: the reference move-assigns a
@@ -417,6 +437,21 @@ void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unr
   const FilterTile* ft = static_cast<const FilterTile*>(filter_tiles);
   if (unrolled) k_filter_binomial2<true><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk);
   else k_filter_binomial2<false><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk);
+  B2P_LAUNCH_CHECK();
+}
+void launch_edge_bc(float* field, const Geom& g, const int lo[3], const int hi[3], unsigned mask, const float v[3]) {
+  ProfScope prof_(KC_OTHER, 0.0);
+  const size_t total = size_t(hi[0] - lo[0]) * size_t(hi[1] - lo[1]) * size_t(hi[2] - lo[2]);
+  if (!total || !(mask & 7u)) return;
+  k_edge_bc<<<unsigned((total + 255) / 256), 256, 0, ctx().stream>>>(field, g, make_int3(lo[0], lo[1], lo[2]),
+                                                                    make_int3(hi[0], hi[1], hi[2]), mask,
+                                                                    make_float3(v[0], v[1], v[2]));
+  B2P_LAUNCH_CHECK();
+}
+void launch_add_lattice(float* J, const float* add, size_t n) {
+  ProfScope prof_(KC_ADD_CURRENT, double(n));
+  if (!n) return;
+  k_add_lattice<<<unsigned((n + 255) / 256), 256, 0, ctx().stream>>>(J, add, n);
   B2P_LAUNCH_CHECK();
 }
 void launch_zero(float* p, size_t n) {

@@ -10,6 +10,10 @@ void launch_add_current(const FieldPtrs* tiles, int ntiles, const Geom& g);
 // filter_tiles: device array of {const float* src; float* dst;} per tile
 void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unrolled);
 void launch_zero(float* p, size_t n);
+// YeeLattice::apply_edge_bc (emf/yee_lattice.c++:263-306): masked components of `field` over the box [lo, hi)
+void launch_edge_bc(float* field, const Geom& g, const int lo[3], const int hi[3], unsigned mask, const float v[3]);
+// J = J + add over n floats (YeeLattice::deposit_current(VecGrid), emf/yee_lattice.c++:361-375)
+void launch_add_lattice(float* J, const float* add, size_t n);
 // which: 0=E 1=B 2=J; nbr: device int[ntiles][27] (tile-table index of the neighbour, -1 = remote)
 // nbr codes: >= 0 local tile slot; -1 none; <= -2 remote, staged slab remote[-(code+2)] (comm.cu)
 void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which, const SlabDesc* remote);

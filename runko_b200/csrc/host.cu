@@ -477,14 +477,95 @@ void phase_deposit(const std::vector<b2p_tile*>& tiles) {
       t->fp_dirty = true;
       if (t->grid) t->grid->table_dirty = true;
       t->pendJ_valid = t->pend_packed = false;
-      continue;
+    } else {
+      t->pendJ_valid = t->pend_packed = false;
+      s.edges.reserve(size_t(3) * t->g.Ch);
+      launch_zero(reinterpret_cast<float*>(s.edges.p), size_t(12) * t->g.Ch);
+      for (Container& c : t->sp)
+        launch_deposit(c.view(), s.edges.p, t->g, t->origo, static_cast<float>(t->cfg.cfl), static_cast<float>(c.charge));
+      launch_edge_gather(s.edges.p, t->J(), t->g);
     }
+    if (t->corr_pending) {                                          // pic/tile.c++:411-414
+      launch_add_lattice(t->J(), t->corrJ.p, t->lattice_floats());
+      t->corr_pending = false;
+    }
+  }
+}
+
+// ------------------------------------------------- pic-shock boundary pieces --
+// emf/tile.c++:808-827
+static bool edge_bc_width(const b2p_tile* t, const b2p_edge_bc& bc, size_t* width) {
+  const int d = bc.direction;
+  const float tile_min = static_cast<float>(t->mins[d]);
+  const float tile_max = static_cast<float>(t->maxs[d]);
+  const size_t Nd = size_t(t->g.N[d]);
+  if (bc.side == 0) {
+    if (bc.position <= tile_min) return false;
+    if (bc.position >= tile_max) { *width = Nd; return true; }
+    *width = static_cast<size_t>(bc.position - tile_min) + 1;
+    return true;
+  }
+  if (bc.position >= tile_max) return false;
+  if (bc.position <= tile_min) { *width = Nd; return true; }
+  *width = Nd - static_cast<size_t>(bc.position - tile_min);
+  return true;
+}
+
+// emf::Tile::apply_edge_bc (emf/tile.c++:835-840) + YeeLattice::apply_edge_bc (emf/yee_lattice.c++:263-306)
+static void apply_edge_bc(b2p_tile* t, const b2p_edge_bc& bc, int mode) {
+  if (bc.direction > 2) throw Error(B2P_ERR_RUNTIME, "edge_bc: direction must be 0, 1 or 2");
+  float* field;
+  unsigned mask;
+  const float* v;
+  switch (mode) {
+    case B2P_COMM_EMF_E: field = t->E.p; mask = bc.E_components; v = bc.E; break;
+    case B2P_COMM_EMF_B: field = t->B.p; mask = bc.B_components; v = bc.B; break;
+    case B2P_COMM_EMF_J: field = t->J(); mask = bc.J_components; v = bc.J; break;
+    default:
+      throw Error(B2P_ERR_RUNTIME, "YeeLattice::apply_edge_bc does not support given communication mode: " + std::to_string(mode));
+  }
+  size_t width = 0;
+  if (!edge_bc_width(t, bc, &width) || width == 0) return;
+  const int d = bc.direction;
+  const int Nd = t->g.N[d];
+  const int w = int(std::min<size_t>(width, size_t(Nd)));
+  int lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    if (a != d) { lo[a] = 0; hi[a] = t->g.Hx[a]; }
+    else if (bc.side == 0) { lo[a] = 0; hi[a] = H + w; }
+    else { lo[a] = H + Nd - w; hi[a] = t->g.Hx[a]; }
+  }
+  launch_edge_bc(field, t->g, lo, hi, mask, v);
+}
+
+void phase_apply_edge_bcs(const std::vector<b2p_tile*>& tiles, int mode) {
+  for (b2p_tile* t : tiles)
+    for (const b2p_edge_bc& bc : t->edge_bcs) apply_edge_bc(t, bc, mode);      // emf/tile.c++:842-847
+}
+
+// pic::Tile::reflect_particles (pic/reflector_wall.c++:241-284)
+void phase_reflect_particles(const std::vector<b2p_tile*>& tiles) {
+  for (b2p_tile* t : tiles) {
+    if (t->walls.empty()) continue;
+    auto wall_is_in_tile = [&](const b2p_reflector_wall& w) {
+      return w.walloc >= float(t->mins[0]) - float(t->cfg.cfl) && w.walloc <= float(t->maxs[0]);
+    };
+    bool any = false;
+    for (const b2p_reflector_wall& w : t->walls) any = any || wall_is_in_tile(w);
+    if (!any) continue;
+    t->corrJ.reserve(t->lattice_floats());
+    t->corr_pending = true;
+    launch_zero(t->corrJ.p, t->lattice_floats());
+    // the particles change after the push: a current deposited inside the push no longer describes them
     t->pendJ_valid = t->pend_packed = false;
-    s.edges.reserve(size_t(3) * t->g.Ch);
-    launch_zero(reinterpret_cast<float*>(s.edges.p), size_t(12) * t->g.Ch);
-    for (Container& c : t->sp)
-      launch_deposit(c.view(), s.edges.p, t->g, t->origo, static_cast<float>(t->cfg.cfl), static_cast<float>(c.charge));
-    launch_edge_gather(s.edges.p, t->J(), t->g);
+    for (const b2p_reflector_wall& w : t->walls) {
+      if (!wall_is_in_tile(w)) continue;
+      for (Container& c : t->sp) {
+        launch_reflect_at_wall(c.view(), t->corrJ.p, t->g, t->origo, static_cast<float>(t->cfg.cfl), w.walloc, w.betawall,
+                               w.gammawall, static_cast<float>(c.charge));
+        c.touch();
+      }
+    }
   }
 }
 
@@ -1134,6 +1215,38 @@ int b2p_tile_kinetic_energy(b2p_tile* t, int sp, double* energy, uint64_t* conta
 }
 
 // --------------------------------------------------------------------- grid --
+int b2p_tile_register_edge_bc(b2p_tile* t, const b2p_edge_bc* bc) {
+  B2P_TRY
+  if (!bc) throw Error(B2P_ERR_RUNTIME, "null edge_bc");
+  T(t)->edge_bcs.push_back(*bc);
+  B2P_CATCH
+}
+int b2p_tile_apply_edge_bcs(b2p_tile* t, int mode) { B2P_TRY phase_apply_edge_bcs({ T(t) }, mode); B2P_CATCH }
+int b2p_tile_apply_edge_bc(b2p_tile* t, const b2p_edge_bc* bc, int mode) {
+  B2P_TRY
+  if (!bc) throw Error(B2P_ERR_RUNTIME, "null edge_bc");
+  apply_edge_bc(T(t), *bc, mode);
+  B2P_CATCH
+}
+int b2p_tile_register_reflector_wall(b2p_tile* t, const b2p_reflector_wall* wall) {
+  B2P_TRY
+  if (!wall) throw Error(B2P_ERR_RUNTIME, "null reflector_wall");
+  T(t)->walls.push_back(*wall);
+  B2P_CATCH
+}
+int b2p_tile_reflect_particles(b2p_tile* t) { B2P_TRY phase_reflect_particles({ T(t) }); B2P_CATCH }
+int b2p_tile_advance_reflector_walls(b2p_tile* t) {                 // pic/reflector_wall.c++:286-297
+  B2P_TRY
+  for (b2p_reflector_wall& w : T(t)->walls) w.walloc += w.betawall * float(t->cfg.cfl);
+  B2P_CATCH
+}
+int b2p_tile_reflector_walls(b2p_tile* t, b2p_reflector_wall* out, uint64_t cap, uint64_t* n) {
+  B2P_TRY
+  if (n) *n = T(t)->walls.size();
+  for (size_t q = 0; out && q < t->walls.size() && q < cap; ++q) out[q] = t->walls[q];
+  B2P_CATCH
+}
+
 int b2p_grid_create(const b2p_config* cfg, b2p_grid** out) {
   B2P_TRY
   if (!cfg || !out) throw Error(B2P_ERR_RUNTIME, "null argument");
@@ -1175,6 +1288,14 @@ int b2p_grid_push_particles(b2p_grid* g) { B2P_TRY phase_push_particles(G(g)->ti
 int b2p_grid_pack_outgoing_particles(b2p_grid* g) { B2P_TRY phase_pack_outgoing(G(g)->tiles); B2P_CATCH }
 int b2p_grid_sort_particles(b2p_grid* g) { B2P_TRY phase_sort(G(g)->tiles); B2P_CATCH }
 int b2p_grid_deposit_current(b2p_grid* g) { B2P_TRY phase_deposit(G(g)->tiles); B2P_CATCH }
+int b2p_grid_apply_edge_bcs(b2p_grid* g, int mode) { B2P_TRY phase_apply_edge_bcs(G(g)->tiles, mode); B2P_CATCH }
+int b2p_grid_reflect_particles(b2p_grid* g) { B2P_TRY phase_reflect_particles(G(g)->tiles); B2P_CATCH }
+int b2p_grid_advance_reflector_walls(b2p_grid* g) {
+  B2P_TRY
+  for (b2p_tile* t : G(g)->tiles)
+    for (b2p_reflector_wall& w : t->walls) w.walloc += w.betawall * float(t->cfg.cfl);
+  B2P_CATCH
+}
 
 int b2p_grid_external_communication(b2p_grid* g, int mode);
 

@@ -56,6 +56,11 @@ struct b2p_tile {
   b2p_grid* grid = nullptr;
   int slot = -1;
   bool deferred = false;                      // queued in the pending batch of per-tile calls (host.cu)
+  // pic-shock boundary pieces
+  std::vector<b2p_edge_bc> edge_bcs;          // emf/tile.h:51
+  std::vector<b2p_reflector_wall> walls;      // pic/tile.h:71
+  b2p::DBuf<float> corrJ;                     // reflector_correction_J_ (pic/tile.h:72), 3*Ch floats
+  bool corr_pending = false;                  // reflector_correction_pending_ (pic/tile.h:73)
 
   float* J() { return Jbuf[jcur].p; }
   b2p::FieldPtrs ptrs() { return b2p::FieldPtrs{ E.p, B.p, J() }; }
@@ -91,6 +96,8 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles);
 void phase_deposit(const std::vector<b2p_tile*>& tiles);
 void phase_sort(const std::vector<b2p_tile*>& tiles);
 void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles);
+void phase_apply_edge_bcs(const std::vector<b2p_tile*>& tiles, int mode);
+void phase_reflect_particles(const std::vector<b2p_tile*>& tiles);
 void grid_local_communication(b2p_grid* g, int mode);
 void flush_deferred();                      // executes the pending batch of per-tile calls (host.cu)
 void set_last_error(const std::string& s);

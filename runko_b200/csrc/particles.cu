@@ -537,34 +537,47 @@ k_gather(const Species src, const Species dst, const unsigned* __restrict__ perm
 __global__ void __launch_bounds__(256)
 k_sort_count(const Species s, const Geom g, const float3 origo, unsigned* __restrict__ keys, unsigned* __restrict__ rank,
              unsigned* __restrict__ cnt, const unsigned dead_key) {
-  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in = n < s.n;
-  unsigned key = dead_key;
-  unsigned long long id = DEAD;
-  float px = 0.f, py = 0.f, pz = 0.f;
-  if (in) { id = ld_pinned(s.id + n); px = ld_pinned(s.x + n); py = ld_pinned(s.y + n); pz = ld_pinned(s.z + n); }
-  if (id != DEAD) {
-    const unsigned i = __float2uint_rz(px - origo.x);
-    const unsigned j = __float2uint_rz(py - origo.y);
-    const unsigned k = __float2uint_rz(pz - origo.z);
-    key = (i * unsigned(g.Hx[1]) + j) * unsigned(g.Hx[2]) + k;
-    if (key > dead_key) key = dead_key;
-  }
-  // one atomic per run of equal keys in the warp (a container sorted a few laps ago is made of such runs)
+  // two slots per thread, 256 apart: both slots' loads, then both atomics, are in flight together
   const unsigned lane = threadIdx.x & 31;
-  const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
-  const bool head = lane == 0 || key != prev || !in;
-  const unsigned hm = __ballot_sync(0xffffffffu, head);
-  const unsigned start = 31u - __clz(hm & (0xFFFFFFFFu >> (31u - lane)));     // my run's first lane
-  const unsigned above = lane == 31 ? 0u : (hm >> (lane + 1));
-  const unsigned len = above ? unsigned(__ffs(above)) : 32u - lane;            // for a head: length of its run
-  // Dead slots are not ranked: they end up behind the alive particles in any order (k_sort_gather).
-  unsigned base = 0;
-  if (head && key != dead_key) base = atomicAdd(&cnt[key], len);
-  base = __shfl_sync(0xffffffffu, base, start);
-  if (in) {
-    keys[n] = key;
-    rank[n] = base + (lane - start);
+  unsigned n[2], key[2], start[2], base[2];
+  bool in[2];
+  unsigned long long id[2];
+  float px[2], py[2], pz[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    n[r] = blockIdx.x * 512u + 256u * r + threadIdx.x;
+    in[r] = n[r] < s.n;
+    id[r] = DEAD; px[r] = py[r] = pz[r] = 0.f;
+    if (in[r]) { id[r] = ld_pinned(s.id + n[r]); px[r] = ld_pinned(s.x + n[r]); py[r] = ld_pinned(s.y + n[r]); pz[r] = ld_pinned(s.z + n[r]); }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    key[r] = dead_key;
+    if (id[r] != DEAD) {
+      const unsigned i = __float2uint_rz(px[r] - origo.x);
+      const unsigned j = __float2uint_rz(py[r] - origo.y);
+      const unsigned k = __float2uint_rz(pz[r] - origo.z);
+      key[r] = (i * unsigned(g.Hx[1]) + j) * unsigned(g.Hx[2]) + k;
+      if (key[r] > dead_key) key[r] = dead_key;
+    }
+    // one atomic per run of equal keys in the warp (a container sorted a few laps ago is made of such runs)
+    const unsigned prev = __shfl_up_sync(0xffffffffu, key[r], 1);
+    const bool head = lane == 0 || key[r] != prev || !in[r];
+    const unsigned hm = __ballot_sync(0xffffffffu, head);
+    start[r] = 31u - __clz(hm & (0xFFFFFFFFu >> (31u - lane)));                 // my run's first lane
+    const unsigned above = lane == 31 ? 0u : (hm >> (lane + 1));
+    const unsigned len = above ? unsigned(__ffs(above)) : 32u - lane;            // for a head: length of its run
+    // Dead slots are not ranked: they end up behind the alive particles in any order (k_sort_gather).
+    base[r] = 0;
+    if (head && key[r] != dead_key) base[r] = atomicAdd(&cnt[key[r]], len);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const unsigned b0 = __shfl_sync(0xffffffffu, base[r], start[r]);
+    if (in[r]) {
+      keys[n[r]] = key[r];
+      rank[n[r]] = b0 + (lane - start[r]);
+    }
   }
 }
 
@@ -875,6 +888,91 @@ k_kinetic_energy(const Species s, double* __restrict__ out) {
   }
 }
 
+// ----------------------------------------------------------- reflector wall --
+// pic/reflector_wall.c++:35-118: zigzag deposit of one sub-trajectory x1 -> x2 (lattice-local
+// coordinates) into the nodal correction lattice.  Same operands and association as the
+// reference; the scalar atomics land in arbitrary order (stated deposit tolerance).
+__device__ __forceinline__ void zigzag_deposit_single(float* __restrict__ J, const Geom& g, const V3 x1, const V3 x2,
+                                                      const float charge) {
+  const V3 fi1 = { floorf(x1.x), floorf(x1.y), floorf(x1.z) };
+  const V3 fi2 = { floorf(x2.x), floorf(x2.y), floorf(x2.z) };
+  auto relay = [](const float f1, const float f2, const float p1, const float p2) {
+    const float a = (f1 < f2 ? f1 : f2) + 1.0f;
+    const float m = f1 > f2 ? f1 : f2;
+    const float h = 0.5f * (p1 + p2);
+    const float b = m > h ? m : h;
+    return a < b ? a : b;
+  };
+  const V3 xr = { relay(fi1.x, fi2.x, x1.x, x2.x), relay(fi1.y, fi2.y, x1.y, x2.y), relay(fi1.z, fi2.z, x1.z, x2.z) };
+  const V3 F1 = charge * (xr - x1);
+  const V3 F2 = charge * (x2 - xr);
+  const V3 W1 = 0.5f * (x1 + xr) - fi1;
+  const V3 W2 = 0.5f * (x2 + xr) - fi2;
+  const unsigned Hy = unsigned(g.Hx[1]), Hz = unsigned(g.Hx[2]);
+  Zigzag z;
+  z.n1 = (__float2uint_rz(fi1.x) * Hy + __float2uint_rz(fi1.y)) * Hz + __float2uint_rz(fi1.z);
+  z.n2 = (__float2uint_rz(fi2.x) * Hy + __float2uint_rz(fi2.y)) * Hz + __float2uint_rz(fi2.z);
+  const float one = 1.0f;
+#define EDGES(F, W, ex, ey, ez)                                                                                \
+  ex = make_float4(F.x * (one - W.y) * (one - W.z), F.x * W.y * (one - W.z), F.x * (one - W.y) * W.z, F.x * W.y * W.z); \
+  ey = make_float4(F.y * (one - W.x) * (one - W.z), F.y * W.x * (one - W.z), F.y * (one - W.x) * W.z, F.y * W.x * W.z); \
+  ez = make_float4(F.z * (one - W.x) * (one - W.y), F.z * W.x * (one - W.y), F.z * (one - W.x) * W.y, F.z * W.x * W.y);
+  EDGES(F1, W1, z.ax, z.ay, z.az)
+  EDGES(F2, W2, z.bx, z.by, z.bz)
+#undef EDGES
+  deposit_split_nodal(z, J, g);
+}
+
+// ParticleContainer::reflect_at_wall (pic/reflector_wall.c++:126-222), one thread per slot.  The
+// reference evaluates every alive particle branch-free with 0/1 float masks; the same expressions
+// are evaluated here (positions and velocities are bit-identical), and only the two correction
+// deposits — which the reference multiplies by mask_refl = 0 for everything but the reflected
+// particles — are skipped when the mask is zero (adding +-0 does not change the lattice).
+__global__ void __launch_bounds__(256)
+k_reflect_at_wall(const Species s, float* __restrict__ corrJ, const Geom g, const float3 origo_, const float c,
+                  const float walloc, const float betawall, const float gammawall, const float charge) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= s.n || s.id[n] == DEAD) return;
+  const float EPS = 1e-10f;
+  const float walloc0 = walloc - betawall * c;
+  const V3 origo = { origo_.x, origo_.y, origo_.z };
+  const V3 pos_1 = { s.x[n], s.y[n], s.z[n] };
+  const V3 u = { s.ux[n], s.uy[n], s.uz[n] };
+  const float gam = sqrtf(1.0f + dot(u, u));
+  const float invgam = 1.0f / gam;
+  const V3 pos_0 = pos_1 - c * invgam * u;
+  const float mask_skip = (pos_1.x >= walloc) ? 1.0f : 0.0f;
+  const float mask_close = (walloc0 - pos_0.x <= c) ? 1.0f : 0.0f;
+  const float denom = betawall * c - c * u.x * invgam;
+  const float dt = fabsf((pos_0.x - walloc0) / (denom + EPS));
+  const float mask_crossed = (dt <= 1.0f) ? 1.0f : 0.0f;
+  const float mask_refl = (1.0f - mask_skip) * mask_close * mask_crossed;
+  const float mask_park = (1.0f - mask_skip) - mask_refl;
+  const V3 pos_col = pos_0 + c * dt * invgam * u;
+  const float ux_new = gammawall * gammawall * gam * (2.0f * betawall - u.x * invgam * (1.0f + betawall * betawall));
+  const V3 u_new = { ux_new, u.y, u.z };
+  const float gam_new = sqrtf(1.0f + dot(u_new, u_new));
+  const float invgam_new = 1.0f / gam_new;
+  const float ratio = fabsf((pos_1.x - pos_col.x) / (pos_1.x - pos_0.x + EPS));
+  const float dt_refl = 1.0f < ratio ? 1.0f : ratio;
+  const V3 pos_refl = pos_col + c * dt_refl * invgam_new * u_new;
+  if (mask_refl != 0.0f) {
+    const V3 p1l = pos_1 - origo;
+    const V3 dep_fwd_from = p1l + mask_refl * (pos_0 - pos_1);
+    const V3 dep_fwd_to = p1l + mask_refl * (pos_col - pos_1);
+    zigzag_deposit_single(corrJ, g, dep_fwd_from, dep_fwd_to, mask_refl * charge);
+    const V3 x1_deposit = pos_refl - c * invgam_new * u_new;
+    const V3 dep_rev_from = p1l + mask_refl * (x1_deposit - pos_1);
+    const V3 dep_rev_to = p1l + mask_refl * (pos_col - pos_1);
+    zigzag_deposit_single(corrJ, g, dep_rev_from, dep_rev_to, mask_refl * (-charge));
+  }
+  s.x[n] = (1.0f - mask_refl) * pos_1.x + mask_refl * pos_refl.x;
+  s.y[n] = (1.0f - mask_refl) * pos_1.y + mask_refl * pos_refl.y;
+  s.z[n] = (1.0f - mask_refl) * pos_1.z + mask_refl * pos_refl.z;
+  s.ux[n] = (1.0f - mask_refl) * u.x + mask_refl * ux_new;
+  if (mask_park > 0.5f) s.id[n] = DEAD;
+}
+
 // ------------------------------------------------- synthetic thermal plasma --
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -1070,7 +1168,7 @@ void launch_sort_count_scan(const Species& s, const Geom& g, const float origo[3
     ProfScope prof_(KC_SORT_KEYS, double(s.n));
     B2P_CUDA(cudaMemsetAsync(cnt, 0, (size_t(nkeys) + 2) * sizeof(unsigned), ctx().stream));
     B2P_CUDA(cudaMemsetAsync(max_pop, 0, sizeof(unsigned), ctx().stream));
-    k_sort_count<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, g, make_float3(origo[0], origo[1], origo[2]), keys, rank, cnt, nkeys);
+    k_sort_count<<<(s.n + 511) / 512, 256, 0, ctx().stream>>>(s, g, make_float3(origo[0], origo[1], origo[2]), keys, rank, cnt, nkeys);
     B2P_LAUNCH_CHECK();
   }
   ProfScope prof_(KC_RADIX_SORT, double(s.n));
@@ -1170,6 +1268,15 @@ void launch_kinetic_energy(const Species& s, double* out) {
   if (!s.n) return;
   const unsigned nb = std::min(blocks_for(s.n), unsigned(ctx().sm_count) * 8);
   k_kinetic_energy<<<nb, 256, 0, ctx().stream>>>(s, out);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_reflect_at_wall(const Species& s, float* corrJ, const Geom& g, const float origo[3], float cfl, float walloc,
+                            float betawall, float gammawall, float charge) {
+  ProfScope prof_(KC_OTHER, double(s.n));
+  if (!s.n) return;
+  k_reflect_at_wall<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, corrJ, g, make_float3(origo[0], origo[1], origo[2]), cfl, walloc,
+                                                              betawall, gammawall, charge);
   B2P_LAUNCH_CHECK();
 }
 

@@ -65,6 +65,9 @@ void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, c
 void launch_selfcheck_divc(const float* x, unsigned long long n, float c, float* out, float* ref);
 void launch_fill_dead(unsigned long long* id, unsigned begin, unsigned end);
 void launch_kinetic_energy(const Species& s, double* out);
+// ParticleContainer::reflect_at_wall (pic/reflector_wall.c++:126-222); corrJ = nodal correction lattice (3*Ch floats)
+void launch_reflect_at_wall(const Species& s, float* corrJ, const Geom& g, const float origo[3], float cfl, float walloc,
+                            float betawall, float gammawall, float charge);
 void launch_inject_thermal(const Species& s, const Geom& g, const float mins[3], unsigned ppc, float theta,
                            unsigned long long seed_pos, unsigned long long seed_vel, unsigned long long id_base);
 }  // namespace b2p

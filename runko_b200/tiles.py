@@ -57,6 +57,26 @@ class ParticleStateD:
         self.vel = list(vel)
 
 
+def edge_bc(*, direction=0, side=0, position=0.0, Ex=0.0, Ey=0.0, Ez=0.0, Bx=0.0, By=0.0, Bz=0.0,
+            Jx=0.0, Jy=0.0, Jz=0.0, E_components=0b111, B_components=0b111, J_components=0b111):
+    """emf.threeD.edge_bc (bindings/pyemf.c++:171-199; keyword-only like the reference)."""
+    bc = _abi.EdgeBC(direction=int(direction), side=int(side), position=float(position),
+                     E_components=int(E_components), B_components=int(B_components), J_components=int(J_components))
+    bc.E[:] = (Ex, Ey, Ez)
+    bc.B[:] = (Bx, By, Bz)
+    bc.J[:] = (Jx, Jy, Jz)
+    return bc
+
+
+def reflector_wall(*, walloc=0.0, betawall=0.0, gammawall=1.0):
+    """pic.threeD.reflector_wall (bindings/pypic.c++:70-90)."""
+    return _abi.ReflectorWall(walloc=float(walloc), betawall=float(betawall), gammawall=float(gammawall))
+
+
+def _mode(m):
+    return m.value if isinstance(m, comm_mode) else int(m)
+
+
 class EmfTileHost:
     """Backend-independent host logic of emf::Tile<3> (emf/tile.c++:184-335,
     bindings/pyemf.c++:32-78): where the Yee-staggered sample points are, what the
@@ -217,6 +237,16 @@ class Tile(EmfTileHost):
         check(lib().b2p_tile_field_energy(self._h, C.byref(b), C.byref(e)))
         return b.value, e.value
 
+    # -- edge boundary conditions (emf/tile.c++:808-847) ------------------------------
+    def register_edge_bc(self, bc):
+        check(lib().b2p_tile_register_edge_bc(self._h, C.byref(bc)))
+
+    def apply_edge_bcs(self, mode):
+        check(lib().b2p_tile_apply_edge_bcs(self._h, _mode(mode)))
+
+    def apply_edge_bc(self, bc, mode):
+        check(lib().b2p_tile_apply_edge_bc(self._h, C.byref(bc), _mode(mode)))
+
 
 class PicTileHost:
     """Backend-independent host logic of pic::Tile<3> (pic/tile.c++:180-322,
@@ -357,6 +387,22 @@ class PicTile(PicTileHost, Tile):
         check(lib().b2p_tile_kinetic_energy(self._h, int(sp), C.byref(e), C.byref(n)))
         return e.value, n.value
 
+    # -- reflector wall (pic/reflector_wall.c++:226-297) --------------------------------
+    def register_reflector_wall(self, wall):
+        check(lib().b2p_tile_register_reflector_wall(self._h, C.byref(wall)))
+
+    def reflect_particles(self):
+        check(lib().b2p_tile_reflect_particles(self._h))
+
+    def advance_reflector_walls(self):
+        check(lib().b2p_tile_advance_reflector_walls(self._h))
+
+    def reflector_walls(self):
+        n = C.c_uint64()
+        out = (_abi.ReflectorWall * 16)()
+        check(lib().b2p_tile_reflector_walls(self._h, out, 16, C.byref(n)))
+        return [(w.walloc, w.betawall, w.gammawall) for w in out[:n.value]]
+
 
 class Grid:
     """The slice of corgi::Grid<3> the PIC lap uses, batched per phase on the device."""
@@ -400,8 +446,40 @@ class Grid:
     def phase(self, name):
         check(getattr(lib(), "b2p_grid_" + name)(self._h))
 
+    def apply_edge_bcs(self, mode):
+        check(lib().b2p_grid_apply_edge_bcs(self._h, _mode(mode)))
+
     def step_pic(self, lap):
         check(lib().b2p_grid_step_pic(self._h, int(lap)))
+
+    def step_shock(self, lap, n_filter_passes=3):
+        """One lap of projects/pic-shock/pic.py:229-279 (injector and IO excluded), phase by phase on
+        the device: edge BCs after every field update, reflector wall between push and pack."""
+        M = comm_mode
+        multi = getattr(self, "_multi", False)
+
+        def comm(m, local=None):
+            if multi:
+                self.external_communication(m)
+            self.local_communication(m if local is None else local)
+
+        self.phase("push_half_b"); self.apply_edge_bcs(M.emf_B); comm(M.emf_B)
+        self.phase("push_particles"); self.phase("reflect_particles"); self.phase("pack_outgoing_particles")
+        comm(M.pic_particle)
+        if lap % 5 == 0:
+            self.phase("sort_particles")
+        self.phase("deposit_current")
+        comm(M.emf_J, M.emf_J_exchange); comm(M.emf_J)
+        self.apply_edge_bcs(M.emf_J)
+        for i in range(n_filter_passes):
+            if i > 0 and i % 3 == 0:
+                comm(M.emf_J)
+            self.phase("filter_current")
+        self.apply_edge_bcs(M.emf_J)
+        self.phase("push_half_b"); self.apply_edge_bcs(M.emf_B); comm(M.emf_B)
+        self.phase("push_e"); self.apply_edge_bcs(M.emf_E)
+        self.phase("add_current"); self.apply_edge_bcs(M.emf_E); comm(M.emf_E)
+        self.phase("advance_reflector_walls")
 
     def step_emf(self):
         check(lib().b2p_grid_step_emf(self._h))

@@ -39,6 +39,12 @@ class OracleTile:
     def get_outgoing(self):
         return self.g.get_outgoing(self.t)
 
+    def register_reflector_wall(self, wall):
+        self.g.register_reflector_wall(self.t, wall)
+
+    def apply_edge_bc(self, bc, mode):
+        self.g.apply_edge_bc(self.t, bc, int(mode))
+
 
 class B200Tile:
     name = "b200"
@@ -72,6 +78,12 @@ class B200Tile:
 
     def get_outgoing(self):
         return self.tile.get_outgoing()
+
+    def register_reflector_wall(self, wall):
+        self.tile.register_reflector_wall(wall)
+
+    def apply_edge_bc(self, bc, mode):
+        self.tile.apply_edge_bc(bc, int(mode))
 
 
 class OracleGridB:

@@ -76,6 +76,15 @@ else:
                 raise RuntimeError(str(e)) from None
 
     class EmfTile(_OracleBacked, _t.EmfTileHost):
+        def _ck(self, f, *a):
+            try:
+                return f(*a)
+            except OracleError as e:
+                raise RuntimeError(str(e)) from None
+
+        def register_edge_bc(self, bc): self._ck(self._g.register_edge_bc, self._t, bc)
+        def apply_edge_bcs(self, mode): self._ck(self._g.apply_edge_bcs, self._t, _t._mode(mode))
+        def apply_edge_bc(self, bc, mode): self._ck(self._g.apply_edge_bc, self._t, bc, _t._mode(mode))
         def push_half_b(self): self._op("push_half_b")
         def push_e(self): self._op("push_e")
         def add_current(self): self._op("add_current")
@@ -100,6 +109,9 @@ else:
         def deposit_current(self): self._op("deposit_current")
         def sort_particles(self): self._op("sort_particles")
         def pack_outgoing_particles(self): self._op("pack_outgoing_particles")
+        def register_reflector_wall(self, wall): self._ck(self._g.register_reflector_wall, self._t, wall)
+        def reflect_particles(self): self._op("reflect_particles")
+        def advance_reflector_walls(self): self._op("advance_reflector_walls")
 
 
 def _module(name, **attrs):
@@ -109,6 +121,8 @@ def _module(name, **attrs):
     return m
 
 
-emf = _module("runko.emf", threeD=_module("runko.emf.threeD", Tile=EmfTile))
+emf = _module("runko.emf", threeD=_module("runko.emf.threeD", Tile=EmfTile, edge_bc=_t.edge_bc))
 pic = _module("runko.pic", threeD=_module("runko.pic.threeD", Tile=PicTile, ParticleState=_t.ParticleStateD,
-                                          ParticleStateBatch=_t.ParticleStateBatch))
+                                          ParticleStateBatch=_t.ParticleStateBatch, reflector_wall=_t.reflector_wall))
+tools = _module("runko.tools", comm_mode=_t.comm_mode)
+from runko_b200.moving_injector import MovingInjector  # noqa: E402,F401

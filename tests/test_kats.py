@@ -339,3 +339,56 @@ def test_migration_into_empty_tiles_and_noop(backend):
     for idx in g.tiles():
         if idx != (0, 0, 0):
             assert len(g.get_particles(idx, 0, alive_only=True)[6]) == 0
+
+
+# ---- tests/py/test_pic_reflector_wall.py:29-133, test_emf_edge_bc.py:85-133 (restated) ------------
+def _reflector_tile(backend):
+    import runko_b200 as rb
+    conf = pic_conf(n_tiles=(4, 4, 4), n_cells=N, cfl=1, q0=-1, current_depositer="zigzag_1st", current_filter=None)
+    t = TILE[backend](conf)
+    t.register_reflector_wall(rb.reflector_wall(walloc=5.0))
+    t.set_fields(ZERO, ZERO, ZERO)
+    return t
+
+
+def test_stationary_wall_reflects_ux(backend):
+    t = _reflector_tile(backend)
+    t.inject(0, ([5.5], [5.5], [6.5]), ([-1.0], [0.0], [0.0]))
+    t.op("push_particles")
+    t.op("reflect_particles")
+    x, y, z, ux, uy, uz, ids = t.get_particles(0, alive_only=True)
+    assert len(x) == 1 and ux[0] > 0 and abs(abs(ux[0]) - 1.0) < 1e-4 and x[0] > 5.0
+    assert abs(uy[0]) < 1e-5 and abs(uz[0]) < 1e-5
+
+
+def test_no_current_behind_wall_after_reflect_and_deposit(backend):
+    t = _reflector_tile(backend)
+    j, k = np.meshgrid(np.arange(N[1]), np.arange(N[2]), indexing="ij")
+    m = j.size
+    t.inject(0, (np.full(m, 5.5), j.ravel() + 0.5, k.ravel() + 0.5), (np.full(m, -0.5), np.zeros(m), np.zeros(m)))
+    for op in ("push_particles", "reflect_particles", "deposit_current"):
+        t.op(op)
+    J = t.get_fields()[2][:, 3:-3, 3:-3, 3:-3]
+    assert np.all(np.abs(J[:, :4]) < 1e-5)          # x-indices 0..3: well behind the wall
+    assert np.any(np.abs(J) > 1e-3)                 # and the reflected current itself is there
+
+
+def test_particle_far_behind_wall_gets_killed(backend):
+    t = _reflector_tile(backend)
+    t.inject(0, ([2.0], [5.5], [6.5]), ([-0.1], [0.0], [0.0]))
+    t.op("push_particles")
+    t.op("reflect_particles")
+    assert len(t.get_particles(0, alive_only=True)[0]) == 0
+
+
+@pytest.mark.parametrize("side,position,expect", [(0, 5.0, slice(0, 6)), (1, 7.0, slice(7, 10))])
+def test_x_edge_sets_correct_cells(backend, side, position, expect):
+    import runko_b200 as rb
+    t = TILE[backend](emf_conf(n_cells=N, n_tiles=(4, 4, 4)))
+    one = np.ones_like(ZERO)
+    t.set_fields(one, ZERO, ZERO)
+    t.apply_edge_bc(rb.edge_bc(direction=0, side=side, position=position, Ex=0.0, Ey=0.0, Ez=0.0), rb.comm_mode.emf_E.value)
+    E = t.get_fields()[0][:, 3:-3, 3:-3, 3:-3]
+    mask = np.zeros(N[0], bool)
+    mask[expect] = True
+    assert np.all(E[:, mask] == 0) and np.all(E[:, ~mask] == 1)

@@ -195,3 +195,125 @@ def test_energies():
     assert ob == rb_ and oe == re_
     for sp in range(2):
         assert org.kinetic_energy(t, sp)[0] == rk[sp]
+
+
+# ---------------------------------------------------------------- pic-shock boundary pieces --
+def _bc(**kw):
+    from runko_b200._abi import EdgeBC
+    b = EdgeBC(direction=kw.get("direction", 0), side=kw.get("side", 0), position=kw.get("position", 0.0),
+               E_components=kw.get("E_components", 7), B_components=kw.get("B_components", 7),
+               J_components=kw.get("J_components", 7))
+    for name in "EBJ":
+        for c, v in enumerate(kw.get(name, (0.0, 0.0, 0.0))):
+            getattr(b, name)[c] = v
+    return b
+
+
+@pytest.mark.parametrize("case", [
+    dict(direction=0, side=0, position=5.0, E=(1.5, -2.0, 0.25), E_components=0b110),
+    dict(direction=0, side=1, position=7.0, B=(0.1, 0.2, 0.3)),
+    dict(direction=1, side=0, position=15.5, J=(3.0, 0.0, -1.0), J_components=0b101),
+    dict(direction=2, side=1, position=13.0, E=(9.0, 8.0, 7.0)),
+    dict(direction=0, side=0, position=100.0, E=(1.0, 1.0, 1.0)),     # tile fully behind the edge
+    dict(direction=0, side=0, position=-3.0, E=(1.0, 1.0, 1.0)),      # tile fully in front: untouched
+])
+def test_edge_bc(case):
+    """emf::Tile::apply_edge_bc(s): the reference's YeeLattice::apply_edge_bc vs the oracle, all three modes."""
+    rng = np.random.default_rng(21)
+    n = (10, 11, 13)
+    conf = pic_conf(n_tiles=(2, 2, 2), n_cells=n)
+    org, t, ref = pair(conf, (0, 1, 1))
+    load_fields(rng, org, t, ref, n)
+    bc = _bc(**case)
+    for mode in (1, 2, 0):                       # emf_E, emf_B, emf_J
+        org.apply_edge_bc(t, bc, mode)
+        ref.apply_edge_bc(bc, mode)
+    same_fields(org, t, ref, "apply_edge_bc ")
+    org.register_edge_bc(t, bc)
+    ref.register_edge_bc(bc)
+    bc2 = _bc(direction=1, side=1, position=14.0, E=(4.0, 4.0, 4.0), B=(5.0, 5.0, 5.0), J=(6.0, 6.0, 6.0))
+    org.register_edge_bc(t, bc2)
+    ref.register_edge_bc(bc2)
+    load_fields(rng, org, t, ref, n)
+    for mode in (0, 1, 2):
+        org.apply_edge_bcs(t, mode)
+        ref.apply_edge_bcs(mode)
+    same_fields(org, t, ref, "apply_edge_bcs ")
+
+
+def test_edge_bc_rejects_other_modes():
+    conf = pic_conf(n_tiles=(1, 1, 1), n_cells=(5, 5, 5))
+    org, t, ref = pair(conf)
+    bc = _bc(direction=0, side=0, position=3.0)
+    from oracle.oracle import OracleError
+    with pytest.raises(OracleError):
+        org.apply_edge_bc(t, bc, 3)
+    with pytest.raises(rbuild.RefError):
+        ref.apply_edge_bc(bc, 3)
+
+
+@pytest.mark.parametrize("beta", [0.0, 0.3])
+@pytest.mark.parametrize("dep", ["zigzag_1st_atomic", "zigzag_1st"])
+def test_reflector_wall(beta, dep):
+    """pic::Tile::reflect_particles / ParticleContainer::reflect_at_wall (the reference's own, compiled from
+    pic/reflector_wall.c++) vs the oracle: particles slot by slot (reflected, parked = dead, untouched), the
+    correction current as it lands in J through deposit_current, and the advancing wall — over several laps
+    of push -> reflect -> deposit -> advance."""
+    from runko_b200._abi import ReflectorWall
+    rng = np.random.default_rng(31)
+    n = (12, 6, 7)
+    conf = pic_conf(n_tiles=(2, 1, 1), n_cells=n, current_depositer=dep, q0=-0.7, q1=0.4, cfl=0.45)
+    org, t, ref = pair(conf, (0, 0, 0))
+    load_fields(rng, org, t, ref, n)
+    # particles in front of the wall, streaming towards it
+    for sp in range(2):
+        m = 6000 + 13 * sp
+        pos = np.stack([5.0 + 6.0 * rng.random(m), 6.0 * rng.random(m), 7.0 * rng.random(m)]).astype(np.float32)
+        vel = (0.6 * rng.standard_normal((3, m))).astype(np.float32)
+        vel[0] -= np.float32(0.8)
+        pos[0, :40] = (2.5 + 2.0 * rng.random(40)).astype(np.float32)   # already behind the wall: parked (-> dead)
+        ids = (np.uint64(sp + 1) << np.uint64(40)) | np.arange(m, dtype=np.uint64)
+        ids[rng.random(m) < 0.05] = DEAD
+        org.set_particles(t, sp, *pos, *vel, ids)
+        ref.set_particles(sp, *pos, *vel, ids)
+    gamma = 1.0 / np.sqrt(1.0 - beta * beta)
+    wall = ReflectorWall(walloc=5.0, betawall=beta, gammawall=gamma)
+    far = ReflectorWall(walloc=40.0, betawall=0.0, gammawall=1.0)        # not in this tile: ignored
+    for w in (wall, far):
+        org.register_reflector_wall(t, w)
+        ref.register_reflector_wall(w)
+    n_dead0 = sum(int(np.sum(ref.get_particles(sp)[6] == DEAD)) for sp in range(2))
+    for lap in range(4):
+        for op in ("push_particles", "reflect_particles"):
+            org.tile_op(t, op)
+            ref.op(op)
+        same_particles(org, t, ref)
+        org.tile_op(t, "deposit_current")
+        ref.op("deposit_current")
+        same_fields(org, t, ref, f"lap {lap} ")
+        org.tile_op(t, "advance_reflector_walls")
+        ref.op("advance_reflector_walls")
+        assert org.reflector_walls(t) == ref.reflector_walls()
+    # the case exercised all three branches: reflected (ux > 0 near the wall), parked (new dead slots)
+    n_dead1 = sum(int(np.sum(ref.get_particles(sp)[6] == DEAD)) for sp in range(2))
+    x, _, _, ux, _, _, ids = ref.get_particles(0, alive_only=True)
+    assert n_dead1 > n_dead0
+    assert np.any(ux > 0.5)
+
+
+def test_reflector_wall_outside_tile_is_a_no_op():
+    from runko_b200._abi import ReflectorWall
+    rng = np.random.default_rng(33)
+    n = (6, 6, 6)
+    conf = pic_conf(n_tiles=(3, 1, 1), n_cells=n)
+    org, t, ref = pair(conf, (2, 0, 0))
+    load_fields(rng, org, t, ref, n)
+    load_particles(rng, org, t, ref, 500)
+    w = ReflectorWall(walloc=3.0, betawall=0.0, gammawall=1.0)
+    org.register_reflector_wall(t, w)
+    ref.register_reflector_wall(w)
+    for op in ("reflect_particles", "deposit_current"):
+        org.tile_op(t, op)
+        ref.op(op)
+    same_particles(org, t, ref)
+    same_fields(org, t, ref)

@@ -1,9 +1,9 @@
 """Pins the CPU oracle with the REFERENCE'S OWN unit tests: the unmodified files under
 /root/reference/tests/py are executed where they lie against tests/refshim/runko, a
 stand-in `runko` package that binds the product's host logic (runko_b200.tiles) to the
-oracle.  103 reference test cases cover fdtd2, the extended stencil, both binomial filters,
+oracle.  137 reference test cases cover fdtd2, the extended stencil, both binomial filters,
 3 pushers x 2 interpolators, both zigzag depositers, sorting, the field setters/getters and
-particle injection.
+particle injection, the edge boundary conditions, the reflector wall and the moving injector.
 
 /root/reference exists only in the build container, so this file is skipped on the GPU box
 (tests/test_kats.py restates the same known-answer cases for both backends there)."""
@@ -25,6 +25,9 @@ FILES = {
     "test_pic_particle_sorting.py": 2,
     "test_emf.py": 8,
     "test_pic.py": 6,
+    "test_emf_edge_bc.py": 15,
+    "test_pic_reflector_wall.py": 6,
+    "test_pic_moving_injector.py": 13,
 }
 
 
