@@ -25,8 +25,25 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's version / debug lines go to stderr
+# stdout carries exactly one JSON line.  Native libraries (NCCL prints its version banner with
+# printf) write to file descriptor 1, so the real stdout is kept aside for the result and fd 1 is
+# pointed at stderr for the rest of the run.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_RESULT_OUT = None
+
+
+def emit_result(obj):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
+def isolate_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 BYTES_PER_PARTICLE_PUSH = 56.0      # R pos,vel,id (32) + W pos,vel (24)
 BYTES_PER_PARTICLE_DEPOSIT = 32.0   # R pos,vel,id
@@ -207,7 +224,7 @@ def run_reference(args):
                          "sample": arm.sample(args.steps)},
         "e2e": {"value": value, "unit": "particle-pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit_result(out)
 
 
 def workload_config(args, n_gpus):
@@ -233,6 +250,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="per-kernel-class timing table on stderr")
     args = ap.parse_args()
+    isolate_stdout()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -361,8 +379,16 @@ def main():
     achieved = bytes_per_unit.get(names[top], 0.0) * units_per_launch / (avg_ms * 1e-3) / 1e9
     step_bytes = (BYTES_PER_PARTICLE_STEP + BYTES_PER_PARTICLE_SORT) * n_part_local + BYTES_PER_CELL_STEP * n_cells_local
     kname = "push+deposit (fused k_push)" if (fused and names[top] == "push") else names[top]
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (not measured live)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_push_traffic.json")
+    if names[top] == "push" and fused and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["traffic_bytes_per_launch"] * units_per_launch / tj["alive_particles_per_launch"]
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_push_traffic.json)",
+                "peak_source": peak_src,
                 "how": f"CUDA events around every launch of the class over {prof_steps} further laps (one sort cycle) run on the "
                        "library stream alone (worker streams off); `step` below is the timed region itself",
                 "avg_launch_ms": avg_ms, "launches": int(pl[top]), "bytes_per_unit": bytes_per_unit.get(names[top], 0.0),
@@ -403,7 +429,7 @@ def main():
             out["e2e"] = e2e
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        emit_result(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
