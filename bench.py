@@ -227,6 +227,180 @@ def run_reference(args):
     emit_result(out)
 
 
+# --------------------------------------------------------------------------- config 3: vacuum EM wave (field-solver roofline)
+def run_emf(args):
+    """BASELINE configs[2] ("projects/emf-wave"): FDTD + binomial filter only.  One step = one lap of
+    projects/emf-wave/emf.py:48-56 (E halo, push_half_b x2, B halo, push_e) over --cells^3 cells per GPU
+    (default 1024^3 in 8^3 tiles of 128^3); `value` = cell-updates/s.  The three binomial filter passes of a PIC lap
+    are timed separately over the same lattices (`filter`)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+    import runko_b200 as rb
+    from runko_b200._lib import check
+    L = rb.lib()
+    check(L.b2p_init(local_rank))
+    cells = args.cells if args.cells != 512 else 1024
+    tile = args.tile if args.tile != 64 else 128
+    tpg, gb = cells // tile, gpu_blocks(world)
+    conf = Conf(n_tiles=[tpg * gb[0], tpg * gb[1], tpg * gb[2]], n_cells_per_tile=[tile] * 3, cfl=1.0, field_propagator="fdtd2",
+                current_filter="binomial2")
+    grid = rb.Grid(conf)
+    bi, bj, bk = rank % gb[0], (rank // gb[0]) % gb[1], rank // (gb[0] * gb[1])
+    tiles = []
+    H = tile + 6
+    for k in range(tpg):
+        # plane wave k = 2 pi (0,0,1)/10 (emf.py:27-35): Ex(z) at z = k, By(z) at z = k + 1/2 — one slab per tile layer
+        z = (bk * tpg + k) * tile + np.arange(H, dtype=np.float64) - 3.0
+        E = np.zeros((3, H, H, H), np.float32)
+        B = np.zeros((3, H, H, H), np.float32)
+        E[0] = np.sin(2 * np.pi * z / 10.0).astype(np.float32)[None, None, :]
+        B[1] = np.sin(2 * np.pi * (z + 0.5) / 10.0).astype(np.float32)[None, None, :]
+        for i in range(tpg):
+            for j in range(tpg):
+                t = rb.Tile((bi * tpg + i, bj * tpg + j, bk * tpg + k), conf)
+                t.set_fields_f32(E, B, None, with_halo=True)
+                grid.add_tile(t)
+                tiles.append(t)
+    if world > 1:
+        T = conf.n_tiles
+        owner = np.zeros(T[0] * T[1] * T[2], np.int32)
+        for k in range(T[2]):
+            for j in range(T[1]):
+                for i in range(T[0]):
+                    owner[i + T[0] * (j + T[1] * k)] = (i // tpg) + gb[0] * ((j // tpg) + gb[1] * (k // tpg))
+        uid = np.zeros(128, np.uint8)
+        if rank == 0:
+            check(L.b2p_nccl_unique_id(uid.ctypes.data_as(C.c_void_p)))
+        lst = [uid.tobytes()]
+        dist.broadcast_object_list(lst, src=0)
+        uid = np.frombuffer(lst[0], np.uint8).copy()
+        check(L.b2p_grid_comm_init(grid._h, rank, world, uid.ctypes.data_as(C.c_void_p), owner.ctypes.data_as(C.c_void_p)))
+    n_cells_local = cells ** 3
+
+    def barrier():
+        rb.sync()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        grid.step_emf()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.b2p_launch_count()
+    check(L.b2p_timer_start())
+    for _ in range(args.steps):
+        grid.step_emf()
+    ms = C.c_float()
+    check(L.b2p_timer_stop(C.byref(ms)))
+    barrier()
+    launches = L.b2p_launch_count() - launches0
+    clocks = sampler.stop()
+    # per-kernel leg (+ three filter passes per lap, as in a PIC lap)
+    check(L.b2p_profile_enable(1))
+    prof_steps = 3
+    for _ in range(prof_steps):
+        grid.step_emf()
+        for _ in range(3):
+            grid.phase("filter_current")
+    rb.sync()
+    nk = L.b2p_profile_num_classes()
+    pms, pl, pu = np.zeros(nk), np.zeros(nk, np.uint64), np.zeros(nk)
+    check(L.b2p_profile_report(pms.ctypes.data_as(C.c_void_p), pl.ctypes.data_as(C.c_void_p), pu.ctypes.data_as(C.c_void_p)))
+    check(L.b2p_profile_enable(0))
+    names = [L.b2p_profile_class_name(k).decode() for k in range(nk)]
+    dev_s = ms.value / 1e3
+    if dist is not None:
+        import torch
+        tt = torch.tensor([dev_s], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_s = float(tt[0])
+    per_step = dev_s / args.steps
+    peak, peak_src = read_peaks()
+    bpu = {"push_b": 36.0, "push_e": 36.0, "filter": 24.0}    # SURVEY.md §8d: 36 B/cell per sweep, 24 B/cell per filter pass
+    per_kernel = {}
+    for nm in ("push_b", "push_e", "filter", "halo_fill"):
+        k = names.index(nm)
+        if pl[k]:
+            avg = pms[k] / int(pl[k])
+            per_kernel[nm] = {"avg_launch_ms": avg, "launches_per_lap": int(pl[k]) // prof_steps,
+                              "GBs": bpu.get(nm, 0.0) * n_cells_local / (avg * 1e-3) / 1e9 if nm in bpu else None}
+    top = "push_b"
+    achieved = per_kernel[top]["GBs"]
+    step_bytes = 108.0 * n_cells_local                          # three sweeps per shipped lap
+    # e2e: one tile's E,B host round trip + the lap through the per-tile API
+    M = rb.comm_mode
+    h0, d0 = C.c_uint64(), C.c_uint64()
+    rb.sync()
+    L.b2p_copy_bytes(C.byref(h0), C.byref(d0))
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for s_ in range(e2e_steps):
+        t = tiles[s_ % len(tiles)]
+        Eh, Bh, _ = t.get_fields_f32(with_halo=True)
+        t.set_fields_f32(Eh, Bh, None, with_halo=True)
+        if world > 1:
+            grid.external_communication(M.emf_E)
+        grid.local_communication(M.emf_E)
+        for t in tiles: t.push_half_b()
+        for t in tiles: t.push_half_b()
+        if world > 1:
+            grid.external_communication(M.emf_B)
+        grid.local_communication(M.emf_B)
+        for t in tiles: t.push_e()
+    barrier()
+    dt = time.perf_counter() - t0
+    h1, d1 = C.c_uint64(), C.c_uint64()
+    L.b2p_copy_bytes(C.byref(h1), C.byref(d1))
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.oracle import OracleGrid
+        nthreads = os.cpu_count() or 1
+        edge = 64
+        tz = 1
+        while tz ** 3 < nthreads:
+            tz += 1
+        oc = Conf(n_tiles=[tz, tz, max(1, -(-nthreads // (tz * tz)))], n_cells_per_tile=[edge] * 3, cfl=1.0, field_propagator="fdtd2")
+        og = OracleGrid(oc)
+        c0, nl = time.perf_counter(), 0
+        while nl < 3 or (time.perf_counter() - c0 < 10.0 and nl < 200):
+            og.step_emf(threads=nthreads)
+            nl += 1
+        cdt = (time.perf_counter() - c0) / nl
+        ncell = edge ** 3 * og.num_tiles
+        cpu = {"value": ncell / cdt, "unit": "cell-updates/s", "cores": nthreads, "kind": "port",
+               "sample": f"{oc.n_tiles} tiles of {edge}^3 cells, {nl} laps of emf.py:48-56, one tile per worker"}
+    if rank == 0:
+        out = {"metric": "cell-updates/s per vacuum field lap (BASELINE configs[2], field-solver roofline)",
+               "value": n_cells_local * world / per_step, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "projects/emf-wave vacuum plane wave (BASELINE configs[2]): E halo, push_half_b x2, B halo, push_e",
+                          "cells_per_gpu": f"{cells}^3", "tile": f"{tile}^3", "gpu_blocks": "x".join(map(str, gb)),
+                          "l2": "E+B = 24 B/cell x cells far exceed the 126 MB L2; no explicit flush"},
+               "clocks": clocks, "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "kernel": "k_push_b_fdtd2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_unit": 36.0,
+                            "units_per_launch": n_cells_local, "per_kernel": per_kernel,
+                            "step": {"algorithmic_bytes_per_gpu": step_bytes, "achieved_GBs": step_bytes / per_step / 1e9,
+                                     "frac_of_peak": step_bytes / per_step / 1e9 / peak}},
+               "e2e": {"value": n_cells_local * world / (dt / e2e_steps), "unit": "cell-updates/s", "steps": e2e_steps,
+                       "h2d_bytes_per_step": int((h1.value - h0.value) / e2e_steps),
+                       "d2h_bytes_per_step": int((d1.value - d0.value) / e2e_steps),
+                       "how": "per-tile API; one tile's E and B make a host round trip every step"}}
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        emit_result(out)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def workload_config(args, n_gpus):
     gb = gpu_blocks(n_gpus)
     return {"workload": "projects/scaling uniform thermal pair plasma (BASELINE configs[4] physics), weak scaling",
@@ -249,12 +423,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="per-kernel-class timing table on stderr")
+    ap.add_argument("--workload", default="scaling", choices=["scaling", "emf-wave"],
+                    help="scaling: BASELINE configs[4], the headline (default); emf-wave: configs[2], fields only, cell-updates/s")
     args = ap.parse_args()
     isolate_stdout()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "emf-wave":
+        return run_emf(args)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
