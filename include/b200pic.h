@@ -217,6 +217,13 @@ int b2p_grid_deposit_current(b2p_grid* g);
 int b2p_grid_apply_edge_bcs(b2p_grid* g, int mode);
 int b2p_grid_reflect_particles(b2p_grid* g);
 int b2p_grid_advance_reflector_walls(b2p_grid* g);
+/* mpiio::FieldsWriter<3>::write (src/runko/io/snapshots/mpiio_fields.c++:221-400, header
+ * mpiio_header.h:56-82): "<prefix>/flds_<lap>.bin" = 512-byte "RNKO" v3
+ * header + (9 + min(nspecies, 5)) dense fp32 arrays [nz][ny][nx] (x fastest): E, B point-sampled
+ * every `stride` cells, J summed over stride^3 blocks, n_s = alive particles per coarse cell.
+ * Every rank writes its own tiles with pwrite() into the shared file (POSIX instead of MPI-IO);
+ * rank 0 also writes the header.  Readable by runko/mpiio_reader.py. */
+int b2p_grid_write_fields_snapshot(b2p_grid* g, const char* prefix, int32_t lap, int32_t stride, int32_t nspecies);
 /* One lap of projects/pic-turbulence/pic.py:187-221 (diagnostics/IO excluded);
  * sort when lap % 5 == 0. */
 int b2p_grid_step_pic(b2p_grid* g, int64_t lap);

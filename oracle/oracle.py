@@ -65,6 +65,7 @@ def lib():
         L.orc_step_pic.argtypes = [vp, C.c_int64, ci]
         L.orc_step_emf.argtypes = [vp, ci]
         L.orc_energies.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, vp]
+        L.orc_write_fields_snapshot.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]
         _lib = L
     return _lib
 
@@ -211,6 +212,9 @@ class OracleGrid:
 
     def step_emf(self, threads=1):
         self._ck(self._L.orc_step_emf(self._g, threads))
+
+    def write_fields_snapshot(self, prefix, lap, stride=1, nspecies=2):
+        self._ck(self._L.orc_write_fields_snapshot(self._g, str(prefix).encode(), int(lap), int(stride), int(nspecies)))
 
     def energies(self):
         b, e = C.c_double(), C.c_double()

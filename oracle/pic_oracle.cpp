@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -1219,6 +1220,89 @@ int orc_step_emf(orc_grid* g, int threads) {
   DO(orc_local_communication(g, B2P_COMM_EMF_B));
   DO(orc_grid_phase(g, "push_e", threads));
 #undef DO
+  return 0;
+}
+
+// mpiio::write_header (io/snapshots/mpiio_fields.c++:22-78; layout mpiio_header.h:56-82)
+static void snapshot_header(char buf[512], int32_t nx, int32_t ny, int32_t nz, int32_t stride, const b2p_config& c, int32_t lap,
+                            int32_t num_fields) {
+  std::memset(buf, 0, 512);
+  auto put = [&](int off, uint32_t v) { std::memcpy(buf + off, &v, 4); };
+  put(0, 0x524E4B4Fu); put(4, 3u); put(8, 512u); put(12, uint32_t(num_fields));
+  put(16, uint32_t(nx)); put(20, uint32_t(ny)); put(24, uint32_t(nz)); put(28, uint32_t(stride));
+  put(32, uint32_t(c.n_tiles[0])); put(36, uint32_t(c.n_tiles[1])); put(40, uint32_t(c.n_tiles[2]));
+  put(44, uint32_t(c.n_cells[0])); put(48, uint32_t(c.n_cells[1])); put(52, uint32_t(c.n_cells[2]));
+  put(56, uint32_t(lap)); put(60, 4u);
+  static const char* names[9] = { "ex", "ey", "ez", "bx", "by", "bz", "jx", "jy", "jz" };
+  for (int f = 0; f < 9; ++f) std::memcpy(buf + 64 + f * 16, names[f], std::strlen(names[f]));
+  for (int s = 0; s < num_fields - 9; ++s) {
+    const std::string nm = "n" + std::to_string(s);
+    std::memcpy(buf + 64 + (9 + s) * 16, nm.data(), std::min<size_t>(nm.size(), 15));
+  }
+}
+
+// FieldsWriter<3>::write: pack_tile (:221-321) + write_payload_ (:345-400), plain stdio instead of MPI-IO
+int orc_write_fields_snapshot(orc_grid* g, const char* prefix, int32_t lap, int32_t stride, int32_t nspecies) {
+  if (stride < 1) { g_err = "snapshot stride must be >= 1"; return B2P_ERR_RUNTIME; }
+  const b2p_config& c = g->cfg;
+  const int nsp = std::min(nspecies, 5);                                   // mpiio_header.h:26
+  const int nf = 9 + std::max(nsp, 0);
+  const int nxt = std::max(1, c.n_cells[0] / stride), nyt = std::max(1, c.n_cells[1] / stride), nzt = std::max(1, c.n_cells[2] / stride);
+  const int nx = c.n_tiles[0] * nxt, ny = c.n_tiles[1] * nyt, nz = c.n_tiles[2] * nzt;
+  const std::string fn = std::string(prefix) + "/flds_" + std::to_string(lap) + ".bin";
+  FILE* fh = std::fopen(fn.c_str(), "wb");
+  if (!fh) { g_err = "cannot open " + fn; return B2P_ERR_RUNTIME; }
+  char hdr[512];
+  snapshot_header(hdr, nx, ny, nz, stride, c, lap, nf);
+  std::fwrite(hdr, 1, 512, fh);
+  const size_t field_elems = size_t(nx) * ny * nz, tile_elems = size_t(nxt) * nyt * nzt;
+  std::vector<float> zeros(field_elems, 0.0f);
+  for (int f = 0; f < nf; ++f) std::fwrite(zeros.data(), 4, field_elems, fh);   // MPI_File_set_size: zero-filled
+  std::vector<float> buf(size_t(nf) * tile_elems);
+  for (const Tile& t : g->tiles) {
+    std::fill(buf.begin(), buf.end(), 0.0f);
+    for (int iz = 0; iz < nzt; ++iz)
+      for (int iy = 0; iy < nyt; ++iy)
+        for (int ix = 0; ix < nxt; ++ix) {
+          const size_t o = (size_t(iz) * nyt + iy) * nxt + ix;
+          const size_t l = t.lin(size_t(ix) * stride + H, size_t(iy) * stride + H, size_t(iz) * stride + H);
+          for (int d = 0; d < 3; ++d) {
+            buf[(0 + d) * tile_elems + o] = t.E[d * t.Ch + l];
+            buf[(3 + d) * tile_elems + o] = t.B[d * t.Ch + l];
+          }
+          float sj[3] = { 0.0f, 0.0f, 0.0f };
+          for (int kk = 0; kk < stride; ++kk)
+            for (int jj = 0; jj < stride; ++jj)
+              for (int ii = 0; ii < stride; ++ii) {
+                const size_t m = t.lin(size_t(ix) * stride + ii + H, size_t(iy) * stride + jj + H, size_t(iz) * stride + kk + H);
+                for (int d = 0; d < 3; ++d) sj[d] += t.J[d * t.Ch + m];
+              }
+          for (int d = 0; d < 3; ++d) buf[(6 + d) * tile_elems + o] = sj[d];
+        }
+    const float mx = float(t.mins[0]), my = float(t.mins[1]), mz = float(t.mins[2]);
+    const float inv_stride = 1.0f / float(stride);
+    const int ndep = std::min<int>(int(t.sp.size()), nsp);
+    for (int s = 0; s < ndep; ++s) {
+      const Container& pc = t.sp[s];
+      for (size_t n = 0; n < pc.size(); ++n) {
+        if (pc.id[n] == DEAD) continue;
+        const size_t ci = size_t(std::floor((pc.x[n] - mx) * inv_stride));
+        const size_t cj = size_t(std::floor((pc.y[n] - my) * inv_stride));
+        const size_t ck = size_t(std::floor((pc.z[n] - mz) * inv_stride));
+        if (ci >= size_t(nxt) || cj >= size_t(nyt) || ck >= size_t(nzt)) continue;   // outside the coarse tile: UB in the reference
+        buf[(9 + s) * tile_elems + (ck * nyt + cj) * nxt + ci] += 1.0f;
+      }
+    }
+    for (int f = 0; f < nf; ++f)
+      for (int ks = 0; ks < nzt; ++ks)
+        for (int js = 0; js < nyt; ++js) {
+          const size_t off = 512 + 4 * (size_t(f) * field_elems +
+                                        (size_t(t.idx[2] * nzt + ks) * ny + size_t(t.idx[1] * nyt + js)) * nx + size_t(t.idx[0]) * nxt);
+          std::fseek(fh, long(off), SEEK_SET);
+          std::fwrite(buf.data() + size_t(f) * tile_elems + (size_t(ks) * nyt + js) * nxt, 4, size_t(nxt), fh);
+        }
+  }
+  std::fclose(fh);
   return 0;
 }
 

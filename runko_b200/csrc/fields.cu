@@ -142,6 +142,36 @@ k_add_lattice(float* __restrict__ J, const float* __restrict__ add, const size_t
   if (q < n) J[q] = J[q] + add[q];
 }
 
+// ---- field snapshot packing (io/snapshots/mpiio_fields.c++:221-275) -------------
+// One thread per coarse cell of the tile: E, B sampled at interior index (ix,iy,iz)*stride, J summed
+// over the stride^3 block in the reference's loop order (kk outermost), density slots zeroed.
+// buf[f][iz][iy][ix], f = ex,ey,ez,bx,by,bz,jx,jy,jz,n0...
+__global__ void __launch_bounds__(256)
+k_pack_snapshot(const FieldPtrs f, const Geom g, const int stride, const int nxt, const int nyt, const int nzt, const int nf,
+                float* __restrict__ buf) {
+  const size_t o = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t te = size_t(nxt) * nyt * nzt;
+  if (o >= te) return;
+  const int ix = int(o % nxt), iy = int((o / nxt) % nyt), iz = int(o / (size_t(nxt) * nyt));
+  const size_t Ch = g.Ch;
+  auto lin = [&](const int i, const int j, const int k) { return (size_t(i + H) * g.Hx[1] + (j + H)) * g.Hx[2] + (k + H); };
+  const size_t l = lin(ix * stride, iy * stride, iz * stride);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    buf[(0 + d) * te + o] = f.E[d * Ch + l];
+    buf[(3 + d) * te + o] = f.B[d * Ch + l];
+  }
+  float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+  for (int kk = 0; kk < stride; ++kk)
+    for (int jj = 0; jj < stride; ++jj)
+      for (int ii = 0; ii < stride; ++ii) {
+        const size_t m = lin(ix * stride + ii, iy * stride + jj, iz * stride + kk);
+        sx += f.J[m]; sy += f.J[Ch + m]; sz += f.J[2 * Ch + m];
+      }
+  buf[6 * te + o] = sx; buf[7 * te + o] = sy; buf[8 * te + o] = sz;
+  for (int s = 9; s < nf; ++s) buf[s * te + o] = 0.0f;
+}
+
 // ---- binomial current filter --------------------------------------------------
 // Both variants write every cell of dst: the region [1,H-1)^3 gets the filtered
 // value, the outermost layer gets 0 (binomial2: the reference move-assigns a
@@ -452,6 +482,12 @@ void launch_add_lattice(float* J, const float* add, size_t n) {
   ProfScope prof_(KC_ADD_CURRENT, double(n));
   if (!n) return;
   k_add_lattice<<<unsigned((n + 255) / 256), 256, 0, ctx().stream>>>(J, add, n);
+  B2P_LAUNCH_CHECK();
+}
+void launch_pack_snapshot(const FieldPtrs& f, const Geom& g, int stride, int nxt, int nyt, int nzt, int nf, float* buf) {
+  ProfScope prof_(KC_OTHER, 0.0);
+  const size_t te = size_t(nxt) * nyt * nzt;
+  k_pack_snapshot<<<unsigned((te + 255) / 256), 256, 0, ctx().stream>>>(f, g, stride, nxt, nyt, nzt, nf, buf);
   B2P_LAUNCH_CHECK();
 }
 void launch_zero(float* p, size_t n) {

@@ -10,6 +10,8 @@ void launch_add_current(const FieldPtrs* tiles, int ntiles, const Geom& g);
 // filter_tiles: device array of {const float* src; float* dst;} per tile
 void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unrolled);
 void launch_zero(float* p, size_t n);
+// FieldsWriter<3>::pack_tile, E/B/J part (io/snapshots/mpiio_fields.c++:221-275): buf[nf][nzt][nyt][nxt]
+void launch_pack_snapshot(const FieldPtrs& f, const Geom& g, int stride, int nxt, int nyt, int nzt, int nf, float* buf);
 // YeeLattice::apply_edge_bc (emf/yee_lattice.c++:263-306): masked components of `field` over the box [lo, hi)
 void launch_edge_bc(float* field, const Geom& g, const int lo[3], const int hi[3], unsigned mask, const float v[3]);
 // J = J + add over n floats (YeeLattice::deposit_current(VecGrid), emf/yee_lattice.c++:361-375)

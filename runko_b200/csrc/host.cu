@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
 #include <numeric>
 
 namespace b2p {
@@ -92,7 +94,7 @@ void* dmalloc(size_t bytes) {
 void dfree(void* p) {
   if (p && g_ctx_ready) cudaFreeAsync(p, g_ctx.stream);
 }
-static void sync() { B2P_CUDA(cudaStreamSynchronize(ctx().stream)); }
+static void stream_sync() { B2P_CUDA(cudaStreamSynchronize(ctx().stream)); }
 template <class T> static void h2d(T* dst, const T* src, size_t n) {
   if (n) { B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx().stream)); g_ctx.h2d_bytes += n * sizeof(T); }
 }
@@ -216,7 +218,7 @@ static unsigned find_P(Container& c) {
     B2P_CUDA(cudaMemsetAsync(s.counters.p, 0, sizeof(unsigned), ctx().stream));
     launch_last_alive(c.id.p, c.n, s.counters.p);
     d2h(&P, s.counters.p, 1);
-    sync();
+    stream_sync();
   }
   c.P = P; c.P_valid = true;
   return P;
@@ -722,7 +724,7 @@ void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles) {
     launch_collect_leavers(s.table.p, unsigned(nc), max_words, s.list[0].p, s.counters.p,
                            unsigned(std::min<size_t>(s.list[0].cap, 0xFFFFFFFFu)), s.counters.p + 1, s.counters.p + 1 + nc);
     d2h(hc.data(), s.counters.p, 1 + 2 * nc);
-    sync();
+    stream_sync();
     if (hc[0] <= s.list[0].cap) break;
     cap = hc[0];   // overflow: nothing was modified yet, collect again into a larger list
   }
@@ -758,7 +760,7 @@ void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles) {
   for (b2p_tile* t : tiles) t->pend_packed = t->pendJ_valid;
   std::vector<unsigned> hcounts(nc * 27);
   d2h(hcounts.data(), counts, nc * 27);
-  sync();
+  stream_sync();
   c = 0;
   for (b2p_tile* t : tiles) {
     unsigned long long next = 0;                                   // pic/particle.c++:327-343
@@ -893,7 +895,7 @@ static const FieldPtrs* table_for(const std::vector<b2p_tile*>& tiles) {
   for (size_t i = 0; i < tiles.size(); ++i) h[i] = tiles[i]->ptrs();
   defer_table().reserve(h.size());
   h2d(defer_table().p, h.data(), h.size());
-  sync();                                   // `h` is pageable host memory about to go out of scope
+  stream_sync();                                   // `h` is pageable host memory about to go out of scope
   return defer_table().p;
 }
 
@@ -967,7 +969,7 @@ extern "C" {
 const char* b2p_last_error(void) { return g_last_error.c_str(); }
 const char* b2p_version(void) { return "b200pic 0.1 (sm_100a)"; }
 int b2p_init(int device) { B2P_TRY b2p::init(device); B2P_CATCH }
-int b2p_sync(void) { B2P_TRY sync(); B2P_CATCH }
+int b2p_sync(void) { B2P_TRY stream_sync(); B2P_CATCH }
 int b2p_set_option(const char* name, int value) {
   B2P_TRY
   b2p::tuning();
@@ -1020,25 +1022,25 @@ int b2p_tile_bounds(const b2p_tile* t, double mins[3], double maxs[3]) {
 static void upload_field(b2p_tile* t, float* dev, const float* host, int with_halo) {
   if (!host) return;
   const Geom& g = t->g;
-  if (with_halo) { h2d(dev, host, t->lattice_floats()); sync(); return; }
+  if (with_halo) { h2d(dev, host, t->lattice_floats()); stream_sync(); return; }
   std::vector<float> tmp(t->lattice_floats());
   d2h(tmp.data(), dev, tmp.size());
-  sync();
+  stream_sync();
   const size_t Ni = size_t(g.N[0]) * g.N[1] * g.N[2];
   for (int c = 0; c < 3; ++c)
     for (int i = 0; i < g.N[0]; ++i) for (int j = 0; j < g.N[1]; ++j)
       std::memcpy(&tmp[c * size_t(g.Ch) + (size_t(i + H) * g.Hx[1] + (j + H)) * g.Hx[2] + H],
                   &host[c * Ni + (size_t(i) * g.N[1] + j) * g.N[2]], sizeof(float) * g.N[2]);
   h2d(dev, tmp.data(), tmp.size());
-  sync();
+  stream_sync();
 }
 static void download_field(b2p_tile* t, const float* dev, float* host, int with_halo) {
   if (!host) return;
   const Geom& g = t->g;
-  if (with_halo) { d2h(host, dev, t->lattice_floats()); sync(); return; }
+  if (with_halo) { d2h(host, dev, t->lattice_floats()); stream_sync(); return; }
   std::vector<float> tmp(t->lattice_floats());
   d2h(tmp.data(), dev, tmp.size());
-  sync();
+  stream_sync();
   const size_t Ni = size_t(g.N[0]) * g.N[1] * g.N[2];
   for (int c = 0; c < 3; ++c)
     for (int i = 0; i < g.N[0]; ++i) for (int j = 0; j < g.N[1]; ++j)
@@ -1078,7 +1080,7 @@ int b2p_tile_field_energy(b2p_tile* t, double* eB, double* eE) {
   launch_field_energy(t->device_entry(), 1, t->g, s.energy.p);
   double h[2];
   d2h(h, s.energy.p, 2);
-  sync();
+  stream_sync();
   if (eB) *eB = h[0] / 2.0;                                                       // emf/yee_lattice.c++:402-403
   if (eE) *eE = h[1] / 2.0;
   B2P_CATCH
@@ -1101,7 +1103,7 @@ int b2p_tile_inject(b2p_tile* t, int sp, uint64_t n, const double* x, const doub
     for (int a = 0; a < 6; ++a) {
       for (uint64_t i = 0; i < n; ++i) f[i] = static_cast<float>(src[a][i]);
       h2d(dst[a] + P, f.data(), n);
-      sync();
+      stream_sync();
     }
     std::vector<unsigned long long> ids(n);
     for (uint64_t i = 0; i < n; ++i) {
@@ -1110,7 +1112,7 @@ int b2p_tile_inject(b2p_tile* t, int sp, uint64_t n, const double* x, const doub
       ids[i] = (t->tile_tag << 40) | ordinal;                                     // pic/tile.c++:470-481
     }
     h2d(c.id.p + P, ids.data(), n);
-    sync();
+    stream_sync();
   }
   c.P = c.n; c.P_valid = true; c.masks_valid = false;
   B2P_CATCH
@@ -1128,7 +1130,7 @@ int b2p_tile_set_particles(b2p_tile* t, int sp, uint64_t n, const float* x, cons
   h2d(c.x.p, x, n); h2d(c.y.p, y, n); h2d(c.z.p, z, n);
   h2d(c.ux.p, ux, n); h2d(c.uy.p, uy, n); h2d(c.uz.p, uz, n);
   h2d(c.id.p, reinterpret_cast<const unsigned long long*>(id), n);
-  sync();
+  stream_sync();
   c.touch();
   B2P_CATCH
 }
@@ -1143,7 +1145,7 @@ int b2p_tile_get_particles(b2p_tile* t, int sp, int alive_only, float* x, float*
   if (!alive_only) {                                                              // raw container: straight copies
     for (int a = 0; a < 6; ++a) if (dst[a]) d2h(dst[a], src[a], n);
     if (id) d2h(reinterpret_cast<unsigned long long*>(id), c.id.p, n);
-    sync();
+    stream_sync();
     if (n_out) *n_out = n;
     return B2P_OK;
   }
@@ -1151,7 +1153,7 @@ int b2p_tile_get_particles(b2p_tile* t, int sp, int alive_only, float* x, float*
   d2h(hid.data(), c.id.p, n);
   std::vector<float> tmp[6];
   for (int a = 0; a < 6; ++a) if (dst[a]) { tmp[a].resize(n); d2h(tmp[a].data(), src[a], n); }
-  sync();
+  stream_sync();
   uint64_t m = 0;
   for (size_t i = 0; i < n; ++i) {                                               // pic/particle.c++:82-168
     if (hid[i] == DEAD) continue;
@@ -1181,7 +1183,7 @@ int b2p_tile_sort_keys(b2p_tile* t, int sp, uint32_t* keys) {
     s.keys[0].reserve(c.n);
     launch_sort_keys(c.view(), t->g, t->origo, s.keys[0].p, nullptr, 0xFFFFFFFFu);
     d2h(keys, s.keys[0].p, c.n);
-    sync();
+    stream_sync();
   }
   B2P_CATCH
 }
@@ -1193,7 +1195,7 @@ int b2p_tile_get_outgoing(b2p_tile* t, b2p_particle_state* buf, uint64_t cap, ui
   if (buf) {
     if (cap < t->out_count) throw Error(B2P_ERR_RUNTIME, "outgoing buffer too small");
     d2h(buf, t->out_buf.p, t->out_count);
-    sync();
+    stream_sync();
   }
   B2P_CATCH
 }
@@ -1207,7 +1209,7 @@ int b2p_tile_kinetic_energy(b2p_tile* t, int sp, double* energy, uint64_t* conta
     B2P_CUDA(cudaMemsetAsync(s.energy.p, 0, sizeof(double), ctx().stream));
     launch_kinetic_energy(c.view(), s.energy.p);
     d2h(&h, s.energy.p, 1);
-    sync();
+    stream_sync();
   }
   if (energy) *energy = h;
   if (container_size) *container_size = c.n;
@@ -1311,6 +1313,69 @@ struct HostTrace {
   }
 };
 
+// mpiio::FieldsWriter<3>::write (io/snapshots/mpiio_fields.c++:221-400; header mpiio_header.h:56-82).
+// POSIX pwrite instead of MPI-IO: every rank places its tiles' rows, rank 0 writes the header.
+int b2p_grid_write_fields_snapshot(b2p_grid* g, const char* prefix, int32_t lap, int32_t stride, int32_t nspecies) {
+  B2P_TRY
+  G(g);
+  if (!prefix) throw Error(B2P_ERR_RUNTIME, "null snapshot prefix");
+  if (stride < 1) throw Error(B2P_ERR_RUNTIME, "snapshot stride must be >= 1");
+  const b2p_config& c = g->cfg;
+  const int nsp = std::max(0, std::min(nspecies, 5));                       // mpiio_header.h:26 max_species
+  const int nf = 9 + nsp;
+  const int nxt = std::max(1, c.n_cells[0] / stride), nyt = std::max(1, c.n_cells[1] / stride), nzt = std::max(1, c.n_cells[2] / stride);
+  if (nxt * stride > c.n_cells[0] || nyt * stride > c.n_cells[1] || nzt * stride > c.n_cells[2])
+    throw Error(B2P_ERR_RUNTIME, "snapshot stride exceeds the tile mesh");
+  const int nx = c.n_tiles[0] * nxt, ny = c.n_tiles[1] * nyt, nz = c.n_tiles[2] * nzt;
+  const std::string fn = std::string(prefix) + "/flds_" + std::to_string(lap) + ".bin";
+  const int fd = ::open(fn.c_str(), O_CREAT | O_WRONLY, 0644);
+  if (fd < 0) throw Error(B2P_ERR_RUNTIME, "cannot open " + fn);
+  struct Closer { int fd; ~Closer() { ::close(fd); } } closer{ fd };
+  const size_t field_elems = size_t(nx) * ny * nz, tile_elems = size_t(nxt) * nyt * nzt;
+  const off_t total = off_t(512) + off_t(nf) * off_t(field_elems) * 4;
+  if (::ftruncate(fd, total) != 0) throw Error(B2P_ERR_RUNTIME, "cannot size " + fn);   // MPI_File_set_size
+  if (g->rank == 0) {
+    char hdr[512];
+    std::memset(hdr, 0, sizeof hdr);
+    auto put = [&](int off, uint32_t v) { std::memcpy(hdr + off, &v, 4); };
+    put(0, 0x524E4B4Fu); put(4, 3u); put(8, 512u); put(12, uint32_t(nf));
+    put(16, uint32_t(nx)); put(20, uint32_t(ny)); put(24, uint32_t(nz)); put(28, uint32_t(stride));
+    put(32, uint32_t(c.n_tiles[0])); put(36, uint32_t(c.n_tiles[1])); put(40, uint32_t(c.n_tiles[2]));
+    put(44, uint32_t(c.n_cells[0])); put(48, uint32_t(c.n_cells[1])); put(52, uint32_t(c.n_cells[2]));
+    put(56, uint32_t(lap)); put(60, 4u);
+    static const char* names[9] = { "ex", "ey", "ez", "bx", "by", "bz", "jx", "jy", "jz" };
+    for (int f = 0; f < 9; ++f) std::memcpy(hdr + 64 + f * 16, names[f], std::strlen(names[f]));
+    for (int s = 0; s < nsp; ++s) {
+      const std::string nm = "n" + std::to_string(s);
+      std::memcpy(hdr + 64 + (9 + s) * 16, nm.data(), std::min<size_t>(nm.size(), 15));
+    }
+    if (::pwrite(fd, hdr, 512, 0) != 512) throw Error(B2P_ERR_RUNTIME, "short write to " + fn);
+  }
+  DBuf<float> dbuf;
+  dbuf.reserve(size_t(nf) * tile_elems);
+  std::vector<float> hbuf(size_t(nf) * tile_elems);
+  const float inv_stride = 1.0f / float(stride);
+  for (b2p_tile* t : g->tiles) {
+    launch_pack_snapshot(t->ptrs(), t->g, stride, nxt, nyt, nzt, nf, dbuf.p);
+    const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
+    const int ndep = std::min<int>(int(t->sp.size()), nsp);
+    for (int sp = 0; sp < ndep; ++sp)
+      launch_snapshot_density(t->sp[sp].view(), mn, inv_stride, nxt, nyt, nzt, dbuf.p + size_t(9 + sp) * tile_elems);
+    d2h(hbuf.data(), dbuf.p, hbuf.size());
+    stream_sync();
+    for (int f = 0; f < nf; ++f)
+      for (int ks = 0; ks < nzt; ++ks)
+        for (int js = 0; js < nyt; ++js) {
+          const off_t off = off_t(512) + 4 * (off_t(f) * off_t(field_elems) +
+                                              (off_t(t->idx[2] * nzt + ks) * ny + off_t(t->idx[1] * nyt + js)) * nx + off_t(t->idx[0]) * nxt);
+          const size_t bytes = size_t(nxt) * 4;
+          if (::pwrite(fd, hbuf.data() + size_t(f) * tile_elems + (size_t(ks) * nyt + js) * nxt, bytes, off) != ssize_t(bytes))
+            throw Error(B2P_ERR_RUNTIME, "short write to " + fn);
+        }
+  }
+  B2P_CATCH
+}
+
 // projects/pic-turbulence/pic.py:187-221
 int b2p_grid_step_pic(b2p_grid* g, int64_t lap) {
   B2P_TRY
@@ -1381,7 +1446,7 @@ int b2p_grid_energies(b2p_grid* g, double* eB, double* eE, double* kinetic, uint
   std::vector<double> h(size_t(2) * nt + ns);
   d2h(h.data(), s.energy.p, size_t(2) * nt);
   d2h(h.data() + 2 * size_t(nt), dk, ns);
-  sync();
+  stream_sync();
   double b = 0, e = 0;
   for (int i = 0; i < nt; ++i) { b += h[2 * i] / 2.0; e += h[2 * i + 1] / 2.0; }
   if (eB) *eB = b;
@@ -1422,7 +1487,7 @@ int b2p_grid_set_uniform_B(b2p_grid* g, float bx, float by, float bz) {
     const float v[3] = { bx, by, bz };
     for (int c = 0; c < 3; ++c) std::fill(h.begin() + size_t(c) * t->g.Ch, h.begin() + size_t(c + 1) * t->g.Ch, v[c]);
     h2d(t->B.p, h.data(), h.size());
-    sync();
+    stream_sync();
   }
   B2P_CATCH
 }
@@ -1445,7 +1510,7 @@ void b2p_copy_bytes(uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
 }
 int b2p_profile_enable(int on) {
   B2P_TRY
-  sync();
+  stream_sync();
   for (auto& r : b2p::g_prof) { b2p::g_event_pool.push_back(r.a); b2p::g_event_pool.push_back(r.b); }
   b2p::g_prof.clear();
   b2p::g_prof_on = on != 0;
@@ -1461,12 +1526,12 @@ int b2p_selfcheck_const_division(const float* x, uint64_t n, float c, float* out
   h2d(dx.p, x, n);
   launch_selfcheck_divc(dx.p, n, c, dout.p, dref.p);
   d2h(out, dout.p, n); d2h(ref, dref.p, n);
-  sync();
+  stream_sync();
   B2P_CATCH
 }
 int b2p_profile_report(double* ms, uint64_t* launches, double* units) {
   B2P_TRY
-  sync();
+  stream_sync();
   for (int k = 0; k < b2p::KC_COUNT; ++k) { ms[k] = 0; launches[k] = 0; units[k] = 0; }
   for (auto& r : b2p::g_prof) {
     float t = 0;

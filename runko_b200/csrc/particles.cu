@@ -973,6 +973,19 @@ k_reflect_at_wall(const Species s, float* __restrict__ corrJ, const Geom g, cons
   if (mask_park > 0.5f) s.id[n] = DEAD;
 }
 
+// FieldsWriter<3>::pack_tile, density part (io/snapshots/mpiio_fields.c++:277-316): alive particles per
+// coarse cell, float atomics (exact for counts < 2^24)
+__global__ void __launch_bounds__(256)
+k_snapshot_density(const Species s, const float3 mins, const float inv_stride, const int nxt, const int nyt, const int nzt,
+                   float* __restrict__ n_out) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= s.n || s.id[n] == DEAD) return;
+  const float fx = floorf((s.x[n] - mins.x) * inv_stride), fy = floorf((s.y[n] - mins.y) * inv_stride),
+              fz = floorf((s.z[n] - mins.z) * inv_stride);
+  if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < float(nxt) && fy < float(nyt) && fz < float(nzt))) return;
+  atomicAdd(&n_out[(size_t(fz) * nyt + size_t(fy)) * nxt + size_t(fx)], 1.0f);
+}
+
 // ------------------------------------------------- synthetic thermal plasma --
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -1277,6 +1290,13 @@ void launch_reflect_at_wall(const Species& s, float* corrJ, const Geom& g, const
   if (!s.n) return;
   k_reflect_at_wall<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, corrJ, g, make_float3(origo[0], origo[1], origo[2]), cfl, walloc,
                                                               betawall, gammawall, charge);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_snapshot_density(const Species& s, const float mins[3], float inv_stride, int nxt, int nyt, int nzt, float* n_out) {
+  ProfScope prof_(KC_OTHER, double(s.n));
+  if (!s.n) return;
+  k_snapshot_density<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, make_float3(mins[0], mins[1], mins[2]), inv_stride, nxt, nyt, nzt, n_out);
   B2P_LAUNCH_CHECK();
 }
 

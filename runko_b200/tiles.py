@@ -449,6 +449,10 @@ class Grid:
     def apply_edge_bcs(self, mode):
         check(lib().b2p_grid_apply_edge_bcs(self._h, _mode(mode)))
 
+    def write_fields_snapshot(self, prefix, lap, stride=1, nspecies=2):
+        """io_emf_snapshot: "<prefix>/flds_<lap>.bin" in the reference's RNKO v3 format (mpiio_fields.c++)."""
+        check(lib().b2p_grid_write_fields_snapshot(self._h, str(prefix).encode(), int(lap), int(stride), int(nspecies)))
+
     def step_pic(self, lap):
         check(lib().b2p_grid_step_pic(self._h, int(lap)))
 
@@ -496,6 +500,24 @@ class Grid:
 
     def set_uniform_B(self, bx, by, bz):
         check(lib().b2p_grid_set_uniform_B(self._h, bx, by, bz))
+
+
+class MpiioFieldsWriter:
+    """emf.threeD.MpiioFieldsWriter (bindings/pyemf.c++:275-281): same constructor arguments; `write(grid, lap)`
+    and `write_collective(grid, lap)` both place every local tile with pwrite()."""
+
+    def __init__(self, prefix, Nx, NxMesh, Ny, NyMesh, Nz, NzMesh, stride, nspecies=2):
+        self.prefix, self.stride, self.nspecies = str(prefix), int(stride), int(nspecies)
+        self.dims = (int(Nx), int(NxMesh), int(Ny), int(NyMesh), int(Nz), int(NzMesh))
+
+    def write(self, grid, lap):
+        c = grid._cfg
+        if (c.n_tiles[0], c.n_cells[0], c.n_tiles[1], c.n_cells[1], c.n_tiles[2], c.n_cells[2]) != self.dims:
+            raise B2PError("MpiioFieldsWriter: grid dimensions differ from the writer's")
+        grid.write_fields_snapshot(self.prefix, lap, self.stride, self.nspecies)
+        return True
+
+    write_collective = write
 
 
 def sync():
