@@ -128,15 +128,33 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
         a[ic][jc][kc] = __ldg(nod + off[ic][jc] + kc);
         b[ic][jc][kc] = __ldg(nodB + off[ic][jc] + kc);
       }
-  // lerp3D (:29-52): along x, then y, then z
-#define LERP3(field, comp)                                                                     \
-  lerp1(dz,                                                                                    \
-        lerp1(dy, lerp1(dx, field[0][0][0].comp, field[1][0][0].comp), lerp1(dx, field[0][1][0].comp, field[1][1][0].comp)), \
-        lerp1(dy, lerp1(dx, field[0][0][1].comp, field[1][0][1].comp), lerp1(dx, field[0][1][1].comp, field[1][1][1].comp)))
+  // lerp3D (:29-52): along x, then y, then z — (1-w)*A + w*B per lerp, the same two products and one sum
+  // as the reference.  The six components travel as three register pairs {Ex,Ey}, {Ez,Bx}, {By,Bz} — exactly
+  // how the LDG.128 / LDG.64 above deliver them — through Blackwell's packed fp32x2 multiply
+  // (FMUL2, round-to-nearest per lane): the 84 products take 42 issue slots.  The sums stay scalar FADDs on
+  // purpose: ptxas contracts a packed add whose operand is a packed product into FFMA2 even under --fmad=false
+  // (checked in SASS), which would change the rounding.
+  const float2 wx = make_float2(dx, dx), wy = make_float2(dy, dy), wz = make_float2(dz, dz);
+  const float2 ox = make_float2(1.0f - dx, 1.0f - dx), oy = make_float2(1.0f - dy, 1.0f - dy), oz = make_float2(1.0f - dz, 1.0f - dz);
+  auto lerp2 = [](const float2 o, const float2 w, const float2 A, const float2 B) {
+    const float2 p = __fmul2_rn(o, A), q = __fmul2_rn(w, B);
+    return make_float2(__fadd_rn(p.x, q.x), __fadd_rn(p.y, q.y));
+  };
+#define LERP3P(sel)                                                                              \
+  lerp2(oz, wz,                                                                                  \
+        lerp2(oy, wy, lerp2(ox, wx, sel(0, 0, 0), sel(1, 0, 0)), lerp2(ox, wx, sel(0, 1, 0), sel(1, 1, 0))), \
+        lerp2(oy, wy, lerp2(ox, wx, sel(0, 0, 1), sel(1, 0, 1)), lerp2(ox, wx, sel(0, 1, 1), sel(1, 1, 1))))
+#define SEL_XY(i_, j_, k_) make_float2(a[i_][j_][k_].x, a[i_][j_][k_].y)
+#define SEL_ZW(i_, j_, k_) make_float2(a[i_][j_][k_].z, a[i_][j_][k_].w)
+#define SEL_B(i_, j_, k_) b[i_][j_][k_]
+  const float2 exy = LERP3P(SEL_XY), ezbx = LERP3P(SEL_ZW), byz = LERP3P(SEL_B);
+#undef SEL_XY
+#undef SEL_ZW
+#undef SEL_B
+#undef LERP3P
   EB eb;
-  eb.E.x = LERP3(a, x); eb.E.y = LERP3(a, y); eb.E.z = LERP3(a, z);
-  eb.B.x = LERP3(a, w); eb.B.y = LERP3(b, x); eb.B.z = LERP3(b, y);
-#undef LERP3
+  eb.E.x = exy.x; eb.E.y = exy.y; eb.E.z = ezbx.x;
+  eb.B.x = ezbx.y; eb.B.y = byz.x; eb.B.z = byz.y;
   return eb;
 }
 
