@@ -193,6 +193,23 @@ int b2p_tile_advance_reflector_walls(b2p_tile* t);
 /* Current state of the registered walls (no reference getter; used by the tests and the injector). */
 int b2p_tile_reflector_walls(b2p_tile* t, b2p_reflector_wall* out, uint64_t cap, uint64_t* n);
 
+/* ---- driven-turbulence antenna ---------------------------------- */
+/* emf::antenna_mode (src/runko/emf/antenna.h:31-45): one vector-potential Fourier mode,
+ * J += Re(cfl * curl(curl(A * phi[lap] * exp(i k.x)))).  `wave_kind` 0: `wave` is the wave vector k;
+ * 1: `wave` is the mode number n (k = 2 pi n / L of the global grid).  `lap_coeffs` = n_lap_coeffs
+ * complex numbers (re, im pairs) consumed one per deposit in the given order, or NULL for phi = 1. */
+typedef struct b2p_antenna_mode {
+  double        A[3];
+  double        wave[3];
+  int32_t       wave_kind;
+  uint64_t      n_lap_coeffs;
+  const double* lap_coeffs;
+} b2p_antenna_mode;
+/* emf::Tile::register_antenna / deposit_antenna_current (emf/tile.c++:566-791).  Depositing with an
+ * exhausted lap_coeffs list fails with B2P_ERR_LOGIC like the reference's std::logic_error. */
+int b2p_tile_register_antenna(b2p_tile* t, const b2p_antenna_mode* mode);
+int b2p_tile_deposit_antenna_current(b2p_tile* t);
+
 /* ---- grid (corgi::Grid surface used by runko/simulation.py) -------------- */
 int  b2p_grid_create(const b2p_config* cfg, b2p_grid** out);
 void b2p_grid_destroy(b2p_grid* g);

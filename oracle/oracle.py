@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from runko_b200._abi import B2PConfig, EdgeBC, ParticleState, ReflectorWall, make_config  # struct layouts only
+from runko_b200._abi import AntennaMode, B2PConfig, EdgeBC, ParticleState, ReflectorWall, make_config  # struct layouts only
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libpic_oracle.so")
@@ -42,7 +42,7 @@ def lib():
         vp, ci = C.c_void_p, C.c_int
         for name in ("push_half_b", "push_e", "add_current", "filter_current", "clear_current",
                      "push_particles", "deposit_current", "sort_particles", "pack_outgoing_particles",
-                     "reflect_particles", "advance_reflector_walls"):
+                     "reflect_particles", "advance_reflector_walls", "deposit_antenna_current"):
             getattr(L, "orc_tile_" + name).argtypes = [vp, ci]
         L.orc_tile_set_fields.argtypes = [vp, ci, vp, vp, vp, ci]
         L.orc_tile_get_fields.argtypes = [vp, ci, vp, vp, vp, ci]
@@ -55,6 +55,7 @@ def lib():
         L.orc_tile_get_outgoing.argtypes = [vp, ci, vp, C.c_uint64, vp, C.POINTER(C.c_uint64)]
         L.orc_tile_kinetic_energy.argtypes = [vp, ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.orc_tile_interpolate.argtypes = [vp, ci, C.c_uint64, vp, vp, vp, vp]
+        L.orc_tile_register_antenna.argtypes = [vp, ci, C.POINTER(AntennaMode)]
         L.orc_tile_register_edge_bc.argtypes = [vp, ci, C.POINTER(EdgeBC)]
         L.orc_tile_apply_edge_bcs.argtypes = [vp, ci, ci]
         L.orc_tile_apply_edge_bc.argtypes = [vp, ci, C.POINTER(EdgeBC), ci]
@@ -190,6 +191,9 @@ class OracleGrid:
 
     def apply_edge_bc(self, t, bc, mode):
         self._ck(self._L.orc_tile_apply_edge_bc(self._g, t, C.byref(bc), int(mode)))
+
+    def register_antenna(self, t, mode):
+        self._ck(self._L.orc_tile_register_antenna(self._g, t, C.byref(mode._as_struct())))
 
     def register_reflector_wall(self, t, wall):
         self._ck(self._L.orc_tile_register_reflector_wall(self._g, t, C.byref(wall)))

@@ -54,6 +54,9 @@ struct Tile {
   std::vector<b2p_particle_state> out_buf;         // subregion_particle_buff_
   std::vector<size_t> out_ends;                    // subregion_particle_ends_
   std::vector<std::vector<Span>> incoming;         // incoming_subregion_particles_
+  struct Antenna { double A[3], wave[3]; int kind; bool has_coeffs; std::vector<std::array<double, 2>> coeffs; size_t next = 0; };
+  std::vector<Antenna> antennas;                   // emf/tile.h:48
+  std::vector<float> vec_pot, gen_B;               // vec_pot_buff_, generated_B_buff_ (emf/tile.h:68-69)
   std::vector<b2p_edge_bc> edge_bcs;               // emf/tile.h:51
   std::vector<b2p_reflector_wall> walls;           // pic/tile.h:71
   std::vector<float> corrJ;                        // reflector_correction_J_ (pic/tile.h:72)
@@ -1061,6 +1064,106 @@ int orc_tile_kinetic_energy(orc_grid* g, int t, int sp, double* energy, uint64_t
   if (container_size) *container_size = c->size();
   return 0;
 }
+int orc_tile_register_antenna(orc_grid* g, int t, const b2p_antenna_mode* m) {   // emf/tile.c++:566-576
+  Tile* tl = get_tile(g, t); if (!tl) return 1;
+  Tile::Antenna a;
+  for (int d = 0; d < 3; ++d) { a.A[d] = m->A[d]; a.wave[d] = m->wave[d]; }
+  a.kind = m->wave_kind;
+  a.has_coeffs = m->lap_coeffs != nullptr;
+  for (uint64_t q = 0; a.has_coeffs && q < m->n_lap_coeffs; ++q) a.coeffs.push_back({ m->lap_coeffs[2 * q], m->lap_coeffs[2 * q + 1] });
+  tl->antennas.push_back(std::move(a));
+  return 0;
+}
+
+// emf::Tile::deposit_antenna_current, emf/tile.c++:578-777
+int orc_tile_deposit_antenna_current(orc_grid* g, int t) {
+  Tile* tp = get_tile(g, t); if (!tp) return 1;
+  Tile& tl = *tp;
+  const size_t nm = tl.antennas.size();
+  std::vector<std::array<float, 3>> A(nm), K(nm);
+  std::vector<std::array<float, 2>> W(nm);
+  for (size_t n = 0; n < nm; ++n) {
+    Tile::Antenna& a = tl.antennas[n];
+    double k[3];
+    if (a.kind == 0) { for (int d = 0; d < 3; ++d) k[d] = a.wave[d]; }
+    else {                                                            // :603-614
+      for (int d = 0; d < 3; ++d) {
+        const double L = g->gmaxs[d] - g->gmins[d];
+        const double tmp = 2 * 3.141592653589793238462643383279502884 * a.wave[d];
+        k[d] = tmp / L;
+      }
+    }
+    for (int d = 0; d < 3; ++d) { A[n][d] = static_cast<float>(a.A[d]); K[n][d] = static_cast<float>(k[d]); }
+    if (a.has_coeffs && a.next >= a.coeffs.size()) {
+      g_err = "Can not deposit antenna current, antenna_mode ran out of lap_coeffs!";
+      return B2P_ERR_LOGIC;
+    } else if (a.has_coeffs) {
+      W[n] = { static_cast<float>(a.coeffs[a.next][0]), static_cast<float>(a.coeffs[a.next][1]) };
+      ++a.next;
+    } else {
+      W[n] = { 1.0f, 0.0f };
+    }
+  }
+  tl.vec_pot.assign(3 * tl.Ch, 0.0f);
+  tl.gen_B.assign(3 * tl.Ch, 0.0f);
+  const double Lt[3] = { tl.maxs[0] - tl.mins[0], tl.maxs[1] - tl.mins[1], tl.maxs[2] - tl.mins[2] };
+  auto gcmap = [&](double i, double j, double k, double out[3]) {     // emf/tile.h:207-229
+    out[0] = tl.mins[0] + (i / double(tl.N[0])) * Lt[0];
+    out[1] = tl.mins[1] + (j / double(tl.N[1])) * Lt[1];
+    out[2] = tl.mins[2] + (k / double(tl.N[2])) * Lt[2];
+  };
+  for (int ii = 0; ii < tl.Hx[0]; ++ii)
+    for (int jj = 0; jj < tl.Hx[1]; ++jj)
+      for (int kk = 0; kk < tl.Hx[2]; ++kk) {
+        const double i = double(ii) - H, j = double(jj) - H, k = double(kk) - H;
+        double loc[3][3];
+        gcmap(i + 0.5, j, k, loc[0]);
+        gcmap(i, j + 0.5, k, loc[1]);
+        gcmap(i, j, k + 0.5, loc[2]);
+        const size_t l = tl.lin(ii, jj, kk);
+        for (size_t n = 0; n < nm; ++n) {
+          for (int c = 0; c < 3; ++c) {
+            double dotv = 0;                                          // toolbox::dot, from 0 left to right
+            for (int d = 0; d < 3; ++d) dotv += loc[c][d] * double(K[n][d]);
+            const float phi = static_cast<float>(dotv);
+            const float re = ::cosf(phi), im = ::sinf(phi);
+            tl.vec_pot[c * tl.Ch + l] = tl.vec_pot[c * tl.Ch + l] + A[n][c] * (W[n][0] * re - W[n][1] * im);
+          }
+        }
+      }
+  // B = curl(vec_pot) on the interior plus a one-deep shell (:700-744)
+  auto X = [&](const std::vector<float>& f, int c, int i, int j, int k) { return f[c * tl.Ch + tl.lin(i, j, k)]; };
+  for (int i = H - 1; i < H + tl.N[0] + 1; ++i)
+    for (int j = H - 1; j < H + tl.N[1] + 1; ++j)
+      for (int k = H - 1; k < H + tl.N[2] + 1; ++k) {
+        const std::vector<float>& P = tl.vec_pot;
+        const size_t l = tl.lin(i, j, k);
+        { const float Dk = X(P, 1, i, j, k + 1) - X(P, 1, i, j, k), Dj = X(P, 2, i, j + 1, k) - X(P, 2, i, j, k);
+          tl.gen_B[0 * tl.Ch + l] = 1.0f * (Dj - Dk); }
+        { const float Di = X(P, 2, i + 1, j, k) - X(P, 2, i, j, k), Dk = X(P, 0, i, j, k + 1) - X(P, 0, i, j, k);
+          tl.gen_B[1 * tl.Ch + l] = 1.0f * (Dk - Di); }
+        { const float Dj = X(P, 0, i, j + 1, k) - X(P, 0, i, j, k), Di = X(P, 1, i + 1, j, k) - X(P, 1, i, j, k);
+          tl.gen_B[2 * tl.Ch + l] = 1.0f * (Di - Dj); }
+      }
+  // curl(B) in the interior, written over vec_pot with coefficient -cfl and backward neighbours (:747-771)
+  const float coeff = static_cast<float>(-g->cfg.cfl);
+  for (int i = H; i < H + tl.N[0]; ++i)
+    for (int j = H; j < H + tl.N[1]; ++j)
+      for (int k = H; k < H + tl.N[2]; ++k) {
+        const std::vector<float>& Bf = tl.gen_B;
+        const size_t l = tl.lin(i, j, k);
+        float o0, o1, o2;
+        { const float Dk = X(Bf, 1, i, j, k - 1) - X(Bf, 1, i, j, k), Dj = X(Bf, 2, i, j - 1, k) - X(Bf, 2, i, j, k); o0 = coeff * (Dj - Dk); }
+        { const float Di = X(Bf, 2, i - 1, j, k) - X(Bf, 2, i, j, k), Dk = X(Bf, 0, i, j, k - 1) - X(Bf, 0, i, j, k); o1 = coeff * (Dk - Di); }
+        { const float Dj = X(Bf, 0, i, j - 1, k) - X(Bf, 0, i, j, k), Di = X(Bf, 1, i - 1, j, k) - X(Bf, 1, i, j, k); o2 = coeff * (Di - Dj); }
+        tl.vec_pot[0 * tl.Ch + l] = o0; tl.vec_pot[1 * tl.Ch + l] = o1; tl.vec_pot[2 * tl.Ch + l] = o2;
+      }
+  // YeeLattice::deposit_current(vec_pot) over the WHOLE haloed lattice (:773; emf/yee_lattice.c++:361-375): outside the
+  // interior vec_pot still holds the potential itself, exactly as in the reference
+  for (size_t n = 0; n < 3 * tl.Ch; ++n) tl.J[n] = tl.J[n] + tl.vec_pot[n];
+  return 0;
+}
+
 int orc_tile_register_edge_bc(orc_grid* g, int t, const b2p_edge_bc* bc) {
   Tile* tl = get_tile(g, t); if (!tl) return 1;
   tl->edge_bcs.push_back(*bc);                                       // emf/tile.c++:829-833

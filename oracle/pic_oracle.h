@@ -84,6 +84,9 @@ int orc_local_communication(orc_grid* g, int mode);
 int orc_grid_phase(orc_grid* g, const char* phase, int threads);
 int orc_step_pic(orc_grid* g, int64_t lap, int threads);
 int orc_step_emf(orc_grid* g, int threads);
+/* emf/tile.c++:566-791 */
+int orc_tile_register_antenna(orc_grid* g, int t, const b2p_antenna_mode* mode);
+int orc_tile_deposit_antenna_current(orc_grid* g, int t);
 /* io/snapshots/mpiio_fields.c++:221-400 + mpiio_header.h:56-82 */
 int orc_write_fields_snapshot(orc_grid* g, const char* prefix, int32_t lap, int32_t stride, int32_t nspecies);
 int orc_energies(orc_grid* g, double* eB, double* eE, double* kinetic, uint64_t* sizes);

@@ -56,6 +56,12 @@ class EdgeBC(C.Structure):
                 ("E_components", C.c_uint8), ("B_components", C.c_uint8), ("J_components", C.c_uint8)]
 
 
+class AntennaMode(C.Structure):
+    """b2p_antenna_mode == emf::antenna_mode flattened (src/runko/emf/antenna.h:31-45)"""
+    _fields_ = [("A", C.c_double * 3), ("wave", C.c_double * 3), ("wave_kind", C.c_int32),
+                ("n_lap_coeffs", C.c_uint64), ("lap_coeffs", C.POINTER(C.c_double))]
+
+
 class ReflectorWall(C.Structure):
     """b2p_reflector_wall == pic::reflector_wall (src/runko/pic/reflector_wall.h:14-25)"""
     _fields_ = [("walloc", C.c_float), ("betawall", C.c_float), ("gammawall", C.c_float)]

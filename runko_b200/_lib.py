@@ -6,7 +6,7 @@ usable when compute is requested, this raises.
 import ctypes as C
 import os
 
-from ._abi import B2PConfig, EdgeBC, ParticleState, ReflectorWall
+from ._abi import AntennaMode, B2PConfig, EdgeBC, ParticleState, ReflectorWall
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libb200pic.so")
@@ -22,6 +22,7 @@ b2p_tile_push_particles b2p_tile_deposit_current b2p_tile_sort_particles b2p_til
 b2p_tile_sort_keys b2p_tile_get_outgoing b2p_tile_kinetic_energy
 b2p_tile_register_edge_bc b2p_tile_apply_edge_bcs b2p_tile_apply_edge_bc
 b2p_tile_register_reflector_wall b2p_tile_reflect_particles b2p_tile_advance_reflector_walls b2p_tile_reflector_walls
+b2p_tile_register_antenna b2p_tile_deposit_antenna_current
 b2p_grid_apply_edge_bcs b2p_grid_reflect_particles b2p_grid_advance_reflector_walls b2p_grid_write_fields_snapshot
 b2p_grid_create b2p_grid_destroy b2p_grid_add_tile b2p_grid_local_communication
 b2p_grid_push_half_b b2p_grid_push_e b2p_grid_add_current b2p_grid_filter_current
@@ -87,6 +88,8 @@ def lib():
     L.b2p_tile_reflect_particles.argtypes = [vp]
     L.b2p_tile_advance_reflector_walls.argtypes = [vp]
     L.b2p_tile_reflector_walls.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.b2p_tile_register_antenna.argtypes = [vp, C.POINTER(AntennaMode)]
+    L.b2p_tile_deposit_antenna_current.argtypes = [vp]
     L.b2p_grid_apply_edge_bcs.argtypes = [vp, ci]
     L.b2p_grid_reflect_particles.argtypes = [vp]
     L.b2p_grid_advance_reflector_walls.argtypes = [vp]

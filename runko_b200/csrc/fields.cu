@@ -142,6 +142,57 @@ k_add_lattice(float* __restrict__ J, const float* __restrict__ add, const size_t
   if (q < n) J[q] = J[q] + add[q];
 }
 
+// ---- antenna (emf/tile.c++:578-777) ---------------------------------------------
+// vec_pot over the whole haloed lattice: sum over modes of A * Re(w * exp(i k.x)) at the Yee-staggered points;
+// coordinates and the phase k.x in fp64 like the reference (global_coordinate_map, emf/tile.h:207-229), the
+// phase then narrowed to fp32 for cosf / sinf.
+__global__ void __launch_bounds__(256)
+k_antenna_vecpot(float* __restrict__ vp, const Geom g, const AntennaModes m, const double3 mins, const double3 L) {
+  const size_t q = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= size_t(g.Ch)) return;
+  const int kk = int(q % g.Hx[2]), jj = int((q / g.Hx[2]) % g.Hx[1]), ii = int(q / (size_t(g.Hx[1]) * g.Hx[2]));
+  const double i = double(ii) - H, j = double(jj) - H, k = double(kk) - H;
+  auto gc = [&](const double a, const double b, const double c, double (&o)[3]) {
+    o[0] = mins.x + (a / double(g.N[0])) * L.x;
+    o[1] = mins.y + (b / double(g.N[1])) * L.y;
+    o[2] = mins.z + (c / double(g.N[2])) * L.z;
+  };
+  double loc[3][3];
+  gc(i + 0.5, j, k, loc[0]);
+  gc(i, j + 0.5, k, loc[1]);
+  gc(i, j, k + 0.5, loc[2]);
+  float acc[3] = { 0.0f, 0.0f, 0.0f };
+  for (int n = 0; n < m.n; ++n) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double dotv = 0.0;
+      dotv = dotv + loc[c][0] * double(m.K[n][0]); dotv = dotv + loc[c][1] * double(m.K[n][1]); dotv = dotv + loc[c][2] * double(m.K[n][2]);
+      const float phi = float(dotv);
+      const float re = cosf(phi), im = sinf(phi);
+      acc[c] = acc[c] + m.A[n][c] * (m.W[n][0] * re - m.W[n][1] * im);
+    }
+  }
+  vp[q] = acc[0]; vp[size_t(g.Ch) + q] = acc[1]; vp[2 * size_t(g.Ch) + q] = acc[2];
+}
+// out = coeff * curl(X) with forward (DIR = +1) or backward (DIR = -1) neighbours over the box [lo, hi)
+// (the `curl` lambda of emf/tile.c++:714-737)
+template <int DIR>
+__global__ void __launch_bounds__(256)
+k_antenna_curl(float* __restrict__ out, const float* __restrict__ X, const Geom g, const int3 lo, const int3 hi, const float coeff) {
+  const size_t q = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t ny = size_t(hi.y - lo.y), nz = size_t(hi.z - lo.z);
+  if (q >= size_t(hi.x - lo.x) * ny * nz) return;
+  const size_t i = lo.x + q / (ny * nz), j = lo.y + (q / nz) % ny, k = lo.z + q % nz;
+  const long sj = g.Hx[2], si = long(g.Hx[1]) * g.Hx[2];
+  const long n = long((i * g.Hx[1] + j) * g.Hx[2] + k);
+  const size_t Ch = g.Ch;
+  const float* X0 = X; const float* X1 = X + Ch; const float* X2 = X + 2 * Ch;
+  const long di = DIR * si, dj = DIR * sj, dk = DIR;
+  { const float Dk = X1[n + dk] - X1[n], Dj = X2[n + dj] - X2[n]; out[n] = coeff * (Dj - Dk); }
+  { const float Di = X2[n + di] - X2[n], Dk = X0[n + dk] - X0[n]; out[Ch + n] = coeff * (Dk - Di); }
+  { const float Dj = X0[n + dj] - X0[n], Di = X1[n + di] - X1[n]; out[2 * Ch + n] = coeff * (Di - Dj); }
+}
+
 // ---- field snapshot packing (io/snapshots/mpiio_fields.c++:221-275) -------------
 // One thread per coarse cell of the tile: E, B sampled at interior index (ix,iy,iz)*stride, J summed
 // over the stride^3 block in the reference's loop order (kk outermost), density slots zeroed.
@@ -482,6 +533,24 @@ void launch_add_lattice(float* J, const float* add, size_t n) {
   ProfScope prof_(KC_ADD_CURRENT, double(n));
   if (!n) return;
   k_add_lattice<<<unsigned((n + 255) / 256), 256, 0, ctx().stream>>>(J, add, n);
+  B2P_LAUNCH_CHECK();
+}
+void launch_antenna(float* J, float* vec_pot, float* gen_B, const Geom& g, const AntennaModes& m, const double mins[3],
+                    const double maxs[3], float cfl_neg) {
+  ProfScope prof_(KC_OTHER, 0.0);
+  const double3 mn = make_double3(mins[0], mins[1], mins[2]);
+  const double3 L = make_double3(maxs[0] - mins[0], maxs[1] - mins[1], maxs[2] - mins[2]);
+  k_antenna_vecpot<<<unsigned((g.Ch + 255) / 256), 256, 0, ctx().stream>>>(vec_pot, g, m, mn, L);
+  B2P_LAUNCH_CHECK();
+  const int3 lo1 = make_int3(H - 1, H - 1, H - 1), hi1 = make_int3(H + g.N[0] + 1, H + g.N[1] + 1, H + g.N[2] + 1);
+  const size_t n1 = size_t(g.N[0] + 2) * (g.N[1] + 2) * (g.N[2] + 2);
+  k_antenna_curl<+1><<<unsigned((n1 + 255) / 256), 256, 0, ctx().stream>>>(gen_B, vec_pot, g, lo1, hi1, 1.0f);
+  B2P_LAUNCH_CHECK();
+  const int3 lo2 = make_int3(H, H, H), hi2 = make_int3(H + g.N[0], H + g.N[1], H + g.N[2]);
+  const size_t n2 = size_t(g.N[0]) * g.N[1] * g.N[2];
+  k_antenna_curl<-1><<<unsigned((n2 + 255) / 256), 256, 0, ctx().stream>>>(vec_pot, gen_B, g, lo2, hi2, cfl_neg);
+  B2P_LAUNCH_CHECK();
+  k_add_lattice<<<unsigned((size_t(3) * g.Ch + 255) / 256), 256, 0, ctx().stream>>>(J, vec_pot, size_t(3) * g.Ch);
   B2P_LAUNCH_CHECK();
 }
 void launch_pack_snapshot(const FieldPtrs& f, const Geom& g, int stride, int nxt, int nyt, int nzt, int nf, float* buf) {

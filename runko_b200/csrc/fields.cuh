@@ -10,6 +10,12 @@ void launch_add_current(const FieldPtrs* tiles, int ntiles, const Geom& g);
 // filter_tiles: device array of {const float* src; float* dst;} per tile
 void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unrolled);
 void launch_zero(float* p, size_t n);
+// emf::Tile::deposit_antenna_current (emf/tile.c++:578-777): J += -cfl * curl_backward(curl_forward(vec_pot)) in the
+// interior (+ vec_pot itself outside it, as the reference adds the whole scratch lattice); modes passed by value
+constexpr int ANTENNA_MAX_MODES = 48;
+struct AntennaModes { float A[ANTENNA_MAX_MODES][3]; float K[ANTENNA_MAX_MODES][3]; float W[ANTENNA_MAX_MODES][2]; int n; };
+void launch_antenna(float* J, float* vec_pot, float* gen_B, const Geom& g, const AntennaModes& m, const double mins[3],
+                    const double maxs[3], float cfl_neg);
 // FieldsWriter<3>::pack_tile, E/B/J part (io/snapshots/mpiio_fields.c++:221-275): buf[nf][nzt][nyt][nxt]
 void launch_pack_snapshot(const FieldPtrs& f, const Geom& g, int stride, int nxt, int nyt, int nzt, int nf, float* buf);
 // YeeLattice::apply_edge_bc (emf/yee_lattice.c++:263-306): masked components of `field` over the box [lo, hi)

@@ -150,6 +150,7 @@ struct Scratch {
   DBuf<unsigned> counters;        // [0]=list count, then per-container last_alive, then counts[ncont][27]
   DBuf<unsigned char> table;      // device staging for job / out-tile tables
   DBuf<double> energy;
+  DBuf<float> antenna[2];         // vec_pot_buff_ / generated_B_buff_ of the tile depositing its antenna current
   Container spare_w[MAX_WORKERS]; // per worker stream: gather target of the sort (swapped with the container)
 };
 static Scratch& scratch() { static Scratch* s = new Scratch; return *s; }
@@ -1217,6 +1218,52 @@ int b2p_tile_kinetic_energy(b2p_tile* t, int sp, double* energy, uint64_t* conta
 }
 
 // --------------------------------------------------------------------- grid --
+int b2p_tile_register_antenna(b2p_tile* t, const b2p_antenna_mode* m) {      // emf/tile.c++:566-576
+  B2P_TRY
+  if (!m) throw Error(B2P_ERR_RUNTIME, "null antenna_mode");
+  if (m->wave_kind != 0 && m->wave_kind != 1) throw Error(B2P_ERR_RUNTIME, "antenna_mode expects k or n to be defined but not both.");
+  b2p_tile::Antenna a;
+  for (int d = 0; d < 3; ++d) { a.A[d] = m->A[d]; a.wave[d] = m->wave[d]; }
+  a.kind = m->wave_kind;
+  a.has_coeffs = m->lap_coeffs != nullptr;
+  for (uint64_t q = 0; a.has_coeffs && q < m->n_lap_coeffs; ++q) a.coeffs.push_back({ m->lap_coeffs[2 * q], m->lap_coeffs[2 * q + 1] });
+  T(t)->antennas.push_back(std::move(a));
+  B2P_CATCH
+}
+int b2p_tile_deposit_antenna_current(b2p_tile* t) {                            // emf/tile.c++:578-777
+  B2P_TRY
+  T(t);
+  const size_t nm = t->antennas.size();
+  // the modes travel as a kernel argument; more than ANTENNA_MAX_MODES are deposited in several sweeps (J += is additive)
+  std::vector<AntennaModes> sweeps((nm + ANTENNA_MAX_MODES - 1) / ANTENNA_MAX_MODES + (nm == 0 ? 1 : 0));
+  for (AntennaModes& sw : sweeps) sw.n = 0;
+  for (size_t n = 0; n < nm; ++n) {
+    b2p_tile::Antenna& a = t->antennas[n];
+    AntennaModes& sw = sweeps[n / ANTENNA_MAX_MODES];
+    const int q = sw.n++;
+    for (int d = 0; d < 3; ++d) {
+      double k = a.wave[d];
+      if (a.kind == 1) {                                                       // :603-614
+        const double L = double(t->cfg.n_tiles[d]) * double(t->cfg.n_cells[d]);
+        const double tmp = 2 * 3.141592653589793238462643383279502884 * a.wave[d];
+        k = tmp / L;
+      }
+      sw.A[q][d] = static_cast<float>(a.A[d]);
+      sw.K[q][d] = static_cast<float>(k);
+    }
+    if (a.has_coeffs && a.next >= a.coeffs.size())
+      throw Error(B2P_ERR_LOGIC, "Can not deposit antenna current, antenna_mode ran out of lap_coeffs!");
+    if (a.has_coeffs) { sw.W[q][0] = static_cast<float>(a.coeffs[a.next][0]); sw.W[q][1] = static_cast<float>(a.coeffs[a.next][1]); ++a.next; }
+    else { sw.W[q][0] = 1.0f; sw.W[q][1] = 0.0f; }
+  }
+  Scratch& s = scratch();
+  s.antenna[0].reserve(t->lattice_floats());
+  s.antenna[1].reserve(t->lattice_floats());
+  for (const AntennaModes& sw : sweeps)
+    launch_antenna(t->J(), s.antenna[0].p, s.antenna[1].p, t->g, sw, t->mins, t->maxs, static_cast<float>(-t->cfg.cfl));
+  B2P_CATCH
+}
+
 int b2p_tile_register_edge_bc(b2p_tile* t, const b2p_edge_bc* bc) {
   B2P_TRY
   if (!bc) throw Error(B2P_ERR_RUNTIME, "null edge_bc");

@@ -56,6 +56,9 @@ struct b2p_tile {
   b2p_grid* grid = nullptr;
   int slot = -1;
   bool deferred = false;                      // queued in the pending batch of per-tile calls (host.cu)
+  // antenna modes (emf/tile.h:48); lap_coeffs are consumed in order
+  struct Antenna { double A[3], wave[3]; int kind; bool has_coeffs; std::vector<std::array<double, 2>> coeffs; size_t next = 0; };
+  std::vector<Antenna> antennas;
   // pic-shock boundary pieces
   std::vector<b2p_edge_bc> edge_bcs;          // emf/tile.h:51
   std::vector<b2p_reflector_wall> walls;      // pic/tile.h:71

@@ -68,6 +68,44 @@ def edge_bc(*, direction=0, side=0, position=0.0, Ex=0.0, Ey=0.0, Ez=0.0, Bx=0.0
     return bc
 
 
+class antenna_mode:
+    """emf.threeD.antenna_mode (bindings/pyemf.c++:102-170): keyword-only A and exactly one of k (wave vector) /
+    n (mode number of the global grid), optional complex lap_coeffs consumed one per deposit."""
+
+    def __init__(self, *, A, k=None, n=None, lap_coeffs=None):
+        if (k is not None and n is not None) or (k is None and n is None):
+            raise B2PError("antenna_mode expects k or n to be defined but not both.")
+
+        def vec3(x):
+            x = np.asarray(x, dtype=np.float64)
+            if x.ndim != 1:
+                raise B2PError("Antenna expects A and k/n to be rank-1 arrays (specifically 3D vectors).")
+            if x.shape[0] != 3:
+                raise B2PError("Antenna expects A and k/n to be 3D vectors.")
+            return x
+
+        self.A = vec3(A)
+        self.wave = vec3(k if k is not None else n)
+        self.wave_kind = 0 if k is not None else 1
+        self.lap_coeffs = None
+        if lap_coeffs is not None:
+            c = np.asarray(lap_coeffs, dtype=np.complex128)
+            if c.ndim != 1:
+                raise B2PError("lap_coeffs must be 1D array.")
+            self.lap_coeffs = np.ascontiguousarray(np.stack([c.real, c.imag], axis=1))
+
+    def _as_struct(self):
+        m = _abi.AntennaMode(wave_kind=self.wave_kind)
+        m.A[:] = self.A
+        m.wave[:] = self.wave
+        if self.lap_coeffs is not None:
+            m.n_lap_coeffs = len(self.lap_coeffs)
+            # a valid non-NULL pointer even for an empty list: NULL means "no lap_coeffs" (phi = 1)
+            self._keep = self.lap_coeffs if len(self.lap_coeffs) else np.zeros((1, 2))
+            m.lap_coeffs = self._keep.ctypes.data_as(C.POINTER(C.c_double))
+        return m
+
+
 def reflector_wall(*, walloc=0.0, betawall=0.0, gammawall=1.0):
     """pic.threeD.reflector_wall (bindings/pypic.c++:70-90)."""
     return _abi.ReflectorWall(walloc=float(walloc), betawall=float(betawall), gammawall=float(gammawall))
@@ -236,6 +274,13 @@ class Tile(EmfTileHost):
         b, e = C.c_double(), C.c_double()
         check(lib().b2p_tile_field_energy(self._h, C.byref(b), C.byref(e)))
         return b.value, e.value
+
+    # -- antenna (emf/tile.c++:566-791) -----------------------------------------------
+    def register_antenna(self, mode):
+        check(lib().b2p_tile_register_antenna(self._h, C.byref(mode._as_struct())))
+
+    def deposit_antenna_current(self):
+        check(lib().b2p_tile_deposit_antenna_current(self._h))
 
     # -- edge boundary conditions (emf/tile.c++:808-847) ------------------------------
     def register_edge_bc(self, bc):

@@ -42,6 +42,9 @@ class OracleTile:
     def register_reflector_wall(self, wall):
         self.g.register_reflector_wall(self.t, wall)
 
+    def register_antenna(self, mode):
+        self.g.register_antenna(self.t, mode)
+
     def apply_edge_bc(self, bc, mode):
         self.g.apply_edge_bc(self.t, bc, int(mode))
 
@@ -81,6 +84,9 @@ class B200Tile:
 
     def register_reflector_wall(self, wall):
         self.tile.register_reflector_wall(wall)
+
+    def register_antenna(self, mode):
+        self.tile.register_antenna(mode)
 
     def apply_edge_bc(self, bc, mode):
         self.tile.apply_edge_bc(bc, int(mode))

@@ -82,6 +82,8 @@ else:
             except OracleError as e:
                 raise RuntimeError(str(e)) from None
 
+        def register_antenna(self, mode): self._ck(self._g.register_antenna, self._t, mode)
+        def deposit_antenna_current(self): self._op("deposit_antenna_current")
         def register_edge_bc(self, bc): self._ck(self._g.register_edge_bc, self._t, bc)
         def apply_edge_bcs(self, mode): self._ck(self._g.apply_edge_bcs, self._t, _t._mode(mode))
         def apply_edge_bc(self, bc, mode): self._ck(self._g.apply_edge_bc, self._t, bc, _t._mode(mode))
@@ -121,7 +123,7 @@ def _module(name, **attrs):
     return m
 
 
-emf = _module("runko.emf", threeD=_module("runko.emf.threeD", Tile=EmfTile, edge_bc=_t.edge_bc))
+emf = _module("runko.emf", threeD=_module("runko.emf.threeD", Tile=EmfTile, edge_bc=_t.edge_bc, antenna_mode=_t.antenna_mode))
 pic = _module("runko.pic", threeD=_module("runko.pic.threeD", Tile=PicTile, ParticleState=_t.ParticleStateD,
                                           ParticleStateBatch=_t.ParticleStateBatch, reflector_wall=_t.reflector_wall))
 tools = _module("runko.tools", comm_mode=_t.comm_mode)

@@ -1,9 +1,9 @@
 """Pins the CPU oracle with the REFERENCE'S OWN unit tests: the unmodified files under
 /root/reference/tests/py are executed where they lie against tests/refshim/runko, a
 stand-in `runko` package that binds the product's host logic (runko_b200.tiles) to the
-oracle.  137 reference test cases cover fdtd2, the extended stencil, both binomial filters,
+oracle.  152 reference test cases cover fdtd2, the extended stencil, both binomial filters,
 3 pushers x 2 interpolators, both zigzag depositers, sorting, the field setters/getters and
-particle injection, the edge boundary conditions, the reflector wall and the moving injector.
+particle injection, the edge boundary conditions, the reflector wall, the moving injector and the antenna.
 
 /root/reference exists only in the build container, so this file is skipped on the GPU box
 (tests/test_kats.py restates the same known-answer cases for both backends there)."""
@@ -28,6 +28,8 @@ FILES = {
     "test_emf_edge_bc.py": 15,
     "test_pic_reflector_wall.py": 6,
     "test_pic_moving_injector.py": 13,
+    "test_emf_antenna.py": 11,
+    "test_emf_antenna_time_evolution.py": 4,
 }
 
 
