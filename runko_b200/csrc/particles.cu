@@ -9,6 +9,10 @@
 // bit-identical to the reference's unfused CPU build.
 #include "particles.cuh"
 
+#ifndef B2P_NODAL_V8
+#define B2P_NODAL_V8 1   // nodal means as one 32-byte record per node (LDG.256 gathers); 0: float4 + float2 arrays (24 B)
+#endif
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -78,7 +82,9 @@ k_nodal_means(const NodalBatch bt, const Geom g) {
   const float* __restrict__ E = bt.E[tile];
   const float* __restrict__ B = bt.B[tile];
   float4* __restrict__ nod = bt.nod[tile];
+#if !B2P_NODAL_V8
   float2* __restrict__ nodB = reinterpret_cast<float2*>(nod + g.Ch);
+#endif
   const int kblocks = (g.Hx[2] + 31) / 32;
   const int k = (blockIdx.x % kblocks) * blockDim.x + threadIdx.x;
   const int j = (blockIdx.x / kblocks) * blockDim.y + threadIdx.y;
@@ -98,8 +104,13 @@ k_nodal_means(const NodalBatch bt, const Geom g) {
     b.x = (By[n] + (By[n - si] + (By[n - 1] + By[n - si - 1]))) / 4.0f;
     b.y = (Bz[n] + (Bz[n - si] + (Bz[n - sj] + Bz[n - si - sj]))) / 4.0f;
   }
+#if B2P_NODAL_V8
+  nod[2 * n] = a;
+  nod[2 * n + 1] = make_float4(b.x, b.y, 0.f, 0.f);
+#else
   nod[n] = a;
   nodB[n] = b;
+#endif
   }
 }
 
@@ -115,7 +126,9 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
   const float dx = lx - float(i), dy = ly - float(j), dz = lz - float(k);
   const unsigned sj = unsigned(g.Hx[2]), si = unsigned(g.Hx[1]) * unsigned(g.Hx[2]);
   const unsigned n = (i * unsigned(g.Hx[1]) + j) * sj + k;
+#if !B2P_NODAL_V8
   const float2* __restrict__ nodB = reinterpret_cast<const float2*>(nod + g.Ch);
+#endif
   const unsigned off[2][2] = { { n, n + sj }, { n + si, n + si + sj } };
   float4 a[2][2][2];
   float2 b[2][2][2];
@@ -125,8 +138,19 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
     for (int jc = 0; jc < 2; ++jc)
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
+#if B2P_NODAL_V8
+        // one 32-byte record per node, one LDG.256 (sm_100) per corner: 8 gathers instead of 16
+        float4& A_ = a[ic][jc][kc];
+        float2& B_ = b[ic][jc][kc];
+        float p0_, p1_;
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(A_.x), "=f"(A_.y), "=f"(A_.z), "=f"(A_.w), "=f"(B_.x), "=f"(B_.y), "=f"(p0_), "=f"(p1_)
+            : "l"(nod + 2 * size_t(off[ic][jc] + kc)));
+        (void)p0_; (void)p1_;
+#else
         a[ic][jc][kc] = __ldg(nod + off[ic][jc] + kc);
         b[ic][jc][kc] = __ldg(nodB + off[ic][jc] + kc);
+#endif
       }
   // lerp3D (:29-52): along x, then y, then z — (1-w)*A + w*B per lerp, the same two products and one sum
   // as the reference.  The six components travel as three register pairs {Ex,Ey}, {Ez,Bx}, {By,Bz} — exactly
