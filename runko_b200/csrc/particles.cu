@@ -10,7 +10,11 @@
 #include "particles.cuh"
 
 #ifndef B2P_NODAL_V8
-#define B2P_NODAL_V8 1   // nodal means as one 32-byte record per node (LDG.256 gathers); 0: float4 + float2 arrays (24 B)
+// 1: nodal means as one 32-byte record per node gathered with LDG.256 (8 gathers per particle instead of 16).
+// Measured on B200 (tools/microbench.py, 256^3): 127 us right after a sort (vs 129) but 150-161 us on the laps
+// after it (vs 140-147) — once the lanes of a warp no longer share nodes, the extra 64 B per particle through the
+// L1 data pipe cost more than the eight saved instructions.  Default: float4 + float2 arrays (24 B per node).
+#define B2P_NODAL_V8 0
 #endif
 
 #include <cub/device/device_radix_sort.cuh>
