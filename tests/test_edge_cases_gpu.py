@@ -137,12 +137,21 @@ def test_container_outgrows_its_capacity_while_receiving():
         few = np.stack([4.0 + rng.random(10), 4.0 + rng.random(10), 4.0 + rng.random(10)])
         org.inject(org.cid(0, 0, 0), sp, *few, *np.zeros((3, 10)))
         tiles[0]._inject_arrays(sp, few, np.zeros((3, 10)))
-    for lap in range(2):
-        org.step_pic(lap)
-        grid.step_pic(lap)
-        for i in range(2):
-            same_containers(org, org.cid(i, 0, 0), tiles[i])
-    assert tiles[0].container_size(0) > 262144        # it did outgrow the first capacity class
+    org.step_pic(0)
+    grid.step_pic(0)
+    for i in range(2):
+        same_containers(org, org.cid(i, 0, 0), tiles[i])      # lap 0: E = 0 going in, bit-exact incl. the appended order
+    assert tiles[0].container_size(0) > 262144                # it did outgrow the first capacity class
+    org.step_pic(1)
+    grid.step_pic(1)
+    for i in range(2):                                        # lap 1 sees the 1e-7 deposit-order noise of J in E: same slots, ulps
+        for sp in range(2):
+            o = org.get_particles(org.cid(i, 0, 0), sp, alive_only=False)
+            g = tiles[i].get_particles(sp, alive_only=False)
+            assert_bits_equal(g[6], o[6], "ids")
+            alive = o[6] != DEAD
+            for c in range(6):
+                assert np.allclose(g[c][alive], o[c][alive], rtol=1e-5, atol=1e-5)
 
 
 def test_laps_on_the_smallest_tiles():
