@@ -640,28 +640,48 @@ k_max_count(const unsigned* __restrict__ cnt, const unsigned nkeys, unsigned* __
 __global__ void __launch_bounds__(256)
 k_sort_scatter(const unsigned* __restrict__ keys, const unsigned* __restrict__ rank, const unsigned* __restrict__ offs,
                unsigned* __restrict__ members, const unsigned n_total, const unsigned dead_key) {
-  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= n_total) return;
-  const unsigned key = keys[n];
-  if (key != dead_key) members[offs[key] + rank[n]] = n;
+  const unsigned n0 = blockIdx.x * 512u + threadIdx.x, n1 = n0 + 256u;   // two slots per thread: both lookups in flight together
+  const bool i0 = n0 < n_total, i1 = n1 < n_total;
+  const unsigned k0 = i0 ? keys[n0] : dead_key, k1 = i1 ? keys[n1] : dead_key;
+  const unsigned r0 = i0 ? rank[n0] : 0u, r1 = i1 ? rank[n1] : 0u;
+  const unsigned o0 = k0 != dead_key ? offs[k0] : 0u, o1 = k1 != dead_key ? offs[k1] : 0u;
+  if (k0 != dead_key) members[o0 + r0] = n0;
+  if (k1 != dead_key) members[o1 + r1] = n1;
 }
 
 // Step 5: dst[p] = src[members[p]] for the offs[dead_key] alive particles; the slots behind them are
-// dead.  Two slots per thread (256 apart) keep fourteen independent gathers in flight.
+// dead.  SORT_GATHER_SLOTS slots per thread (256 apart) keep 7 x SORT_GATHER_SLOTS independent gathers in flight.
+constexpr int SORT_GATHER_SLOTS = 4;
 __global__ void __launch_bounds__(256)
 k_sort_gather(const Species src, const Species dst, const unsigned* __restrict__ members, const unsigned* __restrict__ n_alive) {
-  const unsigned n0 = blockIdx.x * 512u + threadIdx.x, n1 = n0 + 256u;
   const unsigned na = *n_alive;
-  const bool a0 = n0 < na, a1 = n1 < na;
-  const unsigned p0 = a0 ? members[n0] : 0u, p1 = a1 ? members[n1] : 0u;
-  float f0[6], f1[6];
-  unsigned long long i0 = DEAD, i1 = DEAD;
-  if (a0) { f0[0] = src.x[p0]; f0[1] = src.y[p0]; f0[2] = src.z[p0]; f0[3] = src.ux[p0]; f0[4] = src.uy[p0]; f0[5] = src.uz[p0]; i0 = src.id[p0]; }
-  if (a1) { f1[0] = src.x[p1]; f1[1] = src.y[p1]; f1[2] = src.z[p1]; f1[3] = src.ux[p1]; f1[4] = src.uy[p1]; f1[5] = src.uz[p1]; i1 = src.id[p1]; }
-  if (a0) { dst.x[n0] = f0[0]; dst.y[n0] = f0[1]; dst.z[n0] = f0[2]; dst.ux[n0] = f0[3]; dst.uy[n0] = f0[4]; dst.uz[n0] = f0[5]; }
-  if (a1) { dst.x[n1] = f1[0]; dst.y[n1] = f1[1]; dst.z[n1] = f1[2]; dst.ux[n1] = f1[3]; dst.uy[n1] = f1[4]; dst.uz[n1] = f1[5]; }
-  if (n0 < src.n) dst.id[n0] = i0;
-  if (n1 < src.n) dst.id[n1] = i1;
+  unsigned n[SORT_GATHER_SLOTS], p[SORT_GATHER_SLOTS];
+  bool a[SORT_GATHER_SLOTS];
+  float f[SORT_GATHER_SLOTS][6];
+  unsigned long long id[SORT_GATHER_SLOTS];
+#pragma unroll
+  for (int r = 0; r < SORT_GATHER_SLOTS; ++r) {
+    n[r] = blockIdx.x * (256u * SORT_GATHER_SLOTS) + 256u * r + threadIdx.x;
+    a[r] = n[r] < na;
+    p[r] = a[r] ? members[n[r]] : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < SORT_GATHER_SLOTS; ++r) {
+    id[r] = DEAD;
+    if (a[r]) {
+      f[r][0] = src.x[p[r]]; f[r][1] = src.y[p[r]]; f[r][2] = src.z[p[r]];
+      f[r][3] = src.ux[p[r]]; f[r][4] = src.uy[p[r]]; f[r][5] = src.uz[p[r]];
+      id[r] = src.id[p[r]];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < SORT_GATHER_SLOTS; ++r) {
+    if (a[r]) {
+      dst.x[n[r]] = f[r][0]; dst.y[n[r]] = f[r][1]; dst.z[n[r]] = f[r][2];
+      dst.ux[n[r]] = f[r][3]; dst.uy[n[r]] = f[r][4]; dst.uz[n[r]] = f[r][5];
+    }
+    if (n[r] < src.n) dst.id[n[r]] = id[r];
+  }
 }
 
 // Step 4: ascending slot order inside every alive cell.  A block takes blockDim.x (<= 256)
@@ -1245,7 +1265,7 @@ void launch_sort_scatter_place(const Species& src, const Species& dst, const uns
   if (!src.n) return;
   {
     ProfScope prof_(KC_RADIX_SORT, double(src.n));
-    k_sort_scatter<<<blocks_for(src.n), 256, 0, ctx().stream>>>(keys, rank, offs, members, src.n, nkeys);
+    k_sort_scatter<<<(src.n + 511) / 512, 256, 0, ctx().stream>>>(keys, rank, offs, members, src.n, nkeys);
     B2P_LAUNCH_CHECK();
     B2P_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned), ctx().stream));
     // cells per block: about half the staging buffer at the container's mean population
@@ -1258,7 +1278,7 @@ void launch_sort_scatter_place(const Species& src, const Species& dst, const uns
     B2P_LAUNCH_CHECK();
   }
   ProfScope prof_(KC_GATHER, double(src.n));
-  k_sort_gather<<<(src.n + 511) / 512, 256, 0, ctx().stream>>>(src, dst, members, offs + nkeys);
+  k_sort_gather<<<(src.n + 256 * SORT_GATHER_SLOTS - 1) / (256 * SORT_GATHER_SLOTS), 256, 0, ctx().stream>>>(src, dst, members, offs + nkeys);
   B2P_LAUNCH_CHECK();
 }
 
