@@ -61,6 +61,7 @@ static bool set_option(const std::string& name, int value) {
   else if (name == "push_streams") g_tuning.push_streams = value;
   else if (name == "sort_streams") g_tuning.sort_streams = value;
   else if (name == "push_group") g_tuning.push_group = value;
+  else if (name == "sort_overlap") g_tuning.sort_overlap = value;
   else if (name == "sort_counting") g_tuning.sort_counting = value;
   else if (name == "defer_tile_calls") g_tuning.defer_tile_calls = value;
   else return false;
@@ -163,6 +164,7 @@ struct Workers {
   cudaStream_t s[MAX_WORKERS] = {};
   cudaEvent_t fork = nullptr, join[MAX_WORKERS] = {};
   bool ready = false;
+  int sort_pending = 0;       // worker streams still carry an un-joined sort (join_pending_sort)
   void init() {
     if (ready) return;
     for (int w = 0; w < MAX_WORKERS; ++w) {
@@ -174,6 +176,18 @@ struct Workers {
   }
 };
 static Workers& workers() { static Workers w; return w; }
+// The sort of b2p_grid_step_pic is left running on the worker streams while the library stream goes on
+// with the field phase of the lap (J exchange, filters, B and E updates — none of which touches a particle
+// container).  Every C-ABI entry point in this file, and the deposit's fresh-deposit branch, joins it first.
+void join_pending_sort() {
+  Workers& wk = workers();
+  if (!wk.sort_pending) return;
+  for (int w = 0; w < wk.sort_pending; ++w) {
+    B2P_CUDA(cudaEventRecord(wk.join[w], wk.s[w]));
+    B2P_CUDA(cudaStreamWaitEvent(g_ctx.stream, wk.join[w], 0));
+  }
+  wk.sort_pending = 0;
+}
 struct StreamScope {          // makes `st` the stream every launcher / ProfScope / DBuf uses
   cudaStream_t saved;
   explicit StreamScope(cudaStream_t st) : saved(g_ctx.stream) { g_ctx.stream = st; }
@@ -481,6 +495,7 @@ void phase_deposit(const std::vector<b2p_tile*>& tiles) {
       if (t->grid) t->grid->table_dirty = true;
       t->pendJ_valid = t->pend_packed = false;
     } else {
+      join_pending_sort();                                          // a fresh deposit reads the containers
       t->pendJ_valid = t->pend_packed = false;
       s.edges.reserve(size_t(3) * t->g.Ch);
       launch_zero(reinterpret_cast<float*>(s.edges.p), size_t(12) * t->g.Ch);
@@ -622,7 +637,7 @@ struct PopHints {
 };
 static PopHints& pop_hints() { static PopHints* h = new PopHints; return *h; }
 
-void phase_sort(const std::vector<b2p_tile*>& tiles) {
+void phase_sort(const std::vector<b2p_tile*>& tiles, bool leave_running) {
   Scratch& s = scratch();
   struct Item { b2p_tile* t; Container* c; };
   std::vector<Item> items;
@@ -677,11 +692,10 @@ void phase_sort(const std::vector<b2p_tile*>& tiles) {
     swap_storage(c, spare);
     c.touch();
   }
-  if (nw > 1)
-    for (int w = 0; w < nw; ++w) {
-      B2P_CUDA(cudaEventRecord(wk.join[w], wk.s[w]));
-      B2P_CUDA(cudaStreamWaitEvent(main_stream, wk.join[w], 0));
-    }
+  if (nw > 1) {
+    wk.sort_pending = nw;
+    if (!leave_running || !tuning().sort_overlap) join_pending_sort();
+  }
 }
 
 // pic/tile_communication.c++:68-96 + pic/particle.c++:199-348, batched over tiles
@@ -914,7 +928,7 @@ void flush_deferred() {
     case DK_FILTER: phase_filter(tiles); break;
     case DK_PUSH: phase_push_particles(tiles); break;
     case DK_PACK: phase_pack_outgoing(tiles); break;
-    case DK_SORT: phase_sort(tiles); break;
+    case DK_SORT: phase_sort(tiles, false); break;
     case DK_DEPOSIT: phase_deposit(tiles); break;
     default: break;
   }
@@ -949,7 +963,7 @@ void Scratch_table_upload(const void* src, size_t bytes) {
 }
 const void* Scratch_table_ptr() { return scratch().table.p; }
 }  // namespace b2p
-#define B2P_TRY try { b2p::flush_deferred();
+#define B2P_TRY try { b2p::join_pending_sort(); b2p::flush_deferred();
 #define B2P_TRY_DEFER try {
 #define B2P_CATCH                                                              \
   }                                                                            \
@@ -1335,7 +1349,7 @@ int b2p_grid_add_current(b2p_grid* g) { B2P_TRY phase_add_current(G(g)->tiles, g
 int b2p_grid_filter_current(b2p_grid* g) { B2P_TRY phase_filter(G(g)->tiles); B2P_CATCH }
 int b2p_grid_push_particles(b2p_grid* g) { B2P_TRY phase_push_particles(G(g)->tiles); B2P_CATCH }
 int b2p_grid_pack_outgoing_particles(b2p_grid* g) { B2P_TRY phase_pack_outgoing(G(g)->tiles); B2P_CATCH }
-int b2p_grid_sort_particles(b2p_grid* g) { B2P_TRY phase_sort(G(g)->tiles); B2P_CATCH }
+int b2p_grid_sort_particles(b2p_grid* g) { B2P_TRY phase_sort(G(g)->tiles, false); B2P_CATCH }
 int b2p_grid_deposit_current(b2p_grid* g) { B2P_TRY phase_deposit(G(g)->tiles); B2P_CATCH }
 int b2p_grid_apply_edge_bcs(b2p_grid* g, int mode) { B2P_TRY phase_apply_edge_bcs(G(g)->tiles, mode); B2P_CATCH }
 int b2p_grid_reflect_particles(b2p_grid* g) { B2P_TRY phase_reflect_particles(G(g)->tiles); B2P_CATCH }
@@ -1441,7 +1455,7 @@ int b2p_grid_step_pic(b2p_grid* g, int64_t lap) {
   tr.mark("pack", lap);
   ext(B2P_COMM_PIC_PARTICLE); grid_local_communication(g, B2P_COMM_PIC_PARTICLE);
   tr.mark("particle comm", lap);
-  if (lap % 5 == 0) phase_sort(g->tiles);
+  if (lap % 5 == 0) phase_sort(g->tiles, /*leave_running=*/true);   // joined by the next entry point (or a fresh deposit)
   tr.mark("sort enqueue", lap);
   phase_deposit(g->tiles);
   tr.mark("deposit enqueue", lap);

@@ -97,7 +97,8 @@ void phase_add_current(const std::vector<b2p_tile*>& tiles, const FieldPtrs* tab
 void phase_filter(const std::vector<b2p_tile*>& tiles);
 void phase_push_particles(const std::vector<b2p_tile*>& tiles);
 void phase_deposit(const std::vector<b2p_tile*>& tiles);
-void phase_sort(const std::vector<b2p_tile*>& tiles);
+void phase_sort(const std::vector<b2p_tile*>& tiles, bool leave_running = false);
+void join_pending_sort();                   // host.cu: makes the library stream wait for a sort left on the worker streams
 void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles);
 void phase_apply_edge_bcs(const std::vector<b2p_tile*>& tiles, int mode);
 void phase_reflect_particles(const std::vector<b2p_tile*>& tiles);
