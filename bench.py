@@ -495,6 +495,8 @@ def main():
         lap += 1
     barrier()
 
+    alive0 = grid.alive_counts()
+    en0 = grid.energies()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = L.b2p_launch_count()
@@ -579,6 +581,32 @@ def main():
             if pl[k]:
                 print(f"  {names[k]:16s} {pms[k] / prof_steps:9.3f} ms/step  {int(pl[k]) // prof_steps:6d} launches/step", file=sys.stderr)
 
+    # ---- size-independent invariants at the full bench size (no oracle at 4.3e9 particles): particle number,
+    # energy budget, and the sort contract on one container (sorted by cell key, dead slots last, idempotent)
+    alive1, en1 = grid.alive_counts(), grid.energies()
+    tot = [alive0, alive1]
+    if dist is not None:
+        import torch
+        tt = torch.tensor(np.stack(tot).astype(np.int64))
+        dist.all_reduce(tt)
+        tot = [tt[0].numpy(), tt[1].numpy()]
+    m0 = abs(conf.q0)
+    e_tot = [e[0] + e[1] + m0 * float(np.sum(e[2])) for e in (en0, en1)]
+    t0_ = tiles[0]
+    t0_.sort_particles()
+    keys = t0_.sort_keys(0).astype(np.int64)
+    ids_a = t0_.get_particles(0, alive_only=False)[6].copy()
+    t0_.sort_particles()
+    ids_b = t0_.get_particles(0, alive_only=False)[6]
+    dead = ids_a == np.uint64(0xFFFFFFFFFFFFFFFF)
+    n_alive0 = int(np.count_nonzero(~dead))
+    checks = {"particles_before": [int(v) for v in tot[0]], "particles_after": [int(v) for v in tot[1]],
+              "particle_number_conserved": bool(np.array_equal(tot[0], tot[1])),
+              "energy_drift_over_timed_and_profiled_laps": e_tot[1] / e_tot[0] - 1.0,
+              "container_sorted_by_cell_key": bool(np.all(np.diff(keys) >= 0)),
+              "dead_slots_last": bool(not np.any(dead[:n_alive0]) and np.all(dead[n_alive0:])),
+              "sort_idempotent": bool(np.array_equal(ids_a, ids_b))}
+
     # ---- e2e: whole job through the reference-facing per-tile API with host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -602,7 +630,7 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
                "cell_updates_per_s": n_cells_local * world / per_step, "wall_ms_per_step": wall / args.steps * 1e3,
                "kernel_ms_per_step_single_stream": float(pms.sum() / prof_steps),
-               "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+               "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "checks": checks}
         if e2e is not None:
             out["e2e"] = e2e
         if cpu is not None:

@@ -234,6 +234,10 @@ int b2p_grid_deposit_current(b2p_grid* g);
 int b2p_grid_apply_edge_bcs(b2p_grid* g, int mode);
 int b2p_grid_reflect_particles(b2p_grid* g);
 int b2p_grid_advance_reflector_walls(b2p_grid* g);
+/* Alive particles (id != dead) per species over the local tiles.  No reference getter: the reference
+ * counts them while writing particle snapshots (io/snapshots/mpiio_particles.c++); used by the
+ * conservation checks of bench.py and the tests. */
+int b2p_grid_alive_counts(b2p_grid* g, uint64_t* counts);
 /* mpiio::FieldsWriter<3>::write (src/runko/io/snapshots/mpiio_fields.c++:221-400, header
  * mpiio_header.h:56-82): "<prefix>/flds_<lap>.bin" = 512-byte "RNKO" v3
  * header + (9 + min(nspecies, 5)) dense fp32 arrays [nz][ny][nx] (x fastest): E, B point-sampled

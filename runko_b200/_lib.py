@@ -23,7 +23,7 @@ b2p_tile_sort_keys b2p_tile_get_outgoing b2p_tile_kinetic_energy
 b2p_tile_register_edge_bc b2p_tile_apply_edge_bcs b2p_tile_apply_edge_bc
 b2p_tile_register_reflector_wall b2p_tile_reflect_particles b2p_tile_advance_reflector_walls b2p_tile_reflector_walls
 b2p_tile_register_antenna b2p_tile_deposit_antenna_current
-b2p_grid_apply_edge_bcs b2p_grid_reflect_particles b2p_grid_advance_reflector_walls b2p_grid_write_fields_snapshot
+b2p_grid_apply_edge_bcs b2p_grid_reflect_particles b2p_grid_advance_reflector_walls b2p_grid_write_fields_snapshot b2p_grid_alive_counts
 b2p_grid_create b2p_grid_destroy b2p_grid_add_tile b2p_grid_local_communication
 b2p_grid_push_half_b b2p_grid_push_e b2p_grid_add_current b2p_grid_filter_current
 b2p_grid_push_particles b2p_grid_pack_outgoing_particles b2p_grid_sort_particles b2p_grid_deposit_current
@@ -93,6 +93,7 @@ def lib():
     L.b2p_grid_apply_edge_bcs.argtypes = [vp, ci]
     L.b2p_grid_reflect_particles.argtypes = [vp]
     L.b2p_grid_advance_reflector_walls.argtypes = [vp]
+    L.b2p_grid_alive_counts.argtypes = [vp, vp]
     L.b2p_grid_write_fields_snapshot.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]
     L.b2p_grid_create.argtypes = [C.POINTER(B2PConfig), C.POINTER(vp)]
     L.b2p_grid_destroy.argtypes = [vp]

@@ -1516,6 +1516,23 @@ int b2p_grid_energies(b2p_grid* g, double* eB, double* eE, double* kinetic, uint
   B2P_CATCH
 }
 
+int b2p_grid_alive_counts(b2p_grid* g, uint64_t* counts) {
+  B2P_TRY
+  G(g);
+  const int ns = g->cfg.n_species;
+  Scratch& s = scratch();
+  s.energy.reserve(size_t(ns) + 1);
+  unsigned long long* dc = reinterpret_cast<unsigned long long*>(s.energy.p);
+  B2P_CUDA(cudaMemsetAsync(dc, 0, sizeof(unsigned long long) * ns, ctx().stream));
+  for (b2p_tile* t : g->tiles)
+    for (int q = 0; q < ns; ++q) launch_count_alive(t->sp[q].view(), dc + q);
+  std::vector<unsigned long long> h(ns);
+  d2h(h.data(), dc, size_t(ns));
+  stream_sync();
+  for (int q = 0; q < ns; ++q) counts[q] = h[q];
+  B2P_CATCH
+}
+
 int b2p_grid_inject_thermal(b2p_grid* g, int ppc, double delgam, uint64_t seed) {
   B2P_TRY
   G(g);

@@ -1052,6 +1052,16 @@ k_snapshot_density(const Species s, const float3 mins, const float inv_stride, c
   atomicAdd(&n_out[(size_t(fz) * nyt + size_t(fy)) * nxt + size_t(fx)], 1.0f);
 }
 
+// number of alive slots (id != dead) of a container, added to *out
+__global__ void __launch_bounds__(256)
+k_count_alive(const Species s, unsigned long long* __restrict__ out) {
+  unsigned c = 0;
+  for (unsigned n = blockIdx.x * blockDim.x + threadIdx.x; n < s.n; n += gridDim.x * blockDim.x) c += unsigned(s.id[n] != DEAD);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, static_cast<unsigned long long>(c));
+}
+
 // ------------------------------------------------- synthetic thermal plasma --
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -1359,6 +1369,12 @@ void launch_reflect_at_wall(const Species& s, float* corrJ, const Geom& g, const
   B2P_LAUNCH_CHECK();
 }
 
+void launch_count_alive(const Species& s, unsigned long long* out) {
+  ProfScope prof_(KC_OTHER, double(s.n));
+  if (!s.n) return;
+  k_count_alive<<<std::min(blocks_for(s.n), unsigned(ctx().sm_count) * 8), 256, 0, ctx().stream>>>(s, out);
+  B2P_LAUNCH_CHECK();
+}
 void launch_snapshot_density(const Species& s, const float mins[3], float inv_stride, int nxt, int nyt, int nzt, float* n_out) {
   ProfScope prof_(KC_OTHER, double(s.n));
   if (!s.n) return;

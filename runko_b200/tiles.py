@@ -540,6 +540,11 @@ class Grid:
         check(lib().b2p_grid_energies(self._h, C.byref(b), C.byref(e), _ptr(k), _ptr(s)))
         return b.value, e.value, k[:self.n_species], s[:self.n_species]
 
+    def alive_counts(self):
+        c = np.zeros(max(1, self.n_species), np.uint64)
+        check(lib().b2p_grid_alive_counts(self._h, _ptr(c)))
+        return c[:self.n_species]
+
     def inject_thermal(self, ppc, delgam, seed=1):
         check(lib().b2p_grid_inject_thermal(self._h, int(ppc), float(delgam), int(seed)))
 
