@@ -91,6 +91,22 @@ def main():
     org.local_communication(M.emf_J.value)
     grid.external_communication(M.emf_J); grid.local_communication(M.emf_J)
     compare(True, 0.0)
+    # one snapshot file written by all ranks together (pwrite per tile row, header by rank 0) == the oracle's file,
+    # byte for byte (fields after the bit-exact halo phase, density of the freshly injected particles)
+    import tempfile
+    d = [tempfile.mkdtemp(prefix="b2p_snap_") if rank == 0 else None]
+    dist.broadcast_object_list(d, src=0)
+    dist.barrier()
+    grid.write_fields_snapshot(d[0], 3, 2, 2)
+    rb.sync()
+    dist.barrier()
+    if rank == 0:
+        os.makedirs(os.path.join(d[0], "o"))
+        org.write_fields_snapshot(os.path.join(d[0], "o"), 3, 2, 2)
+        a = open(os.path.join(d[0], "flds_3.bin"), "rb").read()
+        b = open(os.path.join(d[0], "o", "flds_3.bin"), "rb").read()
+        assert a == b, "multi-rank snapshot differs from the oracle's"
+    dist.barrier()
     # particle migration across ranks (bit-exact containers)
     for _ in range(2):
         org.phase("push_particles"); grid.phase("push_particles")
