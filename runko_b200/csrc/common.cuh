@@ -66,7 +66,7 @@ struct Tuning {
   int push_minb = 6;      // __launch_bounds__(256, minb) variant of k_push: 5, 6 or 8 resident blocks per SM
   int deposit_minb = 4;   // same for k_deposit_zigzag: 4, 6 or 8
   int deposit_agg = 1;    // warp-level run aggregation before the REDs
-  int agg_min = 6;        // ... a step is taken when at least this many lanes of the warp fold
+  int agg_min = 2;        // ... a step is taken when at least this many lanes of the warp fold
   int filter_chunk = 35;  // i-planes per thread column of k_filter_binomial2
   int push_streams = 4;   // worker streams the per-tile particle phase is round-robined over (1 = library stream only)
   int sort_streams = 4;   // worker streams the per-container sort is round-robined over

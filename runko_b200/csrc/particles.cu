@@ -230,6 +230,9 @@ struct DepositArgs {
 // 8x fewer atomics enter the L1 data pipe, the unit that bounds this kernel (ncu: one wavefront
 // per RED lane).  Unsorted input degenerates to the plain per-lane REDs at the cost of two ballots.  Summation order differs from the
 // reference's serial loop: covered by the stated deposit tolerance.
+#ifndef AGG_MAX_STEP
+#define AGG_MAX_STEP 4   // widest fold: runs of up to 2 * AGG_MAX_STEP lanes collapse into one lane's REDs (a step of 8 measured no better)
+#endif
 template <int AGG>
 __device__ __forceinline__ void reduce_runs_and_red(const unsigned key, float4 ex, float4 ey, float4 ez, float4* __restrict__ Jc,
                                                     const int agg_min) {
@@ -249,7 +252,7 @@ __device__ __forceinline__ void reduce_runs_and_red(const unsigned key, float4 e
     // when at least `agg_min` lanes of the warp fold (warp-uniform decision).
     unsigned stride = 1;
 #pragma unroll
-    for (int d = 1; d <= 4; d <<= 1) {
+    for (int d = 1; d <= AGG_MAX_STEP; d <<= 1) {
       const unsigned folded = __ballot_sync(0xffffffffu, valid && (off & unsigned(2 * d - 1)) == unsigned(d));
       if (int(__popc(folded)) < agg_min) break;
       const bool take = rem > unsigned(d);
