@@ -381,7 +381,7 @@ __device__ __forceinline__ unsigned long long ld_pinned(const unsigned long long
 // 128 B, one per thread of the first two warps).  Blocks run roughly in index order, so asking for
 // the block PREFETCH_BLOCKS ahead (more than one wave of resident blocks) turns that block's
 // DRAM latency at its head into an L2 hit.
-constexpr unsigned PREFETCH_BLOCKS = 1024;
+// (Tuning::push_prefetch; off by default: with the seven streams requested up front it measured no gain.)
 __device__ __forceinline__ void prefetch_streams(const Species& s, const unsigned blk) {
   const unsigned t = threadIdx.x;
   if (t >= 64) return;
@@ -403,6 +403,7 @@ __device__ __forceinline__ void prefetch_streams(const Species& s, const unsigne
 
 struct PushArgs {
   int agg_min;    // see DepositArgs
+  int prefetch;   // blocks ahead whose particle streams are prefetched into L2 (0: off)
   Species s;
   const float4* nod;
   Geom g;
@@ -420,7 +421,7 @@ template <int PUSHER, int MINB, int FUSE>
 __global__ void __launch_bounds__(256, MINB)
 k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float3 mx, float4* __restrict__ Jc, const float charge) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  prefetch_streams(a.s, blockIdx.x + PREFETCH_BLOCKS);
+  if (a.prefetch) prefetch_streams(a.s, blockIdx.x + unsigned(a.prefetch));
   // All seven streams are requested before the id is looked at (pinned loads: the compiler must
   // not sink the six value loads below the dead-slot test, which would put two DRAM round trips
   // in series); dead slots hold unspecified but readable values.
@@ -1156,7 +1157,7 @@ void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g,
                  uint2* masks, const float mins[3], const float maxs[3], float4* Jc, float charge) {
   ProfScope prof_(KC_PUSH, double(s.n));
   if (!s.n) return;
-  PushArgs a{ tuning().agg_min, s, nod, g, make_float3(origo[0], origo[1], origo[2]), cfl, qm };
+  PushArgs a{ tuning().agg_min, tuning().push_prefetch, s, nod, g, make_float3(origo[0], origo[1], origo[2]), cfl, qm };
   const float3 mn = make_float3(mins[0], mins[1], mins[2]), mx = make_float3(maxs[0], maxs[1], maxs[2]);
   const unsigned nb = blocks_for(s.n);
   const int minb = tuning().push_minb;
