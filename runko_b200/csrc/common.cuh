@@ -71,6 +71,7 @@ struct Tuning {
   int push_streams = 4;   // worker streams the per-tile particle phase is round-robined over (1 = library stream only)
   int sort_streams = 4;   // worker streams the per-container sort is round-robined over
   int sort_overlap = 1;   // b2p_grid_step_pic leaves the sort running on the worker streams under the field phase of the lap
+  int push_block = 128;       // threads per block of k_push (128 or 256; 128 measured 1 % faster: finer-grained tail)
   int push_prefetch = 0;      // k_push: L2 prefetch distance in blocks of 256 slots (0: off — measured no gain once all seven streams are requested up front)
   int push_group = 8;     // tiles per launch of the small kernels around the pushes (nodal means, scratch clear, edge gather)
   int sort_counting = 1;  // counting sort by cell (0: always the general radix sort)

@@ -62,6 +62,7 @@ static bool set_option(const std::string& name, int value) {
   else if (name == "sort_streams") g_tuning.sort_streams = value;
   else if (name == "push_group") g_tuning.push_group = value;
   else if (name == "push_prefetch") g_tuning.push_prefetch = value;
+  else if (name == "push_block") g_tuning.push_block = value;
   else if (name == "sort_overlap") g_tuning.sort_overlap = value;
   else if (name == "sort_counting") g_tuning.sort_counting = value;
   else if (name == "defer_tile_calls") g_tuning.defer_tile_calls = value;

@@ -1159,10 +1159,11 @@ void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g,
   if (!s.n) return;
   PushArgs a{ tuning().agg_min, tuning().push_prefetch, s, nod, g, make_float3(origo[0], origo[1], origo[2]), cfl, qm };
   const float3 mn = make_float3(mins[0], mins[1], mins[2]), mx = make_float3(maxs[0], maxs[1], maxs[2]);
-  const unsigned nb = blocks_for(s.n);
+  const unsigned bs = tuning().push_block == 128 ? 128u : 256u;
+  const unsigned nb = (s.n + bs - 1) / bs;
   const int minb = tuning().push_minb;
   const int fuse = Jc ? (tuning().deposit_agg ? 2 : 1) : 0;
-#define PUSH_LAUNCH(P, M, F) k_push<P, M, F><<<nb, 256, 0, ctx().stream>>>(a, masks, mn, mx, Jc, charge)
+#define PUSH_LAUNCH(P, M, F) k_push<P, M, F><<<nb, bs, 0, ctx().stream>>>(a, masks, mn, mx, Jc, charge)
 #define PUSH_CASE(P)                                                                                   \
   case P:                                                                                              \
     if (fuse == 2) { if (minb >= 6) PUSH_LAUNCH(P, 6, 2); else if (minb >= 5) PUSH_LAUNCH(P, 5, 2); else PUSH_LAUNCH(P, 4, 2); } \

@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python tools/microbench.py --cells 256 --laps 5 --out gpurun_out/micro_pf.json "push_streams=1,sort_streams=1,push_prefetch=1024" "push_prefetch=0" "push_prefetch=256" "push_prefetch=512" "push_prefetch=2048" "push_prefetch=4096" "push_prefetch=1024,push_streams=4,sort_streams=4" "push_prefetch=2048" "push_prefetch=512" 2>&1 | grep -v "^ *per lap" | tail -1
+timeout 900 python tools/microbench.py --cells 256 --laps 5 --out gpurun_out/micro_pf.json "push_streams=1,sort_streams=1,push_block=256" "push_block=128" "push_block=256,push_streams=4,sort_streams=4" "push_block=128" 2>&1 | grep -v "^ *per lap" | tail -1
 python - <<'PY'
 import json
 for r in json.load(open('gpurun_out/micro_pf.json')):
