@@ -549,8 +549,8 @@ def main():
     # ---- roofline of the dominant kernel class (largest share of the timed region) ----
     peak, peak_src = read_peaks()
     fused = pl[names.index("deposit")] == 0      # push + deposit fused: credited with both phases' algorithmic bytes
-    bytes_per_unit = {"push": BYTES_PER_PARTICLE_STEP if fused else BYTES_PER_PARTICLE_PUSH, "deposit": BYTES_PER_PARTICLE_DEPOSIT, "gather": 64.0,
-                      "detect_leavers": 20.0, "sort_keys": 28.0, "radix_sort": 64.0, "filter": 24.0, "push_b": 36.0,
+    bytes_per_unit = {"push": BYTES_PER_PARTICLE_STEP if fused else BYTES_PER_PARTICLE_PUSH, "deposit": BYTES_PER_PARTICLE_DEPOSIT, "sort_gather": 64.0,
+                      "detect_leavers": 20.0, "sort_count": 28.0, "sort_place": 64.0, "filter": 24.0, "push_b": 36.0,
                       "push_e": 48.0, "zero": 4.0, "halo_fill": 0.0, "J_exchange": 0.0, "nodal_means": 56.0}
     top = int(np.argmax(pms))
     share = {names[k]: round(float(pms[k] / max(pms.sum(), 1e-9)), 4) for k in np.argsort(-pms)[:8] if pms[k] > 0}

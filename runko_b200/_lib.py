@@ -9,7 +9,8 @@ import os
 from ._abi import AntennaMode, B2PConfig, EdgeBC, ParticleState, ReflectorWall
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libb200pic.so")
+# B2P_LIB: a kernel-variant build of the same library (tools/microbench.py experiments); never a fallback
+SO_PATH = os.environ.get("B2P_LIB") or os.path.join(_HERE, "libb200pic.so")
 
 # every symbol include/b200pic.h declares (checked by tests/test_abi.py)
 SYMBOLS = """

@@ -115,7 +115,7 @@ static cudaEvent_t take_event() {
   cudaEvent_t e; B2P_CUDA(cudaEventCreate(&e)); return e;
 }
 const char* kernel_class_name(int k) {
-  static const char* n[KC_COUNT] = { "nodal_means", "push", "deposit", "sort_keys", "radix_sort", "gather", "detect_leavers",
+  static const char* n[KC_COUNT] = { "nodal_means", "push", "deposit", "sort_count", "sort_place", "sort_gather", "detect_leavers",
                                      "gather_outgoing", "append", "zero", "push_b", "push_e", "add_current", "filter",
                                      "halo_fill", "J_exchange", "energy", "edge_gather", "other" };
   return (k >= 0 && k < KC_COUNT) ? n[k] : "?";
@@ -441,7 +441,7 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
     const int w = int(gi++ % size_t(nw));
     StreamScope on(nw > 1 ? wk.s[w] : main_stream);
     const Geom& g = grp.front()->g;
-    const size_t nod_stride = size_t(2) * g.Ch, edge_stride = size_t(3) * g.Ch;   // float4 per tile
+    const size_t nod_stride = (nodal_float4_per_node() * g.Ch + 1) & ~size_t(1), edge_stride = size_t(3) * g.Ch;   // float4 per tile
     s.nodal_w[w].reserve(nod_stride * grp.size());
     NodalBatch nb{};
     EdgeBatch eb{};

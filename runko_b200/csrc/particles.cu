@@ -17,6 +17,12 @@
 #define B2P_NODAL_V8 0
 #endif
 
+#ifndef B2P_NODAL_BPAIR
+// 1: nodB[n] holds {By,Bz} of node n AND of node n+1 (its k neighbour) as one float4, so the two k-corners of a
+// cell arrive through one LDG.128: 12 gathers per particle instead of 16 for the same 192 B per lane.
+#define B2P_NODAL_BPAIR 0
+#endif
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -80,40 +86,63 @@ struct DivC {
 // 144 scalar gathers, and the L1 data pipe — the unit that bounds the push — returns 192 B per
 // lane instead of 256.  Same operands and same association (2-term sum /2; 4-term right fold /4)
 // => same bits.
+// staggered means of one lattice node; zero where a neighbour would fall outside the lattice
+__device__ __forceinline__ void node_means(const float* __restrict__ E, const float* __restrict__ B, const Geom& g, const int i,
+                                           const int j, const int k, float4& a, float2& b) {
+  a = make_float4(0.f, 0.f, 0.f, 0.f);
+  b = make_float2(0.f, 0.f);
+  if (i < 1 || j < 1 || k < 1 || k >= g.Hx[2]) return;
+  const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2], Ch = g.Ch;
+  const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
+  const float* Ex = E; const float* Ey = E + Ch; const float* Ez = E + 2 * Ch;
+  const float* Bx = B; const float* By = B + Ch; const float* Bz = B + 2 * Ch;
+  a.x = (Ex[n - si] + Ex[n]) / 2.0f;
+  a.y = (Ey[n - sj] + Ey[n]) / 2.0f;
+  a.z = (Ez[n - 1] + Ez[n]) / 2.0f;
+  a.w = (Bx[n] + (Bx[n - sj] + (Bx[n - 1] + Bx[n - sj - 1]))) / 4.0f;
+  b.x = (By[n] + (By[n - si] + (By[n - 1] + By[n - si - 1]))) / 4.0f;
+  b.y = (Bz[n] + (Bz[n - si] + (Bz[n - sj] + Bz[n - si - sj]))) / 4.0f;
+}
+
+// B2P_NODAL_BPAIR layouts (float4 units per tile, n = node index):
+//   0: A[n] at nod[n], {By,Bz}[n] as float2 behind them (24 B/node)
+//   1: A[n] at nod[n], P[n] = {By,Bz}[n], {By,Bz}[n+1] at nod[Ch + n]           (32 B/node)
+//   2: {A[n], A[n+1]} at nod[2n], nod[2n+1] (one LDG.256), P[n] at nod[2Ch + n]  (48 B/node)
+size_t nodal_float4_per_node() { return B2P_NODAL_BPAIR == 2 ? 3 : 2; }
+
 __global__ void __launch_bounds__(256)
 k_nodal_means(const NodalBatch bt, const Geom g) {
   const int tile = blockIdx.y;
   const float* __restrict__ E = bt.E[tile];
   const float* __restrict__ B = bt.B[tile];
   float4* __restrict__ nod = bt.nod[tile];
-#if !B2P_NODAL_V8
-  float2* __restrict__ nodB = reinterpret_cast<float2*>(nod + g.Ch);
-#endif
   const int kblocks = (g.Hx[2] + 31) / 32;
   const int k = (blockIdx.x % kblocks) * blockDim.x + threadIdx.x;
   const int j = (blockIdx.x / kblocks) * blockDim.y + threadIdx.y;
   if (k >= g.Hx[2] || j >= g.Hx[1]) return;
   for (int i = blockIdx.z; i < g.Hx[0]; i += gridDim.z) {
-  const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2], Ch = g.Ch;
-  const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  float2 b = make_float2(0.f, 0.f);
-  if (i >= 1 && j >= 1 && k >= 1) {
-    const float* Ex = E; const float* Ey = E + Ch; const float* Ez = E + 2 * Ch;
-    const float* Bx = B; const float* By = B + Ch; const float* Bz = B + 2 * Ch;
-    a.x = (Ex[n - si] + Ex[n]) / 2.0f;
-    a.y = (Ey[n - sj] + Ey[n]) / 2.0f;
-    a.z = (Ez[n - 1] + Ez[n]) / 2.0f;
-    a.w = (Bx[n] + (Bx[n - sj] + (Bx[n - 1] + Bx[n - sj - 1]))) / 4.0f;
-    b.x = (By[n] + (By[n - si] + (By[n - 1] + By[n - si - 1]))) / 4.0f;
-    b.y = (Bz[n] + (Bz[n - si] + (Bz[n - sj] + Bz[n - si - sj]))) / 4.0f;
-  }
-#if B2P_NODAL_V8
-  nod[2 * n] = a;
-  nod[2 * n + 1] = make_float4(b.x, b.y, 0.f, 0.f);
+    const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
+    float4 a;
+    float2 b;
+    node_means(E, B, g, i, j, k, a, b);
+#if B2P_NODAL_BPAIR
+    float4 a1;
+    float2 b1;
+    node_means(E, B, g, i, j, k + 1, a1, b1);     // the k neighbour, so that both k-corners of a cell share a record
+#if B2P_NODAL_BPAIR == 2
+    nod[2 * n] = a;
+    nod[2 * n + 1] = a1;
+    nod[2 * size_t(g.Ch) + n] = make_float4(b.x, b.y, b1.x, b1.y);
 #else
-  nod[n] = a;
-  nodB[n] = b;
+    nod[n] = a;
+    nod[size_t(g.Ch) + n] = make_float4(b.x, b.y, b1.x, b1.y);
+#endif
+#elif B2P_NODAL_V8
+    nod[2 * n] = a;
+    nod[2 * n + 1] = make_float4(b.x, b.y, 0.f, 0.f);
+#else
+    nod[n] = a;
+    reinterpret_cast<float2*>(nod + g.Ch)[n] = b;
 #endif
   }
 }
@@ -130,12 +159,34 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
   const float dx = lx - float(i), dy = ly - float(j), dz = lz - float(k);
   const unsigned sj = unsigned(g.Hx[2]), si = unsigned(g.Hx[1]) * unsigned(g.Hx[2]);
   const unsigned n = (i * unsigned(g.Hx[1]) + j) * sj + k;
-#if !B2P_NODAL_V8
+#if B2P_NODAL_BPAIR
+  const float4* __restrict__ nodP = nod + (B2P_NODAL_BPAIR == 2 ? 2 : 1) * size_t(g.Ch);
+#elif !B2P_NODAL_V8
   const float2* __restrict__ nodB = reinterpret_cast<const float2*>(nod + g.Ch);
 #endif
   const unsigned off[2][2] = { { n, n + sj }, { n + si, n + si + sj } };
   float4 a[2][2][2];
   float2 b[2][2][2];
+#if B2P_NODAL_BPAIR
+#pragma unroll
+  for (int ic = 0; ic < 2; ++ic)
+#pragma unroll
+    for (int jc = 0; jc < 2; ++jc) {
+#if B2P_NODAL_BPAIR == 2
+      float4& A0 = a[ic][jc][0];
+      float4& A1 = a[ic][jc][1];
+      asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+          : "=f"(A0.x), "=f"(A0.y), "=f"(A0.z), "=f"(A0.w), "=f"(A1.x), "=f"(A1.y), "=f"(A1.z), "=f"(A1.w)
+          : "l"(nod + 2 * size_t(off[ic][jc])));
+#else
+      a[ic][jc][0] = __ldg(nod + off[ic][jc]);
+      a[ic][jc][1] = __ldg(nod + off[ic][jc] + 1);
+#endif
+      const float4 p = __ldg(nodP + off[ic][jc]);
+      b[ic][jc][0] = make_float2(p.x, p.y);
+      b[ic][jc][1] = make_float2(p.z, p.w);
+    }
+#else
 #pragma unroll
   for (int ic = 0; ic < 2; ++ic)
 #pragma unroll
@@ -156,6 +207,7 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
         b[ic][jc][kc] = __ldg(nodB + off[ic][jc] + kc);
 #endif
       }
+#endif
   // lerp3D (:29-52): along x, then y, then z — (1-w)*A + w*B per lerp, the same two products and one sum
   // as the reference.  The six components travel as three register pairs {Ex,Ey}, {Ez,Bx}, {By,Bz} — exactly
   // how the LDG.128 / LDG.64 above deliver them — through Blackwell's packed fp32x2 multiply

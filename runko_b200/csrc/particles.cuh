@@ -31,6 +31,7 @@ struct CollectJobHost {       // mirrors particles.cu::CollectJob: leaver masks 
 constexpr int PUSH_GROUP_MAX = 8;
 struct NodalBatch { const float* E[PUSH_GROUP_MAX]; const float* B[PUSH_GROUP_MAX]; float4* nod[PUSH_GROUP_MAX]; int n; };
 struct EdgeBatch { const float4* Jc[PUSH_GROUP_MAX]; float* J[PUSH_GROUP_MAX]; int n; };
+size_t nodal_float4_per_node();   // float4 slots of nodal staging per lattice node (layout: particles.cu, k_nodal_means)
 void launch_nodal_means(const NodalBatch& bt, const Geom& g);
 void launch_edge_gather(const EdgeBatch& bt, const Geom& g);
 void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* nod);

@@ -89,7 +89,7 @@ def main():
         results.append(row)
         u = row["us_per_launch"]
         print(f"{setting:44s} {row['ms_per_lap']:8.3f} ms/lap  {row['Gpush_per_s']:7.2f} Gp/s | push {u.get('push')}"
-              f" deposit {u.get('deposit')} detect {u.get('detect_leavers')} radix {u.get('radix_sort')} gather {u.get('gather')}"
+              f" deposit {u.get('deposit')} detect {u.get('detect_leavers')} place {u.get('sort_place')} gather {u.get('sort_gather')}"
               f" filter {u.get('filter')}", flush=True)
         print("      per lap (lap%5: ms push deposit): " + "  ".join(f"{q['lap_mod5']}:{q['ms']}/{q['push_us']}/{q['deposit_us']}" for q in per_lap[:5]), flush=True)
     if args.out:
