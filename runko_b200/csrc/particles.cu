@@ -23,6 +23,10 @@
 #define B2P_NODAL_BPAIR 0
 #endif
 
+#ifndef B2P_NODAL_EL
+#define B2P_NODAL_EL 0   // 1: the nodal gathers carry L1::evict_last
+#endif
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -203,8 +207,18 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
             : "l"(nod + 2 * size_t(off[ic][jc] + kc)));
         (void)p0_; (void)p1_;
 #else
+#if B2P_NODAL_EL
+        // gathers ask the L1 to keep the nodal means in preference to everything else that streams through
+        {
+          float4& A_ = a[ic][jc][kc];
+          float2& B_ = b[ic][jc][kc];
+          asm("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(A_.x), "=f"(A_.y), "=f"(A_.z), "=f"(A_.w) : "l"(nod + off[ic][jc] + kc));
+          asm("ld.global.nc.L1::evict_last.v2.f32 {%0,%1}, [%2];" : "=f"(B_.x), "=f"(B_.y) : "l"(nodB + off[ic][jc] + kc));
+        }
+#else
         a[ic][jc][kc] = __ldg(nod + off[ic][jc] + kc);
         b[ic][jc][kc] = __ldg(nodB + off[ic][jc] + kc);
+#endif
 #endif
       }
 #endif
@@ -419,14 +433,24 @@ __device__ __forceinline__ void deposit_split_nodal(const Zigzag& z, float* __re
 
 // ----------------------------------------------------------------- pushers --
 // Loads the compiler may neither drop nor move into a conditional block.
+// B2P_PUSH_NA=1: ... and that leave no line behind in L1 (the particle streams are read once; the L1 is
+// wanted for the nodal means), with the push's stores marked evict-first.
+#ifndef B2P_PUSH_NA
+#define B2P_PUSH_NA 0
+#endif
+#if B2P_PUSH_NA
+#define B2P_LD_STREAM "ld.global.L1::no_allocate"
+#else
+#define B2P_LD_STREAM "ld.global"
+#endif
 __device__ __forceinline__ float ld_pinned(const float* p) {
   float v;
-  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm volatile(B2P_LD_STREAM ".f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ unsigned long long ld_pinned(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  asm volatile(B2P_LD_STREAM ".u64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
 }
 // L2 prefetch of the 256 slots block `blk` will read (8 KB over the seven streams: 64 lines of
@@ -543,8 +567,13 @@ k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float
     const float ginv2 = cfl / sqrtf(cfl * cfl + dot(u2, u2));
     nx = px + vel.x * ginv2 * cfl; ny = py + vel.y * ginv2 * cfl; nz = pz + vel.z * ginv2 * cfl;
   }
+#if B2P_PUSH_NA
+  __stcs(a.s.ux + n, vel.x); __stcs(a.s.uy + n, vel.y); __stcs(a.s.uz + n, vel.z);
+  __stcs(a.s.x + n, nx); __stcs(a.s.y + n, ny); __stcs(a.s.z + n, nz);
+#else
   a.s.ux[n] = vel.x; a.s.uy[n] = vel.y; a.s.uz[n] = vel.z;
   a.s.x[n] = nx; a.s.y[n] = ny; a.s.z[n] = nz;
+#endif
   }
   const bool inside = inside_box(nx, ny, nz, mn, mx);
   publish_masks(alive, inside, n, masks);
