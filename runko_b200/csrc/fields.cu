@@ -275,19 +275,27 @@ k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g, const int
   } else {
     // 27-point sum accumulated from 0 in index_space order, a slowest (:58-73)
     float P[3][9];
-    auto load = [&](float (&dst)[9], const int ii) {
-      const float* p = J + size_t(ii) * HyHz + q;
-#pragma unroll
-      for (int b = 0; b < 3; ++b)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) dst[b * 3 + d] = p[(b - 1) * Hz + (d - 1)];
+    // three row pointers (j-1, j, j+1) that advance one plane per step: the nine loads of a plane
+    // then use immediate offsets -1, 0, +1 instead of nine 64-bit address computations
+    const float* r0 = J + size_t(i - 1) * HyHz + q - Hz;
+    const float* r1 = r0 + Hz;
+    const float* r2 = r1 + Hz;
+    auto load = [&](float (&dst)[9]) {
+      dst[0] = r0[-1]; dst[1] = r0[0]; dst[2] = r0[1];
+      dst[3] = r1[-1]; dst[4] = r1[0]; dst[5] = r1[1];
+      dst[6] = r2[-1]; dst[7] = r2[0]; dst[8] = r2[1];
+      r0 += HyHz; r1 += HyHz; r2 += HyHz;
     };
-    load(P[0], i - 1);
-    load(P[1], i);
-    for (; i < iend; ++i) {
-      const size_t n = size_t(i) * HyHz + q;
-      if (i == g.Hx[0] - 1) { out[n] = 0.0f; break; }
-      load(P[2], i + 1);
+    load(P[0]);
+    load(P[1]);
+    float* o = out + size_t(i) * HyHz + q;
+    const int last = g.Hx[0] - 1;
+    // one output: planes A (i-1), B (i) are in registers, C receives plane i+1.  Called with the three
+    // register planes in rotating roles, so no plane is ever copied.
+    auto step = [&](const float (&A)[9], const float (&B)[9], float (&C)[9]) -> bool {
+      if (i >= iend) return false;
+      if (i == last) { *o = 0.0f; return false; }
+      load(C);
       float acc = 0.0f;
 #pragma unroll
       for (int a = 0; a < 3; ++a)
@@ -296,12 +304,14 @@ k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g, const int
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             const float w = ((a == 1) ? 2.f : 1.f) * ((b == 1) ? 2.f : 1.f) * ((d == 1) ? 2.f : 1.f) / 64.f;
-            acc = acc + w * P[a][b * 3 + d];
+            acc = acc + w * (a == 0 ? A[b * 3 + d] : a == 1 ? B[b * 3 + d] : C[b * 3 + d]);
           }
-      out[n] = acc;
-#pragma unroll
-      for (int m = 0; m < 9; ++m) { P[0][m] = P[1][m]; P[1][m] = P[2][m]; }
-    }
+      *o = acc;
+      ++i;
+      o += HyHz;
+      return true;
+    };
+    while (step(P[0], P[1], P[2]) && step(P[1], P[2], P[0]) && step(P[2], P[0], P[1])) {}
   }
 }
 
