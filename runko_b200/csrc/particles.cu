@@ -23,6 +23,9 @@
 #define B2P_NODAL_BPAIR 0
 #endif
 
+#ifndef B2P_LERP_FMA1
+#define B2P_LERP_FMA1 0  // 1: the interpolation's 42 sums as 21 packed fma(p, 1, q) (see interpolate)
+#endif
 #ifndef B2P_NODAL_EL
 #define B2P_NODAL_EL 0   // 1: the nodal gathers carry L1::evict_last
 #endif
@@ -157,7 +160,7 @@ struct EB { V3 E, B; };
 // Node indices fit 32 bits (Ch < 2^31 is checked at tile creation), so all index
 // arithmetic is 32-bit; only the four row base addresses are widened.
 __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const Geom& g, const float3 origo,
-                                          const float px, const float py, const float pz) {
+                                          const float px, const float py, const float pz, const float one) {
   const float lx = px - origo.x, ly = py - origo.y, lz = pz - origo.z;
   const unsigned i = __float2uint_rz(lx), j = __float2uint_rz(ly), k = __float2uint_rz(lz);
   const float dx = lx - float(i), dy = ly - float(j), dz = lz - float(k);
@@ -230,10 +233,22 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
   // (checked in SASS), which would change the rounding.
   const float2 wx = make_float2(dx, dx), wy = make_float2(dy, dy), wz = make_float2(dz, dz);
   const float2 ox = make_float2(1.0f - dx, 1.0f - dx), oy = make_float2(1.0f - dy, 1.0f - dy), oz = make_float2(1.0f - dz, 1.0f - dz);
+#if B2P_LERP_FMA1
+  // p + q as fma(p, 1, q): one rounding of the exact sum, i.e. the bits of the reference's add — but issued as one
+  // packed FFMA2 instead of two FADDs.  `one` is a kernel parameter (1.0f) so that ptxas cannot turn the fma back into
+  // an add, which it would then contract with the product feeding it (it does so even for add.rn.f32x2).
+  const float2 one2 = make_float2(one, one);
+  auto lerp2 = [one2](const float2 o, const float2 w, const float2 A, const float2 B) {
+    const float2 p = __fmul2_rn(o, A), q = __fmul2_rn(w, B);
+    return __ffma2_rn(p, one2, q);
+  };
+#else
+  (void)one;
   auto lerp2 = [](const float2 o, const float2 w, const float2 A, const float2 B) {
     const float2 p = __fmul2_rn(o, A), q = __fmul2_rn(w, B);
     return make_float2(__fadd_rn(p.x, q.x), __fadd_rn(p.y, q.y));
   };
+#endif
 #define LERP3P(sel)                                                                              \
   lerp2(oz, wz,                                                                                  \
         lerp2(oy, wy, lerp2(ox, wx, sel(0, 0, 0), sel(1, 0, 0)), lerp2(ox, wx, sel(0, 1, 0), sel(1, 1, 0))), \
@@ -495,7 +510,8 @@ struct PushArgs {
 // reside in it after migration — the reference's deposit_current, minus one pass over HBM.
 template <int PUSHER, int MINB, int FUSE>
 __global__ void __launch_bounds__(256, MINB)
-k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float3 mx, float4* __restrict__ Jc, const float charge) {
+k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float3 mx, float4* __restrict__ Jc, const float charge,
+       const float one /* 1.0f, opaque to the compiler: interpolate, B2P_LERP_FMA1 */) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
   if (a.prefetch) prefetch_streams(a.s, blockIdx.x + unsigned(a.prefetch));
   // All seven streams are requested before the id is looked at (pinned loads: the compiler must
@@ -513,7 +529,7 @@ k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float
   float nx = 0.f, ny = 0.f, nz = 0.f;
   V3 vel = { 0.f, 0.f, 0.f };
   if (alive) {
-  const EB eb = interpolate(a.nod, a.g, a.origo, px, py, pz);
+  const EB eb = interpolate(a.nod, a.g, a.origo, px, py, pz, one);
   const float cfl = a.cfl, qm = a.qm;
   const DivC div_cfl(cfl);
   if (PUSHER == B2P_PUSHER_BORIS) {                                // pic/particle_boris.h:37-59
@@ -1244,7 +1260,7 @@ void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g,
   const unsigned nb = (s.n + bs - 1) / bs;
   const int minb = tuning().push_minb;
   const int fuse = Jc ? (tuning().deposit_agg ? 2 : 1) : 0;
-#define PUSH_LAUNCH(P, M, F) k_push<P, M, F><<<nb, bs, 0, ctx().stream>>>(a, masks, mn, mx, Jc, charge)
+#define PUSH_LAUNCH(P, M, F) k_push<P, M, F><<<nb, bs, 0, ctx().stream>>>(a, masks, mn, mx, Jc, charge, 1.0f)
 #define PUSH_CASE(P)                                                                                   \
   case P:                                                                                              \
     if (fuse == 2) { if (minb >= 6) PUSH_LAUNCH(P, 6, 2); else if (minb >= 5) PUSH_LAUNCH(P, 5, 2); else PUSH_LAUNCH(P, 4, 2); } \
