@@ -220,6 +220,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
+        "timed_laps": [1 + args.warmup, args.warmup + args.steps],         # lap 0 ran when the arm was set up
+        "sort_laps_timed": sum(1 for q in range(1 + args.warmup, 1 + args.warmup + args.steps) if q % 5 == 0),
         "cpu_baseline": {"value": value, "unit": "particle-pushes/s", "cores": n_threads, "kind": arm.kind,
                          "sample": arm.sample(args.steps)},
         "e2e": {"value": value, "unit": "particle-pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -627,7 +629,10 @@ def main():
     if rank == 0:
         out = {"metric": "particle-pushes/s per full PIC step", "value": value, "unit": "particle-pushes/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": workload_config(args, world),
+               "timed_laps": [args.warmup, args.warmup + args.steps - 1],      # laps are numbered from 0; multiples of 5 sort
+               "sort_laps_timed": sum(1 for q in range(args.warmup, args.warmup + args.steps) if q % 5 == 0),
                "cell_updates_per_s": n_cells_local * world / per_step, "wall_ms_per_step": wall / args.steps * 1e3,
                "kernel_ms_per_step_single_stream": float(pms.sum() / prof_steps),
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "checks": checks}
