@@ -97,3 +97,21 @@ def test_plan_describe_is_host_only():
     n = rb.lib().b2p_plan_describe(C.byref(cfg), owner.ctypes.data_as(C.c_void_p), 0, rows.ctypes.data_as(C.c_void_p), 256)
     assert n > 0 and n <= 2 * 26
     assert set(rows[:n, 0]) == {1}
+
+
+def test_missing_library_fails_loudly():
+    """No silent fallback when the CUDA library is absent: importing the package's binding with the
+    library path pointing nowhere (B2P_LIB, the experiment override, or a deleted libb200pic.so)
+    raises ImportError naming the missing file."""
+    import subprocess
+    import sys
+    code = ("import runko_b200\n"
+            "try:\n"
+            "    runko_b200.lib()\n"
+            "except ImportError as e:\n"
+            "    assert 'is missing' in str(e) and 'no CPU fallback' in str(e), str(e)\n"
+            "    print('raised')\n")
+    env = dict(os.environ, B2P_LIB="/nonexistent/libb200pic.so")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+    assert r.returncode == 0 and "raised" in r.stdout, r.stdout + r.stderr
