@@ -66,6 +66,7 @@ static bool set_option(const std::string& name, int value) {
   else if (name == "sort_overlap") g_tuning.sort_overlap = value;
   else if (name == "sort_counting") g_tuning.sort_counting = value;
   else if (name == "defer_tile_calls") g_tuning.defer_tile_calls = value;
+  else if (name == "push_kernel") g_tuning.push_kernel = value;
   else return false;
   return true;
 }
@@ -412,9 +413,10 @@ static int sign_of(double v) { return (0.0 < v) - (v < 0.0); }   // tools/math.h
 void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
   const bool fuse = tuning().fuse_deposit != 0;
-  // Tiles that hold particles, in groups of up to `push_group` tiles of one geometry: the small
-  // per-tile kernels around the pushes (nodal means, clearing the cell-edge scratch, edge gather)
-  // run once per group, as launches large enough to fill the GPU.
+  const bool pairs = tuning().push_kernel != 1;   // 2 (default): push.cu k_push2, one launch per group; 1: one-slot-per-thread k_push per container
+  // Tiles that hold particles, in groups of up to `push_group` tiles of one geometry / pusher / cfl: the
+  // kernels of the particle phase (nodal means, clearing the cell-edge scratch, the push of all the
+  // group's containers, edge gather) run once per group, as launches large enough to fill the GPU.
   const int gmax = std::max(1, std::min(tuning().push_group, PUSH_GROUP_MAX));
   std::vector<std::vector<b2p_tile*>> groups;
   for (b2p_tile* t : tiles) {
@@ -422,9 +424,15 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
     bool any = false;
     for (const Container& c : t->sp) any = any || c.n;
     if (!any) continue;
-    if (groups.empty() || int(groups.back().size()) >= gmax || groups.back().front()->g.Ch != t->g.Ch ||
-        std::memcmp(groups.back().front()->g.Hx, t->g.Hx, sizeof(t->g.Hx)) != 0)
-      groups.emplace_back();
+    bool open = !groups.empty() && int(groups.back().size()) < gmax;
+    if (open) {
+      const b2p_tile* f = groups.back().front();
+      size_t nc = t->sp.size();
+      for (const b2p_tile* q : groups.back()) nc += q->sp.size();
+      open = std::memcmp(&f->g, &t->g, sizeof(Geom)) == 0 && f->cfg.particle_pusher == t->cfg.particle_pusher &&
+             f->cfg.cfl == t->cfg.cfl && nc <= size_t(PUSH_JOBS_MAX);
+    }
+    if (!open) groups.emplace_back();
     groups.back().push_back(t);
   }
   if (groups.empty()) return;
@@ -437,6 +445,7 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
     for (int w = 0; w < nw; ++w) B2P_CUDA(cudaStreamWaitEvent(wk.s[w], wk.fork, 0));
   }
   size_t gi = 0;
+  static PushJobs* jobs = new PushJobs;             // 8.7 KB kernel-argument table, filled per group
   for (const std::vector<b2p_tile*>& grp : groups) {
     const int w = int(gi++ % size_t(nw));
     StreamScope on(nw > 1 ? wk.s[w] : main_stream);
@@ -454,6 +463,9 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
       s.edges_w[w].reserve(edge_stride * grp.size());
       launch_zero(reinterpret_cast<float*>(s.edges_w[w].p), size_t(4) * edge_stride * grp.size());
     }
+    int nj = 0;
+    unsigned max_n = 0;
+    double slots = 0;
     for (size_t q = 0; q < grp.size(); ++q) {
       b2p_tile* t = grp[q];
       const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
@@ -462,8 +474,15 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
       for (Container& c : t->sp) {
         if (!c.n) continue;
         const float qm = static_cast<float>(sign_of(c.charge) / c.mass);
-        launch_push(t->cfg.particle_pusher, c.view(), nb.nod[q], t->g, t->origo, static_cast<float>(t->cfg.cfl), qm,
-                    c.mask_words(), mn, mx, Jc, static_cast<float>(c.charge));
+        if (pairs) {
+          jobs->job[nj++] = PushJob{ c.view(), nb.nod[q], Jc, c.mask_words(), make_float3(t->origo[0], t->origo[1], t->origo[2]),
+                                     make_float3(mn[0], mn[1], mn[2]), make_float3(mx[0], mx[1], mx[2]), qm, static_cast<float>(c.charge) };
+          max_n = std::max(max_n, c.n);
+          slots += c.n;
+        } else {
+          launch_push(t->cfg.particle_pusher, c.view(), nb.nod[q], t->g, t->origo, static_cast<float>(t->cfg.cfl), qm,
+                      c.mask_words(), mn, mx, Jc, static_cast<float>(c.charge));
+        }
         c.touch();
         c.masks_valid = true;
       }
@@ -472,6 +491,8 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
         t->pendJ_valid = true;
       }
     }
+    if (pairs)
+      launch_push_jobs(grp.front()->cfg.particle_pusher, *jobs, nj, max_n, slots, g, static_cast<float>(grp.front()->cfg.cfl), fuse);
     if (fuse) {
       eb.n = int(grp.size());
       launch_edge_gather(eb, g);

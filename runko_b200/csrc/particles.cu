@@ -8,27 +8,8 @@
 // reference (citations per function) => push, keys and migration lists are
 // bit-identical to the reference's unfused CPU build.
 #include "particles.cuh"
+#include "pmath.cuh"
 
-#ifndef B2P_NODAL_V8
-// 1: nodal means as one 32-byte record per node gathered with LDG.256 (8 gathers per particle instead of 16).
-// Measured on B200 (tools/microbench.py, 256^3): 127 us right after a sort (vs 129) but 150-161 us on the laps
-// after it (vs 140-147) — once the lanes of a warp no longer share nodes, the extra 64 B per particle through the
-// L1 data pipe cost more than the eight saved instructions.  Default: float4 + float2 arrays (24 B per node).
-#define B2P_NODAL_V8 0
-#endif
-
-#ifndef B2P_NODAL_BPAIR
-// 1: nodB[n] holds {By,Bz} of node n AND of node n+1 (its k neighbour) as one float4, so the two k-corners of a
-// cell arrive through one LDG.128: 12 gathers per particle instead of 16 for the same 192 B per lane.
-#define B2P_NODAL_BPAIR 0
-#endif
-
-#ifndef B2P_LERP_FMA1
-#define B2P_LERP_FMA1 0  // 1: the interpolation's 42 sums as 21 packed fma(p, 1, q) (see interpolate)
-#endif
-#ifndef B2P_NODAL_EL
-#define B2P_NODAL_EL 0   // 1: the nodal gathers carry L1::evict_last
-#endif
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -37,52 +18,6 @@
 
 namespace b2p {
 
-// ---------------------------------------------------------------- helpers --
-struct V3 { float x, y, z; };
-__device__ __forceinline__ V3 operator*(const V3 a, const float s) { return { a.x * s, a.y * s, a.z * s }; }
-__device__ __forceinline__ V3 operator*(const float s, const V3 a) { return a * s; }
-__device__ __forceinline__ V3 operator/(const V3 a, const float s) { return { a.x / s, a.y / s, a.z / s }; }
-__device__ __forceinline__ V3 operator+(const V3 a, const V3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
-__device__ __forceinline__ V3 operator-(const V3 a, const V3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
-// tools/vector.h:248-255: accumulates from 0, left to right
-__device__ __forceinline__ float dot(const V3 a, const V3 b) {
-  float r = 0.0f;
-  r = r + a.x * b.x; r = r + a.y * b.y; r = r + a.z * b.z;
-  return r;
-}
-// tools/vector.h:281-289
-__device__ __forceinline__ V3 cross(const V3 a, const V3 b) {
-  return { a.y * b.z - a.z * b.y, -a.x * b.z + a.z * b.x, a.x * b.y - a.y * b.x };
-}
-__device__ __forceinline__ float lerp1(const float x, const float A, const float B) { return (1.0f - x) * A + x * B; }
-
-// Correctly rounded v / c for a warp-uniform divisor (the pushers divide six values per particle by
-// cfl).  It is the fast path of the IEEE division nvcc emits — MUFU.RCP, one Newton step on the
-// reciprocal, q = x*rc, the exact residual r = x - q*c (FMA) and the correction q + r*rc — with the
-// reciprocal hoisted out of the six divisions and the per-operand FCHK replaced by one range test
-// per vector: for c in [2^-20, 2^20] and |x| in [2^-100, 2^100] no intermediate under- or overflows
-// (r is a multiple of 2^(e_x - 47) >= 2^-147), which is the regime in which that fast path is
-// exact.  Everything else (zeros and their signs, denormals, huge values, inf) takes the plain
-// division.  tests/test_parity_gpu.py::test_const_division_bit_exact checks it against `/`.
-struct DivC {
-  float c, rc, hi;
-  __device__ __forceinline__ explicit DivC(const float c_) : c(c_) {
-    float r0;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(c_));
-    rc = fmaf(r0, fmaf(-c_, r0, 1.0f), r0);
-    hi = (fabsf(c_) >= 0x1p-20f && fabsf(c_) <= 0x1p20f) ? 0x1p100f : -1.0f;
-  }
-  __device__ __forceinline__ float fast(const float x) const {
-    const float q = x * rc;
-    return fmaf(fmaf(-c, q, x), rc, q);
-  }
-  __device__ __forceinline__ V3 operator()(const V3 v) const {
-    const float lo = fminf(fminf(fabsf(v.x), fabsf(v.y)), fabsf(v.z));
-    const float mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fabsf(v.z));
-    if (lo >= 0x1p-100f && mx <= hi) return { fast(v.x), fast(v.y), fast(v.z) };
-    return v / c;
-  }
-};
 
 // ------------------------------------------------------- nodal field means --
 // The interpolator's per-corner staggered averages
@@ -111,11 +46,9 @@ __device__ __forceinline__ void node_means(const float* __restrict__ E, const fl
   b.y = (Bz[n] + (Bz[n - si] + (Bz[n - sj] + Bz[n - si - sj]))) / 4.0f;
 }
 
-// B2P_NODAL_BPAIR layouts (float4 units per tile, n = node index):
-//   0: A[n] at nod[n], {By,Bz}[n] as float2 behind them (24 B/node)
-//   1: A[n] at nod[n], P[n] = {By,Bz}[n], {By,Bz}[n+1] at nod[Ch + n]           (32 B/node)
-//   2: {A[n], A[n+1]} at nod[2n], nod[2n+1] (one LDG.256), P[n] at nod[2Ch + n]  (48 B/node)
-size_t nodal_float4_per_node() { return B2P_NODAL_BPAIR == 2 ? 3 : 2; }
+// nodal staging layout (float4 units per tile, n = node index): A[n] = {Ex,Ey,Ez,Bx} at nod[n],
+// {By,Bz}[n] as float2 right behind the Ch float4s (24 B per node)
+size_t nodal_float4_per_node() { return 2; }
 
 __global__ void __launch_bounds__(256)
 k_nodal_means(const NodalBatch bt, const Geom g) {
@@ -132,25 +65,8 @@ k_nodal_means(const NodalBatch bt, const Geom g) {
     float4 a;
     float2 b;
     node_means(E, B, g, i, j, k, a, b);
-#if B2P_NODAL_BPAIR
-    float4 a1;
-    float2 b1;
-    node_means(E, B, g, i, j, k + 1, a1, b1);     // the k neighbour, so that both k-corners of a cell share a record
-#if B2P_NODAL_BPAIR == 2
-    nod[2 * n] = a;
-    nod[2 * n + 1] = a1;
-    nod[2 * size_t(g.Ch) + n] = make_float4(b.x, b.y, b1.x, b1.y);
-#else
-    nod[n] = a;
-    nod[size_t(g.Ch) + n] = make_float4(b.x, b.y, b1.x, b1.y);
-#endif
-#elif B2P_NODAL_V8
-    nod[2 * n] = a;
-    nod[2 * n + 1] = make_float4(b.x, b.y, 0.f, 0.f);
-#else
     nod[n] = a;
     reinterpret_cast<float2*>(nod + g.Ch)[n] = b;
-#endif
   }
 }
 
@@ -160,71 +76,25 @@ struct EB { V3 E, B; };
 // Node indices fit 32 bits (Ch < 2^31 is checked at tile creation), so all index
 // arithmetic is 32-bit; only the four row base addresses are widened.
 __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const Geom& g, const float3 origo,
-                                          const float px, const float py, const float pz, const float one) {
+                                          const float px, const float py, const float pz) {
   const float lx = px - origo.x, ly = py - origo.y, lz = pz - origo.z;
   const unsigned i = __float2uint_rz(lx), j = __float2uint_rz(ly), k = __float2uint_rz(lz);
   const float dx = lx - float(i), dy = ly - float(j), dz = lz - float(k);
   const unsigned sj = unsigned(g.Hx[2]), si = unsigned(g.Hx[1]) * unsigned(g.Hx[2]);
   const unsigned n = (i * unsigned(g.Hx[1]) + j) * sj + k;
-#if B2P_NODAL_BPAIR
-  const float4* __restrict__ nodP = nod + (B2P_NODAL_BPAIR == 2 ? 2 : 1) * size_t(g.Ch);
-#elif !B2P_NODAL_V8
   const float2* __restrict__ nodB = reinterpret_cast<const float2*>(nod + g.Ch);
-#endif
   const unsigned off[2][2] = { { n, n + sj }, { n + si, n + si + sj } };
   float4 a[2][2][2];
   float2 b[2][2][2];
-#if B2P_NODAL_BPAIR
-#pragma unroll
-  for (int ic = 0; ic < 2; ++ic)
-#pragma unroll
-    for (int jc = 0; jc < 2; ++jc) {
-#if B2P_NODAL_BPAIR == 2
-      float4& A0 = a[ic][jc][0];
-      float4& A1 = a[ic][jc][1];
-      asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-          : "=f"(A0.x), "=f"(A0.y), "=f"(A0.z), "=f"(A0.w), "=f"(A1.x), "=f"(A1.y), "=f"(A1.z), "=f"(A1.w)
-          : "l"(nod + 2 * size_t(off[ic][jc])));
-#else
-      a[ic][jc][0] = __ldg(nod + off[ic][jc]);
-      a[ic][jc][1] = __ldg(nod + off[ic][jc] + 1);
-#endif
-      const float4 p = __ldg(nodP + off[ic][jc]);
-      b[ic][jc][0] = make_float2(p.x, p.y);
-      b[ic][jc][1] = make_float2(p.z, p.w);
-    }
-#else
 #pragma unroll
   for (int ic = 0; ic < 2; ++ic)
 #pragma unroll
     for (int jc = 0; jc < 2; ++jc)
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-#if B2P_NODAL_V8
-        // one 32-byte record per node, one LDG.256 (sm_100) per corner: 8 gathers instead of 16
-        float4& A_ = a[ic][jc][kc];
-        float2& B_ = b[ic][jc][kc];
-        float p0_, p1_;
-        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-            : "=f"(A_.x), "=f"(A_.y), "=f"(A_.z), "=f"(A_.w), "=f"(B_.x), "=f"(B_.y), "=f"(p0_), "=f"(p1_)
-            : "l"(nod + 2 * size_t(off[ic][jc] + kc)));
-        (void)p0_; (void)p1_;
-#else
-#if B2P_NODAL_EL
-        // gathers ask the L1 to keep the nodal means in preference to everything else that streams through
-        {
-          float4& A_ = a[ic][jc][kc];
-          float2& B_ = b[ic][jc][kc];
-          asm("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(A_.x), "=f"(A_.y), "=f"(A_.z), "=f"(A_.w) : "l"(nod + off[ic][jc] + kc));
-          asm("ld.global.nc.L1::evict_last.v2.f32 {%0,%1}, [%2];" : "=f"(B_.x), "=f"(B_.y) : "l"(nodB + off[ic][jc] + kc));
-        }
-#else
         a[ic][jc][kc] = __ldg(nod + off[ic][jc] + kc);
         b[ic][jc][kc] = __ldg(nodB + off[ic][jc] + kc);
-#endif
-#endif
       }
-#endif
   // lerp3D (:29-52): along x, then y, then z — (1-w)*A + w*B per lerp, the same two products and one sum
   // as the reference.  The six components travel as three register pairs {Ex,Ey}, {Ez,Bx}, {By,Bz} — exactly
   // how the LDG.128 / LDG.64 above deliver them — through Blackwell's packed fp32x2 multiply
@@ -233,22 +103,10 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
   // (checked in SASS), which would change the rounding.
   const float2 wx = make_float2(dx, dx), wy = make_float2(dy, dy), wz = make_float2(dz, dz);
   const float2 ox = make_float2(1.0f - dx, 1.0f - dx), oy = make_float2(1.0f - dy, 1.0f - dy), oz = make_float2(1.0f - dz, 1.0f - dz);
-#if B2P_LERP_FMA1
-  // p + q as fma(p, 1, q): one rounding of the exact sum, i.e. the bits of the reference's add — but issued as one
-  // packed FFMA2 instead of two FADDs.  `one` is a kernel parameter (1.0f) so that ptxas cannot turn the fma back into
-  // an add, which it would then contract with the product feeding it (it does so even for add.rn.f32x2).
-  const float2 one2 = make_float2(one, one);
-  auto lerp2 = [one2](const float2 o, const float2 w, const float2 A, const float2 B) {
-    const float2 p = __fmul2_rn(o, A), q = __fmul2_rn(w, B);
-    return __ffma2_rn(p, one2, q);
-  };
-#else
-  (void)one;
   auto lerp2 = [](const float2 o, const float2 w, const float2 A, const float2 B) {
     const float2 p = __fmul2_rn(o, A), q = __fmul2_rn(w, B);
     return make_float2(__fadd_rn(p.x, q.x), __fadd_rn(p.y, q.y));
   };
-#endif
 #define LERP3P(sel)                                                                              \
   lerp2(oz, wz,                                                                                  \
         lerp2(oy, wy, lerp2(ox, wx, sel(0, 0, 0), sel(1, 0, 0)), lerp2(ox, wx, sel(0, 1, 0), sel(1, 1, 0))), \
@@ -267,30 +125,7 @@ __device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const 
   return eb;
 }
 
-// 27-way subregion index of a position relative to the tile box
-// (pic/particle.c++:228-238, communication_common.h:137-147)
-__device__ __forceinline__ int subregion_of(const float x, const float y, const float z, const float3 mn, const float3 mx) {
-  const int i = int(x >= mn.x) - int(x < mx.x);
-  const int j = int(y >= mn.y) - int(y < mx.y);
-  const int k = int(z >= mn.z) - int(z < mx.z);
-  return ((i + 1) * 3 + (j + 1)) * 3 + (k + 1);
-}
 
-// Leaver detection (pic/particle.c++:228-262), shared by the push and the standalone
-// pass.  Every warp publishes two 32-bit ballots for its 32 slots — `leaving` (alive and
-// outside the tile box) and `staying` (alive and inside) — as one uint2 per warp: no
-// atomics, no shared memory and no barrier in the particle sweep.  k_collect_leavers
-// turns the words of all containers into the unordered (container, subregion, slot) key
-// list; a radix sort of that short list restores the reference's order.
-// A particle stays iff per axis (x >= min) == (x < max)  [direction 0 of :228-238].
-__device__ __forceinline__ bool inside_box(const float x, const float y, const float z, const float3 mn, const float3 mx) {
-  return ((x >= mn.x) == (x < mx.x)) & ((y >= mn.y) == (y < mx.y)) & ((z >= mn.z) == (z < mx.z));
-}
-__device__ __forceinline__ void publish_masks(const bool alive, const bool inside, const unsigned n, uint2* __restrict__ masks) {
-  const unsigned lm = __ballot_sync(0xffffffffu, alive && !inside);
-  const unsigned sm = __ballot_sync(0xffffffffu, alive && inside);
-  if ((threadIdx.x & 31) == 0) masks[n >> 5] = make_uint2(lm, sm);
-}
 
 // ---------------------------------------------------------------- deposit --
 struct DepositArgs {
@@ -303,121 +138,6 @@ struct DepositArgs {
   float charge;
 };
 
-// Warp-level pre-aggregation of one segment set before the global REDs.  Lanes whose
-// segment lies in the same cell form contiguous runs whenever the container is (nearly)
-// cell-sorted: the sort every 5th lap orders by the cell of x2, and one lap later the cell of
-// x1 is that same cell.  A segmented shuffle reduction over runs (steps 1, 2, 4) leaves partial
-// sums at every 2nd/4th/8th lane of a run, and only those lanes issue the three RED.128 — up to
-// 8x fewer atomics enter the L1 data pipe, the unit that bounds this kernel (ncu: one wavefront
-// per RED lane).  Unsorted input degenerates to the plain per-lane REDs at the cost of two ballots.  Summation order differs from the
-// reference's serial loop: covered by the stated deposit tolerance.
-#ifndef AGG_MAX_STEP
-#define AGG_MAX_STEP 4   // widest fold: runs of up to 2 * AGG_MAX_STEP lanes collapse into one lane's REDs (a step of 8 measured no better)
-#endif
-template <int AGG>
-__device__ __forceinline__ void reduce_runs_and_red(const unsigned key, float4 ex, float4 ey, float4 ez, float4* __restrict__ Jc,
-                                                    const int agg_min) {
-  const unsigned lane = threadIdx.x & 31;
-  const bool valid = key != 0xFFFFFFFFu;
-  bool issue = valid;
-  if (AGG) {
-    const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = lane == 0 || key != prev;
-    const unsigned hm = __ballot_sync(0xffffffffu, head);
-    const unsigned above = lane == 31 ? 0u : (hm >> (lane + 1));
-    const unsigned rem = above ? unsigned(__ffs(above)) : 32u - lane;   // lanes [lane, lane + rem) share my key
-    const unsigned off = lane - (31u - __clz(hm & (0xFFFFFFFFu >> (31u - lane))));   // my offset inside the run
-    // A step of width d folds the lanes at run offset d (mod 2d) into the lane d below: every folded
-    // lane saves three RED.128 (one L1 wavefront each) and the step costs twelve shuffles (one
-    // wavefront each) plus the adds, so a step — and every wider one after it — is only taken
-    // when at least `agg_min` lanes of the warp fold (warp-uniform decision).
-    unsigned stride = 1;
-#pragma unroll
-    for (int d = 1; d <= AGG_MAX_STEP; d <<= 1) {
-      const unsigned folded = __ballot_sync(0xffffffffu, valid && (off & unsigned(2 * d - 1)) == unsigned(d));
-      if (int(__popc(folded)) < agg_min) break;
-      const bool take = rem > unsigned(d);
-#define B2P_STEP(v) { const float t_ = __shfl_down_sync(0xffffffffu, v, d); if (take) v += t_; }
-      B2P_STEP(ex.x) B2P_STEP(ex.y) B2P_STEP(ex.z) B2P_STEP(ex.w)
-      B2P_STEP(ey.x) B2P_STEP(ey.y) B2P_STEP(ey.z) B2P_STEP(ey.w)
-      B2P_STEP(ez.x) B2P_STEP(ez.y) B2P_STEP(ez.z) B2P_STEP(ez.w)
-#undef B2P_STEP
-      stride = unsigned(2 * d);
-    }
-    issue = issue && ((off & (stride - 1u)) == 0u);
-  }
-  if (issue) {
-    atomicAdd(&Jc[3 * size_t(key) + 0], ex);
-    atomicAdd(&Jc[3 * size_t(key) + 1], ey);
-    atomicAdd(&Jc[3 * size_t(key) + 2], ez);
-  }
-}
-
-// Layout of the deposit scratch (pic/particle_current_zigzag_1st.c++:241-336).  Each of
-// the two zigzag segments touches the 12 edges of one cell (4 x-edges, 4 y-edges,
-// 4 z-edges), so instead of the reference's 42 scalar atomics per particle the
-// 12 values go to a cell-major scratch of 3 float4 per cell with 3 vector RED.128:
-//   Jc[3c+0] = Jx at nodes c+(0,0,0), c+(0,1,0), c+(0,0,1), c+(0,1,1)
-//   Jc[3c+1] = Jy at nodes c+(0,0,0), c+(1,0,0), c+(0,0,1), c+(1,0,1)
-//   Jc[3c+2] = Jz at nodes c+(0,0,0), c+(1,0,0), c+(0,1,0), c+(1,1,0)
-// k_edge_gather then folds the (up to 4) cell records that share a node into the
-// nodal J.  Per-particle values are bit-identical to the reference; only the
-// accumulation order differs (stated tolerance 1e-5 * max|J|).
-// The zigzag split of one particle (pic/particle_current_zigzag_1st.c++:241-336): cells n1, n2 of
-// the two segments and their 12 edge currents each.  `pos`/`u` are the stored fp32 values.
-struct Zigzag {
-  unsigned n1, n2;
-  float4 ax, ay, az, bx, by, bz;
-};
-__device__ __forceinline__ Zigzag zigzag_split(const V3 pos, const V3 u, const float3 origo, const float cfl, const float charge,
-                                               const Geom& g) {
-  Zigzag r;
-  const float invgam = 1.0f / sqrtf(1.0f + dot(u, u));
-  const V3 x2 = pos - V3{ origo.x, origo.y, origo.z };
-  const V3 x1 = x2 - cfl * invgam * u;
-  const V3 fi1 = { floorf(x1.x), floorf(x1.y), floorf(x1.z) };
-  const V3 fi2 = { floorf(x2.x), floorf(x2.y), floorf(x2.z) };
-  auto relay = [](const float f1, const float f2, const float p1, const float p2) {
-    const float lo = (f1 < f2 ? f1 : f2) + 1.0f;
-    const float b1 = f1 > f2 ? f1 : f2;
-    const float b2 = 0.5f * (p1 + p2);
-    const float b = b1 > b2 ? b1 : b2;
-    return lo < b ? lo : b;
-  };
-  const V3 xr = { relay(fi1.x, fi2.x, x1.x, x2.x), relay(fi1.y, fi2.y, x1.y, x2.y), relay(fi1.z, fi2.z, x1.z, x2.z) };
-  const V3 F1 = charge * (xr - x1);
-  const V3 F2 = charge * (x2 - xr);
-  const V3 W1 = 0.5f * (x1 + xr) - fi1;
-  const V3 W2 = 0.5f * (x2 + xr) - fi2;
-  const unsigned Hy = unsigned(g.Hx[1]), Hz = unsigned(g.Hx[2]);
-  r.n1 = (__float2uint_rz(fi1.x) * Hy + __float2uint_rz(fi1.y)) * Hz + __float2uint_rz(fi1.z);
-  r.n2 = (__float2uint_rz(fi2.x) * Hy + __float2uint_rz(fi2.y)) * Hz + __float2uint_rz(fi2.z);
-  const float one = 1.0f;
-#define EDGES(F, W, ex, ey, ez)                                                                                \
-  ex = make_float4(F.x * (one - W.y) * (one - W.z), F.x * W.y * (one - W.z), F.x * (one - W.y) * W.z, F.x * W.y * W.z); \
-  ey = make_float4(F.y * (one - W.x) * (one - W.z), F.y * W.x * (one - W.z), F.y * (one - W.x) * W.z, F.y * W.x * W.z); \
-  ez = make_float4(F.z * (one - W.x) * (one - W.y), F.z * W.x * (one - W.y), F.z * (one - W.x) * W.y, F.z * W.x * W.y);
-  EDGES(F1, W1, r.ax, r.ay, r.az)
-  EDGES(F2, W2, r.bx, r.by, r.bz)
-#undef EDGES
-  return r;
-}
-
-// Accumulate one particle's split into the cell-edge scratch (all 32 lanes must call).
-template <int AGG>
-__device__ __forceinline__ void deposit_split(const bool active, Zigzag z, float4* __restrict__ Jc, const int agg_min) {
-  if (!active) {
-    z.n1 = z.n2 = 0xFFFFFFFFu;
-    z.ax = z.ay = z.az = z.bx = z.by = z.bz = make_float4(0.f, 0.f, 0.f, 0.f);
-  } else if (z.n1 == z.n2) {   // both segments in one cell (about half of a thermal plasma): one record
-    z.bx.x += z.ax.x; z.bx.y += z.ax.y; z.bx.z += z.ax.z; z.bx.w += z.ax.w;
-    z.by.x += z.ay.x; z.by.y += z.ay.y; z.by.z += z.ay.z; z.by.w += z.ay.w;
-    z.bz.x += z.az.x; z.bz.y += z.az.y; z.bz.z += z.az.z; z.bz.w += z.az.w;
-    z.n1 = 0xFFFFFFFFu;
-  }
-  if (__any_sync(0xffffffffu, z.n1 != 0xFFFFFFFFu)) reduce_runs_and_red<AGG>(z.n1, z.ax, z.ay, z.az, Jc, agg_min);
-  reduce_runs_and_red<AGG>(z.n2, z.bx, z.by, z.bz, Jc, agg_min);
-}
 
 // Standalone deposit of a whole container: one thread per particle.
 template <int AGG, int MINB>
@@ -431,43 +151,8 @@ k_deposit_zigzag(const DepositArgs a) {
   deposit_split<AGG>(alive, z, a.Jc, a.agg_min);
 }
 
-// Scalar nodal scatter of one particle's split (arrivals of the migration: ~1% of the particles).
-// Same node pattern as k_edge_gather's fold of the cell-edge records.
-__device__ __forceinline__ void deposit_split_nodal(const Zigzag& z, float* __restrict__ J, const Geom& g) {
-  const size_t Ch = g.Ch;
-  const unsigned sj = unsigned(g.Hx[2]), si = unsigned(g.Hx[1]) * unsigned(g.Hx[2]);
-  auto put = [&](const unsigned c, const float4 ex, const float4 ey, const float4 ez) {
-    float* Jx = J; float* Jy = J + Ch; float* Jz = J + 2 * Ch;
-    atomicAdd(Jx + c, ex.x); atomicAdd(Jx + c + sj, ex.y); atomicAdd(Jx + c + 1, ex.z); atomicAdd(Jx + c + sj + 1, ex.w);
-    atomicAdd(Jy + c, ey.x); atomicAdd(Jy + c + si, ey.y); atomicAdd(Jy + c + 1, ey.z); atomicAdd(Jy + c + si + 1, ey.w);
-    atomicAdd(Jz + c, ez.x); atomicAdd(Jz + c + si, ez.y); atomicAdd(Jz + c + sj, ez.z); atomicAdd(Jz + c + si + sj, ez.w);
-  };
-  put(z.n1, z.ax, z.ay, z.az);
-  put(z.n2, z.bx, z.by, z.bz);
-}
 
 // ----------------------------------------------------------------- pushers --
-// Loads the compiler may neither drop nor move into a conditional block.
-// B2P_PUSH_NA=1: ... and that leave no line behind in L1 (the particle streams are read once; the L1 is
-// wanted for the nodal means), with the push's stores marked evict-first.
-#ifndef B2P_PUSH_NA
-#define B2P_PUSH_NA 0
-#endif
-#if B2P_PUSH_NA
-#define B2P_LD_STREAM "ld.global.L1::no_allocate"
-#else
-#define B2P_LD_STREAM "ld.global"
-#endif
-__device__ __forceinline__ float ld_pinned(const float* p) {
-  float v;
-  asm volatile(B2P_LD_STREAM ".f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ unsigned long long ld_pinned(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile(B2P_LD_STREAM ".u64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
 // L2 prefetch of the 256 slots block `blk` will read (8 KB over the seven streams: 64 lines of
 // 128 B, one per thread of the first two warps).  Blocks run roughly in index order, so asking for
 // the block PREFETCH_BLOCKS ahead (more than one wave of resident blocks) turns that block's
@@ -511,7 +196,7 @@ struct PushArgs {
 template <int PUSHER, int MINB, int FUSE>
 __global__ void __launch_bounds__(256, MINB)
 k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float3 mx, float4* __restrict__ Jc, const float charge,
-       const float one /* 1.0f, opaque to the compiler: interpolate, B2P_LERP_FMA1 */) {
+       const float /*unused*/) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
   if (a.prefetch) prefetch_streams(a.s, blockIdx.x + unsigned(a.prefetch));
   // All seven streams are requested before the id is looked at (pinned loads: the compiler must
@@ -529,7 +214,7 @@ k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float
   float nx = 0.f, ny = 0.f, nz = 0.f;
   V3 vel = { 0.f, 0.f, 0.f };
   if (alive) {
-  const EB eb = interpolate(a.nod, a.g, a.origo, px, py, pz, one);
+  const EB eb = interpolate(a.nod, a.g, a.origo, px, py, pz);
   const float cfl = a.cfl, qm = a.qm;
   const DivC div_cfl(cfl);
   if (PUSHER == B2P_PUSHER_BORIS) {                                // pic/particle_boris.h:37-59
@@ -583,13 +268,8 @@ k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float
     const float ginv2 = cfl / sqrtf(cfl * cfl + dot(u2, u2));
     nx = px + vel.x * ginv2 * cfl; ny = py + vel.y * ginv2 * cfl; nz = pz + vel.z * ginv2 * cfl;
   }
-#if B2P_PUSH_NA
-  __stcs(a.s.ux + n, vel.x); __stcs(a.s.uy + n, vel.y); __stcs(a.s.uz + n, vel.z);
-  __stcs(a.s.x + n, nx); __stcs(a.s.y + n, ny); __stcs(a.s.z + n, nz);
-#else
   a.s.ux[n] = vel.x; a.s.uy[n] = vel.y; a.s.uz[n] = vel.z;
   a.s.x[n] = nx; a.s.y[n] = ny; a.s.z[n] = nz;
-#endif
   }
   const bool inside = inside_box(nx, ny, nz, mn, mx);
   publish_masks(alive, inside, n, masks);

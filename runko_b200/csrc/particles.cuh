@@ -28,7 +28,7 @@ struct CollectJobHost {       // mirrors particles.cu::CollectJob: leaver masks 
 
 // groups of tiles of one geometry handled by one launch of the small per-tile kernels of the
 // particle phase (tables passed by value as kernel arguments)
-constexpr int PUSH_GROUP_MAX = 8;
+constexpr int PUSH_GROUP_MAX = 32;
 struct NodalBatch { const float* E[PUSH_GROUP_MAX]; const float* B[PUSH_GROUP_MAX]; float4* nod[PUSH_GROUP_MAX]; int n; };
 struct EdgeBatch { const float4* Jc[PUSH_GROUP_MAX]; float* J[PUSH_GROUP_MAX]; int n; };
 size_t nodal_float4_per_node();   // float4 slots of nodal staging per lattice node (layout: particles.cu, k_nodal_means)
@@ -40,6 +40,23 @@ void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* n
 void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm,
                  uint2* masks, const float mins[3], const float maxs[3], float4* Jc, float charge);
 // Jc != nullptr: fused push + deposit of the particles that stay inside the tile box
+
+// One container of a batched push launch (push.cu: k_push2, two slots per thread).
+struct PushJob {
+  Species s;
+  const float4* nod;          // nodal means of the container's tile (k_nodal_means layout)
+  float4* Jc;                 // cell-edge accumulators of the tile (fused deposit), or nullptr
+  uint2* masks;               // leaver / stayer ballots, one uint2 per 32 slots
+  float3 origo, mn, mx;       // lattice origin, tile box (float(mins/maxs))
+  float qm, charge;           // sign(q)/m (pic/particle_boris.h:26-27), signed charge (zigzag)
+};
+// The job table travels as a kernel argument (CUDA >= 12.1 allows 32 KB of parameters): no upload, and the
+// compiler knows that every pointer in it addresses global memory.
+constexpr int PUSH_JOBS_MAX = 64;
+struct PushJobs { PushJob job[PUSH_JOBS_MAX]; };
+// the first njobs entries: containers of one geometry / pusher / cfl; max_n = the largest container among them
+void launch_push_jobs(int pusher, const PushJobs& jobs, int njobs, unsigned max_n, double total_slots, const Geom& g, float cfl,
+                      bool fuse);
 void launch_deposit(const Species& s, float4* Jc, const Geom& g, const float origo[3], float cfl, float charge);
 void launch_edge_gather(const float4* Jc, float* J, const Geom& g);
 void launch_sort_keys(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* idx, unsigned dead_key);
