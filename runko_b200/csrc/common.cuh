@@ -72,9 +72,7 @@ struct Tuning {
   int sort_streams = 4;   // worker streams the per-container sort is round-robined over
   int sort_overlap = 1;   // b2p_grid_step_pic leaves the sort running on the worker streams under the field phase of the lap
   int push_block = 128;       // threads per block of k_push (128 or 256; 128 measured 1 % faster: finer-grained tail)
-  int push_prefetch = 0;      // k_push: L2 prefetch distance in blocks of 256 slots (0: off — measured no gain once all seven streams are requested up front)
   int push_group = 32;    // tiles per group of the particle phase: one launch each of nodal means, scratch clear, push (all containers), edge gather
-  int push_kernel = 2;    // 2: push.cu k_push2 (two slots per thread, one launch per group); 1: k_push (one slot per thread, one launch per container)
   int sort_counting = 1;  // counting sort by cell (0: always the general radix sort)
   int defer_tile_calls = 1;   // batch consecutive per-tile calls of one kind (host.cu: deferred per-tile calls)
   int fuse_deposit = 1;   // deposit the stayers' current inside the push kernel (arrivals deposit on append)

@@ -61,12 +61,10 @@ static bool set_option(const std::string& name, int value) {
   else if (name == "push_streams") g_tuning.push_streams = value;
   else if (name == "sort_streams") g_tuning.sort_streams = value;
   else if (name == "push_group") g_tuning.push_group = value;
-  else if (name == "push_prefetch") g_tuning.push_prefetch = value;
   else if (name == "push_block") g_tuning.push_block = value;
   else if (name == "sort_overlap") g_tuning.sort_overlap = value;
   else if (name == "sort_counting") g_tuning.sort_counting = value;
   else if (name == "defer_tile_calls") g_tuning.defer_tile_calls = value;
-  else if (name == "push_kernel") g_tuning.push_kernel = value;
   else return false;
   return true;
 }
@@ -413,7 +411,6 @@ static int sign_of(double v) { return (0.0 < v) - (v < 0.0); }   // tools/math.h
 void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
   const bool fuse = tuning().fuse_deposit != 0;
-  const bool pairs = tuning().push_kernel != 1;   // 2 (default): push.cu k_push2, one launch per group; 1: one-slot-per-thread k_push per container
   // Tiles that hold particles, in groups of up to `push_group` tiles of one geometry / pusher / cfl: the
   // kernels of the particle phase (nodal means, clearing the cell-edge scratch, the push of all the
   // group's containers, edge gather) run once per group, as launches large enough to fill the GPU.
@@ -474,15 +471,10 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
       for (Container& c : t->sp) {
         if (!c.n) continue;
         const float qm = static_cast<float>(sign_of(c.charge) / c.mass);
-        if (pairs) {
-          jobs->job[nj++] = PushJob{ c.view(), nb.nod[q], Jc, c.mask_words(), make_float3(t->origo[0], t->origo[1], t->origo[2]),
-                                     make_float3(mn[0], mn[1], mn[2]), make_float3(mx[0], mx[1], mx[2]), qm, static_cast<float>(c.charge) };
-          max_n = std::max(max_n, c.n);
-          slots += c.n;
-        } else {
-          launch_push(t->cfg.particle_pusher, c.view(), nb.nod[q], t->g, t->origo, static_cast<float>(t->cfg.cfl), qm,
-                      c.mask_words(), mn, mx, Jc, static_cast<float>(c.charge));
-        }
+        jobs->job[nj++] = PushJob{ c.view(), nb.nod[q], Jc, c.mask_words(), make_float3(t->origo[0], t->origo[1], t->origo[2]),
+                                   make_float3(mn[0], mn[1], mn[2]), make_float3(mx[0], mx[1], mx[2]), qm, static_cast<float>(c.charge) };
+        max_n = std::max(max_n, c.n);
+        slots += c.n;
         c.touch();
         c.masks_valid = true;
       }
@@ -491,8 +483,7 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
         t->pendJ_valid = true;
       }
     }
-    if (pairs)
-      launch_push_jobs(grp.front()->cfg.particle_pusher, *jobs, nj, max_n, slots, g, static_cast<float>(grp.front()->cfg.cfl), fuse);
+    launch_push_jobs(grp.front()->cfg.particle_pusher, *jobs, nj, max_n, slots, g, static_cast<float>(grp.front()->cfg.cfl), fuse);
     if (fuse) {
       eb.n = int(grp.size());
       launch_edge_gather(eb, g);
@@ -937,7 +928,27 @@ static const FieldPtrs* table_for(const std::vector<b2p_tile*>& tiles) {
   return defer_table().p;
 }
 
+// A batch that fails when it is finally executed inside an entry point that cannot report (destroy,
+// b2p_launch_count) leaves its error here; the next reporting entry point (b2p_sync included) returns it.
+static int g_sticky_code = 0;
+static std::string g_sticky_msg;
+void record_sticky_error(int code, const std::string& msg) {
+  if (!g_sticky_code) { g_sticky_code = code; g_sticky_msg = msg; }
+}
+void throw_sticky_error() {
+  if (!g_sticky_code) return;
+  const int c = g_sticky_code;
+  g_sticky_code = 0;
+  throw Error(c, "deferred tile call failed: " + g_sticky_msg);
+}
+static void flush_quietly() {               // for entry points without a status: keep the error for the next one
+  try { join_pending_sort(); flush_deferred(); }
+  catch (const Error& e) { record_sticky_error(e.code, e.what()); }
+  catch (const std::exception& e) { record_sticky_error(B2P_ERR_RUNTIME, e.what()); }
+}
+
 void flush_deferred() {
+  join_pending_sort();                      // a sort left on the worker streams owns the containers until it is joined
   if (g_defer_kind == DK_NONE) return;
   const int kind = g_defer_kind;
   std::vector<b2p_tile*> tiles;
@@ -957,6 +968,14 @@ void flush_deferred() {
   }
 }
 
+// Tiles may share a batch only if every parameter a batched phase reads from tiles[0] is the same
+// for all of them: geometry, cfl, propagator + stencil coefficients, filter, pusher.
+static bool same_batch_config(const b2p_tile* a, const b2p_tile* b) {
+  return a->grid == b->grid && std::memcmp(&a->g, &b->g, sizeof(Geom)) == 0 && a->cfg.cfl == b->cfg.cfl &&
+         a->cfg.field_propagator == b->cfg.field_propagator && a->cfg.current_filter == b->cfg.current_filter &&
+         a->cfg.particle_pusher == b->cfg.particle_pusher && std::memcmp(a->stencilM, b->stencilM, sizeof(a->stencilM)) == 0;
+}
+
 static void defer(int kind, b2p_tile* t) {
   ctx();                                    // no usable device: fail at the call, not at the flush
   if (!tuning().defer_tile_calls) {
@@ -965,8 +984,7 @@ static void defer(int kind, b2p_tile* t) {
     flush_deferred();
     return;
   }
-  if (g_defer_kind != kind || t->deferred || (!g_defer_tiles.empty() && g_defer_tiles[0]->grid != t->grid) ||
-      (!g_defer_tiles.empty() && std::memcmp(&g_defer_tiles[0]->g, &t->g, sizeof(Geom)) != 0))
+  if (g_defer_kind != kind || t->deferred || (!g_defer_tiles.empty() && !same_batch_config(g_defer_tiles[0], t)))
     flush_deferred();
   g_defer_kind = kind;
   g_defer_tiles.push_back(t);
@@ -986,7 +1004,7 @@ void Scratch_table_upload(const void* src, size_t bytes) {
 }
 const void* Scratch_table_ptr() { return scratch().table.p; }
 }  // namespace b2p
-#define B2P_TRY try { b2p::join_pending_sort(); b2p::flush_deferred();
+#define B2P_TRY try { b2p::join_pending_sort(); b2p::flush_deferred(); b2p::throw_sticky_error();
 #define B2P_TRY_DEFER try {
 #define B2P_CATCH                                                              \
   }                                                                            \
@@ -1035,7 +1053,7 @@ int b2p_tile_create(const b2p_config* cfg, const int32_t idx[3], b2p_tile** out)
 }
 void b2p_tile_destroy(b2p_tile* t) {
   if (!t) return;
-  try { b2p::flush_deferred(); } catch (...) {}
+  b2p::flush_quietly();                     // also joins a sort still running on the worker streams before the buffers are freed
   if (t->grid) {
     b2p_grid* g = t->grid;
     auto it = std::find(g->tiles.begin(), g->tiles.end(), t);
@@ -1348,7 +1366,7 @@ int b2p_grid_create(const b2p_config* cfg, b2p_grid** out) {
   B2P_CATCH
 }
 void b2p_grid_destroy(b2p_grid* g) {
-  try { b2p::flush_deferred(); } catch (...) {}
+  b2p::flush_quietly();
   delete g;
 }
 int b2p_grid_add_tile(b2p_grid* g, b2p_tile* t) {
@@ -1357,6 +1375,10 @@ int b2p_grid_add_tile(b2p_grid* g, b2p_tile* t) {
   for (int d = 0; d < 3; ++d)
     if (t->cfg.n_tiles[d] != g->cfg.n_tiles[d] || t->cfg.n_cells[d] != g->cfg.n_cells[d])
       throw Error(B2P_ERR_RUNTIME, "tile and grid configurations differ");
+  // the batched grid phases read these from the grid's first tile
+  if (t->cfg.cfl != g->cfg.cfl || t->cfg.field_propagator != g->cfg.field_propagator || t->cfg.current_filter != g->cfg.current_filter ||
+      t->cfg.particle_pusher != g->cfg.particle_pusher || std::memcmp(t->cfg.stencil, g->cfg.stencil, sizeof(g->cfg.stencil)) != 0)
+    throw Error(B2P_ERR_RUNTIME, "tile and grid configurations differ (cfl / field_propagator / current_filter / particle_pusher / stencil)");
   const int c = g->cid(t->idx[0], t->idx[1], t->idx[2]);
   if (g->slot_of_cid[c] >= 0) throw Error(B2P_ERR_RUNTIME, "tile already added at this index");
   t->grid = g; t->slot = int(g->tiles.size());
@@ -1602,7 +1624,7 @@ int b2p_timer_stop(float* ms) {
   B2P_CATCH
 }
 uint64_t b2p_launch_count(void) {
-  try { b2p::flush_deferred(); } catch (...) {}
+  b2p::flush_quietly();
   return g_ctx_ready ? ctx().launches : 0;
 }
 void b2p_copy_bytes(uint64_t* h2d_bytes, uint64_t* d2h_bytes) {

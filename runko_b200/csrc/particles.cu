@@ -70,63 +70,6 @@ k_nodal_means(const NodalBatch bt, const Geom g) {
   }
 }
 
-struct EB { V3 E, B; };
-
-// emf/yee_lattice_interpolate_linear_1st.h:58-138 on top of the nodal means.
-// Node indices fit 32 bits (Ch < 2^31 is checked at tile creation), so all index
-// arithmetic is 32-bit; only the four row base addresses are widened.
-__device__ __forceinline__ EB interpolate(const float4* __restrict__ nod, const Geom& g, const float3 origo,
-                                          const float px, const float py, const float pz) {
-  const float lx = px - origo.x, ly = py - origo.y, lz = pz - origo.z;
-  const unsigned i = __float2uint_rz(lx), j = __float2uint_rz(ly), k = __float2uint_rz(lz);
-  const float dx = lx - float(i), dy = ly - float(j), dz = lz - float(k);
-  const unsigned sj = unsigned(g.Hx[2]), si = unsigned(g.Hx[1]) * unsigned(g.Hx[2]);
-  const unsigned n = (i * unsigned(g.Hx[1]) + j) * sj + k;
-  const float2* __restrict__ nodB = reinterpret_cast<const float2*>(nod + g.Ch);
-  const unsigned off[2][2] = { { n, n + sj }, { n + si, n + si + sj } };
-  float4 a[2][2][2];
-  float2 b[2][2][2];
-#pragma unroll
-  for (int ic = 0; ic < 2; ++ic)
-#pragma unroll
-    for (int jc = 0; jc < 2; ++jc)
-#pragma unroll
-      for (int kc = 0; kc < 2; ++kc) {
-        a[ic][jc][kc] = __ldg(nod + off[ic][jc] + kc);
-        b[ic][jc][kc] = __ldg(nodB + off[ic][jc] + kc);
-      }
-  // lerp3D (:29-52): along x, then y, then z — (1-w)*A + w*B per lerp, the same two products and one sum
-  // as the reference.  The six components travel as three register pairs {Ex,Ey}, {Ez,Bx}, {By,Bz} — exactly
-  // how the LDG.128 / LDG.64 above deliver them — through Blackwell's packed fp32x2 multiply
-  // (FMUL2, round-to-nearest per lane): the 84 products take 42 issue slots.  The sums stay scalar FADDs on
-  // purpose: ptxas contracts a packed add whose operand is a packed product into FFMA2 even under --fmad=false
-  // (checked in SASS), which would change the rounding.
-  const float2 wx = make_float2(dx, dx), wy = make_float2(dy, dy), wz = make_float2(dz, dz);
-  const float2 ox = make_float2(1.0f - dx, 1.0f - dx), oy = make_float2(1.0f - dy, 1.0f - dy), oz = make_float2(1.0f - dz, 1.0f - dz);
-  auto lerp2 = [](const float2 o, const float2 w, const float2 A, const float2 B) {
-    const float2 p = __fmul2_rn(o, A), q = __fmul2_rn(w, B);
-    return make_float2(__fadd_rn(p.x, q.x), __fadd_rn(p.y, q.y));
-  };
-#define LERP3P(sel)                                                                              \
-  lerp2(oz, wz,                                                                                  \
-        lerp2(oy, wy, lerp2(ox, wx, sel(0, 0, 0), sel(1, 0, 0)), lerp2(ox, wx, sel(0, 1, 0), sel(1, 1, 0))), \
-        lerp2(oy, wy, lerp2(ox, wx, sel(0, 0, 1), sel(1, 0, 1)), lerp2(ox, wx, sel(0, 1, 1), sel(1, 1, 1))))
-#define SEL_XY(i_, j_, k_) make_float2(a[i_][j_][k_].x, a[i_][j_][k_].y)
-#define SEL_ZW(i_, j_, k_) make_float2(a[i_][j_][k_].z, a[i_][j_][k_].w)
-#define SEL_B(i_, j_, k_) b[i_][j_][k_]
-  const float2 exy = LERP3P(SEL_XY), ezbx = LERP3P(SEL_ZW), byz = LERP3P(SEL_B);
-#undef SEL_XY
-#undef SEL_ZW
-#undef SEL_B
-#undef LERP3P
-  EB eb;
-  eb.E.x = exy.x; eb.E.y = exy.y; eb.E.z = ezbx.x;
-  eb.B.x = ezbx.y; eb.B.y = byz.x; eb.B.z = byz.y;
-  return eb;
-}
-
-
-
 // ---------------------------------------------------------------- deposit --
 struct DepositArgs {
   int agg_min;     // fewest folding lanes for which a warp aggregation step pays (reduce_runs_and_red)
@@ -151,135 +94,6 @@ k_deposit_zigzag(const DepositArgs a) {
   deposit_split<AGG>(alive, z, a.Jc, a.agg_min);
 }
 
-
-// ----------------------------------------------------------------- pushers --
-// L2 prefetch of the 256 slots block `blk` will read (8 KB over the seven streams: 64 lines of
-// 128 B, one per thread of the first two warps).  Blocks run roughly in index order, so asking for
-// the block PREFETCH_BLOCKS ahead (more than one wave of resident blocks) turns that block's
-// DRAM latency at its head into an L2 hit.
-// (Tuning::push_prefetch; off by default: with the seven streams requested up front it measured no gain.)
-__device__ __forceinline__ void prefetch_streams(const Species& s, const unsigned blk) {
-  const unsigned t = threadIdx.x;
-  if (t >= 64) return;
-  const size_t base = size_t(blk) * 256;
-  const void* p;
-  if (t < 48) {
-    const unsigned which = t >> 3;
-    const float* f = which == 0 ? s.x : which == 1 ? s.y : which == 2 ? s.z : which == 3 ? s.ux : which == 4 ? s.uy : s.uz;
-    const size_t e = base + (t & 7u) * 32u;
-    if (e >= s.n) return;
-    p = f + e;
-  } else {
-    const size_t e = base + (t - 48u) * 16u;
-    if (e >= s.n) return;
-    p = s.id + e;
-  }
-  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-}
-
-struct PushArgs {
-  int agg_min;    // see DepositArgs
-  int prefetch;   // blocks ahead whose particle streams are prefetched into L2 (0: off)
-  Species s;
-  const float4* nod;
-  Geom g;
-  float3 origo;
-  float cfl;
-  float qm;       // sign(q)/m   (pic/particle_boris.h:26-27)
-};
-
-// One thread per slot.  `masks` has one uint2 per 32 slots (rounded up to the block).
-// FUSE: the zigzag current of every particle that STAYS in the tile box is deposited right here
-// from the registers (cell-edge scratch Jc, charge); particles that leave are deposited when they
-// arrive in their new tile (k_append), so every tile's J still receives exactly the particles that
-// reside in it after migration — the reference's deposit_current, minus one pass over HBM.
-template <int PUSHER, int MINB, int FUSE>
-__global__ void __launch_bounds__(256, MINB)
-k_push(const PushArgs a, uint2* __restrict__ masks, const float3 mn, const float3 mx, float4* __restrict__ Jc, const float charge,
-       const float /*unused*/) {
-  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a.prefetch) prefetch_streams(a.s, blockIdx.x + unsigned(a.prefetch));
-  // All seven streams are requested before the id is looked at (pinned loads: the compiler must
-  // not sink the six value loads below the dead-slot test, which would put two DRAM round trips
-  // in series); dead slots hold unspecified but readable values.
-  unsigned long long id = DEAD;
-  float px = 0.f, py = 0.f, pz = 0.f;
-  V3 u = { 0.f, 0.f, 0.f };
-  if (n < a.s.n) {
-    id = ld_pinned(a.s.id + n);
-    px = ld_pinned(a.s.x + n); py = ld_pinned(a.s.y + n); pz = ld_pinned(a.s.z + n);
-    u.x = ld_pinned(a.s.ux + n); u.y = ld_pinned(a.s.uy + n); u.z = ld_pinned(a.s.uz + n);
-  }
-  const bool alive = id != DEAD;                                   // :33
-  float nx = 0.f, ny = 0.f, nz = 0.f;
-  V3 vel = { 0.f, 0.f, 0.f };
-  if (alive) {
-  const EB eb = interpolate(a.nod, a.g, a.origo, px, py, pz);
-  const float cfl = a.cfl, qm = a.qm;
-  const DivC div_cfl(cfl);
-  if (PUSHER == B2P_PUSHER_BORIS) {                                // pic/particle_boris.h:37-59
-    const V3 v0 = cfl * u;
-    const V3 E0 = 0.5f * qm * eb.E;
-    const V3 u0 = v0 + E0;
-    const float ginv = cfl / sqrtf(cfl * cfl + dot(u0, u0));
-    const V3 B0 = div_cfl(0.5f * qm * ginv * eb.B);
-    const float f = 2.0f / (1.0f + dot(B0, B0));
-    const V3 u1 = f * (u0 + cross(u0, B0));
-    const V3 u2 = u0 + cross(u1, B0) + E0;
-    vel = div_cfl(u2);
-    const float ginv2 = cfl / sqrtf(cfl * cfl + dot(u2, u2));
-    nx = px + vel.x * ginv2 * cfl; ny = py + vel.y * ginv2 * cfl; nz = pz + vel.z * ginv2 * cfl;
-  } else if (PUSHER == B2P_PUSHER_HIGUERA_CARY) {                  // pic/particle_higuera_cary.h:26-75
-    const float hqm = 0.5f * qm, cfl2 = cfl * cfl, cinv = 1.0f / cfl, cinv2 = cinv * cinv;
-    const V3 v0 = cfl * u;
-    const V3 E0 = hqm * eb.E;
-    const V3 u0 = v0 + E0;
-    const V3 Bt = hqm * eb.B;
-    const float u0sq = dot(u0, u0), b2 = dot(Bt, Bt), bdotu = dot(Bt, u0);
-    const float gmb = 1.0f + u0sq * cinv2 - b2 * cinv2;
-    const float disc = gmb * gmb + 4.0f * (b2 * cinv2 + bdotu * bdotu * cinv2);
-    const float ginv = 1.0f / sqrtf(0.5f * (gmb + sqrtf(disc)));
-    const float gc = ginv * cinv;
-    const V3 B0 = gc * Bt;
-    const float f = 2.0f / (1.0f + gc * gc * b2);
-    const V3 u1 = f * (u0 + cross(u0, B0));
-    const V3 u2 = u0 + cross(u1, B0) + E0;
-    const float ginv2 = cfl / sqrtf(cfl2 + dot(u2, u2));
-    vel = u2 * cinv;
-    nx = px + u2.x * ginv2; ny = py + u2.y * ginv2; nz = pz + u2.z * ginv2;
-  } else {                                                         // pic/particle_faraday.h:53-107
-    const V3 v0 = cfl * u;
-    const float gcfl = sqrtf(cfl * cfl + dot(v0, v0));
-    const V3 u0 = v0 + 0.5f * qm * eb.E;
-    const float geff_cfl = sqrtf(cfl * cfl + dot(u0, u0));
-    const float kappa = 0.5f * qm / geff_cfl;
-    const V3 eps = kappa * eb.E;
-    const V3 beta = kappa * eb.B;
-    const float w0 = gcfl + dot(eps, v0);
-    const V3 W = v0 + eps * gcfl + cross(v0, beta) + w0 * eps;
-    const float b2 = dot(beta, beta);
-    const float f = 1.0f / (1.0f + b2);
-    const V3 W_rot = f * (W - cross(beta, W) + dot(beta, W) * beta);
-    const float bde = dot(beta, eps);
-    const V3 eps_rot = f * (eps - cross(beta, eps) + bde * beta);
-    const float D = 1.0f - f * (dot(eps, eps) + bde * bde);
-    const V3 u2 = W_rot + eps_rot * (dot(eps, W_rot) / D);
-    vel = div_cfl(u2);
-    const float ginv2 = cfl / sqrtf(cfl * cfl + dot(u2, u2));
-    nx = px + vel.x * ginv2 * cfl; ny = py + vel.y * ginv2 * cfl; nz = pz + vel.z * ginv2 * cfl;
-  }
-  a.s.ux[n] = vel.x; a.s.uy[n] = vel.y; a.s.uz[n] = vel.z;
-  a.s.x[n] = nx; a.s.y[n] = ny; a.s.z[n] = nz;
-  }
-  const bool inside = inside_box(nx, ny, nz, mn, mx);
-  publish_masks(alive, inside, n, masks);
-  if (FUSE) {
-    const bool stays = alive && inside;
-    Zigzag z;
-    if (stays) z = zigzag_split(V3{ nx, ny, nz }, vel, a.origo, a.cfl, charge, a.g);
-    deposit_split<(FUSE > 1)>(stays, z, Jc, a.agg_min);
-  }
-}
 
 // ------------------------------------------------------------ edge gather --
 // Fold the cell-edge records into the nodal current and write ALL of J (this is also
@@ -928,34 +742,6 @@ void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* n
   NodalBatch bt{};
   bt.E[0] = E; bt.B[0] = B; bt.nod[0] = nod; bt.n = 1;
   launch_nodal_means(bt, g);
-}
-
-void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm,
-                 uint2* masks, const float mins[3], const float maxs[3], float4* Jc, float charge) {
-  ProfScope prof_(KC_PUSH, double(s.n));
-  if (!s.n) return;
-  PushArgs a{ tuning().agg_min, tuning().push_prefetch, s, nod, g, make_float3(origo[0], origo[1], origo[2]), cfl, qm };
-  const float3 mn = make_float3(mins[0], mins[1], mins[2]), mx = make_float3(maxs[0], maxs[1], maxs[2]);
-  const unsigned bs = tuning().push_block == 128 ? 128u : 256u;
-  const unsigned nb = (s.n + bs - 1) / bs;
-  const int minb = tuning().push_minb;
-  const int fuse = Jc ? (tuning().deposit_agg ? 2 : 1) : 0;
-#define PUSH_LAUNCH(P, M, F) k_push<P, M, F><<<nb, bs, 0, ctx().stream>>>(a, masks, mn, mx, Jc, charge, 1.0f)
-#define PUSH_CASE(P)                                                                                   \
-  case P:                                                                                              \
-    if (fuse == 2) { if (minb >= 6) PUSH_LAUNCH(P, 6, 2); else if (minb >= 5) PUSH_LAUNCH(P, 5, 2); else PUSH_LAUNCH(P, 4, 2); } \
-    else if (fuse == 1) { if (minb >= 6) PUSH_LAUNCH(P, 6, 1); else if (minb >= 5) PUSH_LAUNCH(P, 5, 1); else PUSH_LAUNCH(P, 4, 1); } \
-    else { if (minb >= 8) PUSH_LAUNCH(P, 8, 0); else if (minb >= 6) PUSH_LAUNCH(P, 6, 0); else PUSH_LAUNCH(P, 5, 0); } \
-    break;
-  switch (pusher) {
-    PUSH_CASE(B2P_PUSHER_BORIS)
-    PUSH_CASE(B2P_PUSHER_HIGUERA_CARY)
-    PUSH_CASE(B2P_PUSHER_FARADAY)
-    default: throw Error(B2P_ERR_LOGIC, "pic::Tile::push_particles: unkown particle pusher");
-  }
-#undef PUSH_CASE
-#undef PUSH_LAUNCH
-  B2P_LAUNCH_CHECK();
 }
 
 void launch_deposit(const Species& s, float4* Jc, const Geom& g, const float origo[3], float cfl, float charge) {

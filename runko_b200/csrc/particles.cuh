@@ -35,13 +35,9 @@ size_t nodal_float4_per_node();   // float4 slots of nodal staging per lattice n
 void launch_nodal_means(const NodalBatch& bt, const Geom& g);
 void launch_edge_gather(const EdgeBatch& bt, const Geom& g);
 void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* nod);
-// the push also publishes the leaver / stayer ballots of every warp (masks: one uint2 per 32 slots,
-// rounded up to whole blocks of 256 slots) for pack_outgoing_particles
-void launch_push(int pusher, const Species& s, const float4* nod, const Geom& g, const float origo[3], float cfl, float qm,
-                 uint2* masks, const float mins[3], const float maxs[3], float4* Jc, float charge);
-// Jc != nullptr: fused push + deposit of the particles that stay inside the tile box
-
-// One container of a batched push launch (push.cu: k_push2, two slots per thread).
+// One container of a batched push launch (push.cu).  The push also publishes the leaver / stayer ballots of
+// every warp (masks: one uint2 per 32 slots, rounded up to whole blocks of 256 slots) for
+// pack_outgoing_particles; Jc != nullptr: fused push + deposit of the particles that stay inside the tile box.
 struct PushJob {
   Species s;
   const float4* nod;          // nodal means of the container's tile (k_nodal_means layout)
