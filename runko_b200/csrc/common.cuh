@@ -69,7 +69,8 @@ struct Tuning {
   int agg_min = 2;        // ... a step is taken when at least this many lanes of the warp fold
   int filter_chunk = 35;  // i-planes per thread column of k_filter_binomial2
   int push_streams = 2;   // worker streams the groups of the particle phase are round-robined over (1 = library stream only)
-  int sort_streams = 4;   // worker streams the per-container sort is round-robined over
+  int sort_streams = 1;   // > 0: b2p_grid_step_pic's sort runs on a worker stream (see sort_overlap); 0: library stream
+  int sort_batch = 16;    // containers per launch of the counting-sort kernels (scratch: ~200 MB per 4 M-slot container)
   int sort_overlap = 1;   // b2p_grid_step_pic leaves the sort running on the worker streams under the field phase of the lap
   int push_block = 128;       // threads per block of k_push (128 or 256; 128 measured 1 % faster: finer-grained tail)
   int push_group = 32;    // tiles per group of the particle phase: one launch each of nodal means, scratch clear, push (all containers), edge gather

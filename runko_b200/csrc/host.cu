@@ -60,6 +60,7 @@ static bool set_option(const std::string& name, int value) {
   else if (name == "filter_chunk") g_tuning.filter_chunk = value;
   else if (name == "push_streams") g_tuning.push_streams = value;
   else if (name == "sort_streams") g_tuning.sort_streams = value;
+  else if (name == "sort_batch") g_tuning.sort_batch = value;
   else if (name == "push_group") g_tuning.push_group = value;
   else if (name == "push_block") g_tuning.push_block = value;
   else if (name == "sort_overlap") g_tuning.sort_overlap = value;
@@ -132,14 +133,14 @@ ProfScope::~ProfScope() {
 
 // process-level scratch shared by all tiles (all work is ordered on one stream)
 constexpr int MAX_WORKERS = 4;
-constexpr int SORT_SLOTS = MAX_WORKERS;
-struct SortSet {                // scratch of one container in flight in the counting sort
-  DBuf<unsigned> keys, rank, members, cnt, offs;
-  DBuf<unsigned char> temp;
+struct SortBatch {              // scratch of one batch of containers in the counting sort (sort.cu)
+  DBuf<unsigned> keys, rank, members;   // one slice per container, sized by its n
+  DBuf<unsigned> cnt, offs;             // one slice of nkeys + 2 counters per container
+  DBuf<SortJob> table;
+  std::vector<Container> spare;         // gather targets (storage swapped with the sorted containers)
 };
 struct Scratch {
-  SortSet sort_set[SORT_SLOTS];
-  DBuf<unsigned> sort_maxpop;
+  SortBatch sort_batch;
   DBuf<float4> nodal_w[MAX_WORKERS];   // per worker stream: nodal field means of the tile being pushed
   DBuf<float4> edges_w[MAX_WORKERS];   // per worker stream: cell-edge current accumulators
   DBuf<float4>& nodal = nodal_w[0];
@@ -654,61 +655,113 @@ static PopHints& pop_hints() { static PopHints* h = new PopHints; return *h; }
 void phase_sort(const std::vector<b2p_tile*>& tiles, bool leave_running) {
   Scratch& s = scratch();
   struct Item { b2p_tile* t; Container* c; };
-  std::vector<Item> items;
-  for (b2p_tile* t : tiles)
-    for (Container& c : t->sp)
-      if (c.n >= 2) items.push_back(Item{ t, &c });
-  if (items.empty()) return;
-  const int nw = std::max(1, std::min({ tuning().sort_streams, MAX_WORKERS, int(items.size()) }));
+  std::vector<Item> items, crowded;
   const bool counting = tuning().sort_counting != 0;
+  for (b2p_tile* t : tiles)
+    for (Container& c : t->sp) {
+      if (c.n < 2) continue;
+      volatile unsigned* hint = pop_hints().slot(c.pop_hint_slot);
+      if (!counting || (*hint != PopHints::UNKNOWN && *hint > SORT_RADIX_POP)) crowded.push_back(Item{ t, &c });
+      else items.push_back(Item{ t, &c });
+    }
+  if (items.empty() && crowded.empty()) return;
+  // The whole sort runs on one worker stream, so that b2p_grid_step_pic can leave it running under the
+  // field phase of the lap (leave_running); launches are per batch of containers, not per container.
   Workers& wk = workers();
   cudaStream_t main_stream = ctx().stream;
-  if (nw > 1) {
+  const bool on_worker = tuning().sort_streams > 0 && leave_running && tuning().sort_overlap;
+  if (on_worker) {
     wk.init();
     B2P_CUDA(cudaEventRecord(wk.fork, main_stream));
-    for (int w = 0; w < nw; ++w) B2P_CUDA(cudaStreamWaitEvent(wk.s[w], wk.fork, 0));
+    B2P_CUDA(cudaStreamWaitEvent(wk.s[0], wk.fork, 0));
   }
-  s.sort_maxpop.reserve(MAX_WORKERS);
-  for (size_t q = 0; q < items.size(); ++q) {
-    const Item& it = items[q];
-    const int w = int(q % size_t(nw));
-    StreamScope on(nw > 1 ? wk.s[w] : main_stream);
-    Container& c = *it.c;
-    volatile unsigned* hint = pop_hints().slot(c.pop_hint_slot);
-    if (!counting || (*hint != PopHints::UNKNOWN && *hint > SORT_RADIX_POP)) {
-      sort_radix(it.t, c, w);
-      // let a crowded container return to the counting sort once it has thinned out: probe again
-      // every few sorts (the probe itself is the cheap first half of the counting sort)
-      if (counting && ++c.radix_sorts_since_probe >= 8) { c.radix_sorts_since_probe = 0; *hint = PopHints::UNKNOWN; }
-      continue;
+  {
+    StreamScope on(on_worker ? wk.s[0] : main_stream);
+    SortBatch& sb = s.sort_batch;
+    const size_t B = size_t(std::max(1, tuning().sort_batch));
+    if (sb.spare.size() < B) sb.spare.resize(B);
+    size_t q = 0;
+    while (q < items.size()) {
+      // a batch: up to B containers of one lattice geometry
+      const Geom& g = items[q].t->g;
+      const unsigned nkeys = g.Ch;
+      std::vector<Item> batch;
+      while (q < items.size() && batch.size() < B && std::memcmp(&items[q].t->g, &g, sizeof(Geom)) == 0) batch.push_back(items[q++]);
+      // per container: nkeys + 2 counters, then the scan's chunk totals + 1 (zeroed together with the counters)
+      const size_t ncnt = (size_t(nkeys) + 2 + 63) & ~size_t(63);
+      const size_t ncount = ncnt + ((size_t(sort_scan_chunks(nkeys)) + 1 + 63) & ~size_t(63));
+      size_t total = 0;
+      unsigned max_n = 0;
+      std::vector<size_t> off(batch.size());
+      for (size_t b = 0; b < batch.size(); ++b) { off[b] = total; total += (size_t(batch[b].c->n) + 63) & ~size_t(63); max_n = std::max(max_n, batch[b].c->n); }
+      sb.keys.reserve(total); sb.rank.reserve(total); sb.members.reserve(total);
+      sb.cnt.reserve(ncount * batch.size()); sb.offs.reserve(ncount * batch.size());
+      sb.table.reserve(B);
+      bool first_timer = false;
+      auto build = [&](const std::vector<Item>& bt, std::vector<SortJob>& jobs, double& slots) {
+        jobs.clear(); slots = 0; max_n = 0;
+        for (size_t b = 0; b < bt.size(); ++b) {
+          Container& c = *bt[b].c;
+          Container& spare = sb.spare[b];
+          spare.reserve(c.capacity(), /*exact=*/true);
+          spare.n = c.n;
+          volatile unsigned* hint = pop_hints().slot(c.pop_hint_slot);
+          jobs.push_back(SortJob{ c.view(), spare.view(), sb.keys.p + off[b], sb.rank.p + off[b], sb.members.p + off[b],
+                                  sb.cnt.p + ncount * b, sb.cnt.p + ncount * b + ncnt, sb.offs.p + ncount * b, const_cast<unsigned*>(hint),
+                                  make_float3(bt[b].t->origo[0], bt[b].t->origo[1], bt[b].t->origo[2]) });
+          slots += c.n;
+          max_n = std::max(max_n, c.n);
+        }
+      };
+      for (const Item& it : batch) first_timer = first_timer || *pop_hints().slot(it.c->pop_hint_slot) == PopHints::UNKNOWN;
+      std::vector<SortJob> jobs;
+      double slots = 0;
+      build(batch, jobs, slots);
+      h2d(sb.table.p, jobs.data(), jobs.size());
+      B2P_CUDA(cudaMemsetAsync(sb.cnt.p, 0, ncount * batch.size() * sizeof(unsigned), ctx().stream));
+      // the scan leaves every container's largest cell population in its page-locked hint slot (zero-copy store)
+      launch_sort_count_scan(sb.table.p, int(jobs.size()), max_n, slots, g, nkeys);
+      if (first_timer) {
+        // no history for some container of the batch: wait for the populations once and re-route the crowded ones
+        B2P_CUDA(cudaStreamSynchronize(ctx().stream));
+        std::vector<Item> keep;
+        std::vector<size_t> keep_off;
+        for (size_t b = 0; b < batch.size(); ++b) {
+          if (*pop_hints().slot(batch[b].c->pop_hint_slot) > SORT_RADIX_POP) crowded.push_back(batch[b]);
+          else { keep.push_back(batch[b]); keep_off.push_back(b); }
+        }
+        if (keep.size() != batch.size()) {
+          // the scratch slices stay where the count / scan kernels filled them: rebuild the table for the kept jobs only
+          std::vector<SortJob> kj;
+          for (size_t i = 0; i < keep.size(); ++i) {
+            SortJob j = jobs[keep_off[i]];
+            Container& spare = sb.spare[i];
+            spare.reserve(keep[i].c->capacity(), /*exact=*/true);
+            spare.n = keep[i].c->n;
+            j.dst = spare.view();
+            kj.push_back(j);
+          }
+          batch.swap(keep);
+          jobs.swap(kj);
+          slots = 0; max_n = 0;
+          for (const Item& it : batch) { slots += it.c->n; max_n = std::max(max_n, it.c->n); }
+          if (!jobs.empty()) h2d(sb.table.p, jobs.data(), jobs.size());
+        }
+      }
+      if (!jobs.empty()) {
+        launch_sort_scatter_place(sb.table.p, int(jobs.size()), max_n, slots, nkeys);
+        for (size_t b = 0; b < batch.size(); ++b) { swap_storage(*batch[b].c, sb.spare[b]); batch[b].c->touch(); }
+      }
     }
-    SortSet& ss = s.sort_set[w];
-    const unsigned nkeys = it.t->g.Ch;
-    ss.keys.reserve(c.n); ss.rank.reserve(c.n); ss.members.reserve(c.n);
-    ss.cnt.reserve(size_t(nkeys) + 2); ss.offs.reserve(size_t(nkeys) + 2);
-    const size_t tb = scan_temp_bytes(nkeys + 2);
-    ss.temp.reserve(tb);
-    const bool first = *hint == PopHints::UNKNOWN;
-    launch_sort_count_scan(c.view(), it.t->g, it.t->origo, ss.keys.p, ss.rank.p, ss.cnt.p, ss.offs.p, nkeys, ss.temp.p, tb,
-                           s.sort_maxpop.p + w, first);
-    if (first) {
-      // no history for this container: wait for its population once
-      B2P_CUDA(cudaMemcpyAsync(const_cast<unsigned*>(hint), s.sort_maxpop.p + w, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
-      B2P_CUDA(cudaStreamSynchronize(ctx().stream));
-      if (*hint > SORT_RADIX_POP) { sort_radix(it.t, c, w); continue; }
+    for (const Item& it : crowded) {
+      sort_radix(it.t, *it.c, 0);
+      // let a crowded container return to the counting sort once it has thinned out: probe again every few sorts
+      volatile unsigned* hint = pop_hints().slot(it.c->pop_hint_slot);
+      if (counting && ++it.c->radix_sorts_since_probe >= 8) { it.c->radix_sorts_since_probe = 0; *hint = PopHints::UNKNOWN; }
     }
-    Container& spare = s.spare_w[w];
-    spare.reserve(c.capacity(), /*exact=*/true);
-    spare.n = c.n;
-    launch_sort_scatter_place(c.view(), spare.view(), ss.keys.p, ss.rank.p, ss.offs.p, ss.members.p, ss.cnt.p, nkeys,
-                              s.sort_maxpop.p + w);
-    B2P_CUDA(cudaMemcpyAsync(const_cast<unsigned*>(hint), s.sort_maxpop.p + w, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
-    swap_storage(c, spare);
-    c.touch();
   }
-  if (nw > 1) {
-    wk.sort_pending = nw;
-    if (!leave_running || !tuning().sort_overlap) join_pending_sort();
+  if (on_worker) {
+    wk.sort_pending = 1;
   }
 }
 

@@ -11,8 +11,6 @@
 #include "pmath.cuh"
 
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 
@@ -123,259 +121,6 @@ k_edge_gather(const EdgeBatch bt, const Geom g) {
   if (pj) jz += Jc[3 * (n - sj) + 2].z;
   if (pi && pj) jz += Jc[3 * (n - si - sj) + 2].w;
   J[n] = jx; J[size_t(g.Ch) + n] = jy; J[2 * size_t(g.Ch) + n] = jz;
-  }
-}
-
-// ------------------------------------------------------------------- sort --
-// pic/tile.c++:430-435 + pic/particle.h:607-614: key = layout_right cell index in
-// the haloed lattice (uint32), dead -> UINT32_MAX.
-__global__ void __launch_bounds__(256)
-k_sort_keys(const Species s, const Geom g, const float3 origo, unsigned* __restrict__ keys, unsigned* __restrict__ idx,
-            const unsigned dead_key) {
-  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= s.n) return;
-  unsigned key = dead_key;
-  if (s.id[n] != DEAD) {
-    const unsigned i = __float2uint_rz(s.x[n] - origo.x);
-    const unsigned j = __float2uint_rz(s.y[n] - origo.y);
-    const unsigned k = __float2uint_rz(s.z[n] - origo.z);
-    key = (i * unsigned(g.Hx[1]) + j) * unsigned(g.Hx[2]) + k;
-    if (dead_key != 0xFFFFFFFFu && key > dead_key) key = dead_key;   // sort path: clamp to the dead key (= Ch)
-  }
-  keys[n] = key;
-  if (idx) idx[n] = n;
-}
-
-// gather all seven streams through the sort permutation (pic/particle.h:640-701)
-__global__ void __launch_bounds__(256)
-k_gather(const Species src, const Species dst, const unsigned* __restrict__ perm) {
-  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= src.n) return;
-  const unsigned p = perm[n];
-  dst.x[n] = src.x[p]; dst.y[n] = src.y[p]; dst.z[n] = src.z[p];
-  dst.ux[n] = src.ux[p]; dst.uy[n] = src.uy[p]; dst.uz[n] = src.uz[p];
-  dst.id[n] = src.id[p];
-}
-
-// ------------------------------------------------------- counting sort (fast path) --
-// The contract of ParticleContainer::sort is "stable sort by cell key, dead slots last"
-// (pic/particle.h:575-703).  Keys are lattice cell indices < Ch with a few tens of particles per
-// key, so instead of a general radix sort of (key, slot) pairs the container is sorted by counting:
-//   1. k_sort_count   key[n], rank[n] = arrival order among the particles of that key (one atomic
-//                     on cnt[key] per run of equal keys inside a warp; NOT in slot order yet)
-//   2. exclusive scan of cnt -> offs (CUB DeviceScan over Ch + 2 counters) and the largest
-//                     population of a cell (a hint for the NEXT sort of this container)
-//   3. k_sort_scatter members[offs[key] + rank] = n: the slots of every cell, in arrival order
-//   4. k_sort_fix     one thread per cell puts its (short, almost ordered) member list into
-//                     ascending slot order by insertion; cells with more than SORT_THREAD_POP
-//                     members are queued for k_sort_fix_big (one block per cell, rank by counting)
-//   5. k_gather       dst[p] = src[members[p]]: coalesced writes, reads within a few hundred slots
-//                     of p for a container that was sorted a few laps ago.
-// Result: exactly the stable order for any input.  Dead slots (key Ch, clamped like the radix
-// path) keep their arrival order — the contents of dead slots are unspecified in the reference.
-// Step 4 is quadratic in the population of a cell, so the host routes containers whose last known
-// largest cell population exceeds SORT_RADIX_POP to the general radix sort instead.
-__global__ void __launch_bounds__(256)
-k_sort_count(const Species s, const Geom g, const float3 origo, unsigned* __restrict__ keys, unsigned* __restrict__ rank,
-             unsigned* __restrict__ cnt, const unsigned dead_key) {
-  // two slots per thread, 256 apart: both slots' loads, then both atomics, are in flight together
-  const unsigned lane = threadIdx.x & 31;
-  unsigned n[2], key[2], start[2], base[2];
-  bool in[2];
-  unsigned long long id[2];
-  float px[2], py[2], pz[2];
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    n[r] = blockIdx.x * 512u + 256u * r + threadIdx.x;
-    in[r] = n[r] < s.n;
-    id[r] = DEAD; px[r] = py[r] = pz[r] = 0.f;
-    if (in[r]) { id[r] = ld_pinned(s.id + n[r]); px[r] = ld_pinned(s.x + n[r]); py[r] = ld_pinned(s.y + n[r]); pz[r] = ld_pinned(s.z + n[r]); }
-  }
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    key[r] = dead_key;
-    if (id[r] != DEAD) {
-      const unsigned i = __float2uint_rz(px[r] - origo.x);
-      const unsigned j = __float2uint_rz(py[r] - origo.y);
-      const unsigned k = __float2uint_rz(pz[r] - origo.z);
-      key[r] = (i * unsigned(g.Hx[1]) + j) * unsigned(g.Hx[2]) + k;
-      if (key[r] > dead_key) key[r] = dead_key;
-    }
-    // one atomic per run of equal keys in the warp (a container sorted a few laps ago is made of such runs)
-    const unsigned prev = __shfl_up_sync(0xffffffffu, key[r], 1);
-    const bool head = lane == 0 || key[r] != prev || !in[r];
-    const unsigned hm = __ballot_sync(0xffffffffu, head);
-    start[r] = 31u - __clz(hm & (0xFFFFFFFFu >> (31u - lane)));                 // my run's first lane
-    const unsigned above = lane == 31 ? 0u : (hm >> (lane + 1));
-    const unsigned len = above ? unsigned(__ffs(above)) : 32u - lane;            // for a head: length of its run
-    // Dead slots are not ranked: they end up behind the alive particles in any order (k_sort_gather).
-    base[r] = 0;
-    if (head && key[r] != dead_key) base[r] = atomicAdd(&cnt[key[r]], len);
-  }
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const unsigned b0 = __shfl_sync(0xffffffffu, base[r], start[r]);
-    if (in[r]) {
-      keys[n[r]] = key[r];
-      rank[n[r]] = b0 + (lane - start[r]);
-    }
-  }
-}
-
-// largest population among the alive keys [0, nkeys)
-__global__ void __launch_bounds__(256)
-k_max_count(const unsigned* __restrict__ cnt, const unsigned nkeys, unsigned* __restrict__ out) {
-  unsigned m = 0;
-  for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < nkeys; c += gridDim.x * blockDim.x) m = max(m, cnt[c]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
-}
-
-__global__ void __launch_bounds__(256)
-k_sort_scatter(const unsigned* __restrict__ keys, const unsigned* __restrict__ rank, const unsigned* __restrict__ offs,
-               unsigned* __restrict__ members, const unsigned n_total, const unsigned dead_key) {
-  const unsigned n0 = blockIdx.x * 512u + threadIdx.x, n1 = n0 + 256u;   // two slots per thread: both lookups in flight together
-  const bool i0 = n0 < n_total, i1 = n1 < n_total;
-  const unsigned k0 = i0 ? keys[n0] : dead_key, k1 = i1 ? keys[n1] : dead_key;
-  const unsigned r0 = i0 ? rank[n0] : 0u, r1 = i1 ? rank[n1] : 0u;
-  const unsigned o0 = k0 != dead_key ? offs[k0] : 0u, o1 = k1 != dead_key ? offs[k1] : 0u;
-  if (k0 != dead_key) members[o0 + r0] = n0;
-  if (k1 != dead_key) members[o1 + r1] = n1;
-}
-
-// Step 5: dst[p] = src[members[p]] for the offs[dead_key] alive particles; the slots behind them are
-// dead.  SORT_GATHER_SLOTS slots per thread (256 apart) keep 7 x SORT_GATHER_SLOTS independent gathers in flight.
-constexpr int SORT_GATHER_SLOTS = 4;
-__global__ void __launch_bounds__(256)
-k_sort_gather(const Species src, const Species dst, const unsigned* __restrict__ members, const unsigned* __restrict__ n_alive) {
-  const unsigned na = *n_alive;
-  unsigned n[SORT_GATHER_SLOTS], p[SORT_GATHER_SLOTS];
-  bool a[SORT_GATHER_SLOTS];
-  float f[SORT_GATHER_SLOTS][6];
-  unsigned long long id[SORT_GATHER_SLOTS];
-#pragma unroll
-  for (int r = 0; r < SORT_GATHER_SLOTS; ++r) {
-    n[r] = blockIdx.x * (256u * SORT_GATHER_SLOTS) + 256u * r + threadIdx.x;
-    a[r] = n[r] < na;
-    p[r] = a[r] ? members[n[r]] : 0u;
-  }
-#pragma unroll
-  for (int r = 0; r < SORT_GATHER_SLOTS; ++r) {
-    id[r] = DEAD;
-    if (a[r]) {
-      f[r][0] = src.x[p[r]]; f[r][1] = src.y[p[r]]; f[r][2] = src.z[p[r]];
-      f[r][3] = src.ux[p[r]]; f[r][4] = src.uy[p[r]]; f[r][5] = src.uz[p[r]];
-      id[r] = src.id[p[r]];
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < SORT_GATHER_SLOTS; ++r) {
-    if (a[r]) {
-      dst.x[n[r]] = f[r][0]; dst.y[n[r]] = f[r][1]; dst.z[n[r]] = f[r][2];
-      dst.ux[n[r]] = f[r][3]; dst.uy[n[r]] = f[r][4]; dst.uz[n[r]] = f[r][5];
-    }
-    if (n[r] < src.n) dst.id[n[r]] = id[r];
-  }
-}
-
-// Step 4: ascending slot order inside every alive cell.  A block takes blockDim.x (<= 256)
-// consecutive cells — one contiguous piece of `members` — and stages the piece and the cells'
-// offsets in shared memory with coalesced loads.  One thread per cell labels its members with the
-// cell's local index; then one thread per MEMBER flags its cell if it sits behind a larger slot
-// index, and the members of flagged cells count the members of their cell with a smaller slot
-// index (the lanes of a warp read at most a few distinct shared-memory words per step:
-// broadcasts) and write themselves to their stable position.  Cells with more than
-// SORT_THREAD_POP members, and all cells of a piece that does not fit the staging buffer, are
-// queued in `big` = {count, cells...} for k_sort_fix_big.
-constexpr unsigned SORT_FIX_STAGE = 8192;   // entries (32 KB + 8 KB of labels)
-__global__ void __launch_bounds__(256)
-k_sort_fix(const unsigned* __restrict__ offs, unsigned* __restrict__ members, const unsigned nkeys, unsigned* __restrict__ big,
-           unsigned* __restrict__ max_pop) {
-  __shared__ unsigned sm[SORT_FIX_STAGE];
-  __shared__ unsigned char cellof[SORT_FIX_STAGE];
-  __shared__ unsigned so[257];
-  __shared__ unsigned char unsorted[256];
-  const unsigned c0 = blockIdx.x * blockDim.x, nc = min(blockDim.x, nkeys - c0);
-  for (unsigned t = threadIdx.x; t <= nc; t += blockDim.x) so[t] = offs[c0 + t];
-  unsorted[threadIdx.x] = 0;
-  __syncthreads();
-  const unsigned lo0 = so[0], total = so[nc] - lo0;
-  const bool staged = total <= SORT_FIX_STAGE;
-  {   // largest cell population of the container (the hint for its next sort)
-    unsigned m = threadIdx.x < nc ? so[threadIdx.x + 1] - so[threadIdx.x] : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 1) atomicMax(max_pop, m);
-  }
-  if (threadIdx.x < nc) {
-    const unsigned lo = so[threadIdx.x] - lo0, hi = so[threadIdx.x + 1] - lo0;
-    if (hi - lo >= 2 && (!staged || hi - lo > SORT_THREAD_POP)) big[1 + atomicAdd(big, 1u)] = c0 + threadIdx.x;
-    if (staged)
-      for (unsigned t = lo; t < hi; ++t) cellof[t] = static_cast<unsigned char>(threadIdx.x);
-  }
-  if (!staged) return;
-  for (unsigned t = threadIdx.x; t < total; t += blockDim.x) sm[t] = members[lo0 + t];
-  __syncthreads();
-  for (unsigned e = threadIdx.x; e < total; e += blockDim.x) {
-    const unsigned a = cellof[e];
-    if (e > so[a] - lo0 && sm[e - 1] > sm[e]) unsorted[a] = 1;
-  }
-  __syncthreads();
-  for (unsigned e = threadIdx.x; e < total; e += blockDim.x) {
-    const unsigned a = cellof[e];
-    if (!unsorted[a]) continue;
-    const unsigned lo = so[a] - lo0, hi = so[a + 1] - lo0;
-    if (hi - lo > SORT_THREAD_POP) continue;
-    const unsigned v = sm[e];
-    unsigned before = 0;
-    for (unsigned q = lo; q < hi; ++q) before += unsigned(sm[q] < v);
-    if (lo + before != e) members[lo0 + lo + before] = v;
-  }
-}
-
-// Queued cells: one warp per cell, rank by counting.  Up to 32 members sit one per lane and are
-// ranked over shuffles; up to 128 sit four per lane and are ranked against the list re-read
-// through L1 (warp-uniform addresses); larger cells go through `tmp` (>= container size; the
-// arrival ranks are no longer needed).  All ranks are known before the first member is rewritten.
-__global__ void __launch_bounds__(256)
-k_sort_fix_big(const unsigned* __restrict__ offs, unsigned* __restrict__ members, unsigned* __restrict__ tmp,
-               const unsigned* __restrict__ big) {
-  const unsigned nbig = big[0];
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (unsigned e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < nbig; e += nwarps) {
-    const unsigned c = big[1 + e];
-    const unsigned lo = offs[c], pop = offs[c + 1] - lo;
-    if (pop <= 32) {
-      const unsigned v = lane < pop ? members[lo + lane] : 0xFFFFFFFFu;
-      unsigned before = 0;
-      for (unsigned q = 0; q < pop; ++q) before += unsigned(__shfl_sync(0xffffffffu, v, int(q)) < v);
-      if (lane < pop && before != lane) members[lo + before] = v;
-    } else if (pop <= 128) {
-      unsigned v[4], before[4] = { 0u, 0u, 0u, 0u };
-#pragma unroll
-      for (int r = 0; r < 4; ++r) v[r] = lane + 32u * r < pop ? members[lo + lane + 32u * r] : 0xFFFFFFFFu;
-      for (unsigned q = 0; q < pop; ++q) {
-        const unsigned w = members[lo + q];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) before[r] += unsigned(w < v[r]);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        if (lane + 32u * r < pop) members[lo + before[r]] = v[r];
-    } else {
-      for (unsigned t = lane; t < pop; t += 32) {
-        const unsigned v = members[lo + t];
-        unsigned before = 0;
-        for (unsigned q = 0; q < pop; ++q) before += unsigned(members[lo + q] < v);
-        tmp[lo + before] = v;
-      }
-      __syncwarp();
-      for (unsigned t = lane; t < pop; t += 32) members[lo + t] = tmp[lo + t];
-    }
-    __syncwarp();
   }
 }
 
@@ -773,98 +518,6 @@ void launch_edge_gather(const float4* Jc, float* J, const Geom& g) {
   EdgeBatch bt{};
   bt.Jc[0] = Jc; bt.J[0] = J; bt.n = 1;
   launch_edge_gather(bt, g);
-}
-
-void launch_sort_keys(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* idx, unsigned dead_key) {
-  ProfScope prof_(KC_SORT_KEYS, double(s.n));
-  if (!s.n) return;
-  k_sort_keys<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, g, make_float3(origo[0], origo[1], origo[2]), keys, idx, dead_key);
-  B2P_LAUNCH_CHECK();
-}
-
-size_t sort_pairs_temp_bytes(unsigned n, int end_bit) {
-  size_t bytes = 0;
-  cub::DoubleBuffer<unsigned> k(nullptr, nullptr), v(nullptr, nullptr);
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, int(n), 0, end_bit, ctx().stream);
-  return bytes;
-}
-// stable LSD radix sort of (key, slot) pairs; returns which half of the double
-// buffers holds the result
-int sort_pairs(void* temp, size_t temp_bytes, unsigned* keys[2], unsigned* vals[2], unsigned n, int end_bit) {
-  ProfScope prof_(KC_RADIX_SORT, double(n));
-  cub::DoubleBuffer<unsigned> k(keys[0], keys[1]), v(vals[0], vals[1]);
-  B2P_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, int(n), 0, end_bit, ctx().stream));
-  count_launch((end_bit + 7) / 8 + 2);
-  return v.selector;
-}
-size_t sort_keys64_temp_bytes(unsigned n, int end_bit) {
-  size_t bytes = 0;
-  cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
-  cub::DeviceRadixSort::SortKeys(nullptr, bytes, k, int(n), 0, end_bit, ctx().stream);
-  return bytes;
-}
-int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit) {
-  ProfScope prof_(KC_RADIX_SORT, double(n));
-  cub::DoubleBuffer<unsigned long long> k(keys[0], keys[1]);
-  B2P_CUDA(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, k, int(n), 0, end_bit, ctx().stream));
-  count_launch((end_bit + 7) / 8 + 2);
-  return k.selector;
-}
-
-size_t scan_temp_bytes(unsigned n) {
-  size_t bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, bytes, static_cast<unsigned*>(nullptr), static_cast<unsigned*>(nullptr), int(n), ctx().stream);
-  return bytes;
-}
-// steps 1-2 of the counting sort: keys, arrival ranks, offs = exclusive scan of the per-key
-// populations (nkeys alive keys + the dead key + one pad entry), *max_pop = largest alive population
-void launch_sort_count_scan(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* rank, unsigned* cnt,
-                            unsigned* offs, unsigned nkeys, void* temp, size_t temp_bytes, unsigned* max_pop, bool with_max) {
-  if (!s.n) return;
-  {
-    ProfScope prof_(KC_SORT_KEYS, double(s.n));
-    B2P_CUDA(cudaMemsetAsync(cnt, 0, (size_t(nkeys) + 2) * sizeof(unsigned), ctx().stream));
-    B2P_CUDA(cudaMemsetAsync(max_pop, 0, sizeof(unsigned), ctx().stream));
-    k_sort_count<<<(s.n + 511) / 512, 256, 0, ctx().stream>>>(s, g, make_float3(origo[0], origo[1], origo[2]), keys, rank, cnt, nkeys);
-    B2P_LAUNCH_CHECK();
-  }
-  ProfScope prof_(KC_RADIX_SORT, double(s.n));
-  B2P_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, cnt, offs, int(nkeys + 2), ctx().stream));
-  count_launch(1);
-  if (with_max) {
-    k_max_count<<<std::min(blocks_for(nkeys), 296u), 256, 0, ctx().stream>>>(cnt, nkeys, max_pop);
-    B2P_LAUNCH_CHECK();
-  }
-}
-// steps 3-5.  `cnt` (nkeys + 2 counters, free after the scan) becomes the queue of crowded cells,
-// `rank` (free after the scatter) the scratch of k_sort_fix_big.
-void launch_sort_scatter_place(const Species& src, const Species& dst, const unsigned* keys, unsigned* rank,
-                               const unsigned* offs, unsigned* members, unsigned* cnt, unsigned nkeys, unsigned* max_pop) {
-  if (!src.n) return;
-  {
-    ProfScope prof_(KC_RADIX_SORT, double(src.n));
-    k_sort_scatter<<<(src.n + 511) / 512, 256, 0, ctx().stream>>>(keys, rank, offs, members, src.n, nkeys);
-    B2P_LAUNCH_CHECK();
-    B2P_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned), ctx().stream));
-    // cells per block: about half the staging buffer at the container's mean population
-    const unsigned mean = std::max(1u, src.n / std::max(1u, nkeys));
-    unsigned cells = 256;
-    while (cells > 32 && cells * mean > SORT_FIX_STAGE / 2) cells >>= 1;
-    k_sort_fix<<<(nkeys + cells - 1) / cells, cells, 0, ctx().stream>>>(offs, members, nkeys, cnt, max_pop);
-    B2P_LAUNCH_CHECK();
-    k_sort_fix_big<<<592, 256, 0, ctx().stream>>>(offs, members, rank, cnt);
-    B2P_LAUNCH_CHECK();
-  }
-  ProfScope prof_(KC_GATHER, double(src.n));
-  k_sort_gather<<<(src.n + 256 * SORT_GATHER_SLOTS - 1) / (256 * SORT_GATHER_SLOTS), 256, 0, ctx().stream>>>(src, dst, members, offs + nkeys);
-  B2P_LAUNCH_CHECK();
-}
-
-void launch_gather(const Species& src, const Species& dst, const unsigned* perm) {
-  ProfScope prof_(KC_GATHER, double(src.n));
-  if (!src.n) return;
-  k_gather<<<blocks_for(src.n), 256, 0, ctx().stream>>>(src, dst, perm);
-  B2P_LAUNCH_CHECK();
 }
 
 void launch_make_masks(const Species& s, uint2* masks, const float mins[3], const float maxs[3]) {

@@ -61,14 +61,22 @@ int sort_pairs(void* temp, size_t temp_bytes, unsigned* keys[2], unsigned* vals[
 size_t sort_keys64_temp_bytes(unsigned n, int end_bit);
 int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit);
 void launch_gather(const Species& src, const Species& dst, const unsigned* perm);
-// counting sort by cell key (fast path of sort_particles; particles.cu)
-constexpr unsigned SORT_THREAD_POP = 128;    // largest cell whose member list one thread orders by insertion
+// batched counting sort by cell key (sort.cu): one container of a batch
+struct SortJob {
+  Species src, dst;           // dst: spare storage of the same capacity (swapped with the container afterwards)
+  unsigned* keys;             // [src.n] cell key per slot (dead -> nkeys)
+  unsigned* rank;             // [src.n] arrival rank inside the cell
+  unsigned* members;          // [src.n] slots of every cell, cell by cell
+  unsigned* cnt;              // [nkeys + 2] per-key populations (zeroed by the caller)
+  unsigned* chunk_sums;       // [sort_scan_chunks(nkeys) + 1] scan scratch (last entry zeroed by the caller)
+  unsigned* offs;             // [nkeys + 2] exclusive scan of cnt; offs[nkeys] = alive particles
+  unsigned* max_pop;          // largest population of a cell
+  float3 origo;
+};
 constexpr unsigned SORT_RADIX_POP = 4096;    // containers whose last known largest cell exceeds this take the radix sort
-size_t scan_temp_bytes(unsigned n);
-void launch_sort_count_scan(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* rank, unsigned* cnt,
-                            unsigned* offs, unsigned nkeys, void* temp, size_t temp_bytes, unsigned* max_pop, bool with_max);
-void launch_sort_scatter_place(const Species& src, const Species& dst, const unsigned* keys, unsigned* rank,
-                               const unsigned* offs, unsigned* members, unsigned* cnt, unsigned nkeys, unsigned* max_pop);
+unsigned sort_scan_chunks(unsigned nkeys);
+void launch_sort_count_scan(const SortJob* jobs, int njobs, unsigned max_n, double total_slots, const Geom& g, unsigned nkeys);
+void launch_sort_scatter_place(const SortJob* jobs, int njobs, unsigned max_n, double total_slots, unsigned nkeys);
 void launch_make_masks(const Species& s, uint2* masks, const float mins[3], const float maxs[3]);
 void launch_collect_leavers(const void* jobs, unsigned ncont, unsigned max_words, unsigned long long* list, unsigned* list_count,
                             unsigned list_cap, unsigned* last_alive, unsigned* cont_count);
