@@ -127,4 +127,13 @@ emf = _module("runko.emf", threeD=_module("runko.emf.threeD", Tile=EmfTile, edge
 pic = _module("runko.pic", threeD=_module("runko.pic.threeD", Tile=PicTile, ParticleState=_t.ParticleStateD,
                                           ParticleStateBatch=_t.ParticleStateBatch, reflector_wall=_t.reflector_wall))
 tools = _module("runko.tools", comm_mode=_t.comm_mode)
-from runko_b200.moving_injector import MovingInjector  # noqa: E402,F401
+
+# runko.MovingInjector is pure Python in the reference: its own file is loaded where it lies (this package only
+# exists to run the reference's unit tests, which need /root/reference anyway)
+import importlib.util as _ilu  # noqa: E402
+_mi = "/root/reference/runko/moving_injector.py"
+if os.path.exists(_mi):
+    _spec = _ilu.spec_from_file_location("runko.moving_injector", _mi)
+    _mod = _ilu.module_from_spec(_spec)
+    _spec.loader.exec_module(_mod)
+    MovingInjector = _mod.MovingInjector

@@ -132,14 +132,6 @@ def test_reflector_wall_parity(beta, fuse):
         check(rb.lib().b2p_set_option(b"fuse_deposit", 1))
 
 
-class _Sim:
-    def __init__(self, tiles):
-        self.lap, self._tiles = 0, tiles
-
-    def local_tiles(self):
-        return self._tiles
-
-
 class _OracleTileFace:
     """the slice of the tile API MovingInjector / batch_inject_in_x_stripe need, on the oracle"""
 
@@ -216,9 +208,23 @@ def test_shock_lap_parity():
             for tile, face in faces:
                 for _ in range(2):
                     (tile if side == 0 else face).batch_inject_in_x_stripe(sp, pg, walloc, injloc0)
-    inj = [rb.MovingInjector(injloc=injloc0, beta_inj=1.0, beta_flow=beta, cfl=conf.cfl, n_inj=2, walloc=walloc, Lx=Lx)
-           for _ in range(2)]
-    sims = [_Sim([tf[0] for tf in faces]), _Sim([tf[1] for tf in faces])]
+    # the injection front of projects/pic-shock (runko/moving_injector.py): every lap > 0 the stripe between the drifted
+    # previous front and the advanced front is filled, until the front nears the right end of the box
+    def stripes(injloc, stride, margin=10.0):
+        lap = 0
+        while True:
+            if lap > 0:
+                left, right = max(injloc - beta * stride, walloc), injloc + 1.0 * stride
+                if right >= Lx - margin:
+                    return
+                injloc = right
+                yield lap, left, right, injloc
+            else:
+                yield lap, None, None, injloc
+            lap += 1
+    fronts = [stripes(injloc0, conf.cfl) for _ in range(2)]
+    last_front = [injloc0, injloc0]
+    sides = [[tf[0] for tf in faces], [tf[1] for tf in faces]]
     pg_lap = [[make_pgen(200 + sp) for sp in range(2)] for _ in range(2)]
 
     def oracle_lap(lap, passes=4):
@@ -244,12 +250,17 @@ def test_shock_lap_parity():
         oracle_lap(lap)
         grid.step_shock(lap, n_filter_passes=4)
         for side in (0, 1):
-            sims[side].lap = lap
-            inj[side].inject(sims[side], [(sp, pg_lap[side][sp]) for sp in range(2)], 1)
+            step = next(fronts[side], None)
+            if step is None or step[1] is None:
+                continue
+            _, x_left, x_right, last_front[side] = step
+            for tile in sides[side]:
+                for sp in range(2):
+                    tile.batch_inject_in_x_stripe(sp, pg_lap[side][sp], x_left, x_right)
         if lap == 0:
             for (i, j, k), tile in tiles.items():
                 _same_particles(org, org.cid(i, j, k), tile)
-    assert inj[0].injloc == inj[1].injloc and inj[0].injloc > injloc0
+    assert last_front[0] == last_front[1] and last_front[0] > injloc0
     n_total = 0
     for (i, j, k), tile in tiles.items():
         t = org.cid(i, j, k)
