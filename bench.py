@@ -89,6 +89,24 @@ def binit(conf, ppc, delgam=0.3, sigma=10.0):
     return float(np.sqrt(gammath * oppc * m0 * conf.cfl ** 2 * sigma))   # pic.py:64-67
 
 
+def juttner_synge(rng, n, theta):
+    """Isotropic Juettner-Synge momenta by Sobol's rejection method — what runko/sample_thermal_distributions.py:58-127 does
+    for theta > 0.2 and what the CUDA arm's device generator (k_inject_thermal) restates: (3, n) float64."""
+    u = np.empty(n)
+    todo = np.arange(n)
+    while todo.size:
+        x = rng.random((4, todo.size))
+        uu = -theta * np.log(x[0] * x[1] * x[2])
+        eta = -theta * np.log(x[0] * x[1] * x[2] * x[3])
+        ok = eta * eta - uu * uu > 1.0
+        u[todo[ok]] = uu[ok]
+        todo = todo[~ok]
+    mu = 2.0 * rng.random(n) - 1.0
+    phi = 2.0 * np.pi * rng.random(n)
+    st = np.sqrt(np.maximum(0.0, 1.0 - mu * mu))
+    return np.stack([u * st * np.cos(phi), u * st * np.sin(phi), u * mu])
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -141,13 +159,13 @@ class CpuArm:
 
     def __init__(self, args, n_threads):
         from oracle import reference_build as rbuild
-        edge = 32
+        edge = args.tile                                       # the CUDA arm's tile size (64^3)
         nt = max(1, n_threads)
         tz = 1
         while tz * tz * tz < nt:
             tz += 1
         self.tiles = (tz, tz, max(1, -(-nt // (tz * tz))))
-        self.edge, self.n_threads = edge, nt
+        self.edge, self.n_threads, self.ppc = edge, nt, args.ppc
         conf, _, _ = make_conf(argparse.Namespace(cells=edge, tile=edge, ppc=args.ppc), 1)
         conf.n_tiles = list(self.tiles)
         use_ref = rbuild.available() and rbuild.cpu_ok()
@@ -169,13 +187,16 @@ class CpuArm:
             self.g = OracleGrid(conf)
             T = self.tiles
             items = [((t % T[0], (t // T[0]) % T[1], t // (T[0] * T[1])), t) for t in range(self.g.num_tiles)]
+        # one tile's worth of plasma (cell corner + U[0,1)^3, species 1 on top of species 0: pic.py:141-156), repeated in every tile
         ii, jj, kk = np.meshgrid(np.arange(edge), np.arange(edge), np.arange(edge), indexing="ij")
+        corner = np.stack([ii.ravel(), jj.ravel(), kk.ravel()]).astype(np.float64)
+        pos0 = np.concatenate([corner + rng.random((3, ncell)) for _ in range(args.ppc)], axis=1)
+        n = pos0.shape[1]
+        vels = [juttner_synge(rng, n, 0.3) for _ in range(2)]      # the CUDA arm's momentum distribution (theta = 0.3)
         for (i, j, k), t in items:
-            corner = np.stack([ii.ravel() + i * edge, jj.ravel() + j * edge, kk.ravel() + k * edge]).astype(np.float64)
-            pos = np.concatenate([corner + rng.random((3, ncell)) for _ in range(args.ppc)], axis=1)
-            n = pos.shape[1]
+            pos = pos0 + np.array([i * edge, j * edge, k * edge], np.float64)[:, None]
             for sp in range(2):
-                vel = 0.55 * rng.standard_normal((3, n))       # ~ theta = 0.3 thermal spread
+                vel = vels[sp]
                 if use_ref:
                     ids = (np.uint64(sp + 1) << np.uint64(40)) + np.arange(n, dtype=np.uint64)
                     t.set_particles(sp, *pos.astype(np.float32), *vel.astype(np.float32), ids)
@@ -198,8 +219,8 @@ class CpuArm:
 
     def sample(self, laps):
         t = self.tiles
-        return (f"{t[0]}x{t[1]}x{t[2]} tiles of {self.edge}^3 cells, 2 species x 16 ppc = {self.n_part} particles per lap, "
-                f"{laps} laps, one tile per worker")
+        return (f"{t[0]}x{t[1]}x{t[2]} tiles of {self.edge}^3 cells (periodic), 2 species x {self.ppc} ppc, Juettner-Synge theta = 0.3, "
+                f"uniform Bz = {self.n_part} particles per lap, {laps} laps of the same lap function, one tile per worker thread")
 
 
 def run_reference(args):
@@ -220,6 +241,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
+        # the CPU arm times a BOUNDED SAMPLE of that workload (same tile size, ppc, momentum distribution, lap function);
+        # `value` is its particle-pushes/s on this sample, i.e. a per-particle rate, not a 512^3 run
+        "sample": arm.sample(args.steps),
         "timed_laps": [1 + args.warmup, args.warmup + args.steps],         # lap 0 ran when the arm was set up
         "sort_laps_timed": sum(1 for q in range(1 + args.warmup, 1 + args.warmup + args.steps) if q % 5 == 0),
         "cpu_baseline": {"value": value, "unit": "particle-pushes/s", "cores": n_threads, "kind": arm.kind,
@@ -230,24 +254,33 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- config 3: vacuum EM wave (field-solver roofline)
-def run_emf(args):
-    """BASELINE configs[2] ("projects/emf-wave"): FDTD + binomial filter only.  One step = one lap of
-    projects/emf-wave/emf.py:48-56 (E halo, push_half_b x2, B halo, push_e) over --cells^3 cells per GPU
-    (default 1024^3 in 8^3 tiles of 128^3); `value` = cell-updates/s.  The three binomial filter passes of a PIC lap
-    are timed separately over the same lattices (`filter`)."""
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("gloo")
-    import runko_b200 as rb
+def owner_map(conf, tpg, gb):
+    T = conf.n_tiles
+    owner = np.zeros(T[0] * T[1] * T[2], np.int32)
+    for k in range(T[2]):
+        for j in range(T[1]):
+            for i in range(T[0]):
+                owner[i + T[0] * (j + T[1] * k)] = (i // tpg) + gb[0] * ((j // tpg) + gb[1] * (k // tpg))
+    return owner
+
+
+def comm_init(L, dist, grid, rank, world, owner):
     from runko_b200._lib import check
-    L = rb.lib()
-    check(L.b2p_init(local_rank))
-    cells = args.cells if args.cells != 512 else 1024
-    tile = args.tile if args.tile != 64 else 128
+    uid = np.zeros(128, np.uint8)
+    if rank == 0:
+        check(L.b2p_nccl_unique_id(uid.ctypes.data_as(C.c_void_p)))
+    lst = [uid.tobytes()]
+    dist.broadcast_object_list(lst, src=0)
+    uid = np.frombuffer(lst[0], np.uint8).copy()
+    check(L.b2p_grid_comm_init(grid._h, rank, world, uid.ctypes.data_as(C.c_void_p), owner.ctypes.data_as(C.c_void_p)))
+
+
+def measure_emf(rb, L, dist, rank, world, local_rank, cells, tile, steps, warmup, with_cpu, with_e2e=True):
+    """BASELINE configs[2] ("projects/emf-wave"): FDTD + binomial filter only.  One step = one lap of
+    projects/emf-wave/emf.py:48-56 (E halo, push_half_b x2, B halo, push_e) over cells^3 cells per GPU;
+    `value` = cell-updates/s.  The three binomial filter passes of a PIC lap are timed separately over the
+    same lattices (`per_kernel.filter`)."""
+    from runko_b200._lib import check
     tpg, gb = cells // tile, gpu_blocks(world)
     conf = Conf(n_tiles=[tpg * gb[0], tpg * gb[1], tpg * gb[2]], n_cells_per_tile=[tile] * 3, cfl=1.0, field_propagator="fdtd2",
                 current_filter="binomial2")
@@ -269,19 +302,7 @@ def run_emf(args):
                 grid.add_tile(t)
                 tiles.append(t)
     if world > 1:
-        T = conf.n_tiles
-        owner = np.zeros(T[0] * T[1] * T[2], np.int32)
-        for k in range(T[2]):
-            for j in range(T[1]):
-                for i in range(T[0]):
-                    owner[i + T[0] * (j + T[1] * k)] = (i // tpg) + gb[0] * ((j // tpg) + gb[1] * (k // tpg))
-        uid = np.zeros(128, np.uint8)
-        if rank == 0:
-            check(L.b2p_nccl_unique_id(uid.ctypes.data_as(C.c_void_p)))
-        lst = [uid.tobytes()]
-        dist.broadcast_object_list(lst, src=0)
-        uid = np.frombuffer(lst[0], np.uint8).copy()
-        check(L.b2p_grid_comm_init(grid._h, rank, world, uid.ctypes.data_as(C.c_void_p), owner.ctypes.data_as(C.c_void_p)))
+        comm_init(L, dist, grid, rank, world, owner_map(conf, tpg, gb))
     n_cells_local = cells ** 3
 
     def barrier():
@@ -289,14 +310,14 @@ def run_emf(args):
         if dist is not None:
             dist.barrier()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         grid.step_emf()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = L.b2p_launch_count()
     check(L.b2p_timer_start())
-    for _ in range(args.steps):
+    for _ in range(steps):
         grid.step_emf()
     ms = C.c_float()
     check(L.b2p_timer_stop(C.byref(ms)))
@@ -322,7 +343,7 @@ def run_emf(args):
         tt = torch.tensor([dev_s], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_s = float(tt[0])
-    per_step = dev_s / args.steps
+    per_step = dev_s / steps
     peak, peak_src = read_peaks()
     bpu = {"push_b": 36.0, "push_e": 36.0, "filter": 24.0}    # 36 B/cell per sweep, 24 B/cell per filter pass
     per_kernel = {}
@@ -330,37 +351,47 @@ def run_emf(args):
         k = names.index(nm)
         if pl[k]:
             avg = pms[k] / int(pl[k])
-            per_kernel[nm] = {"avg_launch_ms": avg, "launches_per_lap": int(pl[k]) // prof_steps,
-                              "GBs": bpu.get(nm, 0.0) * n_cells_local / (avg * 1e-3) / 1e9 if nm in bpu else None}
+            per_lap = pms[k] / prof_steps
+            per_kernel[nm] = {"avg_launch_ms": avg, "launches_per_lap": int(pl[k]) / prof_steps, "ms_per_lap": per_lap}
+            if nm in bpu:
+                passes = {"push_b": 2, "push_e": 1, "filter": 3}[nm]
+                per_kernel[nm]["GBs"] = bpu[nm] * n_cells_local * passes / (per_lap * 1e-3) / 1e9
+                per_kernel[nm]["frac_of_peak"] = per_kernel[nm]["GBs"] / peak
     top = "push_b"
     achieved = per_kernel[top]["GBs"]
     step_bytes = 108.0 * n_cells_local                          # three sweeps per shipped lap
-    # e2e: one tile's E,B host round trip + the lap through the per-tile API
-    M = rb.comm_mode
-    h0, d0 = C.c_uint64(), C.c_uint64()
-    rb.sync()
-    L.b2p_copy_bytes(C.byref(h0), C.byref(d0))
-    t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
-    for s_ in range(e2e_steps):
-        t = tiles[s_ % len(tiles)]
-        Eh, Bh, _ = t.get_fields_f32(with_halo=True)
-        t.set_fields_f32(Eh, Bh, None, with_halo=True)
-        if world > 1:
-            grid.external_communication(M.emf_E)
-        grid.local_communication(M.emf_E)
-        for t in tiles: t.push_half_b()
-        for t in tiles: t.push_half_b()
-        if world > 1:
-            grid.external_communication(M.emf_B)
-        grid.local_communication(M.emf_B)
-        for t in tiles: t.push_e()
-    barrier()
-    dt = time.perf_counter() - t0
-    h1, d1 = C.c_uint64(), C.c_uint64()
-    L.b2p_copy_bytes(C.byref(h1), C.byref(d1))
+    e2e = None
+    if with_e2e:
+        # e2e: one tile's E,B host round trip + the lap through the per-tile API
+        M = rb.comm_mode
+        h0, d0 = C.c_uint64(), C.c_uint64()
+        rb.sync()
+        L.b2p_copy_bytes(C.byref(h0), C.byref(d0))
+        t0 = time.perf_counter()
+        e2e_steps = max(2, min(steps, 5))
+        for s_ in range(e2e_steps):
+            t = tiles[s_ % len(tiles)]
+            Eh, Bh, _ = t.get_fields_f32(with_halo=True)
+            t.set_fields_f32(Eh, Bh, None, with_halo=True)
+            if world > 1:
+                grid.external_communication(M.emf_E)
+            grid.local_communication(M.emf_E)
+            for t in tiles: t.push_half_b()
+            for t in tiles: t.push_half_b()
+            if world > 1:
+                grid.external_communication(M.emf_B)
+            grid.local_communication(M.emf_B)
+            for t in tiles: t.push_e()
+        barrier()
+        dt = time.perf_counter() - t0
+        h1, d1 = C.c_uint64(), C.c_uint64()
+        L.b2p_copy_bytes(C.byref(h1), C.byref(d1))
+        e2e = {"value": n_cells_local * world / (dt / e2e_steps), "unit": "cell-updates/s", "steps": e2e_steps,
+               "h2d_bytes_per_step": int((h1.value - h0.value) / e2e_steps),
+               "d2h_bytes_per_step": int((d1.value - d0.value) / e2e_steps),
+               "how": "per-tile API; one tile's E and B make a host round trip every step"}
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and with_cpu:
         from oracle.oracle import OracleGrid
         nthreads = os.cpu_count() or 1
         edge = 64
@@ -377,26 +408,43 @@ def run_emf(args):
         ncell = edge ** 3 * og.num_tiles
         cpu = {"value": ncell / cdt, "unit": "cell-updates/s", "cores": nthreads, "kind": "port",
                "sample": f"{oc.n_tiles} tiles of {edge}^3 cells, {nl} laps of emf.py:48-56, one tile per worker"}
+    out = {"metric": "cell-updates/s per vacuum field lap (BASELINE configs[2], field-solver roofline)",
+           "value": n_cells_local * world / per_step, "unit": "cell-updates/s", "n_gpus": world, "steps": steps,
+           "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "projects/emf-wave vacuum plane wave (BASELINE configs[2]): E halo, push_half_b x2, B halo, push_e",
+                      "cells_per_gpu": f"{cells}^3", "tile": f"{tile}^3", "gpu_blocks": "x".join(map(str, gb)),
+                      "l2": "E+B = 24 B/cell x cells far exceed the 126 MB L2; no explicit flush"},
+           "clocks": clocks, "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "kernel": "k_push_b_fdtd2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_unit": 36.0,
+                        "units_per_launch": n_cells_local, "per_kernel": per_kernel,
+                        "step": {"algorithmic_bytes_per_gpu": step_bytes, "achieved_GBs": step_bytes / per_step / 1e9,
+                                 "frac_of_peak": step_bytes / per_step / 1e9 / peak}}}
+    if e2e is not None:
+        out["e2e"] = e2e
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    del tiles, grid
+    return out
+
+
+def run_emf(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+    import runko_b200 as rb
+    from runko_b200._lib import check
+    L = rb.lib()
+    check(L.b2p_init(local_rank))
+    cells = args.cells if args.cells != 512 else 1024
+    tile = args.tile if args.tile != 64 else 128
+    out = measure_emf(rb, L, dist, rank, world, local_rank, cells, tile, args.steps, args.warmup, not args.no_cpu_baseline)
     if rank == 0:
-        out = {"metric": "cell-updates/s per vacuum field lap (BASELINE configs[2], field-solver roofline)",
-               "value": n_cells_local * world / per_step, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "projects/emf-wave vacuum plane wave (BASELINE configs[2]): E halo, push_half_b x2, B halo, push_e",
-                          "cells_per_gpu": f"{cells}^3", "tile": f"{tile}^3", "gpu_blocks": "x".join(map(str, gb)),
-                          "l2": "E+B = 24 B/cell x cells far exceed the 126 MB L2; no explicit flush"},
-               "clocks": clocks, "gpu_launches": int(launches),
-               "roofline": {"bound": "hbm", "kernel": "k_push_b_fdtd2", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_unit": 36.0,
-                            "units_per_launch": n_cells_local, "per_kernel": per_kernel,
-                            "step": {"algorithmic_bytes_per_gpu": step_bytes, "achieved_GBs": step_bytes / per_step / 1e9,
-                                     "frac_of_peak": step_bytes / per_step / 1e9 / peak}},
-               "e2e": {"value": n_cells_local * world / (dt / e2e_steps), "unit": "cell-updates/s", "steps": e2e_steps,
-                       "h2d_bytes_per_step": int((h1.value - h0.value) / e2e_steps),
-                       "d2h_bytes_per_step": int((d1.value - d0.value) / e2e_steps),
-                       "how": "per-tile API; one tile's E and B make a host round trip every step"}}
-        if cpu is not None:
-            out["cpu_baseline"] = cpu
         emit_result(out)
     if dist is not None:
         dist.barrier()
@@ -409,7 +457,78 @@ def workload_config(args, n_gpus):
             "cells_per_gpu": f"{args.cells}^3", "tile": f"{args.tile}^3", "species": 2, "ppc_per_species": args.ppc,
             "particles_per_gpu": 2 * args.ppc * args.cells ** 3, "gpu_blocks": "x".join(map(str, gb)),
             "lap": "pic-turbulence/pic.py:187-221, sort every 5th lap, fdtd2 + boris + linear_1st + zigzag_1st_atomic + 3x binomial2",
+            "fp": "fp32, IEEE div/sqrt, NO FMA contraction on either arm (nvcc -fmad=false; CPU arm -ffp-contract=off): the convention "
+                  "the bit-exact parity tests pin (the reference's own presets would let the compiler contract)",
             "l2": "per-step working set (32 B x particles >= 17 GB) far exceeds the 126 MB L2; no explicit flush"}
+
+
+def multi_gpu_equals_single(rb, L, dist, rank, world, gb):
+    """Parity evidence a multi-GPU run can carry: a small periodic grid (same physics, 2^3 tiles of 16^3 cells per rank,
+    2 x 4 ppc) is advanced (a) by every rank alone, all tiles local, and (b) by the N ranks together, each owning its
+    block, halos / currents / particles crossing NCCL.  After lap 0 (push, migration, sort, deposit, field update) every
+    owned container must hold bit-identical particles in identical slots and B must agree bit for bit; after 6 laps the
+    particle ids per (tile, species) still agree and the fields agree within the deposit tolerance (atomic order)."""
+    tpb, edge, ppc = 2, 16, 4
+    conf, _, _ = make_conf(argparse.Namespace(cells=tpb * edge, tile=edge, ppc=ppc), world)
+    T = conf.n_tiles
+    own = lambda i, j, k: (i // tpb) + gb[0] * ((j // tpb) + gb[1] * (k // tpb))      # noqa: E731
+    grids, tiles = [], []
+    for multi in (False, True):
+        g = rb.Grid(conf)
+        ts = {}
+        for i in range(T[0]):
+            for j in range(T[1]):
+                for k in range(T[2]):
+                    if not multi or own(i, j, k) == rank:
+                        t = rb.PicTile((i, j, k), conf)
+                        g.add_tile(t)
+                        ts[(i, j, k)] = t
+        if multi:
+            comm_init(L, dist, g, rank, world, owner_map(conf, tpb, gb))
+        g.set_uniform_B(0.0, 0.0, binit(conf, ppc))
+        g.inject_thermal(ppc, 0.3, seed=7)
+        for m in (rb.comm_mode.emf_E, rb.comm_mode.emf_B):
+            if multi:
+                g.external_communication(m)
+            g.local_communication(m)
+        grids.append(g)
+        tiles.append(ts)
+
+    def compare(exact):
+        ok_p, ok_b, ferr = True, True, 0.0
+        for idx, tm in tiles[1].items():
+            ts = tiles[0][idx]
+            for sp in range(2):
+                a, b = ts.get_particles(sp, alive_only=False), tm.get_particles(sp, alive_only=False)
+                if exact:
+                    alive = a[6] != np.uint64(0xFFFFFFFFFFFFFFFF)
+                    ok_p = ok_p and len(a[6]) == len(b[6]) and bool(np.array_equal(a[6], b[6])) and \
+                        all(np.array_equal(a[c][alive].view(np.uint32), b[c][alive].view(np.uint32)) for c in range(6))
+                else:
+                    ok_p = ok_p and bool(np.array_equal(np.sort(ts.get_ids(sp)), np.sort(tm.get_ids(sp))))
+            fa, fb = ts.get_fields_f32(with_halo=False), tm.get_fields_f32(with_halo=False)
+            ok_b = ok_b and bool(np.array_equal(fa[1].view(np.uint32), fb[1].view(np.uint32)))
+            for x, y in zip(fa, fb):
+                ferr = max(ferr, float(np.max(np.abs(x - y)) / max(float(np.max(np.abs(x))), 1e-30)))
+        return ok_p, ok_b, ferr
+
+    for g in grids:
+        g.step_pic(0)
+    p0, b0, _ = compare(True)
+    for lap in range(1, 6):
+        for g in grids:
+            g.step_pic(lap)
+    p5, _, f5 = compare(False)
+    import torch
+    flags = torch.tensor([int(p0), int(b0), int(p5)], dtype=torch.int64)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    err = torch.tensor([f5], dtype=torch.float64)
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    del tiles, grids
+    return {"grid": f"{T[0]}x{T[1]}x{T[2]} tiles of {edge}^3 cells, 2 x {ppc} ppc, {world} ranks vs 1 rank",
+            "lap0_particles_bit_exact": bool(flags[0]), "lap0_B_bit_exact": bool(flags[1]),
+            "lap5_ids_per_tile_equal": bool(flags[2]), "lap5_max_field_rel_err": float(err[0]),
+            "ok": bool(flags[0]) and bool(flags[1]) and bool(flags[2]) and float(err[0]) <= 1e-3}
 
 
 # --------------------------------------------------------------------------- CUDA arm
@@ -424,6 +543,7 @@ def main():
     ap.add_argument("--ppc", type=int, default=16, help="particles per cell per species")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-emf", action="store_true", help="skip the emf-wave sub-record of the default workload")
     ap.add_argument("--profile", action="store_true", help="per-kernel-class timing table on stderr")
     ap.add_argument("--workload", default="scaling", choices=["scaling", "emf-wave"],
                     help="scaling: BASELINE configs[4], the headline (default); emf-wave: configs[2], fields only, cell-updates/s")
@@ -462,19 +582,7 @@ def main():
                 grid.add_tile(t)
                 tiles.append(t)
     if world > 1:
-        T = conf.n_tiles
-        owner = np.zeros(T[0] * T[1] * T[2], np.int32)
-        for k in range(T[2]):
-            for j in range(T[1]):
-                for i in range(T[0]):
-                    owner[i + T[0] * (j + T[1] * k)] = (i // tpg) + gb[0] * ((j // tpg) + gb[1] * (k // tpg))
-        uid = np.zeros(128, np.uint8)
-        if rank == 0:
-            check(L.b2p_nccl_unique_id(uid.ctypes.data_as(C.c_void_p)))
-        lst = [uid.tobytes()]
-        dist.broadcast_object_list(lst, src=0)
-        uid = np.frombuffer(lst[0], np.uint8).copy()
-        check(L.b2p_grid_comm_init(grid._h, rank, world, uid.ctypes.data_as(C.c_void_p), owner.ctypes.data_as(C.c_void_p)))
+        comm_init(L, dist, grid, rank, world, owner_map(conf, tpg, gb))
     grid.set_uniform_B(0.0, 0.0, binit(conf, args.ppc))
     grid.inject_thermal(args.ppc, 0.3, seed=42)
     n_part_local = 2 * args.ppc * args.cells ** 3
@@ -522,8 +630,8 @@ def main():
     # that every kernel class runs alone on the library stream and a CUDA-event pair around each
     # launch measures that launch only (in the timed region above up to 4 tiles' kernels overlap)
     prof_steps = 5
-    for name in (b"push_streams", b"sort_streams"):
-        check(L.b2p_set_option(name, 1))
+    check(L.b2p_set_option(b"push_streams", 1))
+    check(L.b2p_set_option(b"sort_streams", 0))
     check(L.b2p_profile_enable(1))
     for _ in range(prof_steps):
         grid.step_pic(lap)
@@ -533,8 +641,8 @@ def main():
     pms, pl, pu = np.zeros(nk), np.zeros(nk, np.uint64), np.zeros(nk)
     check(L.b2p_profile_report(pms.ctypes.data_as(C.c_void_p), pl.ctypes.data_as(C.c_void_p), pu.ctypes.data_as(C.c_void_p)))
     check(L.b2p_profile_enable(0))
-    for name in (b"push_streams", b"sort_streams"):
-        check(L.b2p_set_option(name, 4))
+    check(L.b2p_set_option(b"push_streams", 2))      # the defaults of common.cuh: Tuning
+    check(L.b2p_set_option(b"sort_streams", 1))
     names = [L.b2p_profile_class_name(k).decode() for k in range(nk)]
     barrier()
 
@@ -557,19 +665,25 @@ def main():
     top = int(np.argmax(pms))
     share = {names[k]: round(float(pms[k] / max(pms.sum(), 1e-9)), 4) for k in np.argsort(-pms)[:8] if pms[k] > 0}
     avg_ms = pms[top] / max(int(pl[top]), 1)
-    units_per_launch = pu[top] / max(int(pl[top]), 1)
+    units_per_launch = pu[top] / max(int(pl[top]), 1)            # container slots (dead ones included)
+    if names[top] in ("push", "deposit"):
+        # credited per ALIVE particle: the containers carry dead slots (leavers, slack) that the kernel skips
+        units_per_launch = float(np.sum(grid.alive_counts())) * prof_steps / max(int(pl[top]), 1)
     achieved = bytes_per_unit.get(names[top], 0.0) * units_per_launch / (avg_ms * 1e-3) / 1e9
     step_bytes = (BYTES_PER_PARTICLE_STEP + BYTES_PER_PARTICLE_SORT) * n_part_local + BYTES_PER_CELL_STEP * n_cells_local
     kname = "push+deposit (fused k_push)" if (fused and names[top] == "push") else names[top]
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (not measured live)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_push_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_push_traffic.json")
     if names[top] == "push" and fused and os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
         traffic = tj["traffic_bytes_per_launch"] * units_per_launch / tj["alive_particles_per_launch"]
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_push_traffic.json)",
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture scaled to this launch's alive particles, profiles/r02_push_traffic.json)",
+                "dram_frac": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "units": "alive particles per launch",
                 "peak_source": peak_src,
                 "how": f"CUDA events around every launch of the class over {prof_steps} further laps (one sort cycle) run on the "
                        "library stream alone (worker streams off); `step` below is the timed region itself",
@@ -614,6 +728,18 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(args, rb, L, conf, grid, tiles, world, dist)
 
+    if world > 1:
+        checks["multi_gpu_equals_single"] = multi_gpu_equals_single(rb, L, dist, rank, world, gb)
+
+    # ---- field-solver sub-record (BASELINE configs[2]) on the same box, after the PIC state is freed
+    emf = None
+    if not args.no_emf:
+        del t0_, tiles, grid
+        rb.sync()
+        emf_cells = min(args.cells, 512)
+        emf = measure_emf(rb, L, dist, rank, world, local_rank, emf_cells, min(128, emf_cells), 10, 3, with_cpu=False, with_e2e=False)
+        emf = {k: emf[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "gpu_launches", "roofline")}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_threads = os.cpu_count() or 1
@@ -638,6 +764,8 @@ def main():
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "checks": checks}
         if e2e is not None:
             out["e2e"] = e2e
+        if emf is not None:
+            out["emf_wave"] = emf
         if cpu is not None:
             out["cpu_baseline"] = cpu
         emit_result(out)
