@@ -25,6 +25,9 @@ namespace b2p {
 // emf/yee_lattice_fdtd2.c++:43-57 — the reference's three per-component sweeps
 // fused into one pass (each B component depends on E only, so fusing does not
 // change any operand): 36 B/cell algorithmic.
+// TWICE: two consecutive half pushes from the same E (projects/emf-wave/emf.py:50-51) in one pass — B1 = B + dt*curl E,
+// B2 = B1 + dt*curl E, the same two roundings as two calls, for one read of E and one read + write of B.
+template <bool TWICE>
 __global__ void __launch_bounds__(256)
 k_push_b_fdtd2(const FieldPtrs* __restrict__ tiles, const Geom g, const float dt) {
   INTERIOR_CELL_OR_RETURN();
@@ -38,9 +41,10 @@ k_push_b_fdtd2(const FieldPtrs* __restrict__ tiles, const Geom g, const float dt
   const float DkEx = Ex[n + 1] - ex;
   const float DjEx = Ex[n + sj] - ex;
   const float DiEy = Ey[n + si] - ey;
-  f.B[n] = f.B[n] + dt * (DkEy - DjEz);
-  f.B[Ch + n] = f.B[Ch + n] + dt * (DiEz - DkEx);
-  f.B[2 * Ch + n] = f.B[2 * Ch + n] + dt * (DjEx - DiEy);
+  const float cx = dt * (DkEy - DjEz), cy = dt * (DiEz - DkEx), cz = dt * (DjEx - DiEy);
+  float bx = f.B[n] + cx, by = f.B[Ch + n] + cy, bz = f.B[2 * Ch + n] + cz;
+  if (TWICE) { bx = bx + cx; by = by + cy; bz = bz + cz; }
+  f.B[n] = bx; f.B[Ch + n] = by; f.B[2 * Ch + n] = bz;
 }
 
 // emf/yee_lattice_fdtd2.c++:96-110, optionally followed by add_current
@@ -485,11 +489,12 @@ static void check_tiles(int ntiles) {
   if (ntiles > MAX_TILES_PER_LAUNCH) throw Error(B2P_ERR_RUNTIME, "more than 65535 local tiles per GPU are not supported");
 }
 
-void launch_push_b_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt) {
-  ProfScope prof_(KC_PUSH_B, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
+void launch_push_b_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, bool twice) {
+  ProfScope prof_(KC_PUSH_B, double(ntiles) * g.N[0] * g.N[1] * g.N[2] * (twice ? 2.0 : 1.0));
   if (!ntiles) return;
   check_tiles(ntiles);
-  k_push_b_fdtd2<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
+  if (twice) k_push_b_fdtd2<true><<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
+  else k_push_b_fdtd2<false><<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt);
   B2P_LAUNCH_CHECK();
 }
 void launch_push_b_stencil(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, const float M[3][3][5]) {

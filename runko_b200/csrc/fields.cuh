@@ -3,7 +3,7 @@
 #include "common.cuh"
 
 namespace b2p {
-void launch_push_b_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt);
+void launch_push_b_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, bool twice = false);   // twice: two half pushes from the same E in one pass
 void launch_push_b_stencil(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, const float M[3][3][5]);
 void launch_push_e_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, bool add_current);
 void launch_add_current(const FieldPtrs* tiles, int ntiles, const Geom& g);

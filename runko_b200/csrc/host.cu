@@ -149,8 +149,8 @@ struct Scratch {
   DBuf<unsigned char> cub_temp_w[MAX_WORKERS];
   DBuf<unsigned> (&keys)[2] = keys_w[0];
   DBuf<unsigned char>& cub_temp = cub_temp_w[0];
-  DBuf<unsigned long long> list[2];
-  DBuf<unsigned> counters;        // [0]=list count, then per-container last_alive, then counts[ncont][27]
+  DBuf<unsigned> counters;        // pack: P per container | leaver total per tile | seg[27][nseg] per container
+  DBuf<unsigned long long> pack_ends;   // pack: subregion ends per container [27]
   DBuf<unsigned char> table;      // device staging for job / out-tile tables
   DBuf<double> energy;
   DBuf<float> antenna[2];         // vec_pot_buff_ / generated_B_buff_ of the tile depositing its antenna current
@@ -365,13 +365,16 @@ static b2p_tile* create_tile(const b2p_config& cfg, const int32_t idx[3]) {
 static float half_dt(const b2p_config& c) { return static_cast<float>(c.cfl / 2); }    // emf/tile.c++:365
 static float full_dt(const b2p_config& c) { return static_cast<float>(c.cfl); }        // emf/tile.c++:384
 
-void phase_push_half_b(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table) {
+void phase_push_half_b(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table, int times) {
   if (tiles.empty()) return;
   b2p_tile* t0 = tiles[0];
-  if (t0->cfg.field_propagator == B2P_PROPAGATOR_STENCIL)
-    launch_push_b_stencil(table, int(tiles.size()), t0->g, half_dt(t0->cfg), t0->stencilM);
-  else
-    launch_push_b_fdtd2(table, int(tiles.size()), t0->g, half_dt(t0->cfg));
+  if (t0->cfg.field_propagator == B2P_PROPAGATOR_STENCIL) {
+    for (int q = 0; q < times; ++q) launch_push_b_stencil(table, int(tiles.size()), t0->g, half_dt(t0->cfg), t0->stencilM);
+  } else {
+    // two back-to-back half pushes (emf.py:50-51) read the same E: one pass, same roundings
+    for (int q = 0; q + 1 < times; q += 2) launch_push_b_fdtd2(table, int(tiles.size()), t0->g, half_dt(t0->cfg), true);
+    if (times & 1) launch_push_b_fdtd2(table, int(tiles.size()), t0->g, half_dt(t0->cfg), false);
+  }
 }
 void phase_push_e(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table, bool add_current) {
   if (tiles.empty()) return;
@@ -771,87 +774,85 @@ void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
   for (b2p_tile* t : tiles) { t->out_ends.assign(27 * t->sp.size(), 0); t->out_count = 0; }
   std::vector<Container*> conts;
-  std::vector<CollectJobHost> jobs;
-  size_t total_slots = 0;
-  unsigned max_words = 0;
+  std::vector<PackJob> jobs;
+  std::vector<PackTile> ptiles;
+  std::vector<b2p_tile*> owners;            // tiles that hold at least one container, in ptiles order
+  size_t total_slots = 0, seg_total = 0;
+  unsigned max_nseg = 0;
   for (b2p_tile* t : tiles) {
     const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
     const float mx[3] = { float(t->maxs[0]), float(t->maxs[1]), float(t->maxs[2]) };
+    if (t->sp.empty()) continue;
+    ptiles.push_back(PackTile{ unsigned(jobs.size()), unsigned(t->sp.size()), nullptr });
+    owners.push_back(t);
     for (Container& c : t->sp) {
       uint2* words = c.mask_words();
       if (!c.masks_valid) {                                            // not pushed since the last change
         launch_make_masks(c.view(), words, mn, mx);
         t->pendJ_valid = false;
       }
-      const unsigned nwords = unsigned((size_t(c.n) + 31) / 32);
-      jobs.push_back(CollectJobHost{ words, nwords, c.view(), make_float3(mn[0], mn[1], mn[2]), make_float3(mx[0], mx[1], mx[2]) });
+      PackJob jb{};
+      jb.masks = words;
+      jb.nwords = unsigned((size_t(c.n) + 31) / 32);
+      jb.nseg = pack_segments(c.n);
+      jb.s = c.view();
+      jb.mn = make_float3(mn[0], mn[1], mn[2]); jb.mx = make_float3(mx[0], mx[1], mx[2]);
+      jobs.push_back(jb);
       conts.push_back(&c);
       total_slots += c.n;
-      max_words = std::max(max_words, nwords);
+      seg_total += size_t(27) * jb.nseg;
+      max_nseg = std::max(max_nseg, jb.nseg);
     }
   }
-  const size_t nc = conts.size();
+  const size_t nc = conts.size(), nt = ptiles.size();
   if (nc == 0) return;
-  if (nc >= (size_t(1) << 26)) throw Error(B2P_ERR_RUNTIME, "too many containers in one pack call");
-  // device counters: [0] list length | [1..nc] P per container | [1+nc..1+2nc) leavers per container | counts[nc][27]
-  const size_t ncounters = 1 + 2 * nc + nc * 27;
-  s.counters.reserve(ncounters);
-  s.table.reserve(nc * sizeof(CollectJobHost));
-  h2d(reinterpret_cast<CollectJobHost*>(s.table.p), jobs.data(), nc);
-  std::vector<unsigned> hc(1 + 2 * nc);
-  size_t cap = std::max<size_t>(total_slots / 24 + 65536, s.list[0].cap);
-  for (;;) {
-    s.list[0].reserve(cap); s.list[1].reserve(cap);
-    B2P_CUDA(cudaMemsetAsync(s.counters.p, 0, ncounters * sizeof(unsigned), ctx().stream));
-    launch_collect_leavers(s.table.p, unsigned(nc), max_words, s.list[0].p, s.counters.p,
-                           unsigned(std::min<size_t>(s.list[0].cap, 0xFFFFFFFFu)), s.counters.p + 1, s.counters.p + 1 + nc);
-    d2h(hc.data(), s.counters.p, 1 + 2 * nc);
-    stream_sync();
-    if (hc[0] <= s.list[0].cap) break;
-    cap = hc[0];   // overflow: nothing was modified yet, collect again into a larger list
+  // device scratch: per container P and seg[27][nseg]; per tile the leaver total; per container ends[27] (u64)
+  s.counters.reserve(nc + nt + seg_total);
+  s.pack_ends.reserve(nc * 27);
+  unsigned* d_P = s.counters.p;
+  unsigned* d_tot = s.counters.p + nc;
+  unsigned* d_seg = s.counters.p + nc + nt;
+  size_t so = 0;
+  for (size_t c = 0; c < nc; ++c) {
+    jobs[c].last_alive = d_P + c;
+    jobs[c].seg = d_seg + so;
+    jobs[c].ends = s.pack_ends.p + 27 * c;
+    so += size_t(27) * jobs[c].nseg;
   }
-  const unsigned total = hc[0];
-  for (size_t c = 0; c < nc; ++c) { conts[c]->P = hc[1 + c]; conts[c]->P_valid = true; }
-  if (total == 0) { for (b2p_tile* t : tiles) t->pend_packed = t->pendJ_valid; return; }
-  // restore the reference's (species, subregion, container order) order
-  int cbits = 1;
-  while ((size_t(1) << cbits) < nc) ++cbits;
-  const int end_bit = 37 + cbits;
-  const size_t tb = sort_keys64_temp_bytes(total, end_bit);
-  s.cub_temp.reserve(tb);
-  unsigned long long* k[2] = { s.list[0].p, s.list[1].p };
-  const int sel = sort_keys64(s.cub_temp.p, tb, k, total, end_bit);
-  const unsigned* cont_count = hc.data() + 1 + nc;
-  std::vector<OutTileHost> ot(nc);
-  unsigned long long run = 0;
-  size_t c = 0;
-  for (b2p_tile* t : tiles) {
-    unsigned long long tile_total = 0;
-    for (size_t q = 0; q < t->sp.size(); ++q) tile_total += cont_count[c + q];
-    t->out_buf.reserve(std::max<size_t>(tile_total, 1));
-    t->out_count = tile_total;
-    for (size_t q = 0; q < t->sp.size(); ++q) ot[c + q] = OutTileHost{ t->out_buf.p, run, conts[c + q]->view() };
-    run += tile_total;
-    c += t->sp.size();
-  }
-  s.table.reserve(nc * sizeof(OutTileHost));
-  h2d(reinterpret_cast<OutTileHost*>(s.table.p), ot.data(), nc);
-  unsigned* counts = s.counters.p + 1 + 2 * nc;
-  launch_gather_outgoing(k[sel], total, s.table.p, counts);
-  for (Container* ct : conts) ct->masks_valid = false;              // leavers are dead now
-  for (b2p_tile* t : tiles) t->pend_packed = t->pendJ_valid;
-  std::vector<unsigned> hcounts(nc * 27);
-  d2h(hcounts.data(), counts, nc * 27);
+  for (size_t q = 0; q < nt; ++q) ptiles[q].total = d_tot + q;
+  s.table.reserve(nc * sizeof(PackJob) + nt * sizeof(PackTile) + 64);
+  PackJob* d_jobs = reinterpret_cast<PackJob*>(s.table.p);
+  PackTile* d_tiles = reinterpret_cast<PackTile*>(s.table.p + ((nc * sizeof(PackJob) + 15) & ~size_t(15)));
+  h2d(d_jobs, jobs.data(), nc);
+  h2d(d_tiles, ptiles.data(), nt);
+  B2P_CUDA(cudaMemsetAsync(d_P, 0, nc * sizeof(unsigned), ctx().stream));
+  if (max_nseg) launch_pack_count_scan(d_jobs, unsigned(nc), max_nseg, d_tiles, unsigned(nt), double(total_slots));
+  // the one host round trip of the pack: P per container, leaver totals per tile, subregion ends
+  std::vector<unsigned> hc(nc + nt, 0);
+  std::vector<unsigned long long> hends(nc * 27, 0);
+  d2h(hc.data(), s.counters.p, nc + nt);
+  if (max_nseg) d2h(hends.data(), s.pack_ends.p, nc * 27);
   stream_sync();
-  c = 0;
-  for (b2p_tile* t : tiles) {
-    unsigned long long next = 0;                                   // pic/particle.c++:327-343
-    for (size_t q = 0; q < t->sp.size(); ++q, ++c)
-      for (int r = 0; r < 27; ++r) {
-        if (r != 13) next += hcounts[c * 27 + r];
-        t->out_ends[27 * q + r] = next;
-      }
+  unsigned long long total = 0;
+  for (size_t c = 0; c < nc; ++c) { conts[c]->P = hc[c]; conts[c]->P_valid = true; }
+  size_t c = 0;
+  for (size_t q = 0; q < nt; ++q) {
+    b2p_tile* t = owners[q];
+    const unsigned tile_total = max_nseg ? hc[nc + q] : 0u;
+    t->out_count = tile_total;
+    total += tile_total;
+    t->out_buf.reserve(std::max<size_t>(tile_total, 1));
+    for (size_t sp = 0; sp < t->sp.size(); ++sp, ++c) {
+      jobs[c].out = t->out_buf.p;
+      for (int r = 0; r < 27; ++r) t->out_ends[27 * sp + r] = hends[27 * c + r];   // pic/particle.c++:327-343
+    }
   }
+  if (total) {
+    h2d(d_jobs, jobs.data(), nc);                                    // now with the tiles' buffers
+    launch_pack_write(d_jobs, unsigned(nc), max_nseg, double(total));
+    for (Container* ct : conts) ct->masks_valid = false;              // leavers are dead now
+  }
+  for (b2p_tile* t : tiles) t->pend_packed = t->pendJ_valid;
 }
 
 // ---------------------------------------------------------- communication --
@@ -1582,8 +1583,7 @@ int b2p_grid_step_emf(b2p_grid* g) {
     if (multi) { const int rc = b2p_grid_external_communication(g, mode); if (rc) throw Error(rc, g_last_error); }
   };
   ext(B2P_COMM_EMF_E); grid_local_communication(g, B2P_COMM_EMF_E);
-  phase_push_half_b(g->tiles, g->device_table());
-  phase_push_half_b(g->tiles, g->device_table());
+  phase_push_half_b(g->tiles, g->device_table(), 2);
   ext(B2P_COMM_EMF_B); grid_local_communication(g, B2P_COMM_EMF_B);
   phase_push_e(g->tiles, g->device_table(), false);
   B2P_CATCH

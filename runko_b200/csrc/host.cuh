@@ -91,7 +91,7 @@ struct b2p_grid {
 
 namespace b2p {
 // phase implementations shared by the per-tile and the batched grid entry points
-void phase_push_half_b(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table);
+void phase_push_half_b(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table, int times = 1);
 void phase_push_e(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table, bool add_current);
 void phase_add_current(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table);
 void phase_filter(const std::vector<b2p_tile*>& tiles);

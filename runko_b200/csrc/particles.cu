@@ -135,93 +135,6 @@ k_make_masks(const Species s, uint2* __restrict__ masks, const float3 mn, const 
   publish_masks(alive, inside_box(x, y, z, mn, mx), n, masks);
 }
 
-struct CollectJob {           // one container
-  const uint2* masks;
-  unsigned nwords;
-  Species s;
-  float3 mn, mx;
-};
-
-// Mask words of all containers -> key list (container << 37) | (subregion << 32) | slot,
-// per-container leaver counts and P = 1 + the largest slot that stays alive
-// (ParticleContainer::append, pic/particle.h:469-488).  One thread per mask word, one
-// list-position atomic per block.  blockIdx.y = container.
-__global__ void __launch_bounds__(256)
-k_collect_leavers(const CollectJob* __restrict__ jobs, const unsigned first_container, unsigned long long* __restrict__ list,
-                  unsigned* __restrict__ list_count, const unsigned list_cap, unsigned* __restrict__ last_alive,
-                  unsigned* __restrict__ cont_count) {
-  const unsigned c = first_container + blockIdx.y;
-  const CollectJob jb = jobs[c];
-  __shared__ unsigned sh_cnt[8], sh_base, sh_last;
-  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (unsigned w0 = blockIdx.x * blockDim.x; w0 < jb.nwords; w0 += gridDim.x * blockDim.x) {
-    const unsigned w = w0 + threadIdx.x;
-    uint2 m = make_uint2(0u, 0u);
-    if (w < jb.nwords) m = jb.masks[w];
-    const unsigned cnt = __popc(m.x);
-    // exclusive scan of cnt over the block
-    unsigned incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= unsigned(o)) incl += t; }
-    unsigned last = m.y ? w * 32u + (32u - __clz(m.y)) : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-    if (threadIdx.x == 0) sh_last = 0;
-    if (lane == 31) sh_cnt[wid] = incl;
-    __syncthreads();
-    if (lane == 0 && last) atomicMax(&sh_last, last);
-    if (threadIdx.x == 0) {
-      unsigned total = 0;
-      for (int q = 0; q < 8; ++q) { const unsigned v = sh_cnt[q]; sh_cnt[q] = total; total += v; }
-      unsigned base = 0;
-      if (total) { base = atomicAdd(list_count, total); atomicAdd(&cont_count[c], total); }
-      sh_base = base;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && sh_last) atomicMax(&last_alive[c], sh_last);
-    unsigned pos = sh_base + sh_cnt[wid] + incl - cnt;
-    unsigned bits = m.x;
-    while (bits) {
-      const unsigned b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const unsigned n = w * 32u + b;
-      const int sub = subregion_of(jb.s.x[n], jb.s.y[n], jb.s.z[n], jb.mn, jb.mx);
-      if (pos < list_cap)
-        list[pos] = (static_cast<unsigned long long>(c) << 37) | (static_cast<unsigned long long>(sub) << 32) | n;
-      ++pos;
-    }
-    __syncthreads();
-  }
-}
-
-struct OutTile {              // per container: where its leavers go
-  b2p_particle_state* buf;    // tile's outgoing AoS buffer
-  unsigned long long base;    // index of this tile's first entry in the sorted list
-  Species s;
-};
-
-// Sorted leaver list -> AoS ParticleState (pic/particle.c++:268-291) + mark the
-// source slots dead (:304-312) + per-(container, subregion) counts (:336-346).
-__global__ void __launch_bounds__(256)
-k_gather_outgoing(const unsigned long long* __restrict__ sorted, const unsigned total, const OutTile* __restrict__ cont,
-                  unsigned* __restrict__ counts /*[ncont][27]*/) {
-  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= total) return;
-  const unsigned long long key = sorted[q];
-  const unsigned c = unsigned(key >> 37), sub = unsigned(key >> 32) & 31u, n = unsigned(key);
-  const OutTile t = cont[c];
-  b2p_particle_state st;
-  st.pos[0] = t.s.x[n]; st.pos[1] = t.s.y[n]; st.pos[2] = t.s.z[n];
-  st.vel[0] = t.s.ux[n]; st.vel[1] = t.s.uy[n]; st.vel[2] = t.s.uz[n];
-  st.id = t.s.id[n];
-  t.buf[q - t.base] = st;
-  t.s.id[n] = DEAD;
-  // the list is sorted by (container, subregion): one count atomic per run inside the warp
-  const unsigned grp = unsigned(key >> 32);
-  const unsigned peers = __match_any_sync(__activemask(), grp);
-  if ((threadIdx.x & 31) == unsigned(__ffs(peers) - 1)) atomicAdd(&counts[c * 27 + sub], unsigned(__popc(peers)));
-}
-
 // Full-pass fallback for P = 1 + last alive slot (pic/particle.h:469-488), used
 // when no detection pass has produced it (inject outside the lap).
 __global__ void __launch_bounds__(256)
@@ -525,26 +438,6 @@ void launch_make_masks(const Species& s, uint2* masks, const float mins[3], cons
   if (!s.n) return;
   k_make_masks<<<blocks_for(s.n), 256, 0, ctx().stream>>>(s, masks, make_float3(mins[0], mins[1], mins[2]),
                                                          make_float3(maxs[0], maxs[1], maxs[2]));
-  B2P_LAUNCH_CHECK();
-}
-
-void launch_collect_leavers(const void* jobs, unsigned ncont, unsigned max_words, unsigned long long* list, unsigned* list_count,
-                            unsigned list_cap, unsigned* last_alive, unsigned* cont_count) {
-  ProfScope prof_(KC_DETECT, double(max_words) * 32.0 * ncont);
-  if (!ncont || !max_words) return;
-  const unsigned bx = std::min(blocks_for(max_words), 2048u);
-  for (unsigned c0 = 0; c0 < ncont; c0 += 65535u) {
-    const unsigned nc = std::min(65535u, ncont - c0);
-    k_collect_leavers<<<dim3(bx, nc), 256, 0, ctx().stream>>>(static_cast<const CollectJob*>(jobs), c0, list, list_count, list_cap,
-                                                              last_alive, cont_count);
-    B2P_LAUNCH_CHECK();
-  }
-}
-
-void launch_gather_outgoing(const unsigned long long* sorted, unsigned total, const void* out_tiles, unsigned* counts) {
-  ProfScope prof_(KC_GATHER_OUT, double(total));
-  if (!total) return;
-  k_gather_outgoing<<<blocks_for(total), 256, 0, ctx().stream>>>(sorted, total, static_cast<const OutTile*>(out_tiles), counts);
   B2P_LAUNCH_CHECK();
 }
 

@@ -4,11 +4,6 @@
 
 namespace b2p {
 
-struct OutTileHost {          // mirrors particles.cu::OutTile
-  b2p_particle_state* buf;
-  unsigned long long base;
-  Species s;
-};
 struct AppendJobHost {        // mirrors particles.cu::AppendJob
   const b2p_particle_state* src;
   unsigned count;
@@ -19,12 +14,6 @@ struct AppendJobHost {        // mirrors particles.cu::AppendJob
   float charge;
 };
 
-struct CollectJobHost {       // mirrors particles.cu::CollectJob: leaver masks of one container
-  const uint2* masks;
-  unsigned nwords;
-  Species s;
-  float3 mn, mx;              // tile box (float(mins/maxs), pic/tile_communication.c++:71-79)
-};
 
 // groups of tiles of one geometry handled by one launch of the small per-tile kernels of the
 // particle phase (tables passed by value as kernel arguments)
@@ -58,8 +47,6 @@ void launch_edge_gather(const float4* Jc, float* J, const Geom& g);
 void launch_sort_keys(const Species& s, const Geom& g, const float origo[3], unsigned* keys, unsigned* idx, unsigned dead_key);
 size_t sort_pairs_temp_bytes(unsigned n, int end_bit);
 int sort_pairs(void* temp, size_t temp_bytes, unsigned* keys[2], unsigned* vals[2], unsigned n, int end_bit);
-size_t sort_keys64_temp_bytes(unsigned n, int end_bit);
-int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit);
 void launch_gather(const Species& src, const Species& dst, const unsigned* perm);
 // batched counting sort by cell key (sort.cu): one container of a batch
 struct SortJob {
@@ -77,10 +64,22 @@ constexpr unsigned SORT_RADIX_POP = 4096;    // containers whose last known larg
 unsigned sort_scan_chunks(unsigned nkeys);
 void launch_sort_count_scan(const SortJob* jobs, int njobs, unsigned max_n, double total_slots, const Geom& g, unsigned nkeys);
 void launch_sort_scatter_place(const SortJob* jobs, int njobs, unsigned max_n, double total_slots, unsigned nkeys);
+// batched, ordered pack_outgoing_particles (migrate.cu)
+struct PackJob {              // one container
+  const uint2* masks;         // leaver / stayer ballots per 32 slots
+  unsigned nwords, nseg;      // mask words; segments of the container (pack_segments)
+  Species s;
+  float3 mn, mx;              // tile box (float(mins/maxs), pic/tile_communication.c++:71-79)
+  unsigned* seg;              // [27][nseg]: leavers per (subregion, segment), then their bases in the tile's buffer
+  unsigned* last_alive;       // P = 1 + last slot that stays alive (zeroed by the caller)
+  unsigned long long* ends;   // [27] subregion_particle_ends_ of this species (absolute offsets in the tile's buffer)
+  b2p_particle_state* out;    // the tile's outgoing buffer (filled in for the write pass)
+};
+struct PackTile { unsigned first, count; unsigned* total; };   // a tile's containers in the job table; its leaver total
+unsigned pack_segments(unsigned n_slots);
+void launch_pack_count_scan(const PackJob* jobs, unsigned ncont, unsigned max_nseg, const PackTile* tiles, unsigned ntiles, double total_slots);
+void launch_pack_write(const PackJob* jobs, unsigned ncont, unsigned max_nseg, double total_leavers);
 void launch_make_masks(const Species& s, uint2* masks, const float mins[3], const float maxs[3]);
-void launch_collect_leavers(const void* jobs, unsigned ncont, unsigned max_words, unsigned long long* list, unsigned* list_count,
-                            unsigned list_cap, unsigned* last_alive, unsigned* cont_count);
-void launch_gather_outgoing(const unsigned long long* sorted, unsigned total, const void* out_tiles, unsigned* counts);
 void launch_last_alive(const unsigned long long* id, unsigned n, unsigned* last_alive);
 void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, const float wmin[3], const float wmax[3],
                    const Geom& g, float cfl);

@@ -307,20 +307,6 @@ int sort_pairs(void* temp, size_t temp_bytes, unsigned* keys[2], unsigned* vals[
   count_launch((end_bit + 7) / 8 + 2);
   return v.selector;
 }
-size_t sort_keys64_temp_bytes(unsigned n, int end_bit) {
-  size_t bytes = 0;
-  cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
-  cub::DeviceRadixSort::SortKeys(nullptr, bytes, k, int(n), 0, end_bit, ctx().stream);
-  return bytes;
-}
-int sort_keys64(void* temp, size_t temp_bytes, unsigned long long* keys[2], unsigned n, int end_bit) {
-  ProfScope prof_(KC_RADIX_SORT, double(n));
-  cub::DoubleBuffer<unsigned long long> k(keys[0], keys[1]);
-  B2P_CUDA(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, k, int(n), 0, end_bit, ctx().stream));
-  count_launch((end_bit + 7) / 8 + 2);
-  return k.selector;
-}
-
 void launch_gather(const Species& src, const Species& dst, const unsigned* perm) {
   ProfScope prof_(KC_GATHER, double(src.n));
   if (!src.n) return;
