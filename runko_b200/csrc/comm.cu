@@ -118,14 +118,25 @@ struct CommPlan {
   std::map<std::pair<int, int>, int> entry_of;  // (tile slot, dir index) -> entry
   std::vector<PeerBuffers> peers;
   DBuf<float> sendbuf, recvbuf;
-  DBuf<SlabDesc> d_pack, d_remote_fill, d_remote_exch;
+  DBuf<SlabDesc> d_remote_fill, d_remote_exch;
+  // Pack tables are persistent: one per (mode, which of a tile's two J buffers is current), rebuilt only when the
+  // lattice pointers behind it change (the exchanges of a lap reuse four tables that are uploaded once).
+  struct PackTable { std::vector<const float*> sig; DBuf<SlabDesc> d; size_t n = 0; };
+  PackTable pack[4];
   std::vector<size_t> recv_slab_off[2];         // per entry, per kind: float offset in recvbuf
   // particles
   DBuf<b2p_particle_state> psend, precv;
   DBuf<unsigned> d_cnt_send, d_cnt_recv;
   std::vector<std::vector<std::pair<size_t, unsigned>>> pspan;   // [entry][species] -> (offset in precv, count)
   bool pspan_valid = false;
-  ~CommPlan() { if (comm) nccl().CommDestroy(comm); }
+  cudaStream_t cstream = nullptr;               // the plan's own stream for exchanges that overlap compute
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+  ~CommPlan() {
+    if (comm) nccl().CommDestroy(comm);
+    if (cstream) cudaStreamDestroy(cstream);
+    if (ev_ready) cudaEventDestroy(ev_ready);
+    if (ev_done) cudaEventDestroy(ev_done);
+  }
 };
 
 // ----------------------------------------------------------------- kernels --
@@ -232,33 +243,47 @@ static void finalize_plan(b2p_grid* g) {
 static void exchange_fields(b2p_grid* g, int mode) {
   CommPlan& p = *g->comm;
   const int nk = mode == B2P_COMM_EMF_J ? 2 : 1;
-  std::vector<SlabDesc> pack;
-  for (const PeerBuffers& pb : p.peers) {
-    size_t o = pb.send_off;
-    for (int kind = 0; kind < nk; ++kind)
-      for (int i : pb.send_order) {
-        const PlanEntry& e = p.entries[i];
-        b2p_tile* t = g->tiles[g->slot_of_cid[e.cid]];
-        SlabDesc s;
-        s.base = p.sendbuf.p + o;
-        s.field = mode == B2P_COMM_EMF_E ? t->E.p : (mode == B2P_COMM_EMF_B ? t->B.p : t->J());
-        send_region_begin(e, g->cfg, kind, s.begin);
-        for (int d = 0; d < 3; ++d) s.dims[d] = e.dims[d];
-        pack.push_back(s);
-        o += 3 * e.volume();
-      }
-  }
-  if (!pack.empty()) {
-    p.d_pack.reserve(pack.size());
-    B2P_CUDA(cudaMemcpyAsync(p.d_pack.p, pack.data(), pack.size() * sizeof(SlabDesc), cudaMemcpyHostToDevice, ctx().stream));
-    for (size_t b = 0; b < pack.size(); b += 65535) {
-      ProfScope prof_(KC_HALO, 0.0);
-      const unsigned nb = unsigned(std::min<size_t>(65535, pack.size() - b));
-      k_pack_slabs<<<dim3(8, nb), 256, 0, ctx().stream>>>(p.d_pack.p + b, g->g);
-      B2P_LAUNCH_CHECK();
+  // which persistent table: E, B, J with the first local tile's jcur (all tiles of a grid flip together)
+  const int which = mode == B2P_COMM_EMF_E ? 0 : (mode == B2P_COMM_EMF_B ? 1 : 2 + (g->tiles.empty() ? 0 : g->tiles[0]->jcur));
+  CommPlan::PackTable& pt = p.pack[which];
+  std::vector<const float*> sig;
+  for (const PeerBuffers& pb : p.peers)
+    for (int i : pb.send_order) {
+      b2p_tile* t = g->tiles[g->slot_of_cid[p.entries[i].cid]];
+      sig.push_back(mode == B2P_COMM_EMF_E ? t->E.p : (mode == B2P_COMM_EMF_B ? t->B.p : t->J()));
+    }
+  if (sig != pt.sig || pt.n == 0) {
+    std::vector<SlabDesc> pack;
+    for (const PeerBuffers& pb : p.peers) {
+      size_t o = pb.send_off;
+      for (int kind = 0; kind < nk; ++kind)
+        for (int i : pb.send_order) {
+          const PlanEntry& e = p.entries[i];
+          b2p_tile* t = g->tiles[g->slot_of_cid[e.cid]];
+          SlabDesc s;
+          s.base = p.sendbuf.p + o;
+          s.field = mode == B2P_COMM_EMF_E ? t->E.p : (mode == B2P_COMM_EMF_B ? t->B.p : t->J());
+          send_region_begin(e, g->cfg, kind, s.begin);
+          for (int d = 0; d < 3; ++d) s.dims[d] = e.dims[d];
+          pack.push_back(s);
+          o += 3 * e.volume();
+        }
+    }
+    pt.n = pack.size();
+    pt.sig.swap(sig);
+    if (pt.n) {
+      pt.d.reserve(pt.n);
+      B2P_CUDA(cudaMemcpyAsync(pt.d.p, pack.data(), pt.n * sizeof(SlabDesc), cudaMemcpyHostToDevice, ctx().stream));
     }
   }
+  for (size_t b = 0; b < pt.n; b += 65535) {
+    ProfScope prof_(KC_HALO, 0.0);
+    const unsigned nb = unsigned(std::min<size_t>(65535, pt.n - b));
+    k_pack_slabs<<<dim3(8, nb), 256, 0, ctx().stream>>>(pt.d.p + b, g->g);
+    B2P_LAUNCH_CHECK();
+  }
   Nccl& n = nccl();
+  ProfScope prof_nccl_(KC_NCCL, 0.0);     // send/recv kernels + the wait for the slowest peer
   B2P_NCCL(n.GroupStart());
   for (const PeerBuffers& pb : p.peers) {
     size_t ns = 0, nr = 0;
@@ -295,6 +320,7 @@ static void exchange_particles(b2p_grid* g) {
     }
   p.d_cnt_send.reserve(cs.size()); p.d_cnt_recv.reserve(cr.size());
   B2P_CUDA(cudaMemcpyAsync(p.d_cnt_send.p, cs.data(), cs.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx().stream));
+  ProfScope* prof_hs_ = new ProfScope(KC_NCCL, 0.0);
   B2P_NCCL(n.GroupStart());
   size_t so = 0, ro = 0;
   for (const PeerBuffers& pb : p.peers) {
@@ -303,6 +329,7 @@ static void exchange_particles(b2p_grid* g) {
     so += pb.send_order.size() * ns; ro += pb.recv_order.size() * ns;
   }
   B2P_NCCL(n.GroupEnd());
+  delete prof_hs_;
   B2P_CUDA(cudaMemcpyAsync(cr.data(), p.d_cnt_recv.p, cr.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
   sync_stream();
   // payload: contiguous per peer
@@ -328,6 +355,7 @@ static void exchange_particles(b2p_grid* g) {
       B2P_LAUNCH_CHECK();
     }
   }
+  ProfScope prof_pl_(KC_NCCL, 0.0);
   B2P_NCCL(n.GroupStart());
   size_t sq = 0, rq = 0, soff = 0, roff = 0;
   p.pspan.assign(p.entries.size(), std::vector<std::pair<size_t, unsigned>>(ns));
@@ -348,6 +376,30 @@ static void exchange_particles(b2p_grid* g) {
   }
   B2P_NCCL(n.GroupEnd());
   p.pspan_valid = true;
+}
+
+// The exchange of one field mode on the plan's own stream: it starts when the work enqueued so far on the library
+// stream is done, and the library stream only waits for it at comm_wait_exchange — kernels enqueued in between run
+// concurrently with the pack kernel and the NCCL transfer.
+void comm_exchange_fields_on_comm_stream(b2p_grid* g, int mode) {
+  CommPlan& p = *g->comm;
+  if (!p.cstream) {
+    B2P_CUDA(cudaStreamCreateWithFlags(&p.cstream, cudaStreamNonBlocking));
+    B2P_CUDA(cudaEventCreateWithFlags(&p.ev_ready, cudaEventDisableTiming));
+    B2P_CUDA(cudaEventCreateWithFlags(&p.ev_done, cudaEventDisableTiming));
+  }
+  Context& c = ctx();
+  B2P_CUDA(cudaEventRecord(p.ev_ready, c.stream));
+  B2P_CUDA(cudaStreamWaitEvent(p.cstream, p.ev_ready, 0));
+  cudaStream_t saved = c.stream;
+  c.stream = p.cstream;
+  try { exchange_fields(g, mode); } catch (...) { c.stream = saved; throw; }
+  c.stream = saved;
+  B2P_CUDA(cudaEventRecord(p.ev_done, p.cstream));
+}
+void comm_wait_exchange(b2p_grid* g) {
+  CommPlan& p = *g->comm;
+  if (p.ev_done) B2P_CUDA(cudaStreamWaitEvent(ctx().stream, p.ev_done, 0));
 }
 
 // used by grid_local_communication (host.cu)

@@ -51,7 +51,7 @@ void count_launch(int n = 1);
 // (bench.py's roofline leg).  Off by default: zero overhead on the hot path.
 enum KernelClass {
   KC_NODAL, KC_PUSH, KC_DEPOSIT, KC_SORT_KEYS, KC_RADIX_SORT, KC_GATHER, KC_DETECT, KC_GATHER_OUT, KC_APPEND,
-  KC_ZERO, KC_PUSH_B, KC_PUSH_E, KC_ADD_CURRENT, KC_FILTER, KC_HALO, KC_J_EXCHANGE, KC_ENERGY, KC_EDGE_GATHER, KC_OTHER, KC_COUNT
+  KC_ZERO, KC_PUSH_B, KC_PUSH_E, KC_ADD_CURRENT, KC_FILTER, KC_HALO, KC_J_EXCHANGE, KC_ENERGY, KC_EDGE_GATHER, KC_OTHER, KC_NCCL, KC_COUNT
 };
 const char* kernel_class_name(int k);
 struct ProfScope {
@@ -70,6 +70,7 @@ struct Tuning {
   int filter_chunk = 35;  // i-planes per thread column of k_filter_binomial2
   int push_streams = 2;   // worker streams the groups of the particle phase are round-robined over (1 = library stream only)
   int sort_streams = 1;   // > 0: b2p_grid_step_pic's sort runs on a worker stream (see sort_overlap); 0: library stream
+  int comm_overlap = 1;   // multi-GPU b2p_grid_step_pic: the B halo exchange runs on its own stream under the pushes of the interior tiles
   int sort_batch = 16;    // containers per launch of the counting-sort kernels (scratch: ~200 MB per 4 M-slot container)
   int sort_overlap = 1;   // b2p_grid_step_pic leaves the sort running on the worker streams under the field phase of the lap
   int push_block = 128;       // threads per block of k_push (128 or 256; 128 measured 1 % faster: finer-grained tail)

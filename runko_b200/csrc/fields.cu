@@ -330,7 +330,7 @@ __device__ __forceinline__ int dir_of_halo(int a, int N) { return a < H ? -1 : (
 // cell and component; interior cells exit. `which` selects E/B/J.
 __global__ void __launch_bounds__(256)
 k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, const Geom g, const int which,
-            const SlabDesc* __restrict__ remote) {
+            const SlabDesc* __restrict__ remote, const int part /* 0: all halo cells; 1: those fed by a local tile; 2: by a remote rank */) {
   // Only halo cells get a thread.  They are enumerated as three groups (k fastest in each):
   //   A: the six full (j,k) planes with i in the halo        6 * Hy * Hz
   //   B: for interior i, the six halo rows in j              Nx * 6 * Hz
@@ -368,6 +368,7 @@ k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, co
   const int di = dir_of_halo(i, g.N[0]), dj = dir_of_halo(j, g.N[1]), dk = dir_of_halo(k, g.N[2]);
   const int o = nbr[tile * 27 + ((di + 1) * 3 + (dj + 1)) * 3 + (dk + 1)];
   if (o == -1) return;
+  if ((part == 1 && o < -1) || (part == 2 && o >= 0)) return;
   const size_t n = (size_t(i) * g.Hx[1] + j) * g.Hx[2] + k;
   if (o < -1) {
     // remote neighbour: its corresponding_subregion(d) was staged by the external exchange
@@ -578,12 +579,12 @@ void launch_zero(float* p, size_t n) {
   B2P_CUDA(cudaMemsetAsync(p, 0, n * sizeof(float), ctx().stream));   // +0.0f is all-zero bits
   count_launch();
 }
-void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which, const SlabDesc* remote) {
+void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which, const SlabDesc* remote, int part) {
   ProfScope prof_(KC_HALO, double(ntiles) * g.Ch);
   if (!ntiles) return;
   check_tiles(ntiles);
   const int nhalo = 2 * H * g.Hx[1] * g.Hx[2] + g.N[0] * 2 * H * g.Hx[2] + g.N[0] * g.N[1] * 2 * H;
-  k_halo_fill<<<dim3((nhalo + 255) / 256, 1, unsigned(ntiles)), 256, 0, ctx().stream>>>(tiles, nbr, g, which, remote);
+  k_halo_fill<<<dim3((nhalo + 255) / 256, 1, unsigned(ntiles)), 256, 0, ctx().stream>>>(tiles, nbr, g, which, remote, part);
   B2P_LAUNCH_CHECK();
 }
 void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, const SlabDesc* remote) {

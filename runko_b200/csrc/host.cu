@@ -61,6 +61,7 @@ static bool set_option(const std::string& name, int value) {
   else if (name == "push_streams") g_tuning.push_streams = value;
   else if (name == "sort_streams") g_tuning.sort_streams = value;
   else if (name == "sort_batch") g_tuning.sort_batch = value;
+  else if (name == "comm_overlap") g_tuning.comm_overlap = value;
   else if (name == "push_group") g_tuning.push_group = value;
   else if (name == "push_block") g_tuning.push_block = value;
   else if (name == "sort_overlap") g_tuning.sort_overlap = value;
@@ -117,7 +118,7 @@ static cudaEvent_t take_event() {
 const char* kernel_class_name(int k) {
   static const char* n[KC_COUNT] = { "nodal_means", "push", "deposit", "sort_count", "sort_place", "sort_gather", "detect_leavers",
                                      "gather_outgoing", "append", "zero", "push_b", "push_e", "add_current", "filter",
-                                     "halo_fill", "J_exchange", "energy", "edge_gather", "other" };
+                                     "halo_fill", "J_exchange", "energy", "edge_gather", "other", "nccl_exchange" };
   return (k >= 0 && k < KC_COUNT) ? n[k] : "?";
 }
 ProfScope::ProfScope(KernelClass k, double units) {
@@ -164,7 +165,7 @@ static Scratch& scratch() { static Scratch* s = new Scratch; return *s; }
 // the library stays stream-ordered for the caller.
 struct Workers {
   cudaStream_t s[MAX_WORKERS] = {};
-  cudaEvent_t fork = nullptr, join[MAX_WORKERS] = {};
+  cudaEvent_t fork = nullptr, fork2 = nullptr, join[MAX_WORKERS] = {};
   bool ready = false;
   int sort_pending = 0;       // worker streams still carry an un-joined sort (join_pending_sort)
   void init() {
@@ -174,6 +175,7 @@ struct Workers {
       B2P_CUDA(cudaEventCreateWithFlags(&join[w], cudaEventDisableTiming));
     }
     B2P_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    B2P_CUDA(cudaEventCreateWithFlags(&fork2, cudaEventDisableTiming));
     ready = true;
   }
 };
@@ -412,7 +414,7 @@ static int sign_of(double v) { return (0.0 < v) - (v < 0.0); }   // tools/math.h
 // pic/tile.c++:326-365.  Every push also publishes the leaver/stayer ballots of the pushed
 // positions (Container::masks), which pack_outgoing_particles consumes if nothing touched
 // the container in between.
-void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
+void phase_push_particles(const std::vector<b2p_tile*>& tiles, size_t n_first, const std::function<void()>& between) {
   Scratch& s = scratch();
   const bool fuse = tuning().fuse_deposit != 0;
   // Tiles that hold particles, in groups of up to `push_group` tiles of one geometry / pusher / cfl: the
@@ -420,12 +422,15 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
   // group's containers, edge gather) run once per group, as launches large enough to fill the GPU.
   const int gmax = std::max(1, std::min(tuning().push_group, PUSH_GROUP_MAX));
   std::vector<std::vector<b2p_tile*>> groups;
-  for (b2p_tile* t : tiles) {
+  size_t groups_first = ~size_t(0);                   // groups [0, groups_first) hold the first n_first tiles
+  for (size_t ti = 0; ti < tiles.size(); ++ti) {
+    b2p_tile* t = tiles[ti];
     t->pendJ_valid = t->pend_packed = false;
+    if (ti == n_first) groups_first = groups.size();
     bool any = false;
     for (const Container& c : t->sp) any = any || c.n;
     if (!any) continue;
-    bool open = !groups.empty() && int(groups.back().size()) < gmax;
+    bool open = !groups.empty() && int(groups.back().size()) < gmax && groups.size() != groups_first;
     if (open) {
       const b2p_tile* f = groups.back().front();
       size_t nc = t->sp.size();
@@ -436,7 +441,8 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
     if (!open) groups.emplace_back();
     groups.back().push_back(t);
   }
-  if (groups.empty()) return;
+  if (groups.empty()) { if (between) between(); return; }
+  if (groups_first > groups.size()) groups_first = groups.size();
   const int nw = std::max(1, std::min({ tuning().push_streams, MAX_WORKERS, int(groups.size()) }));
   Workers& wk = workers();
   cudaStream_t main_stream = ctx().stream;
@@ -447,7 +453,17 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
   }
   size_t gi = 0;
   static PushJobs* jobs = new PushJobs;             // 8.7 KB kernel-argument table, filled per group
+  bool between_done = !between;
   for (const std::vector<b2p_tile*>& grp : groups) {
+    if (!between_done && gi >= groups_first) {
+      // everything after this point needs what `between` enqueues on the library stream
+      between();
+      between_done = true;
+      if (nw > 1) {
+        B2P_CUDA(cudaEventRecord(wk.fork2, main_stream));
+        for (int w = 0; w < nw; ++w) B2P_CUDA(cudaStreamWaitEvent(wk.s[w], wk.fork2, 0));
+      }
+    }
     const int w = int(gi++ % size_t(nw));
     StreamScope on(nw > 1 ? wk.s[w] : main_stream);
     const Geom& g = grp.front()->g;
@@ -498,6 +514,7 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles) {
       B2P_CUDA(cudaEventRecord(wk.join[w], wk.s[w]));
       B2P_CUDA(cudaStreamWaitEvent(main_stream, wk.join[w], 0));
     }
+  if (!between_done) between();
 }
 
 // pic/tile.c++:369-415.  clear_current + scratch accumulate + `J += scratch`
@@ -899,13 +916,13 @@ static void append_spans(std::vector<Container*>& conts, std::vector<b2p_tile*>&
 }
 
 // corgi::Grid::local_communication (external/corgi/src/corgi/corgi.h:1697-1718)
-void grid_local_communication(b2p_grid* g, int mode) {
+void grid_local_communication(b2p_grid* g, int mode, int part) {
   const int nt = int(g->tiles.size());
   if (!nt) return;
   switch (mode) {
-    case B2P_COMM_EMF_E: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 0, static_cast<const SlabDesc*>(comm_remote_table(g, 0))); return;
-    case B2P_COMM_EMF_B: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 1, static_cast<const SlabDesc*>(comm_remote_table(g, 0))); return;
-    case B2P_COMM_EMF_J: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 2, static_cast<const SlabDesc*>(comm_remote_table(g, 0))); return;
+    case B2P_COMM_EMF_E: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 0, static_cast<const SlabDesc*>(comm_remote_table(g, 0)), part); return;
+    case B2P_COMM_EMF_B: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 1, static_cast<const SlabDesc*>(comm_remote_table(g, 0)), part); return;
+    case B2P_COMM_EMF_J: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 2, static_cast<const SlabDesc*>(comm_remote_table(g, 0)), part); return;
     case B2P_COMM_EMF_J_EXCHANGE: launch_J_exchange(g->device_table(), g->device_nbr(), nt, g->g, static_cast<const SlabDesc*>(comm_remote_table(g, 1))); return;
     case B2P_COMM_PIC_PARTICLE: break;
     default:
@@ -1546,9 +1563,28 @@ int b2p_grid_step_pic(b2p_grid* g, int64_t lap) {
     if (multi) { const int rc = b2p_grid_external_communication(g, mode); if (rc) throw Error(rc, g_last_error); }
   };
   phase_push_half_b(g->tiles, g->device_table());
-  ext(B2P_COMM_EMF_B); grid_local_communication(g, B2P_COMM_EMF_B);
-  tr.mark("fields", lap);
-  phase_push_particles(g->tiles);         // also publishes the leaver masks pack_outgoing consumes
+  if (multi && tuning().comm_overlap) {
+    // The B halo exchange flies on the plan's own stream while the tiles that have no remote neighbour are pushed:
+    // halo cells fed by local tiles are filled at once, those fed by remote ranks when the exchange has landed,
+    // right before the boundary tiles' pushes.
+    comm_exchange_fields_on_comm_stream(g, B2P_COMM_EMF_B);
+    grid_local_communication(g, B2P_COMM_EMF_B, /*part=*/1);
+    std::vector<b2p_tile*> order;
+    size_t n_interior = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (b2p_tile* t : g->tiles) {
+        bool remote = false;
+        for (int di = 0; di < 27 && !remote; ++di) { int e = 0; remote = comm_remote_entry(g, t->slot, di, &e); }
+        if (remote == (pass == 1)) order.push_back(t);
+        if (pass == 0 && !remote) ++n_interior;
+      }
+    tr.mark("fields", lap);
+    phase_push_particles(order, n_interior, [&] { comm_wait_exchange(g); grid_local_communication(g, B2P_COMM_EMF_B, /*part=*/2); });
+  } else {
+    ext(B2P_COMM_EMF_B); grid_local_communication(g, B2P_COMM_EMF_B);
+    tr.mark("fields", lap);
+    phase_push_particles(g->tiles);         // also publishes the leaver masks pack_outgoing consumes
+  }
   tr.mark("push enqueue", lap);
   phase_pack_outgoing(g->tiles);
   tr.mark("pack", lap);

@@ -1,6 +1,7 @@
 // host.cuh — host-side objects behind the C-ABI handles (b2p_tile, b2p_grid).
 #pragma once
 #include <array>
+#include <functional>
 #include <memory>
 
 #include "common.cuh"
@@ -95,14 +96,18 @@ void phase_push_half_b(const std::vector<b2p_tile*>& tiles, const FieldPtrs* tab
 void phase_push_e(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table, bool add_current);
 void phase_add_current(const std::vector<b2p_tile*>& tiles, const FieldPtrs* table);
 void phase_filter(const std::vector<b2p_tile*>& tiles);
-void phase_push_particles(const std::vector<b2p_tile*>& tiles);
+// The first n_first tiles are pushed, then `between` runs on the library stream, then the rest (used to hide the B halo
+// exchange under the pushes of the tiles that have no remote neighbour).
+void phase_push_particles(const std::vector<b2p_tile*>& tiles, size_t n_first = ~size_t(0), const std::function<void()>& between = nullptr);
 void phase_deposit(const std::vector<b2p_tile*>& tiles);
 void phase_sort(const std::vector<b2p_tile*>& tiles, bool leave_running = false);
 void join_pending_sort();                   // host.cu: makes the library stream wait for a sort left on the worker streams
 void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles);
 void phase_apply_edge_bcs(const std::vector<b2p_tile*>& tiles, int mode);
 void phase_reflect_particles(const std::vector<b2p_tile*>& tiles);
-void grid_local_communication(b2p_grid* g, int mode);
+void grid_local_communication(b2p_grid* g, int mode, int part = 0);   // part: fields.cuh launch_halo_fill
+void comm_exchange_fields_on_comm_stream(b2p_grid* g, int mode);      // comm.cu: exchange on the plan's own stream, ordered after the library stream
+void comm_wait_exchange(b2p_grid* g);                                   // library stream waits for that exchange
 void flush_deferred();                      // executes the pending batch of per-tile calls (host.cu)
 void set_last_error(const std::string& s);
 void Scratch_table_upload(const void* src, size_t bytes);   // host -> the shared device table scratch

@@ -101,10 +101,11 @@ __global__ void __launch_bounds__(256)
 k_pack_write(const PackJob* __restrict__ jobs) {
   const PackJob& jb = jobs[blockIdx.y];
   if (blockIdx.x >= jb.nseg) return;
-  __shared__ unsigned l_slot[PACK_SEG_WORDS * 32];         // the segment's leavers, in slot order
+  __shared__ unsigned short l_off[PACK_SEG_WORDS * 32];    // the segment's leavers, in slot order: slot - first slot of the segment
   __shared__ unsigned char l_sub[PACK_SEG_WORDS * 32];
   __shared__ unsigned s_base[27];
   const unsigned w = blockIdx.x * PACK_SEG_WORDS + threadIdx.x;
+  const unsigned seg_first = blockIdx.x * PACK_SEG_WORDS * 32u;
   uint2 m = make_uint2(0u, 0u);
   if (w < jb.nwords) m = jb.masks[w];
   unsigned L;
@@ -116,19 +117,20 @@ k_pack_write(const PackJob* __restrict__ jobs) {
     const unsigned b = __ffs(bits) - 1;
     bits &= bits - 1;
     const unsigned n = w * 32u + b;
-    l_slot[pos] = n;
+    l_off[pos] = static_cast<unsigned short>(n - seg_first);
     l_sub[pos] = static_cast<unsigned char>(subregion_of(jb.s.x[n], jb.s.y[n], jb.s.z[n], jb.mn, jb.mx));
     ++pos;
   }
   __syncthreads();
+  // one thread per leaver of the compact list (the first L threads: full warps issue the seven gathers)
   for (unsigned e = threadIdx.x; e < L; e += 256u) {
-    const unsigned sub = l_sub[e], n = l_slot[e];
-    unsigned rank = 0;
-    for (unsigned q = 0; q < e; ++q) rank += unsigned(l_sub[q] == sub);
+    const unsigned sub = l_sub[e], n = seg_first + l_off[e];
     b2p_particle_state st;
     st.pos[0] = jb.s.x[n]; st.pos[1] = jb.s.y[n]; st.pos[2] = jb.s.z[n];
     st.vel[0] = jb.s.ux[n]; st.vel[1] = jb.s.uy[n]; st.vel[2] = jb.s.uz[n];
     st.id = jb.s.id[n];
+    unsigned rank = 0;
+    for (unsigned q = 0; q < e; ++q) rank += unsigned(l_sub[q] == sub);
     jb.out[s_base[sub] + rank] = st;
     jb.s.id[n] = DEAD;
   }
