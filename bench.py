@@ -451,6 +451,389 @@ def run_emf(args):
         dist.destroy_process_group()
 
 
+
+# --------------------------------------------------------------------------- configs[1] beam and configs[3] shock
+STENCIL_X = dict(stencil_x_delta=-0.13512912586798165, stencil_x_gamma=0.016100341594971104, stencil_x_beta_p1=0.022350417588794424,
+                 stencil_x_beta_p2=0.022350417588794424, stencil_x_zeta_p1=0.012206124727660462, stencil_x_zeta_p2=0.012206124727660462)
+
+
+def named_workload(name, n_gpus, cells_arg=None):
+    """Shapes and physics of BASELINE configs[1] / configs[3] (per GPU; more GPUs extend the box along gpu_blocks)."""
+    gb = gpu_blocks(n_gpus)
+    if name == "beam":
+        # projects/pic-beam-instabilities/beam.py:46-137: one species, two cold counter-streaming beams (gamma_b = 3) of 8 ppc each,
+        # thin-z 3-D box, filter off as shipped (enable_filter = False)
+        cells, tile = (cells_arg or 1024, cells_arg or 1024, 6), (64, 64, 6)
+        cfl, skin, n0 = 0.45, 10.0, 16
+        gmean = 3.0
+        q = -((cfl / skin) ** 2) * gmean / n0
+        conf = Conf(cfl=cfl, field_propagator="fdtd2", q0=q, m0=1.0, particle_pusher="boris", field_interpolator="linear_1st",
+                    current_depositer="zigzag_1st_atomic", current_filter=None)
+        desc = {"workload": "projects/pic-beam-instabilities two-stream / filamentation (BASELINE configs[1]): 1 species, 2 cold beams "
+                            "gamma_b = 3 along +-x, 2 x 8 ppc, no current filter (beam.py:60)", "ppc_total": 16}
+        species, ppc_total = 1, 16
+    else:
+        # projects/pic-shock/pic.py + 3d_shock_mini.ini physics: sigma = 3, upstream gamma = 5, theta = 1e-5, faraday + stencil +
+        # binomial2_unrolled + linear_1st_unrolled, 4 filter passes, wall at x = 15, moving injector
+        cells, tile = (cells_arg or 2048, (cells_arg or 2048) // 8, (cells_arg or 2048) // 8), (64, 64, 64)
+        cfl, skin, ppc = 0.45, 10.0, 4
+        oppc = 2 * ppc
+        q = -((cfl / skin) ** 2) * 5.0 / (0.5 * oppc * (1.0 + 1.0))   # pic.py:47-50 (omp = cfl/c_omp, m0 = m1 = 1)
+        conf = Conf(cfl=cfl, field_propagator="stencil", q0=q, m0=1.0, q1=abs(q), m1=1.0, particle_pusher="faraday",
+                    field_interpolator="linear_1st_unrolled", current_depositer="zigzag_1st_atomic", current_filter="binomial2_unrolled",
+                    prealloc_per_species=int(2.0 * ppc * tile[0] * tile[1] * tile[2]), **STENCIL_X)
+        desc = {"workload": "projects/pic-shock reflecting-wall shock with moving injector (BASELINE configs[3]): 2 species x 4 ppc upstream "
+                            "(8 ppc), sigma = 3, gamma_up = 5, faraday + stencil + binomial2_unrolled x4 + linear_1st_unrolled, wall at x = 15",
+                "ppc_total": 8}
+        species, ppc_total = 2, 8
+    tpg = tuple(cells[d] // tile[d] for d in range(3))
+    conf.n_tiles = [tpg[d] * gb[d] for d in range(3)]
+    conf.n_cells_per_tile = list(tile)
+    desc.update({"cells_per_gpu": "x".join(map(str, cells)), "tile": "x".join(map(str, tile)), "gpu_blocks": "x".join(map(str, gb)),
+                 "fp": "fp32, IEEE div/sqrt, NO FMA contraction on either arm",
+                 "l2": "particle streams (32 B x particles) far exceed the 126 MB L2; no explicit flush"})
+    return conf, tpg, gb, desc, species, ppc_total
+
+
+class ShockState:
+    """what projects/pic-shock/pic.py keeps on the host around the lap: upstream fields, wall, edge BCs, injector front"""
+
+    def __init__(self, conf, Lx):
+        self.Lx, self.walloc, self.gamma_up, self.theta, self.ppc = float(Lx), 15.0, 5.0, 1e-5, 4
+        self.beta = float(np.sqrt(1.0 - 1.0 / self.gamma_up ** 2))
+        oppc, sigma = 2 * self.ppc, 3.0
+        m0 = abs(conf.q0)
+        self.binit = float(np.sqrt(self.gamma_up * oppc * 0.5 * conf.cfl ** 2 * m0 * 2.0 * sigma))      # pic.py:61
+        self.E_up, self.B_up = (0.0, -self.beta * self.binit, 0.0), (0.0, 0.0, self.binit)          # b_proj = (0, 0, 1)
+        self.injloc = self.walloc + 0.6 * (self.Lx - self.walloc)       # a shock that has been running: 60 % of the box is filled
+        self.n_inj = 5
+
+    def inject_front(self, grid, lap, cfl, seed):
+        if lap == 0 or lap % self.n_inj:
+            return
+        stride = self.n_inj * cfl                                        # runko/moving_injector.py
+        left, right = max(self.injloc - self.beta * stride, self.walloc), self.injloc + 1.0 * stride
+        if right >= self.Lx - 10.0:
+            return
+        for sp in range(2):
+            grid.inject_drifting_stripe(sp, self.ppc, self.theta, self.gamma_up, -1, left, right, seed=seed + lap)
+        self.injloc = right
+
+
+def run_named(args):
+    """--workload beam | shock: the same JSON contract as the headline workload (value = alive particles pushed per second over whole
+    laps, roofline of the dominant kernel class, e2e through the per-tile API with a host round trip, cpu_baseline = the oracle
+    port on a bounded sample of the same physics)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+    import runko_b200 as rb
+    from runko_b200._lib import check
+    L = rb.lib()
+    check(L.b2p_init(local_rank))
+    name = args.workload
+    conf, tpg, gb, desc, n_species, ppc_total = named_workload(name, world, args.cells if args.cells != 512 else None)
+    tile = conf.n_cells_per_tile
+    grid = rb.Grid(conf)
+    bi, bj, bk = rank % gb[0], (rank // gb[0]) % gb[1], rank // (gb[0] * gb[1])
+    Lx = conf.n_tiles[0] * tile[0]
+    shock = ShockState(conf, Lx) if name == "shock" else None
+    tiles = []
+    if shock:
+        shape = (3, tile[0] + 6, tile[1] + 6, tile[2] + 6)
+        E0, B0 = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+        for c in range(3):
+            E0[c], B0[c] = shock.E_up[c], shock.B_up[c]
+        wall = rb.reflector_wall(walloc=shock.walloc)
+        cbc = rb.edge_bc(direction=0, side=0, position=shock.walloc, E_components=0b110, B_components=0, J_components=0b111)
+        ubc = rb.edge_bc(direction=0, side=1, position=Lx - 5.0, Ex=shock.E_up[0], Ey=shock.E_up[1], Ez=shock.E_up[2],
+                         Bx=shock.B_up[0], By=shock.B_up[1], Bz=shock.B_up[2], J_components=0b111)
+    for i in range(tpg[0]):
+        for j in range(tpg[1]):
+            for k in range(tpg[2]):
+                t = rb.PicTile((bi * tpg[0] + i, bj * tpg[1] + j, bk * tpg[2] + k), conf)
+                if shock:
+                    t.set_fields_f32(E0, B0, None, with_halo=True)
+                    t.register_reflector_wall(wall); t.register_edge_bc(cbc); t.register_edge_bc(ubc)
+                grid.add_tile(t)
+                tiles.append(t)
+    if world > 1:
+        # block decomposition with non-cubic tile counts per GPU
+        T = conf.n_tiles
+        owner = np.zeros(T[0] * T[1] * T[2], np.int32)
+        for k in range(T[2]):
+            for j in range(T[1]):
+                for i in range(T[0]):
+                    owner[i + T[0] * (j + T[1] * k)] = (i // tpg[0]) + gb[0] * ((j // tpg[1]) + gb[1] * (k // tpg[2]))
+        comm_init(L, dist, grid, rank, world, owner)
+        grid._multi = True
+    if name == "beam":
+        for sign in (+1, -1):
+            grid.inject_drifting_stripe(0, 8, 1e-5, 3.0, sign, 0.0, float(Lx), seed=42)      # both beams on the same positions (beam.py:127)
+    else:
+        for sp in range(2):
+            grid.inject_drifting_stripe(sp, shock.ppc, shock.theta, shock.gamma_up, -1, shock.walloc, shock.injloc, seed=42)
+    rb.sync()
+
+    def barrier():
+        rb.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def step(lap):
+        if shock:
+            grid.step_shock(lap, n_filter_passes=4)
+            shock.inject_front(grid, lap, conf.cfl, 1000)
+        else:
+            grid.step_pic(lap)
+
+    for m in (rb.comm_mode.emf_E, rb.comm_mode.emf_B):
+        if world > 1:
+            grid.external_communication(m)
+        grid.local_communication(m)
+    lap = 0
+    for _ in range(args.warmup):
+        step(lap); lap += 1
+    barrier()
+    alive0 = grid.alive_counts()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.b2p_launch_count()
+    barrier()
+    check(L.b2p_timer_start())
+    for _ in range(args.steps):
+        step(lap); lap += 1
+    ms = C.c_float()
+    check(L.b2p_timer_stop(C.byref(ms)))
+    barrier()
+    launches = L.b2p_launch_count() - launches0
+    clocks = sampler.stop()
+    alive1 = grid.alive_counts()
+    n_part_local = 0.5 * (float(np.sum(alive0)) + float(np.sum(alive1)))     # alive particles pushed per lap (the shock's count grows)
+    # per-kernel leg
+    prof_steps = 5
+    check(L.b2p_set_option(b"push_streams", 1)); check(L.b2p_set_option(b"sort_streams", 0))
+    check(L.b2p_profile_enable(1))
+    for _ in range(prof_steps):
+        step(lap); lap += 1
+    rb.sync()
+    nk = L.b2p_profile_num_classes()
+    pms, pl, pu = np.zeros(nk), np.zeros(nk, np.uint64), np.zeros(nk)
+    check(L.b2p_profile_report(pms.ctypes.data_as(C.c_void_p), pl.ctypes.data_as(C.c_void_p), pu.ctypes.data_as(C.c_void_p)))
+    check(L.b2p_profile_enable(0))
+    check(L.b2p_set_option(b"push_streams", 2)); check(L.b2p_set_option(b"sort_streams", 1))
+    names = [L.b2p_profile_class_name(k).decode() for k in range(nk)]
+    dev_s = ms.value / 1e3
+    tot_part = n_part_local
+    if dist is not None:
+        import torch
+        tt = torch.tensor([dev_s], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_s = float(tt[0])
+        tp = torch.tensor([n_part_local], dtype=torch.float64)
+        dist.all_reduce(tp)
+        tot_part = float(tp[0])
+    per_step = dev_s / args.steps
+    peak, peak_src = read_peaks()
+    top = int(np.argmax(pms))
+    share = {names[k]: round(float(pms[k] / max(pms.sum(), 1e-9)), 4) for k in np.argsort(-pms)[:8] if pms[k] > 0}
+    fused = pl[names.index("deposit")] == 0 or pms[names.index("deposit")] < 0.2 * pms[names.index("push")]
+    push_ms = pms[names.index("push")] / prof_steps
+    alive_now = float(np.sum(grid.alive_counts()))
+    achieved = BYTES_PER_PARTICLE_STEP * alive_now / (push_ms * 1e-3) / 1e9 if fused else BYTES_PER_PARTICLE_PUSH * alive_now / (push_ms * 1e-3) / 1e9
+    n_cells_local = int(np.prod(tpg)) * int(np.prod(tile))
+    step_bytes = (BYTES_PER_PARTICLE_STEP + BYTES_PER_PARTICLE_SORT) * n_part_local + BYTES_PER_CELL_STEP * n_cells_local
+    roofline = {"bound": "hbm", "kernel": "push+deposit (fused k_push)" if fused else "push (k_push; deposit separate where the wall reflects)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_unit": BYTES_PER_PARTICLE_STEP if fused else BYTES_PER_PARTICLE_PUSH, "units": "alive particles per lap",
+                "ms_per_lap": push_ms, "share_of_step": share, "dominant_class": names[top],
+                "step": {"algorithmic_bytes_per_gpu": step_bytes, "achieved_GBs": step_bytes / per_step / 1e9,
+                         "frac_of_peak": step_bytes / per_step / 1e9 / peak, "frac_of_8TBs": step_bytes / per_step / 8e12}}
+    if args.profile and rank == 0:
+        for k in np.argsort(-pms):
+            if pl[k]:
+                print(f"  {names[k]:16s} {pms[k] / prof_steps:9.3f} ms/step  {int(pl[k]) // prof_steps:6d} launches/step", file=sys.stderr)
+    checks = {"alive_before": [int(v) for v in alive0], "alive_after": [int(v) for v in alive1]}
+    if name == "beam":
+        checks["particle_number_conserved"] = bool(np.array_equal(alive0, alive1))
+    # ---- e2e: the lap tile by tile through the reference-facing API, one tile's particles making a host round trip per step
+    e2e = None
+    if not args.no_e2e:
+        M = rb.comm_mode
+        multi = world > 1
+
+        def comm(m, local=None):
+            if multi:
+                grid.external_communication(m)
+            grid.local_communication(m if local is None else local)
+
+        def each(method, *a):
+            for t in tiles:
+                getattr(t, method)(*a)
+
+        def lap_api(lp):
+            each("push_half_b")
+            if shock: each("apply_edge_bcs", M.emf_B)
+            comm(M.emf_B)
+            each("push_particles")
+            if shock: each("reflect_particles")
+            each("pack_outgoing_particles"); comm(M.pic_particle)
+            if lp % 5 == 0: each("sort_particles")
+            each("deposit_current"); comm(M.emf_J, M.emf_J_exchange); comm(M.emf_J)
+            if shock:
+                each("apply_edge_bcs", M.emf_J)
+                for q in range(4):
+                    if q > 0 and q % 3 == 0: comm(M.emf_J)
+                    each("filter_current")
+                each("apply_edge_bcs", M.emf_J)
+            each("push_half_b")
+            if shock: each("apply_edge_bcs", M.emf_B)
+            comm(M.emf_B)
+            each("push_e")
+            if shock: each("apply_edge_bcs", M.emf_E)
+            each("add_current")
+            if shock: each("apply_edge_bcs", M.emf_E)
+            comm(M.emf_E)
+            if shock: each("advance_reflector_walls")
+            return grid.energies()
+
+        steps = max(2, min(args.steps, 5))
+        h0, d0 = C.c_uint64(), C.c_uint64()
+        barrier()
+        L.b2p_copy_bytes(C.byref(h0), C.byref(d0))
+        t0 = time.perf_counter()
+        for s_ in range(steps):
+            t = tiles[(len(tiles) // 2 + s_) % len(tiles)]
+            for sp in range(n_species):
+                st = t.get_particles(sp, alive_only=False)
+                t.set_particles_raw(sp, *st)
+            lap_api(lap + s_)
+        barrier()
+        dt = time.perf_counter() - t0
+        lap += steps
+        h1, d1 = C.c_uint64(), C.c_uint64()
+        L.b2p_copy_bytes(C.byref(h1), C.byref(d1))
+        if dist is not None:
+            import torch
+            tt = torch.tensor([dt], dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt[0])
+        e2e = {"value": tot_part / (dt / steps), "unit": "particle-pushes/s", "steps": steps,
+               "h2d_bytes_per_step": int((h1.value - h0.value) / steps), "d2h_bytes_per_step": int((d1.value - d0.value) / steps),
+               "how": "lap driven tile-by-tile through the PicTile API; every step one tile's particle state makes a host round trip "
+                      "(get_particles -> set_particles) and the energy diagnostics are read back; wall clock, max over ranks"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = named_cpu_baseline(name, os.cpu_count() or 1)
+    if rank == 0:
+        out = {"metric": "particle-pushes/s per full PIC step", "value": tot_part / per_step, "unit": "particle-pushes/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": desc,
+               "particles_per_gpu": n_part_local, "cell_updates_per_s": n_cells_local * world / per_step,
+               "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "checks": checks}
+        if e2e is not None:
+            out["e2e"] = e2e
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        emit_result(out)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def named_cpu_baseline(name, n_threads):
+    """The oracle port (kind "port") on a bounded sample of the same physics: one tile per worker thread, the workload's own tile
+    shape and particle density, the same lap function (for the shock: wall tile row + upstream rows, edge BCs, 4 filter passes)."""
+    from oracle.oracle import OracleGrid
+    conf, tpg, gb, desc, n_species, ppc_total = named_workload(name, 1)
+    tile = conf.n_cells_per_tile
+    rng = np.random.default_rng(42)
+    if name == "beam":
+        ty = max(1, int(np.sqrt(n_threads)))
+        conf.n_tiles = [max(1, n_threads // ty), ty, 1]
+    else:
+        tile = [32, 32, 32]                                  # 64^3 tiles x 8 ppc x all cores would run for minutes per lap
+        conf.n_cells_per_tile = tile
+        conf.prealloc_per_species = int(2.0 * 4 * 32 ** 3)
+        conf.n_tiles = [max(2, n_threads // 2), 2, 1]
+    T = conf.n_tiles
+    og = OracleGrid(conf)
+    Lx = T[0] * tile[0]
+    shock = ShockState(conf, Lx) if name == "shock" else None
+    ii, jj, kk = np.meshgrid(np.arange(tile[0]), np.arange(tile[1]), np.arange(tile[2]), indexing="ij")
+    corner = np.stack([ii.ravel(), jj.ravel(), kk.ravel()]).astype(np.float64)
+    n_part = 0
+
+    def drifting(n, theta, Gamma, sign):
+        u = np.sqrt(theta) * rng.standard_normal((3, n))
+        g = np.sqrt(1.0 + np.sum(u * u, axis=0))
+        beta = np.sqrt(1.0 - 1.0 / Gamma ** 2)
+        flip = -beta * u[0] / g > rng.random(n)
+        u[0, flip] = -u[0, flip]
+        u[0] = sign * Gamma * (u[0] + beta * g)
+        return u
+
+    for t in range(og.num_tiles):
+        i, j, k = t % T[0], (t // T[0]) % T[1], t // (T[0] * T[1])
+        org = np.array([i * tile[0], j * tile[1], k * tile[2]], np.float64)[:, None]
+        if name == "beam":
+            pos = np.concatenate([corner + rng.random(corner.shape) for _ in range(8)], axis=1) + org
+            for sign in (+1, -1):
+                og.inject(t, 0, *pos, *drifting(pos.shape[1], 1e-5, 3.0, sign))
+                n_part += pos.shape[1]
+        else:
+            shape = (3, tile[0] + 6, tile[1] + 6, tile[2] + 6)
+            E0, B0 = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+            for c in range(3):
+                E0[c], B0[c] = shock.E_up[c], shock.B_up[c]
+            og.set_fields(t, E0, B0, None, with_halo=True)
+            import runko_b200.tiles as _t
+            og.register_reflector_wall(t, _t.reflector_wall(walloc=shock.walloc))
+            og.register_edge_bc(t, _t.edge_bc(direction=0, side=0, position=shock.walloc, E_components=0b110, B_components=0, J_components=0b111))
+            og.register_edge_bc(t, _t.edge_bc(direction=0, side=1, position=Lx - 5.0, Ex=shock.E_up[0], Ey=shock.E_up[1], Ez=shock.E_up[2],
+                                              Bx=shock.B_up[0], By=shock.B_up[1], Bz=shock.B_up[2], J_components=0b111))
+            pos = np.concatenate([corner + rng.random(corner.shape) for _ in range(shock.ppc)], axis=1) + org
+            keep = (pos[0] >= shock.walloc) & (pos[0] < shock.injloc)
+            pos = pos[:, keep]
+            for sp in range(2):
+                og.inject(t, sp, *pos, *drifting(pos.shape[1], shock.theta, shock.gamma_up, -1))
+                n_part += pos.shape[1]
+
+    def lap_fn(lap):
+        if name == "beam":
+            og.step_pic(lap, threads=n_threads)
+            return
+        ph, lc = (lambda nm: og.phase(nm, threads=n_threads)), og.local_communication
+        ph("push_half_b"); ph("apply_edge_bcs_B"); lc(2)
+        ph("push_particles"); ph("reflect_particles"); ph("pack_outgoing_particles"); lc(3)
+        if lap % 5 == 0:
+            ph("sort_particles")
+        ph("deposit_current"); lc(6); lc(0); ph("apply_edge_bcs_J")
+        for q in range(4):
+            if q > 0 and q % 3 == 0:
+                lc(0)
+            ph("filter_current")
+        ph("apply_edge_bcs_J")
+        ph("push_half_b"); ph("apply_edge_bcs_B"); lc(2)
+        ph("push_e"); ph("apply_edge_bcs_E"); ph("add_current"); ph("apply_edge_bcs_E"); lc(1)
+        ph("advance_reflector_walls")
+
+    for m in (1, 2):
+        og.local_communication(m)
+    lap_fn(0)
+    c0, nl = time.perf_counter(), 0
+    while nl < 3 or (time.perf_counter() - c0 < 12.0 and nl < 50):
+        lap_fn(1 + nl)
+        nl += 1
+    cdt = (time.perf_counter() - c0) / nl
+    return {"value": n_part / cdt, "unit": "particle-pushes/s", "cores": n_threads, "kind": "port",
+            "sample": f"{T[0]}x{T[1]}x{T[2]} tiles of {tile[0]}x{tile[1]}x{tile[2]} cells, {n_part} particles, {nl} laps of the workload's lap function, one tile per worker thread"}
+
+
 def workload_config(args, n_gpus):
     gb = gpu_blocks(n_gpus)
     return {"workload": "projects/scaling uniform thermal pair plasma (BASELINE configs[4] physics), weak scaling",
@@ -545,8 +928,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-emf", action="store_true", help="skip the emf-wave sub-record of the default workload")
     ap.add_argument("--profile", action="store_true", help="per-kernel-class timing table on stderr")
-    ap.add_argument("--workload", default="scaling", choices=["scaling", "emf-wave"],
-                    help="scaling: BASELINE configs[4], the headline (default); emf-wave: configs[2], fields only, cell-updates/s")
+    ap.add_argument("--workload", default="scaling", choices=["scaling", "emf-wave", "beam", "shock"],
+                    help="scaling: BASELINE configs[4], the headline (default); emf-wave: configs[2], fields only, cell-updates/s; "
+                         "beam: configs[1] (1024x1024x6, 16 ppc); shock: configs[3] (2048x256x256, 8 ppc, wall + injector)")
     args = ap.parse_args()
     isolate_stdout()
     if args.warmup < 3:
@@ -555,6 +939,8 @@ def main():
         return run_reference(args)
     if args.workload == "emf-wave":
         return run_emf(args)
+    if args.workload in ("beam", "shock"):
+        return run_named(args)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -260,6 +260,14 @@ int b2p_grid_energies(b2p_grid* g, double* energy_B, double* energy_E,
  * positions cell corner + U[0,1)^3, momenta Maxwellian with spread `delgam`,
  * counter-based RNG seeded by (seed, tile, species). No reference equivalent. */
 int b2p_grid_inject_thermal(b2p_grid* g, int ppc, double delgam, uint64_t seed);
+/* Synthetic drifting plasma for the beam / shock bench workloads, generated on the device: ppc particles of species
+ * sp per cell in the cells pic::Tile::batch_inject_in_x_stripe(sp, pgen, x_left, x_right) would visit
+ * (pic/tile.c++:235-322), appended after each container's last alive particle (containers pre-sized by
+ * prealloc_per_species take them in their dead slots); momenta: Maxwellian of spread `delgam` boosted by
+ * `gamma_drift` along dir_sign * x.  The same seed gives every species the same positions.  No reference equivalent
+ * (the reference's drivers generate on the host: projects/pic-shock/pic.py:136-149, beam.py:123-137). */
+int b2p_grid_inject_drifting_stripe(b2p_grid* g, int sp, int ppc, double delgam, double gamma_drift, int dir_sign,
+                                    double x_left, double x_right, uint64_t seed);
 int b2p_grid_set_uniform_B(b2p_grid* g, float bx, float by, float bz);
 
 /* ---- multi-GPU (replaces corgi's MPI transport, corgi.h:1560-1692) ------- */

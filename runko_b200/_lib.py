@@ -28,7 +28,7 @@ b2p_grid_apply_edge_bcs b2p_grid_reflect_particles b2p_grid_advance_reflector_wa
 b2p_grid_create b2p_grid_destroy b2p_grid_add_tile b2p_grid_local_communication
 b2p_grid_push_half_b b2p_grid_push_e b2p_grid_add_current b2p_grid_filter_current
 b2p_grid_push_particles b2p_grid_pack_outgoing_particles b2p_grid_sort_particles b2p_grid_deposit_current
-b2p_grid_step_pic b2p_grid_step_emf b2p_grid_energies b2p_grid_inject_thermal b2p_grid_set_uniform_B
+b2p_grid_step_pic b2p_grid_step_emf b2p_grid_energies b2p_grid_inject_thermal b2p_grid_inject_drifting_stripe b2p_grid_set_uniform_B
 b2p_nccl_unique_id b2p_grid_comm_init b2p_grid_external_communication b2p_plan_describe
 b2p_timer_start b2p_timer_stop b2p_launch_count b2p_copy_bytes
 b2p_profile_enable b2p_profile_num_classes b2p_profile_class_name b2p_profile_report
@@ -107,6 +107,7 @@ def lib():
     L.b2p_grid_step_pic.argtypes = [vp, C.c_int64]
     L.b2p_grid_energies.argtypes = [vp, dp, dp, vp, vp]
     L.b2p_grid_inject_thermal.argtypes = [vp, ci, C.c_double, u64]
+    L.b2p_grid_inject_drifting_stripe.argtypes = [vp, ci, ci, C.c_double, C.c_double, ci, C.c_double, C.c_double, u64]
     L.b2p_grid_set_uniform_B.argtypes = [vp, C.c_float, C.c_float, C.c_float]
     L.b2p_nccl_unique_id.argtypes = [vp]
     L.b2p_grid_comm_init.argtypes = [vp, ci, ci, vp, vp]

@@ -521,6 +521,7 @@ void phase_push_particles(const std::vector<b2p_tile*>& tiles, size_t n_first, c
 // collapse to "zero J, accumulate into J" (0 + x == x).
 void phase_deposit(const std::vector<b2p_tile*>& tiles) {
   Scratch& s = scratch();
+  std::vector<b2p_tile*> fresh;
   for (b2p_tile* t : tiles) {
     if (t->pendJ_valid && t->pend_packed) {
       // the fused push (stayers) and the particle exchange (arrivals) already accumulated this
@@ -530,14 +531,36 @@ void phase_deposit(const std::vector<b2p_tile*>& tiles) {
       if (t->grid) t->grid->table_dirty = true;
       t->pendJ_valid = t->pend_packed = false;
     } else {
-      join_pending_sort();                                          // a fresh deposit reads the containers
+      fresh.push_back(t);
       t->pendJ_valid = t->pend_packed = false;
-      s.edges.reserve(size_t(3) * t->g.Ch);
-      launch_zero(reinterpret_cast<float*>(s.edges.p), size_t(12) * t->g.Ch);
-      for (Container& c : t->sp)
-        launch_deposit(c.view(), s.edges.p, t->g, t->origo, static_cast<float>(t->cfg.cfl), static_cast<float>(c.charge));
-      launch_edge_gather(s.edges.p, t->J(), t->g);
     }
+  }
+  if (!fresh.empty()) {
+    // Fresh deposits (tiles whose particles changed after the push: reflector wall, injection, uploads — and tiles
+    // that hold no particles at all), in groups of one geometry: one clear of the group's cell-edge scratch, one
+    // deposit per non-empty container, one edge gather (= clear_current + `J += generated_J`) per group.
+    join_pending_sort();                                            // a fresh deposit reads the containers
+    const int gmax = std::max(1, std::min(tuning().push_group, PUSH_GROUP_MAX));
+    for (size_t b = 0; b < fresh.size();) {
+      const Geom g = fresh[b]->g;
+      size_t e = b;
+      while (e < fresh.size() && e - b < size_t(gmax) && std::memcmp(&fresh[e]->g, &g, sizeof(Geom)) == 0) ++e;
+      const size_t edge_stride = size_t(3) * g.Ch;
+      s.edges.reserve(edge_stride * (e - b));
+      EdgeBatch eb{};
+      launch_zero(reinterpret_cast<float*>(s.edges.p), size_t(4) * edge_stride * (e - b));
+      for (size_t q = b; q < e; ++q) {
+        b2p_tile* t = fresh[q];
+        float4* Jc = s.edges.p + (q - b) * edge_stride;
+        for (Container& c : t->sp)
+          if (c.n) launch_deposit(c.view(), Jc, t->g, t->origo, static_cast<float>(t->cfg.cfl), static_cast<float>(c.charge));
+        eb.Jc[eb.n] = Jc; eb.J[eb.n] = t->J(); ++eb.n;              // a tile without particles gathers zeros: J = 0
+      }
+      if (eb.n) launch_edge_gather(eb, g);
+      b = e;
+    }
+  }
+  for (b2p_tile* t : tiles) {
     if (t->corr_pending) {                                          // pic/tile.c++:411-414
       launch_add_lattice(t->J(), t->corrJ.p, t->lattice_floats());
       t->corr_pending = false;
@@ -1687,6 +1710,37 @@ int b2p_grid_inject_thermal(b2p_grid* g, int ppc, double delgam, uint64_t seed) 
       t->next_ordinal[q] += total;
       c.P = c.n; c.P_valid = true; c.masks_valid = false;
     }
+  }
+  B2P_CATCH
+}
+
+int b2p_grid_inject_drifting_stripe(b2p_grid* g, int sp, int ppc, double delgam, double gamma_drift, int dir_sign, double x_left,
+                                    double x_right, uint64_t seed) {
+  B2P_TRY
+  G(g);
+  if (ppc < 0 || gamma_drift < 1.0 || (dir_sign != 1 && dir_sign != -1)) throw Error(B2P_ERR_RUNTIME, "inject_drifting_stripe: bad arguments");
+  for (b2p_tile* t : g->tiles) {
+    Container& c = C(t, sp);
+    // the cell range of pic::Tile::batch_inject_in_x_stripe (pic/tile.c++:235-262)
+    const double xmin = t->mins[0], xmax = t->maxs[0];
+    if (x_right <= xmin || x_left >= xmax) continue;
+    const int nx = t->g.N[0];
+    const double dl = x_left - xmin, dr = x_right - xmin;
+    const int i0 = dl <= 0.0 ? 0 : std::min(nx, int(std::floor(dl)));
+    const int i1 = dr >= double(nx) ? nx : int(std::ceil(dr));
+    if (i0 >= i1) continue;
+    const size_t total = size_t(i1 - i0) * t->g.N[1] * t->g.N[2] * size_t(ppc);
+    const unsigned P = find_P(c);
+    if (size_t(P) + total >= (size_t(1) << 32)) throw Error(B2P_ERR_RUNTIME, "particle container exceeds uint32 indexing");
+    c.reserve(size_t(P) + total);
+    if (size_t(P) + total > c.n) c.n = unsigned(P + total);      // pre-allocated containers take the batch in their dead slots
+    t->pendJ_valid = false;
+    const float mn[3] = { float(t->mins[0]), float(t->mins[1]), float(t->mins[2]) };
+    const unsigned long long pos_seed = seed * 0x9E3779B97F4A7C15ull + t->tile_tag * 0xC2B2AE3D27D4EB4Full;   // the same positions for every species
+    launch_inject_drifting(c.view(), P, t->g, mn, i0, i1, unsigned(ppc), float(delgam), float(gamma_drift), float(dir_sign), pos_seed,
+                           pos_seed ^ (0xA5A5A5A5ull * (sp + 1)) ^ (dir_sign > 0 ? 0x5151ull : 0ull), (t->tile_tag << 40) | t->next_ordinal[sp]);
+    t->next_ordinal[sp] += total;
+    c.P = unsigned(P + total); c.P_valid = true; c.masks_valid = false;
   }
   B2P_CATCH
 }

@@ -369,6 +369,42 @@ k_inject_thermal(const Species s, const Geom g, const float3 mins, const unsigne
   s.id[p] = id_base + p;
 }
 
+// Bench-only generator for the drifting plasmas of the beam and shock workloads (no reference equivalent): ppc
+// particles per cell in the cells [i0, i1) x all j x all k of the tile (pic::Tile::batch_inject_in_x_stripe's cell
+// range and i -> j -> k order, pic/tile.c++:235-322), written to the slots [first, first + ppc * cells).  Momentum: a
+// Maxwellian of spread sqrt(theta) in the rest frame, flux-weighted flip and boost by Gamma along +-x
+// (runko/sample_thermal_distributions.py:58-127 for theta <= 0.2, statistically — not bitwise).
+__global__ void __launch_bounds__(256)
+k_inject_drifting(const Species s, const unsigned first, const Geom g, const float3 mins, const int i0, const int i1, const unsigned ppc,
+                  const float theta, const float Gamma, const float dir, const unsigned long long seed_pos,
+                  const unsigned long long seed_vel, const unsigned long long id_base) {
+  const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned ncell = unsigned(i1 - i0) * g.N[1] * g.N[2];
+  if (p >= ncell * ppc) return;
+  const unsigned cell = p % ncell;
+  const unsigned k = cell % g.N[2], j = (cell / g.N[2]) % g.N[1], i = unsigned(i0) + cell / (g.N[2] * g.N[1]);
+  const unsigned long long gcell = (static_cast<unsigned long long>(i) * g.N[1] + j) * g.N[2] + k;
+  const unsigned long long key = (gcell * 64ull + p / ncell) * 0xD6E8FEB86659FD93ull;
+  Rng rp{ mix64(seed_pos ^ key) };
+  const unsigned n = first + p;
+  s.x[n] = mins.x + float(i) + rp.uniform() * 0.999999f;
+  s.y[n] = mins.y + float(j) + rp.uniform() * 0.999999f;
+  s.z[n] = mins.z + float(k) + rp.uniform() * 0.999999f;
+  Rng rv{ mix64(seed_vel ^ key) };
+  const float sig = sqrtf(theta);
+  const float r1 = sqrtf(-2.0f * logf(rv.uniform())), a1 = 6.2831853f * rv.uniform();
+  const float r2 = sqrtf(-2.0f * logf(rv.uniform())), a2 = 6.2831853f * rv.uniform();
+  float ux = sig * r1 * cosf(a1);
+  const float uy = sig * r1 * sinf(a1), uz = sig * r2 * cosf(a2);
+  const float gam = sqrtf(1.0f + ux * ux + uy * uy + uz * uz);
+  const float beta = sqrtf(fmaxf(0.0f, 1.0f - 1.0f / (Gamma * Gamma)));
+  if (-beta * ux / gam > rv.uniform()) ux = -ux;
+  s.ux[n] = dir * Gamma * (ux + beta * gam);
+  s.uy[n] = uy;
+  s.uz[n] = uz;
+  s.id[n] = id_base + p;
+}
+
 __global__ void __launch_bounds__(256)
 k_selfcheck_divc(const float* __restrict__ x, const unsigned long long n, const float c, float* __restrict__ out, float* __restrict__ ref) {
   const DivC d(c);
@@ -503,6 +539,16 @@ void launch_inject_thermal(const Species& s, const Geom& g, const float mins[3],
   if (!total) return;
   k_inject_thermal<<<blocks_for(total), 256, 0, ctx().stream>>>(s, g, make_float3(mins[0], mins[1], mins[2]), ppc, theta,
                                                                  seed_pos, seed_vel, id_base);
+  B2P_LAUNCH_CHECK();
+}
+
+void launch_inject_drifting(const Species& s, unsigned first, const Geom& g, const float mins[3], int i0, int i1, unsigned ppc, float theta,
+                            float Gamma, float dir, unsigned long long seed_pos, unsigned long long seed_vel, unsigned long long id_base) {
+  ProfScope prof_(KC_OTHER, 0.0);
+  const size_t total = size_t(std::max(0, i1 - i0)) * g.N[1] * g.N[2] * ppc;
+  if (!total) return;
+  k_inject_drifting<<<blocks_for(total), 256, 0, ctx().stream>>>(s, first, g, make_float3(mins[0], mins[1], mins[2]), i0, i1, ppc, theta, Gamma,
+                                                                  dir, seed_pos, seed_vel, id_base);
   B2P_LAUNCH_CHECK();
 }
 

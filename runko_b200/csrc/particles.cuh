@@ -94,4 +94,6 @@ void launch_reflect_at_wall(const Species& s, float* corrJ, const Geom& g, const
                             float betawall, float gammawall, float charge);
 void launch_inject_thermal(const Species& s, const Geom& g, const float mins[3], unsigned ppc, float theta,
                            unsigned long long seed_pos, unsigned long long seed_vel, unsigned long long id_base);
+void launch_inject_drifting(const Species& s, unsigned first, const Geom& g, const float mins[3], int i0, int i1, unsigned ppc, float theta,
+                            float Gamma, float dir, unsigned long long seed_pos, unsigned long long seed_vel, unsigned long long id_base);
 }  // namespace b2p

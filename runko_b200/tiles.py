@@ -548,6 +548,10 @@ class Grid:
     def inject_thermal(self, ppc, delgam, seed=1):
         check(lib().b2p_grid_inject_thermal(self._h, int(ppc), float(delgam), int(seed)))
 
+    def inject_drifting_stripe(self, sp, ppc, delgam, gamma_drift, dir_sign, x_left, x_right, seed=1):
+        check(lib().b2p_grid_inject_drifting_stripe(self._h, int(sp), int(ppc), float(delgam), float(gamma_drift), int(dir_sign),
+                                                    float(x_left), float(x_right), int(seed)))
+
     def set_uniform_B(self, bx, by, bz):
         check(lib().b2p_grid_set_uniform_B(self._h, bx, by, bz))
 
