@@ -6,6 +6,8 @@
 // reference's unfused CPU arithmetic.
 #include "fields.cuh"
 
+#include <algorithm>
+
 namespace b2p {
 
 // thread <-> cell mapping shared by the interior sweeps: x->k, y->j, z->(tile,i)
@@ -138,6 +140,20 @@ k_edge_bc(float* __restrict__ f, const Geom g, const int3 lo, const int3 hi, con
   if (mask & 1u) f[n] = v.x;
   if (mask & 2u) f[size_t(g.Ch) + n] = v.y;
   if (mask & 4u) f[2 * size_t(g.Ch) + n] = v.z;
+}
+// the same for a table of (lattice, box, mask, value) operations on DIFFERENT lattices: blockIdx.y = operation
+__global__ void __launch_bounds__(256)
+k_edge_bc_batch(const EdgeBcOp* __restrict__ ops, const Geom g) {
+  const EdgeBcOp op = ops[blockIdx.y];
+  const size_t ny = size_t(op.hi.y - op.lo.y), nz = size_t(op.hi.z - op.lo.z);
+  const size_t total = size_t(op.hi.x - op.lo.x) * ny * nz;
+  for (size_t q = size_t(blockIdx.x) * blockDim.x + threadIdx.x; q < total; q += size_t(gridDim.x) * blockDim.x) {
+    const size_t i = op.lo.x + q / (ny * nz), j = op.lo.y + (q / nz) % ny, k = op.lo.z + q % nz;
+    const size_t n = (i * g.Hx[1] + j) * g.Hx[2] + k;
+    if (op.mask & 1u) op.f[n] = op.v.x;
+    if (op.mask & 2u) op.f[size_t(g.Ch) + n] = op.v.y;
+    if (op.mask & 4u) op.f[2 * size_t(g.Ch) + n] = op.v.z;
+  }
 }
 // J = J + add over whole haloed lattices (emf/yee_lattice.c++:361-375)
 __global__ void __launch_bounds__(256)
@@ -542,6 +558,15 @@ void launch_edge_bc(float* field, const Geom& g, const int lo[3], const int hi[3
                                                                     make_int3(hi[0], hi[1], hi[2]), mask,
                                                                     make_float3(v[0], v[1], v[2]));
   B2P_LAUNCH_CHECK();
+}
+void launch_edge_bc_batch(const EdgeBcOp* ops, int nops, size_t max_cells, const Geom& g) {
+  ProfScope prof_(KC_OTHER, 0.0);
+  if (!nops || !max_cells) return;
+  const unsigned bx = unsigned(std::min<size_t>((max_cells + 255) / 256, 1024));
+  for (int o = 0; o < nops; o += 65535) {
+    k_edge_bc_batch<<<dim3(bx, unsigned(std::min(65535, nops - o))), 256, 0, ctx().stream>>>(ops + o, g);
+    B2P_LAUNCH_CHECK();
+  }
 }
 void launch_add_lattice(float* J, const float* add, size_t n) {
   ProfScope prof_(KC_ADD_CURRENT, double(n));

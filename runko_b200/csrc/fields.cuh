@@ -19,6 +19,8 @@ void launch_antenna(float* J, float* vec_pot, float* gen_B, const Geom& g, const
 // FieldsWriter<3>::pack_tile, E/B/J part (io/snapshots/mpiio_fields.c++:221-275): buf[nf][nzt][nyt][nxt]
 void launch_pack_snapshot(const FieldPtrs& f, const Geom& g, int stride, int nxt, int nyt, int nzt, int nf, float* buf);
 // YeeLattice::apply_edge_bc (emf/yee_lattice.c++:263-306): masked components of `field` over the box [lo, hi)
+struct EdgeBcOp { float* f; int3 lo, hi; unsigned mask; float3 v; };   // one edge BC on one lattice (box of the haloed lattice)
+void launch_edge_bc_batch(const EdgeBcOp* ops /*device*/, int nops, size_t max_cells, const Geom& g);   // operations on different lattices
 void launch_edge_bc(float* field, const Geom& g, const int lo[3], const int hi[3], unsigned mask, const float v[3]);
 // J = J + add over n floats (YeeLattice::deposit_current(VecGrid), emf/yee_lattice.c++:361-375)
 void launch_add_lattice(float* J, const float* add, size_t n);

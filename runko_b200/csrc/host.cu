@@ -588,7 +588,8 @@ static bool edge_bc_width(const b2p_tile* t, const b2p_edge_bc& bc, size_t* widt
 }
 
 // emf::Tile::apply_edge_bc (emf/tile.c++:835-840) + YeeLattice::apply_edge_bc (emf/yee_lattice.c++:263-306)
-static void apply_edge_bc(b2p_tile* t, const b2p_edge_bc& bc, int mode) {
+// the lattice, component mask, values and box of one BC on one tile; false: the BC does not reach this tile
+static bool edge_bc_op(b2p_tile* t, const b2p_edge_bc& bc, int mode, EdgeBcOp* op) {
   if (bc.direction > 2) throw Error(B2P_ERR_RUNTIME, "edge_bc: direction must be 0, 1 or 2");
   float* field;
   unsigned mask;
@@ -601,7 +602,7 @@ static void apply_edge_bc(b2p_tile* t, const b2p_edge_bc& bc, int mode) {
       throw Error(B2P_ERR_RUNTIME, "YeeLattice::apply_edge_bc does not support given communication mode: " + std::to_string(mode));
   }
   size_t width = 0;
-  if (!edge_bc_width(t, bc, &width) || width == 0) return;
+  if (!edge_bc_width(t, bc, &width) || width == 0 || !(mask & 7u)) return false;
   const int d = bc.direction;
   const int Nd = t->g.N[d];
   const int w = int(std::min<size_t>(width, size_t(Nd)));
@@ -611,12 +612,52 @@ static void apply_edge_bc(b2p_tile* t, const b2p_edge_bc& bc, int mode) {
     else if (bc.side == 0) { lo[a] = 0; hi[a] = H + w; }
     else { lo[a] = H + Nd - w; hi[a] = t->g.Hx[a]; }
   }
-  launch_edge_bc(field, t->g, lo, hi, mask, v);
+  *op = EdgeBcOp{ field, make_int3(lo[0], lo[1], lo[2]), make_int3(hi[0], hi[1], hi[2]), mask, make_float3(v[0], v[1], v[2]) };
+  return true;
 }
 
+// emf::Tile::apply_edge_bc (emf/tile.c++:835-840) + YeeLattice::apply_edge_bc (emf/yee_lattice.c++:263-306)
+static void apply_edge_bc(b2p_tile* t, const b2p_edge_bc& bc, int mode) {
+  EdgeBcOp op;
+  if (!edge_bc_op(t, bc, mode, &op)) return;
+  const int lo[3] = { op.lo.x, op.lo.y, op.lo.z }, hi[3] = { op.hi.x, op.hi.y, op.hi.z };
+  const float v[3] = { op.v.x, op.v.y, op.v.z };
+  launch_edge_bc(op.f, t->g, lo, hi, op.mask, v);
+}
+
+// emf/tile.c++:842-847 for many tiles: a tile's BCs apply in registration order, tiles are independent, so round r
+// applies the r-th BC of every tile in one launch
 void phase_apply_edge_bcs(const std::vector<b2p_tile*>& tiles, int mode) {
-  for (b2p_tile* t : tiles)
-    for (const b2p_edge_bc& bc : t->edge_bcs) apply_edge_bc(t, bc, mode);      // emf/tile.c++:842-847
+  if (tiles.size() == 1) {
+    for (const b2p_edge_bc& bc : tiles[0]->edge_bcs) apply_edge_bc(tiles[0], bc, mode);
+    return;
+  }
+  Scratch& s = scratch();
+  size_t rounds = 0;
+  for (b2p_tile* t : tiles) rounds = std::max(rounds, t->edge_bcs.size());
+  for (size_t r = 0; r < rounds; ++r) {
+    // group by geometry (the kernel takes one Geom)
+    std::vector<EdgeBcOp> ops;
+    size_t max_cells = 0;
+    const Geom* g = nullptr;
+    auto flush = [&] {
+      if (ops.empty()) return;
+      s.table.reserve(ops.size() * sizeof(EdgeBcOp));
+      h2d(reinterpret_cast<EdgeBcOp*>(s.table.p), ops.data(), ops.size());
+      launch_edge_bc_batch(reinterpret_cast<const EdgeBcOp*>(s.table.p), int(ops.size()), max_cells, *g);
+      ops.clear(); max_cells = 0;
+    };
+    for (b2p_tile* t : tiles) {
+      if (r >= t->edge_bcs.size()) continue;
+      EdgeBcOp op;
+      if (!edge_bc_op(t, t->edge_bcs[r], mode, &op)) continue;
+      if (g && std::memcmp(g, &t->g, sizeof(Geom)) != 0) flush();
+      g = &t->g;
+      ops.push_back(op);
+      max_cells = std::max(max_cells, size_t(op.hi.x - op.lo.x) * size_t(op.hi.y - op.lo.y) * size_t(op.hi.z - op.lo.z));
+    }
+    flush();
+  }
 }
 
 // pic::Tile::reflect_particles (pic/reflector_wall.c++:241-284)
@@ -827,7 +868,7 @@ void phase_pack_outgoing(const std::vector<b2p_tile*>& tiles) {
     owners.push_back(t);
     for (Container& c : t->sp) {
       uint2* words = c.mask_words();
-      if (!c.masks_valid) {                                            // not pushed since the last change
+      if (!c.masks_valid && c.n) {                                     // not pushed since the last change
         launch_make_masks(c.view(), words, mn, mx);
         t->pendJ_valid = false;
       }
