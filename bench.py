@@ -625,7 +625,7 @@ def run_named(args):
     pms, pl, pu = np.zeros(nk), np.zeros(nk, np.uint64), np.zeros(nk)
     check(L.b2p_profile_report(pms.ctypes.data_as(C.c_void_p), pl.ctypes.data_as(C.c_void_p), pu.ctypes.data_as(C.c_void_p)))
     check(L.b2p_profile_enable(0))
-    check(L.b2p_set_option(b"push_streams", 2)); check(L.b2p_set_option(b"sort_streams", 1))
+    check(L.b2p_set_option(b"push_streams", 1)); check(L.b2p_set_option(b"sort_streams", 2))
     names = [L.b2p_profile_class_name(k).decode() for k in range(nk)]
     dev_s = ms.value / 1e3
     tot_part = n_part_local
@@ -1027,8 +1027,8 @@ def main():
     pms, pl, pu = np.zeros(nk), np.zeros(nk, np.uint64), np.zeros(nk)
     check(L.b2p_profile_report(pms.ctypes.data_as(C.c_void_p), pl.ctypes.data_as(C.c_void_p), pu.ctypes.data_as(C.c_void_p)))
     check(L.b2p_profile_enable(0))
-    check(L.b2p_set_option(b"push_streams", 2))      # the defaults of common.cuh: Tuning
-    check(L.b2p_set_option(b"sort_streams", 1))
+    check(L.b2p_set_option(b"push_streams", 1))      # the defaults of common.cuh: Tuning
+    check(L.b2p_set_option(b"sort_streams", 2))
     names = [L.b2p_profile_class_name(k).decode() for k in range(nk)]
     barrier()
 

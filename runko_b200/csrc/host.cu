@@ -141,7 +141,7 @@ struct SortBatch {              // scratch of one batch of containers in the cou
   std::vector<Container> spare;         // gather targets (storage swapped with the sorted containers)
 };
 struct Scratch {
-  SortBatch sort_batch;
+  SortBatch sort_batch[2];        // two batches in flight (alternating worker streams)
   DBuf<float4> nodal_w[MAX_WORKERS];   // per worker stream: nodal field means of the tile being pushed
   DBuf<float4> edges_w[MAX_WORKERS];   // per worker stream: cell-edge current accumulators
   DBuf<float4>& nodal = nodal_w[0];
@@ -749,23 +749,26 @@ void phase_sort(const std::vector<b2p_tile*>& tiles, bool leave_running) {
       else items.push_back(Item{ t, &c });
     }
   if (items.empty() && crowded.empty()) return;
-  // The whole sort runs on one worker stream, so that b2p_grid_step_pic can leave it running under the
-  // field phase of the lap (leave_running); launches are per batch of containers, not per container.
+  // The sort runs on worker streams — batches alternate between two of them, so that the atomic-latency-bound
+  // count of one batch overlaps the bandwidth-bound gather of the other — and b2p_grid_step_pic can leave it
+  // running under the field phase of the lap (leave_running); launches are per batch, not per container.
   Workers& wk = workers();
   cudaStream_t main_stream = ctx().stream;
-  const bool on_worker = tuning().sort_streams > 0 && leave_running && tuning().sort_overlap;
-  if (on_worker) {
+  const int nws = std::max(0, std::min(tuning().sort_streams, 2));
+  if (nws) {
     wk.init();
     B2P_CUDA(cudaEventRecord(wk.fork, main_stream));
-    B2P_CUDA(cudaStreamWaitEvent(wk.s[0], wk.fork, 0));
+    for (int w = 0; w < nws; ++w) B2P_CUDA(cudaStreamWaitEvent(wk.s[w], wk.fork, 0));
   }
   {
-    StreamScope on(on_worker ? wk.s[0] : main_stream);
-    SortBatch& sb = s.sort_batch;
     const size_t B = size_t(std::max(1, tuning().sort_batch));
-    if (sb.spare.size() < B) sb.spare.resize(B);
-    size_t q = 0;
+    size_t q = 0, nbatch = 0;
     while (q < items.size()) {
+      const int w = nws ? int(nbatch % size_t(nws)) : 0;
+      ++nbatch;
+      StreamScope on(nws ? wk.s[w] : main_stream);
+      SortBatch& sb = s.sort_batch[w];
+      if (sb.spare.size() < B) sb.spare.resize(B);
       // a batch: up to B containers of one lattice geometry
       const Geom& g = items[q].t->g;
       const unsigned nkeys = g.Ch;
@@ -837,6 +840,7 @@ void phase_sort(const std::vector<b2p_tile*>& tiles, bool leave_running) {
         for (size_t b = 0; b < batch.size(); ++b) { swap_storage(*batch[b].c, sb.spare[b]); batch[b].c->touch(); }
       }
     }
+    StreamScope on_crowded(nws ? wk.s[0] : main_stream);
     for (const Item& it : crowded) {
       sort_radix(it.t, *it.c, 0);
       // let a crowded container return to the counting sort once it has thinned out: probe again every few sorts
@@ -844,8 +848,9 @@ void phase_sort(const std::vector<b2p_tile*>& tiles, bool leave_running) {
       if (counting && ++it.c->radix_sorts_since_probe >= 8) { it.c->radix_sorts_since_probe = 0; *hint = PopHints::UNKNOWN; }
     }
   }
-  if (on_worker) {
-    wk.sort_pending = 1;
+  if (nws) {
+    wk.sort_pending = nws;
+    if (!leave_running || !tuning().sort_overlap) join_pending_sort();
   }
 }
 
