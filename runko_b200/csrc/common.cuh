@@ -71,6 +71,7 @@ struct Tuning {
   int push_streams = 1;   // worker streams the groups of the particle phase are round-robined over (1 = library stream only: with 32 tiles per launch measured 3 % faster than 2)
   int sort_streams = 2;   // worker streams the sort's batches alternate over (0: library stream; at most 2)
   int comm_overlap = 1;   // multi-GPU b2p_grid_step_pic: the B halo exchange runs on its own stream under the pushes of the interior tiles
+  int filter_pairs = 1;   // binomial2 on lattices with even Hz: two k-adjacent outputs per thread, packed fp32x2 (0: one output per thread)
   int sort_batch = 16;    // containers per launch of the counting-sort kernels (scratch: ~200 MB per 4 M-slot container)
   int sort_overlap = 1;   // b2p_grid_step_pic leaves the sort running on the worker streams under the field phase of the lap
   int push_block = 128;       // threads per block of k_push (128 or 256; 128 measured 1 % faster: finer-grained tail)

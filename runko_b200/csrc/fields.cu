@@ -335,6 +335,77 @@ k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g, const int
   }
 }
 
+// binomial2 (the 27-point variant) with TWO k-adjacent outputs per thread, k = 1 + 2 kp and k + 1 (lattices with an
+// even Hz; the outermost layer is written by k_filter_binomial2_shell).  Every row of a plane arrives as two aligned
+// LDG.64 (cells k-1..k+2), and the 27 products + 27 sums of the pair run on the packed fp32x2 pipe: FMUL2, and
+// FFMA2(p, 1, acc) — the fma rounds the exact p*1 + acc once, i.e. the add's bits; the 1 is a kernel argument because
+// ptxas contracts a packed add with the packed product feeding it even under -fmad=false.  Same terms, same
+// index_space order (a slowest) from 0 => bit-identical to the scalar kernel, at half its issue slots.
+__global__ void __launch_bounds__(256)
+k_filter_binomial2_pairs(const FilterTile* __restrict__ tiles, const Geom g, const int chunk, const float one) {
+  const int Hz = g.Hx[2], HyHz = g.Hx[1] * Hz, npair = (Hz - 2) / 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (g.Hx[1] - 2) * npair) return;
+  const int j = 1 + q / npair, k = 1 + 2 * (q - (j - 1) * npair);
+  const int tile = blockIdx.z / 3, c = blockIdx.z - 3 * tile;
+  const int ibeg = max(1, int(blockIdx.y) * chunk), iend = min(int(blockIdx.y + 1) * chunk, g.Hx[0] - 1);
+  if (ibeg >= iend) return;
+  const float* __restrict__ J = tiles[tile].src + size_t(c) * g.Ch;
+  float* __restrict__ out = tiles[tile].dst + size_t(c) * g.Ch;
+  const float2 one2 = make_float2(one, one);
+  // a plane: rows j-1, j, j+1, each as the pairs (k-1,k), (k,k+1), (k+1,k+2) = the operands of the two outputs for d = -1, 0, +1
+  float2 P[3][9];
+  const float* r0 = J + size_t(ibeg - 1) * HyHz + size_t(j - 1) * Hz + (k - 1);     // k - 1 is even and Hz is even: 8-byte aligned
+  auto load = [&](float2 (&dst)[9]) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const float2 lo = *reinterpret_cast<const float2*>(r0 + b * Hz), hi = *reinterpret_cast<const float2*>(r0 + b * Hz + 2);
+      dst[b * 3 + 0] = lo;
+      dst[b * 3 + 1] = make_float2(lo.y, hi.x);
+      dst[b * 3 + 2] = hi;
+    }
+    r0 += HyHz;
+  };
+  load(P[0]);
+  load(P[1]);
+  int i = ibeg;
+  float* o = out + size_t(i) * HyHz + size_t(j) * Hz + k;
+  auto step = [&](const float2 (&A)[9], const float2 (&B)[9], float2 (&C)[9]) -> bool {
+    if (i >= iend) return false;
+    load(C);
+    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float w = ((a == 1) ? 2.f : 1.f) * ((b == 1) ? 2.f : 1.f) * ((d == 1) ? 2.f : 1.f) / 64.f;
+          const float2 x = a == 0 ? A[b * 3 + d] : a == 1 ? B[b * 3 + d] : C[b * 3 + d];
+          acc = __ffma2_rn(__fmul2_rn(make_float2(w, w), x), one2, acc);
+        }
+    o[0] = acc.x; o[1] = acc.y;
+    ++i;
+    o += HyHz;
+    return true;
+  };
+  while (step(P[0], P[1], P[2]) && step(P[1], P[2], P[0]) && step(P[2], P[0], P[1])) {}
+}
+// the outermost layer of dst for the pair kernel: 0 (binomial2 move-assigns a value-initialised grid)
+__global__ void __launch_bounds__(256)
+k_filter_binomial2_shell(const FilterTile* __restrict__ tiles, const Geom g) {
+  const int Hx = g.Hx[0], Hy = g.Hx[1], Hz = g.Hx[2];
+  const int nA = 2 * Hy * Hz, nB = (Hx - 2) * 2 * Hz, nC = (Hx - 2) * (Hy - 2) * 2;
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nA + nB + nC) return;
+  int i, j, k;
+  if (q < nA) { i = q < Hy * Hz ? 0 : Hx - 1; q %= Hy * Hz; j = q / Hz; k = q - j * Hz; }
+  else if (q < nA + nB) { q -= nA; i = 1 + q / (2 * Hz); q %= 2 * Hz; j = q < Hz ? 0 : Hy - 1; k = q % Hz; }
+  else { q -= nA + nB; i = 1 + q / ((Hy - 2) * 2); q %= (Hy - 2) * 2; j = 1 + q / 2; k = (q & 1) ? Hz - 1 : 0; }
+  const int tile = blockIdx.z / 3, c = blockIdx.z - 3 * tile;
+  tiles[tile].dst[size_t(c) * g.Ch + (size_t(i) * Hy + j) * Hz + k] = 0.0f;
+}
+
 // ---- halo fill / J exchange (corgi local_communication, Moore order) ----------
 // Per axis, region of direction d (emf/yee_lattice.h:493-517, 580-602):
 //   subregion(d):               d=-1 [0,3)   d=0 [3,3+N)   d=+1 [3+N,6+N)
@@ -547,7 +618,14 @@ void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unr
   const dim3 grid((g.Hx[1] * g.Hx[2] + 255) / 256, (g.Hx[0] + chunk - 1) / chunk, unsigned(ntiles) * 3);
   const FilterTile* ft = static_cast<const FilterTile*>(filter_tiles);
   if (unrolled) k_filter_binomial2<true><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk);
-  else k_filter_binomial2<false><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk);
+  else if ((g.Hx[2] & 1) == 0 && tuning().filter_pairs) {
+    // even Hz: two outputs per thread on the packed fp32x2 pipe + the zeroed outermost layer
+    const int npair = (g.Hx[1] - 2) * ((g.Hx[2] - 2) / 2);
+    k_filter_binomial2_pairs<<<dim3((npair + 255) / 256, grid.y, grid.z), 256, 0, ctx().stream>>>(ft, g, chunk, 1.0f);
+    B2P_LAUNCH_CHECK();
+    const int nshell = 2 * g.Hx[1] * g.Hx[2] + (g.Hx[0] - 2) * 2 * g.Hx[2] + (g.Hx[0] - 2) * (g.Hx[1] - 2) * 2;
+    k_filter_binomial2_shell<<<dim3((nshell + 255) / 256, 1, grid.z), 256, 0, ctx().stream>>>(ft, g);
+  } else k_filter_binomial2<false><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk);
   B2P_LAUNCH_CHECK();
 }
 void launch_edge_bc(float* field, const Geom& g, const int lo[3], const int hi[3], unsigned mask, const float v[3]) {

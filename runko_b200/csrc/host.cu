@@ -62,6 +62,7 @@ static bool set_option(const std::string& name, int value) {
   else if (name == "sort_streams") g_tuning.sort_streams = value;
   else if (name == "sort_batch") g_tuning.sort_batch = value;
   else if (name == "comm_overlap") g_tuning.comm_overlap = value;
+  else if (name == "filter_pairs") g_tuning.filter_pairs = value;
   else if (name == "push_group") g_tuning.push_group = value;
   else if (name == "push_block") g_tuning.push_block = value;
   else if (name == "sort_overlap") g_tuning.sort_overlap = value;
