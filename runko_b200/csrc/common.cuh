@@ -115,6 +115,15 @@ struct DBuf {
   }
 };
 
+// Pointers read from a job table in device memory are generic to the compiler; telling it that they address global
+// memory turns LD / ST / ATOM (+ an address-space query per atomic) into LDG / STG / RED.
+#define B2P_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#define B2P_GLOBAL_SPECIES(s)                                                                               \
+  do {                                                                                                      \
+    B2P_GLOBAL((s).x); B2P_GLOBAL((s).y); B2P_GLOBAL((s).z); B2P_GLOBAL((s).ux); B2P_GLOBAL((s).uy);        \
+    B2P_GLOBAL((s).uz); B2P_GLOBAL((s).id);                                                                 \
+  } while (0)
+
 // ---- device-visible descriptors -------------------------------------------
 struct Geom {                 // identical for every tile of a grid
   int N[3];                   // interior cells

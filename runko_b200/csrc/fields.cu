@@ -539,6 +539,7 @@ k_J_exchange(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, c
 // double (the reference's serial fp32 sum is reproduced only to tolerance).
 __global__ void __launch_bounds__(256)
 k_field_energy(const FieldPtrs* __restrict__ tiles, const Geom g, double* __restrict__ out /*[ntiles][2]*/) {
+  B2P_GLOBAL(tiles[blockIdx.y].E); B2P_GLOBAL(tiles[blockIdx.y].B);
   const int tile = blockIdx.y;
   const size_t Ni = size_t(g.N[0]) * g.N[1] * g.N[2];
   double sB = 0, sE = 0;

@@ -39,8 +39,9 @@ __device__ __forceinline__ unsigned block_excl_256(const unsigned v, unsigned* t
 
 __global__ void __launch_bounds__(256)
 k_pack_count(const PackJob* __restrict__ jobs) {
-  const PackJob& jb = jobs[blockIdx.y];
+  const PackJob jb = jobs[blockIdx.y];
   if (blockIdx.x >= jb.nseg) return;
+  B2P_GLOBAL(jb.masks); B2P_GLOBAL(jb.seg); B2P_GLOBAL(jb.last_alive); B2P_GLOBAL_SPECIES(jb.s);
   __shared__ unsigned hist[27];
   __shared__ unsigned s_last;
   if (threadIdx.x < 27) hist[threadIdx.x] = 0;

@@ -163,6 +163,7 @@ struct AppendJob {            // one incoming span (pic/tile_communication.c++:1
 __global__ void __launch_bounds__(256)
 k_append(const AppendJob* __restrict__ jobs, const int wrap, const float3 wmin, const float3 wmax, const Geom g, const float cfl) {
   const AppendJob jb = jobs[blockIdx.y];
+  B2P_GLOBAL(jb.src); B2P_GLOBAL(jb.Jpend); B2P_GLOBAL_SPECIES(jb.dst);
   const float Lx = wmax.x - wmin.x, Ly = wmax.y - wmin.y, Lz = wmax.z - wmin.z;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.count; i += gridDim.x * blockDim.x) {
     const b2p_particle_state st = jb.src[i];

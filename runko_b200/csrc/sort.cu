@@ -71,11 +71,12 @@ __device__ __forceinline__ unsigned cell_key(const float px, const float py, con
 
 __global__ void __launch_bounds__(256)
 k_sort_count(const SortJob* __restrict__ jobs, const Geom g, const unsigned dead_key) {
-  const SortJob& jb = jobs[blockIdx.y];
+  const SortJob jb = jobs[blockIdx.y];
   const unsigned n_total = jb.src.n;
   const unsigned first = blockIdx.x * (256u * SORT_SLOTS_PER_THREAD);
   if (first >= n_total) return;
   const Species s = jb.src;
+  B2P_GLOBAL_SPECIES(s); B2P_GLOBAL(jb.cnt); B2P_GLOBAL(jb.keys); B2P_GLOBAL(jb.rank);
   const float3 origo = jb.origo;
   unsigned* __restrict__ cnt = jb.cnt;
   // SORT_SLOTS_PER_THREAD slots per thread, 256 apart: all loads, then all atomics, are in flight together
@@ -134,7 +135,8 @@ __device__ __forceinline__ unsigned block_exclusive_scan_256(const unsigned v, u
 }
 __global__ void __launch_bounds__(256)
 k_sort_chunk_sums(const SortJob* __restrict__ jobs, const unsigned nkeys, const unsigned nchunks) {
-  const SortJob& jb = jobs[blockIdx.y];
+  const SortJob jb = jobs[blockIdx.y];
+  B2P_GLOBAL(jb.cnt); B2P_GLOBAL(jb.chunk_sums);
   const unsigned ncount = nkeys + 2u;
   const unsigned i0 = blockIdx.x * SCAN_CHUNK + threadIdx.x * 8u;
   unsigned sum = 0, mx = 0;
@@ -159,7 +161,8 @@ k_sort_chunk_sums(const SortJob* __restrict__ jobs, const unsigned nkeys, const 
 }
 __global__ void __launch_bounds__(256)
 k_sort_scan_chunks(const SortJob* __restrict__ jobs, const unsigned nkeys, const unsigned nchunks) {
-  const SortJob& jb = jobs[blockIdx.y];
+  const SortJob jb = jobs[blockIdx.y];
+  B2P_GLOBAL(jb.cnt); B2P_GLOBAL(jb.chunk_sums); B2P_GLOBAL(jb.offs);
   const unsigned ncount = nkeys + 2u;
   // totals of the chunks before mine
   unsigned part = 0;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Turn what tools/gpu/collect_evidence.sh brings back in gpurun_out/ into the summaries kept under profiles/.
-usage: tools/profile_summaries.py TAG OUT_SUFFIX     (e.g. 30 i  ->  profiles/r01_*_i.json)"""
+"""Turn what tools/gpu/r02_evidence.sh brings back in gpurun_out/ into the summaries kept under profiles/.
+usage: tools/profile_summaries.py TAG     (e.g. b  ->  profiles/r02_*_b.json, profiles/r02_push_traffic.json)"""
 import collections
 import csv
 import gzip
@@ -64,15 +64,26 @@ def raw(path):
 
 
 def main():
-    tag, suf = sys.argv[1], sys.argv[2]
-    ks = launches(f"gpurun_out/launches{tag}.csv.gz", f"profiles/r01_launches_summary_{suf}.json")
+    tag = sys.argv[1]
+    ks = launches(f"gpurun_out/r02_launches_{tag}.csv.gz", f"profiles/r02_launches_summary_{tag}.json")
     for k in ks[:8]:
         print(k)
-    push = raw(f"gpurun_out/r{tag}_push_raw.csv")
-    rest = raw(f"gpurun_out/r{tag}_rest_raw.csv")
-    json.dump({"how": "ncu --set full --clock-control none on tools/microbench.py --cells 128 (8 tiles of 64^3, 4.19 M particles per "
-                      "container), worker streams off; one launch per entry", "k_push (fused push+deposit)": push,
-               "other kernels": rest}, open(f"profiles/r01_ncu_summary_{suf}.json", "w"), indent=1)
+    push = raw(f"gpurun_out/r02_{tag}_push_raw.csv")
+    rest = raw(f"gpurun_out/r02_{tag}_rest_raw.csv")
+    json.dump({"how": "ncu --set full --clock-control none on tools/microbench.py --cells 128 (8 tiles of 64^3: ONE k_push launch covers "
+                      "16 containers of 4.19 M particles = 67.1 M alive particles), worker streams off; one launch per entry",
+               "k_push (fused push+deposit, 16 containers per launch)": push, "other kernels": rest},
+              open(f"profiles/r02_ncu_summary_{tag}.json", "w"), indent=1)
+    alive = 2 * 16 * 128 ** 3
+    d = push[-1]
+    rd = next(v for k, v in d.items() if k.startswith("dram__bytes_read.sum"))
+    wr = next(v for k, v in d.items() if k.startswith("dram__bytes_write.sum"))
+    unit = next(k for k in d if k.startswith("dram__bytes_read.sum"))
+    scale = 1e6 if "Mbyte" in unit else (1e9 if "Gbyte" in unit else (1e3 if "Kbyte" in unit else 1.0))
+    json.dump({"source": f"profiles/r02_ncu_summary_{tag}.json: dram__bytes_read.sum + dram__bytes_write.sum of one k_push launch "
+                         "(16 containers, fused push+deposit)",
+               "traffic_bytes_per_launch": (rd + wr) * scale, "alive_particles_per_launch": alive,
+               "bytes_per_alive_particle": (rd + wr) * scale / alive}, open("profiles/r02_push_traffic.json", "w"), indent=1)
     for d in push:
         print(json.dumps(d, indent=1))
 
