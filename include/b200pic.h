@@ -292,6 +292,9 @@ int b2p_timer_stop(float* ms);
 uint64_t b2p_launch_count(void);
 /* bytes this library has copied host->device / device->host since process start */
 void b2p_copy_bytes(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* wall-clock milliseconds the calling host thread has spent blocked in stream synchronisations inside this
+ * library since process start (bench.py: host wall time per step minus this = time spent enqueueing) */
+void b2p_host_wait_ms(double* ms);
 /* Per-kernel-class device timing (CUDA events on the launch stream around every
  * launch of the class).  enable(1) clears and starts, enable(0) stops; report()
  * fills arrays of b2p_profile_num_classes() entries: total ms, launches and

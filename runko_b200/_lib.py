@@ -30,7 +30,7 @@ b2p_grid_push_half_b b2p_grid_push_e b2p_grid_add_current b2p_grid_filter_curren
 b2p_grid_push_particles b2p_grid_pack_outgoing_particles b2p_grid_sort_particles b2p_grid_deposit_current
 b2p_grid_step_pic b2p_grid_step_emf b2p_grid_energies b2p_grid_inject_thermal b2p_grid_inject_drifting_stripe b2p_grid_set_uniform_B
 b2p_nccl_unique_id b2p_grid_comm_init b2p_grid_external_communication b2p_plan_describe
-b2p_timer_start b2p_timer_stop b2p_launch_count b2p_copy_bytes
+b2p_timer_start b2p_timer_stop b2p_launch_count b2p_copy_bytes b2p_host_wait_ms
 b2p_profile_enable b2p_profile_num_classes b2p_profile_class_name b2p_profile_report
 b2p_selfcheck_const_division
 """.split()
@@ -117,6 +117,8 @@ def lib():
     L.b2p_timer_stop.argtypes = [C.POINTER(C.c_float)]
     L.b2p_copy_bytes.argtypes = [C.POINTER(u64), C.POINTER(u64)]
     L.b2p_copy_bytes.restype = None
+    L.b2p_host_wait_ms.argtypes = [C.POINTER(C.c_double)]
+    L.b2p_host_wait_ms.restype = None
     L.b2p_profile_enable.argtypes = [ci]
     L.b2p_profile_class_name.argtypes = [ci]
     L.b2p_profile_class_name.restype = C.c_char_p

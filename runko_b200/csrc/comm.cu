@@ -173,7 +173,7 @@ b2p_grid::~b2p_grid() {
 
 namespace b2p {
 
-static void sync_stream() { B2P_CUDA(cudaStreamSynchronize(ctx().stream)); }
+static void sync_stream() { timed_stream_sync(); }
 
 // region of tile lattice that is SENT for entry e: kind 0 = corresponding_subregion(-dir)
 // (my interior edge facing the peer), kind 1 = subregion(dir) (my halo facing the peer)

@@ -5,6 +5,7 @@
 //   particles: per (tile, species) SoA streams x,y,z,ux,uy,uz (fp32) + id (u64)
 #pragma once
 #include <cuda_runtime.h>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -37,6 +38,7 @@ struct Context {
   int sm_count = 148;
   unsigned long long launches = 0;
   unsigned long long h2d_bytes = 0, d2h_bytes = 0;
+  double host_wait_ms = 0.0;   // wall time the host has spent blocked in stream synchronisations (b2p_host_wait_ms)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 Context& ctx();          // initialises lazily on device 0; throws if no GPU
@@ -54,6 +56,9 @@ enum KernelClass {
   KC_ZERO, KC_PUSH_B, KC_PUSH_E, KC_ADD_CURRENT, KC_FILTER, KC_HALO, KC_J_EXCHANGE, KC_ENERGY, KC_EDGE_GATHER, KC_OTHER, KC_NCCL, KC_COUNT
 };
 const char* kernel_class_name(int k);
+// cudaStreamSynchronize on the library's current stream, with the blocked wall time booked to Context::host_wait_ms
+void timed_stream_sync();
+
 struct ProfScope {
   int idx = -1;
   explicit ProfScope(KernelClass k, double units = 0.0);

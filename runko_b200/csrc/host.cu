@@ -99,7 +99,12 @@ void* dmalloc(size_t bytes) {
 void dfree(void* p) {
   if (p && g_ctx_ready) cudaFreeAsync(p, g_ctx.stream);
 }
-static void stream_sync() { B2P_CUDA(cudaStreamSynchronize(ctx().stream)); }
+void timed_stream_sync() {
+  const auto t0 = std::chrono::steady_clock::now();
+  B2P_CUDA(cudaStreamSynchronize(ctx().stream));
+  g_ctx.host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+static void stream_sync() { timed_stream_sync(); }
 template <class T> static void h2d(T* dst, const T* src, size_t n) {
   if (n) { B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx().stream)); g_ctx.h2d_bytes += n * sizeof(T); }
 }
@@ -1820,6 +1825,9 @@ uint64_t b2p_launch_count(void) {
 void b2p_copy_bytes(uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
   if (h2d_bytes) *h2d_bytes = g_ctx_ready ? ctx().h2d_bytes : 0;
   if (d2h_bytes) *d2h_bytes = g_ctx_ready ? ctx().d2h_bytes : 0;
+}
+void b2p_host_wait_ms(double* ms) {
+  if (ms) *ms = g_ctx_ready ? ctx().host_wait_ms : 0.0;
 }
 int b2p_profile_enable(int on) {
   B2P_TRY
