@@ -330,7 +330,11 @@ static void exchange_particles(b2p_grid* g) {
   }
   B2P_NCCL(n.GroupEnd());
   delete prof_hs_;
-  B2P_CUDA(cudaMemcpyAsync(cr.data(), p.d_cnt_recv.p, cr.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
+  {
+    const auto t0 = std::chrono::steady_clock::now();     // pageable destination: the copy blocks until the stream gets there
+    B2P_CUDA(cudaMemcpyAsync(cr.data(), p.d_cnt_recv.p, cr.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
+    ctx().host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
   sync_stream();
   // payload: contiguous per peer
   size_t send_total = 0, recv_total = 0;

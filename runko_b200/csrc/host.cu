@@ -109,7 +109,13 @@ template <class T> static void h2d(T* dst, const T* src, size_t n) {
   if (n) { B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx().stream)); g_ctx.h2d_bytes += n * sizeof(T); }
 }
 template <class T> static void d2h(T* dst, const T* src, size_t n) {
-  if (n) { B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream)); g_ctx.d2h_bytes += n * sizeof(T); }
+  if (!n) return;
+  // a device-to-host copy into pageable memory returns only when the data has landed: the wait for the stream to get there
+  // is booked as blocked time, like a synchronisation
+  const auto t0 = std::chrono::steady_clock::now();
+  B2P_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream));
+  g_ctx.host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  g_ctx.d2h_bytes += n * sizeof(T);
 }
 
 // ----------------------------------------------------------------- profiler --

@@ -9,15 +9,16 @@
 //   2. k_sort_chunk_sums + k_sort_scan_chunks   offs = exclusive scan of cnt (nkeys + 2 counters) and the largest
 //                     cell population (a routing hint for the container's NEXT sort)
 //   3. k_sort_scatter members[offs[key] + rank] = n: the slots of every cell, in arrival order
-//   4. k_sort_place   one thread per destination slot: its member n, the member's STABLE position inside its cell
-//                     (= offs[key] + number of members of the cell with a smaller slot index; the cell's list is a
-//                     few tens of entries that the neighbouring lanes read too: L1 broadcasts), and the gather of
-//                     the seven streams dst[pos] = src[n]; destination slots behind the alive particles get the dead id.
+//   4. k_sort_cells   one thread per cell puts the cell's list into slot order in shared memory (insertion sort of a
+//                     few tens of entries); lists longer than 64 are ranked by the whole block
+//   5. k_sort_place   one thread per destination slot: dst[e] = src[members[e]] for the seven streams; destination
+//                     slots behind the alive particles get the dead id.
 // Result: exactly the stable order for any input.  Step 4 is quadratic in the population of a cell, so the host
 // routes containers whose last known largest cell exceeded SORT_RADIX_POP to a general radix sort of (key, slot)
 // pairs (CUB; crowded containers only — never the steady state of a plasma).
 #include "particles.cuh"
 #include "pmath.cuh"
+#include "sortnet.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -213,29 +214,141 @@ k_sort_scatter(const SortJob* __restrict__ jobs, const unsigned dead_key) {
     if (k[r] != dead_key) jb.members[o[r] + r_[r]] = n[r];
 }
 
+// Step 4: every cell's member list, which the scatter left in ARRIVAL order, is put into slot order — the stable
+// order of the reference's sort (pic/particle.h:607-640).  One thread per cell: a block stages the lists of its 256
+// consecutive cells (one contiguous range of `members`) in shared memory with coalesced loads, each thread sorts its
+// own list (registers, a fixed min/max network for up to 32 entries; an insertion sort up to 64), and the range is
+// written back.  Lists longer than CELLS_SMALL_POP are ranked by the whole block afterwards (every entry counts the smaller
+// entries of its list; `rank`, dead since the scatter, is the staging buffer); ranges that do not fit the staging
+// buffer are ordered in global memory.
+constexpr unsigned CELLS_SMALL_POP = 64;
+constexpr unsigned CELLS_STAGE = 6144;       // entries staged per block
+// Lists of a uniform plasma start 16 entries apart, i.e. on two of the 32 banks: one padding word per 16 entries
+// (start 17 apart) spreads the threads' lists over all banks.
+__device__ __forceinline__ unsigned pad16(const unsigned i) { return i + (i >> 4); }
+
+template <class At>
+__device__ __forceinline__ void insertion_sort(At at, const unsigned n) {
+  for (unsigned i = 1; i < n; ++i) {
+    const unsigned v = at(i);
+    unsigned j = i;
+    while (j > 0) {
+      const unsigned w = at(j - 1);
+      if (w <= v) break;
+      at(j) = w;
+      --j;
+    }
+    at(j) = v;
+  }
+}
+
+// Batcher's odd-even merge sort of N = 2^m values held in registers: a fixed network of min/max pairs (63 for 16,
+// 191 for 32), no branches and no memory traffic — the lanes of a warp sort their lists in lockstep whatever the
+// arrival order was (an insertion sort pays the longest list and the worst order of the 32 lanes at every step).
+template <int N, class At>
+__device__ __forceinline__ void network_sort(At at, const unsigned n, const bool active) {
+  static_assert(N == 16 || N == 32, "networks are generated for 16 and 32 inputs (sortnet.cuh)");
+  unsigned v[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    v[k] = 0xFFFFFFFFu;
+    if (active && unsigned(k) < n) v[k] = at(unsigned(k));
+  }
+#define B2P_CE(a, b) { const unsigned lo_ = min(v[a], v[b]), hi_ = max(v[a], v[b]); v[a] = lo_; v[b] = hi_; }
+  if (N == 16) { B2P_SORTNET16(B2P_CE) } else { B2P_SORTNET32(B2P_CE) }
+#undef B2P_CE
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    if (active && unsigned(k) < n) at(unsigned(k)) = v[k];
+}
+
+// one thread orders one list of 2..CELLS_SMALL_POP entries; the network width is a warp-uniform choice
+template <class At>
+__device__ __forceinline__ void order_list(At at, const unsigned pop) {
+  const bool net = pop >= 2u && pop <= 32u;
+  const unsigned wmax = __reduce_max_sync(0xffffffffu, net ? pop : 0u);
+  if (wmax > 16u) network_sort<32>(at, pop, net);
+  else if (wmax >= 2u) network_sort<16>(at, pop, net);
+  if (pop > 32u && pop <= CELLS_SMALL_POP) insertion_sort(at, pop);
+}
+
+#ifndef B2P_CELLS_MINB
+#define B2P_CELLS_MINB 4
+#endif
+__global__ void __launch_bounds__(256, B2P_CELLS_MINB)
+k_sort_cells(const SortJob* __restrict__ jobs, const unsigned nkeys) {
+  const SortJob jb = jobs[blockIdx.y];
+  B2P_GLOBAL(jb.offs); B2P_GLOBAL(jb.members); B2P_GLOBAL(jb.rank);
+  const unsigned c0 = blockIdx.x * 256u;
+  if (c0 >= nkeys) return;
+  __shared__ unsigned s_off[257];
+  __shared__ unsigned buf[CELLS_STAGE + CELLS_STAGE / 16 + 1];
+  __shared__ unsigned n_large;
+  __shared__ unsigned short large[256];
+  const unsigned c = c0 + threadIdx.x;
+  s_off[threadIdx.x] = jb.offs[min(c, nkeys)];
+  if (threadIdx.x == 255) s_off[256] = jb.offs[min(c + 1u, nkeys)];
+  if (threadIdx.x == 0) n_large = 0;
+  __syncthreads();
+  const unsigned blo = s_off[0], B = s_off[256] - blo;
+  if (B == 0) return;                                               // halo cells: nothing lives there
+  const unsigned lo = s_off[threadIdx.x], pop = s_off[threadIdx.x + 1] - lo;
+  unsigned* __restrict__ members = jb.members;
+  if (pop > CELLS_SMALL_POP) large[atomicAdd(&n_large, 1u)] = (unsigned short)threadIdx.x;
+  if (B <= CELLS_STAGE) {
+    for (unsigned i = threadIdx.x; i < B; i += 256u) buf[pad16(i)] = members[blo + i];
+    __syncthreads();
+    const unsigned base = lo - blo;
+    order_list([&](const unsigned k) -> unsigned& { return buf[pad16(base + k)]; }, pop);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < B; i += 256u) members[blo + i] = buf[pad16(i)];
+  } else {
+    order_list([&](const unsigned k) -> unsigned& { return members[lo + k]; }, pop);
+  }
+  __syncthreads();
+  // crowded cells: stable rank by counting, the whole block per cell
+  unsigned* __restrict__ tmp = jb.rank;
+  for (unsigned q = 0; q < n_large; ++q) {
+    const unsigned t = large[q], l0 = s_off[t], l1 = s_off[t + 1];
+    for (unsigned i = l0 + threadIdx.x; i < l1; i += 256u) {
+      const unsigned v = members[i];
+      unsigned before = 0;
+      for (unsigned k = l0; k < l1; ++k) before += unsigned(members[k] < v);
+      tmp[l0 + before] = v;
+    }
+    __syncthreads();
+    for (unsigned i = l0 + threadIdx.x; i < l1; i += 256u) members[i] = tmp[i];
+    __syncthreads();
+  }
+}
+
+// Step 5: one thread per destination slot moves the seven streams of its member; destination slots behind the alive
+// particles get the dead id.
+#ifndef B2P_PLACE_SLOTS
+#define B2P_PLACE_SLOTS 4
+#endif
+constexpr int PLACE_SLOTS_PER_THREAD = B2P_PLACE_SLOTS;
 __global__ void __launch_bounds__(256)
 k_sort_place(const SortJob* __restrict__ jobs, const unsigned nkeys) {
-  const SortJob& jb = jobs[blockIdx.y];
+  const SortJob jb = jobs[blockIdx.y];
   const Species src = jb.src, dst = jb.dst;
-  const unsigned first = blockIdx.x * (256u * SORT_SLOTS_PER_THREAD);
+  B2P_GLOBAL_SPECIES(src); B2P_GLOBAL_SPECIES(dst); B2P_GLOBAL(jb.members); B2P_GLOBAL(jb.offs);
+  const unsigned first = blockIdx.x * (256u * PLACE_SLOTS_PER_THREAD);
   if (first >= src.n) return;
   const unsigned* __restrict__ members = jb.members;
-  const unsigned* __restrict__ keys = jb.keys;
-  const unsigned* __restrict__ offs = jb.offs;
-  const unsigned na = offs[nkeys];                                 // alive particles
-  unsigned e[SORT_SLOTS_PER_THREAD], p[SORT_SLOTS_PER_THREAD], pos[SORT_SLOTS_PER_THREAD];
-  bool a[SORT_SLOTS_PER_THREAD];
-  float f[SORT_SLOTS_PER_THREAD][6];
-  unsigned long long id[SORT_SLOTS_PER_THREAD];
+  const unsigned na = jb.offs[nkeys];                              // alive particles
+  unsigned e[PLACE_SLOTS_PER_THREAD], p[PLACE_SLOTS_PER_THREAD];
+  bool a[PLACE_SLOTS_PER_THREAD];
+  float f[PLACE_SLOTS_PER_THREAD][6];
+  unsigned long long id[PLACE_SLOTS_PER_THREAD];
 #pragma unroll
-  for (int r = 0; r < SORT_SLOTS_PER_THREAD; ++r) {
+  for (int r = 0; r < PLACE_SLOTS_PER_THREAD; ++r) {
     e[r] = first + 256u * r + threadIdx.x;
     a[r] = e[r] < na;
     p[r] = a[r] ? members[e[r]] : 0u;
   }
-  // the seven gathers of every slot are requested before the cell lists are walked
 #pragma unroll
-  for (int r = 0; r < SORT_SLOTS_PER_THREAD; ++r) {
+  for (int r = 0; r < PLACE_SLOTS_PER_THREAD; ++r) {
     id[r] = DEAD;
     if (a[r]) {
       f[r][0] = src.x[p[r]]; f[r][1] = src.y[p[r]]; f[r][2] = src.z[p[r]];
@@ -243,42 +356,12 @@ k_sort_place(const SortJob* __restrict__ jobs, const unsigned nkeys) {
       id[r] = src.id[p[r]];
     }
   }
-  // Stable position of every member inside its cell: the cell's list is walked four entries at a time (aligned
-  // 16-byte loads that the neighbouring lanes of the same cell share), the walks of the thread's slots interleaved.
-  unsigned lo[SORT_SLOTS_PER_THREAD], hi[SORT_SLOTS_PER_THREAD], q4[SORT_SLOTS_PER_THREAD], before[SORT_SLOTS_PER_THREAD];
 #pragma unroll
-  for (int r = 0; r < SORT_SLOTS_PER_THREAD; ++r) {
-    lo[r] = hi[r] = q4[r] = before[r] = 0;
+  for (int r = 0; r < PLACE_SLOTS_PER_THREAD; ++r) {
     if (a[r]) {
-      const unsigned key = keys[p[r]];
-      lo[r] = offs[key]; hi[r] = offs[key + 1];
-      q4[r] = lo[r] & ~3u;
-    }
-  }
-  const uint4* __restrict__ members4 = reinterpret_cast<const uint4*>(members);   // slices are 256-byte aligned
-  for (;;) {
-    bool more = false;
-#pragma unroll
-    for (int r = 0; r < SORT_SLOTS_PER_THREAD; ++r) {
-      if (q4[r] < hi[r]) {
-        const uint4 m = members4[q4[r] >> 2];
-        const unsigned q = q4[r];
-        before[r] += unsigned(q >= lo[r] && m.x < p[r]) + unsigned(q + 1 >= lo[r] && q + 1 < hi[r] && m.y < p[r]) +
-                     unsigned(q + 2 >= lo[r] && q + 2 < hi[r] && m.z < p[r]) + unsigned(q + 3 >= lo[r] && q + 3 < hi[r] && m.w < p[r]);
-        q4[r] += 4;
-        more = more || q4[r] < hi[r];
-      }
-    }
-    if (!more) break;
-  }
-#pragma unroll
-  for (int r = 0; r < SORT_SLOTS_PER_THREAD; ++r) pos[r] = a[r] ? lo[r] + before[r] : e[r];
-#pragma unroll
-  for (int r = 0; r < SORT_SLOTS_PER_THREAD; ++r) {
-    if (a[r]) {
-      dst.x[pos[r]] = f[r][0]; dst.y[pos[r]] = f[r][1]; dst.z[pos[r]] = f[r][2];
-      dst.ux[pos[r]] = f[r][3]; dst.uy[pos[r]] = f[r][4]; dst.uz[pos[r]] = f[r][5];
-      dst.id[pos[r]] = id[r];
+      dst.x[e[r]] = f[r][0]; dst.y[e[r]] = f[r][1]; dst.z[e[r]] = f[r][2];
+      dst.ux[e[r]] = f[r][3]; dst.uy[e[r]] = f[r][4]; dst.uz[e[r]] = f[r][5];
+      dst.id[e[r]] = id[r];
     } else if (e[r] < src.n) {
       dst.id[e[r]] = DEAD;
     }
@@ -344,8 +427,14 @@ void launch_sort_scatter_place(const SortJob* jobs, int njobs, unsigned max_n, d
     k_sort_scatter<<<grid, 256, 0, ctx().stream>>>(jobs, nkeys);
     B2P_LAUNCH_CHECK();
   }
+  {
+    ProfScope prof_(KC_RADIX_SORT, total_slots);
+    k_sort_cells<<<dim3((nkeys + 255u) / 256u, unsigned(njobs)), 256, 0, ctx().stream>>>(jobs, nkeys);
+    B2P_LAUNCH_CHECK();
+  }
   ProfScope prof_(KC_GATHER, total_slots);
-  k_sort_place<<<grid, 256, 0, ctx().stream>>>(jobs, nkeys);
+  const dim3 pgrid((max_n + 256 * PLACE_SLOTS_PER_THREAD - 1) / (256 * PLACE_SLOTS_PER_THREAD), unsigned(njobs));
+  k_sort_place<<<pgrid, 256, 0, ctx().stream>>>(jobs, nkeys);
   B2P_LAUNCH_CHECK();
 }
 
