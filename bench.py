@@ -1238,6 +1238,21 @@ def run_e2e(args, rb, L, conf, grid, tiles, world, dist):
     dt = time.perf_counter() - t0
     h1, d1 = C.c_uint64(), C.c_uint64()
     L.b2p_copy_bytes(C.byref(h1), C.byref(d1))
+    if args.profile and world == 1:
+        # where an end-to-end step spends its time (one further step, a synchronisation after every section; not timed above)
+        t = tiles[steps % len(tiles)]
+        ta = time.perf_counter()
+        state = [t.get_particles(sp, alive_only=False, out=host[sp]) for sp in range(2)]
+        rb.sync(); tb = time.perf_counter()
+        for sp in range(2):
+            t.set_particles_raw(sp, *state[sp])
+        rb.sync(); tc = time.perf_counter()
+        lap_via_tile_api(lap + steps)
+        rb.sync(); td = time.perf_counter()
+        grid.energies()
+        te = time.perf_counter()
+        print(f"  e2e step sections [ms]: tile state D2H {1e3 * (tb - ta):.1f}, H2D {1e3 * (tc - tb):.1f}, "
+              f"lap through the tile API + diagnostics {1e3 * (td - tc):.1f}, diagnostics alone {1e3 * (te - td):.1f}", file=sys.stderr)
     for sp in range(2):
         for a in host[sp]:
             L.b2p_host_unregister(a.ctypes.data_as(C.c_void_p))

@@ -1706,6 +1706,31 @@ int b2p_grid_step_emf(b2p_grid* g) {
   B2P_CATCH
 }
 
+// one k_kinetic_energy_batch launch per 256 containers of the grid: per-species sums into energy[q] / alive[q]
+static void energy_jobs(b2p_grid* g, double* energy, unsigned long long* alive) {
+  const int ns = g->cfg.n_species;
+  std::vector<EnergyJob> jobs;
+  unsigned max_n = 0;
+  double slots = 0;
+  auto flush = [&] {
+    if (jobs.empty()) return;
+    Scratch& s = scratch();
+    s.table.reserve(jobs.size() * sizeof(EnergyJob));
+    h2d(reinterpret_cast<EnergyJob*>(s.table.p), jobs.data(), jobs.size());
+    launch_kinetic_energy_batch(reinterpret_cast<const EnergyJob*>(s.table.p), int(jobs.size()), max_n, slots);
+    jobs.clear(); max_n = 0; slots = 0;      // (a pageable source is staged before cudaMemcpyAsync returns)
+  };
+  for (b2p_tile* t : g->tiles)
+    for (int q = 0; q < ns; ++q) {
+      Container& c = t->sp[q];
+      if (!c.n) continue;
+      jobs.push_back(EnergyJob{ c.view(), energy ? energy + q : nullptr, alive ? alive + q : nullptr });
+      max_n = std::max(max_n, c.n); slots += c.n;
+      if (jobs.size() == 4096) flush();
+    }
+  flush();
+}
+
 int b2p_grid_energies(b2p_grid* g, double* eB, double* eE, double* kinetic, uint64_t* sizes) {
   B2P_TRY
   G(g);
@@ -1717,8 +1742,9 @@ int b2p_grid_energies(b2p_grid* g, double* eB, double* eE, double* kinetic, uint
   launch_field_energy(g->device_table(), nt, g->g, s.energy.p);
   B2P_CUDA(cudaMemsetAsync(dk, 0, sizeof(double) * (ns + 1), ctx().stream));
   std::vector<uint64_t> hs(ns, 0);
+  energy_jobs(g, dk, nullptr);
   for (b2p_tile* t : g->tiles)
-    for (int q = 0; q < ns; ++q) { launch_kinetic_energy(t->sp[q].view(), dk + q); hs[q] += t->sp[q].n; }
+    for (int q = 0; q < ns; ++q) hs[q] += t->sp[q].n;
   std::vector<double> h(size_t(2) * nt + ns);
   d2h(h.data(), s.energy.p, size_t(2) * nt);
   d2h(h.data() + 2 * size_t(nt), dk, ns);
@@ -1739,8 +1765,7 @@ int b2p_grid_alive_counts(b2p_grid* g, uint64_t* counts) {
   s.energy.reserve(size_t(ns) + 1);
   unsigned long long* dc = reinterpret_cast<unsigned long long*>(s.energy.p);
   B2P_CUDA(cudaMemsetAsync(dc, 0, sizeof(unsigned long long) * ns, ctx().stream));
-  for (b2p_tile* t : g->tiles)
-    for (int q = 0; q < ns; ++q) launch_count_alive(t->sp[q].view(), dc + q);
+  energy_jobs(g, nullptr, dc);
   std::vector<unsigned long long> h(ns);
   d2h(h.data(), dc, size_t(ns));
   stream_sync();

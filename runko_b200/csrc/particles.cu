@@ -208,6 +208,35 @@ k_kinetic_energy(const Species s, double* __restrict__ out) {
   }
 }
 
+// The same sum for many containers in one launch (blockIdx.y = job; the grid-wide diagnostics of every lap,
+// io_average_kinetic_energy): 12 + 8 B per slot, HBM-bound.
+__global__ void __launch_bounds__(256)
+k_kinetic_energy_batch(const EnergyJob* __restrict__ jobs) {
+  const EnergyJob jb = jobs[blockIdx.y];
+  const Species s = jb.s;
+  B2P_GLOBAL_SPECIES(s); B2P_GLOBAL(jb.energy); B2P_GLOBAL(jb.alive);
+  if (blockIdx.x * blockDim.x >= s.n) return;
+  double acc = 0.0;
+  unsigned cnt = 0;
+  for (unsigned n = blockIdx.x * blockDim.x + threadIdx.x; n < s.n; n += gridDim.x * blockDim.x) {
+    const V3 v = { s.ux[n], s.uy[n], s.uz[n] };
+    const float e = sqrtf(1.0f + dot(v, v)) - 1.0f;
+    if (s.id[n] != DEAD) { acc += double(e); ++cnt; }
+  }
+  for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  __shared__ double sh[8];
+  __shared__ unsigned sc[8];
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = acc; sc[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    unsigned long long c = 0;
+    for (int q = 0; q < int(blockDim.x >> 5); ++q) { t += sh[q]; c += sc[q]; }
+    if (jb.energy) atomicAdd(jb.energy, t);
+    if (jb.alive) atomicAdd(jb.alive, c);
+  }
+}
+
 // ----------------------------------------------------------- reflector wall --
 // pic/reflector_wall.c++:35-118: zigzag deposit of one sub-trajectory x1 -> x2 (lattice-local
 // coordinates) into the nodal correction lattice.  Same operands and association as the
@@ -508,6 +537,16 @@ void launch_kinetic_energy(const Species& s, double* out) {
   if (!s.n) return;
   const unsigned nb = std::min(blocks_for(s.n), unsigned(ctx().sm_count) * 8);
   k_kinetic_energy<<<nb, 256, 0, ctx().stream>>>(s, out);
+  B2P_LAUNCH_CHECK();
+}
+
+// njobs containers of the DEVICE table `jobs`; max_n = the largest container
+void launch_kinetic_energy_batch(const EnergyJob* jobs, int njobs, unsigned max_n, double total_slots) {
+  ProfScope prof_(KC_ENERGY, total_slots);
+  if (!njobs || !max_n) return;
+  // about two waves of resident blocks over the whole batch, every block striding through its container
+  const unsigned per_job = std::max(1u, std::min(blocks_for(max_n), unsigned(ctx().sm_count) * 16u / unsigned(njobs) + 1u));
+  k_kinetic_energy_batch<<<dim3(per_job, unsigned(njobs)), 256, 0, ctx().stream>>>(jobs);
   B2P_LAUNCH_CHECK();
 }
 

@@ -86,6 +86,9 @@ void launch_append(const void* jobs, int njobs, unsigned max_count, bool wrap, c
 void launch_selfcheck_divc(const float* x, unsigned long long n, float c, float* out, float* ref);
 void launch_fill_dead(unsigned long long* id, unsigned begin, unsigned end);
 void launch_kinetic_energy(const Species& s, double* out);
+// one launch for many containers: *energy += sum over alive of (gamma - 1), *alive += number of alive slots (either may be null)
+struct EnergyJob { Species s; double* energy; unsigned long long* alive; };
+void launch_kinetic_energy_batch(const EnergyJob* jobs, int njobs, unsigned max_n, double total_slots);
 void launch_count_alive(const Species& s, unsigned long long* out);   // *out += number of alive slots
 // FieldsWriter<3>::pack_tile density (io/snapshots/mpiio_fields.c++:277-316)
 void launch_snapshot_density(const Species& s, const float mins[3], float inv_stride, int nxt, int nyt, int nzt, float* n_out);
