@@ -280,20 +280,21 @@ k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g, const int
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
         const float* r = p + (b - 1) * Hz;
-        t1[b] = 0.25f * r[-1] + 0.5f * r[0] + 0.25f * r[1];
+        t1[b] = __fmaf_rn(0.25f, r[1], __fmaf_rn(0.5f, r[0], 0.25f * r[-1]));
       }
-      return 0.25f * t1[0] + 0.5f * t1[1] + 0.25f * t1[2];
+      return __fmaf_rn(0.25f, t1[2], __fmaf_rn(0.5f, t1[1], 0.25f * t1[0]));
     };
     float a0 = t2_of(i - 1), a1 = t2_of(i);
     for (; i < iend; ++i) {
       const size_t n = size_t(i) * HyHz + q;
       if (i == g.Hx[0] - 1) { out[n] = J[n]; break; }
       const float a2 = t2_of(i + 1);
-      out[n] = 0.25f * a0 + 0.5f * a1 + 0.25f * a2;
+      out[n] = __fmaf_rn(0.25f, a2, __fmaf_rn(0.5f, a1, 0.25f * a0));
       a0 = a1; a1 = a2;
     }
   } else {
-    // 27-point sum accumulated from 0 in index_space order, a slowest (:58-73)
+    // 27-point sum accumulated from 0 in index_space order, a slowest (:58-73); the weights are powers of two, so the
+    // fma below equals the reference's product-then-add bit for bit (see k_filter_binomial2_pairs)
     float P[3][9];
     // three row pointers (j-1, j, j+1) that advance one plane per step: the nine loads of a plane
     // then use immediate offsets -1, 0, +1 instead of nine 64-bit address computations
@@ -324,7 +325,7 @@ k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g, const int
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             const float w = ((a == 1) ? 2.f : 1.f) * ((b == 1) ? 2.f : 1.f) * ((d == 1) ? 2.f : 1.f) / 64.f;
-            acc = acc + w * (a == 0 ? A[b * 3 + d] : a == 1 ? B[b * 3 + d] : C[b * 3 + d]);
+            acc = __fmaf_rn(w, a == 0 ? A[b * 3 + d] : a == 1 ? B[b * 3 + d] : C[b * 3 + d], acc);
           }
       *o = acc;
       ++i;
@@ -337,12 +338,13 @@ k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g, const int
 
 // binomial2 (the 27-point variant) with TWO k-adjacent outputs per thread, k = 1 + 2 kp and k + 1 (lattices with an
 // even Hz; the outermost layer is written by k_filter_binomial2_shell).  Every row of a plane arrives as two aligned
-// LDG.64 (cells k-1..k+2), and the 27 products + 27 sums of the pair run on the packed fp32x2 pipe: FMUL2, and
-// FFMA2(p, 1, acc) — the fma rounds the exact p*1 + acc once, i.e. the add's bits; the 1 is a kernel argument because
-// ptxas contracts a packed add with the packed product feeding it even under -fmad=false.  Same terms, same
-// index_space order (a slowest) from 0 => bit-identical to the scalar kernel, at half its issue slots.
+// LDG.64 (cells k-1..k+2), and the 27 terms of the pair are 27 packed FFMA2.
+// Why an fma is allowed here although the parity contract forbids contraction: every weight is a power of two
+// (1, 2, 4, 8 / 64), so the product w * x is exact and fma(w, x, acc) = rn(w * x + acc) = rn(rn(w * x) + acc), the
+// reference's product-then-add, bit for bit (the only exception: a product that is subnormal, |x| < 2^-120).
+// Same terms, same index_space order (a slowest) from 0 => bit-identical to the scalar kernel.
 __global__ void __launch_bounds__(256)
-k_filter_binomial2_pairs(const FilterTile* __restrict__ tiles, const Geom g, const int chunk, const float one) {
+k_filter_binomial2_pairs(const FilterTile* __restrict__ tiles, const Geom g, const int chunk, const int ahead) {
   const int Hz = g.Hx[2], HyHz = g.Hx[1] * Hz, npair = (Hz - 2) / 2;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (g.Hx[1] - 2) * npair) return;
@@ -352,9 +354,9 @@ k_filter_binomial2_pairs(const FilterTile* __restrict__ tiles, const Geom g, con
   if (ibeg >= iend) return;
   const float* __restrict__ J = tiles[tile].src + size_t(c) * g.Ch;
   float* __restrict__ out = tiles[tile].dst + size_t(c) * g.Ch;
-  const float2 one2 = make_float2(one, one);
   // a plane: rows j-1, j, j+1, each as the pairs (k-1,k), (k,k+1), (k+1,k+2) = the operands of the two outputs for d = -1, 0, +1
   float2 P[3][9];
+  const float* const jend = J + g.Ch;
   const float* r0 = J + size_t(ibeg - 1) * HyHz + size_t(j - 1) * Hz + (k - 1);     // k - 1 is even and Hz is even: 8-byte aligned
   auto load = [&](float2 (&dst)[9]) {
 #pragma unroll
@@ -363,6 +365,12 @@ k_filter_binomial2_pairs(const FilterTile* __restrict__ tiles, const Geom g, con
       dst[b * 3 + 0] = lo;
       dst[b * 3 + 1] = make_float2(lo.y, hi.x);
       dst[b * 3 + 2] = hi;
+    }
+    // the own row of the plane `ahead` steps further is requested into L2 now (no register is held for it): the
+    // kernel waits on load latency, not on bandwidth, and an L2 hit is a third of a DRAM round trip
+    if (ahead > 0) {
+      const float* pf = r0 + Hz + size_t(ahead) * HyHz;
+      if (pf < jend) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
     }
     r0 += HyHz;
   };
@@ -382,7 +390,7 @@ k_filter_binomial2_pairs(const FilterTile* __restrict__ tiles, const Geom g, con
         for (int d = 0; d < 3; ++d) {
           const float w = ((a == 1) ? 2.f : 1.f) * ((b == 1) ? 2.f : 1.f) * ((d == 1) ? 2.f : 1.f) / 64.f;
           const float2 x = a == 0 ? A[b * 3 + d] : a == 1 ? B[b * 3 + d] : C[b * 3 + d];
-          acc = __ffma2_rn(__fmul2_rn(make_float2(w, w), x), one2, acc);
+          acc = __ffma2_rn(make_float2(w, w), x, acc);
         }
     o[0] = acc.x; o[1] = acc.y;
     ++i;
@@ -622,7 +630,7 @@ void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unr
   else if ((g.Hx[2] & 1) == 0 && tuning().filter_pairs) {
     // even Hz: two outputs per thread on the packed fp32x2 pipe + the zeroed outermost layer
     const int npair = (g.Hx[1] - 2) * ((g.Hx[2] - 2) / 2);
-    k_filter_binomial2_pairs<<<dim3((npair + 255) / 256, grid.y, grid.z), 256, 0, ctx().stream>>>(ft, g, chunk, 1.0f);
+    k_filter_binomial2_pairs<<<dim3((npair + 255) / 256, grid.y, grid.z), 256, 0, ctx().stream>>>(ft, g, chunk, tuning().filter_ahead);
     B2P_LAUNCH_CHECK();
     const int nshell = 2 * g.Hx[1] * g.Hx[2] + (g.Hx[0] - 2) * 2 * g.Hx[2] + (g.Hx[0] - 2) * (g.Hx[1] - 2) * 2;
     k_filter_binomial2_shell<<<dim3((nshell + 255) / 256, 1, grid.z), 256, 0, ctx().stream>>>(ft, g);

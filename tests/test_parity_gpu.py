@@ -142,12 +142,14 @@ def test_sort_bit_exact():
     assert np.all(np.diff(k.astype(np.int64)) >= 0)
 
 
-@pytest.mark.parametrize("case", ["uniform-200k", "nearly-sorted", "crowded-cell", "very-crowded-cell", "radix-path"])
+@pytest.mark.parametrize("case", ["uniform-200k", "thirty-per-cell", "nearly-sorted", "crowded-cell", "very-crowded-cell", "radix-path"])
 def test_sort_bit_exact_cases(case):
-    """Counting sort (uniform / nearly sorted input; a crowded cell whose member list is ordered by the
-    block-per-cell kernel), its hand-over to the radix sort when the largest cell exceeds SORT_RADIX_POP
-    (decided from the first probe, then from the previous sort's hint), and the radix path forced by
-    option: all must give the oracle's stable order."""
+    """Counting sort, every way k_sort_cells orders a cell's member list: the 16- / 32-input register networks
+    (test_sort_bit_exact: 14 per cell), the insertion sort for 33..64 (crowded cases: 40 per cell), the whole block
+    ranking a long list (uniform-200k: 132 per cell; crowded-cell: 3000 in one), block ranges too long for the
+    shared-memory staging (thirty-per-cell: networks and insertion sorts working in global memory); the hand-over to
+    the radix sort when the largest cell exceeds SORT_RADIX_POP (decided from the first probe, then from the previous
+    sort's hint), and the radix path forced by option: all must give the oracle's stable order."""
     import ctypes as C
     from runko_b200._lib import check
     rng = np.random.default_rng(55)
@@ -158,10 +160,10 @@ def test_sort_bit_exact_cases(case):
     if case == "radix-path":
         check(L.b2p_set_option(b"sort_counting", 0))
     try:
-        n = 200000 if "crowded" not in case else 60000
+        n = 60000 if "crowded" in case else (48000 if case == "thirty-per-cell" else 200000)
         load_particles(rng, org, tile, conf, n, dead_frac=0.07)
         if "crowded" in case:
-            # 3000 particles in one cell: over SORT_THREAD_POP -> k_sort_fix_big for that cell;
+            # 3000 particles in one cell: ranked by the whole block in k_sort_cells;
             # 9000: over SORT_RADIX_POP -> radix sort for that container
             m = 3000 if case == "crowded-cell" else 9000
             for sp in range(2):
