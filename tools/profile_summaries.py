@@ -70,9 +70,12 @@ def main():
         print(k)
     push = raw(f"gpurun_out/r02_{tag}_push_raw.csv")
     rest = raw(f"gpurun_out/r02_{tag}_rest_raw.csv")
+    import os
+    sort = raw(f"gpurun_out/r02_{tag}_sort_raw.csv") if os.path.exists(f"gpurun_out/r02_{tag}_sort_raw.csv") else []
     json.dump({"how": "ncu --set full --clock-control none on tools/microbench.py --cells 128 (8 tiles of 64^3: ONE k_push launch covers "
                       "16 containers of 4.19 M particles = 67.1 M alive particles), worker streams off; one launch per entry",
-               "k_push (fused push+deposit, 16 containers per launch)": push, "other kernels": rest},
+               "k_push (fused push+deposit, 16 containers per launch)": push,
+               "counting sort (16 containers per launch, five laps after their last sort)": sort, "other kernels": rest},
               open(f"profiles/r02_ncu_summary_{tag}.json", "w"), indent=1)
     alive = 2 * 16 * 128 ** 3
     d = push[-1]
