@@ -144,12 +144,15 @@ struct CommPlan {
 __global__ void __launch_bounds__(256)
 k_pack_slabs(const SlabDesc* __restrict__ slabs, const Geom g) {
   const SlabDesc s = slabs[blockIdx.y];
-  const size_t vol = size_t(s.dims[0]) * s.dims[1] * s.dims[2];
-  for (size_t q = size_t(blockIdx.x) * blockDim.x + threadIdx.x; q < 3 * vol; q += size_t(gridDim.x) * blockDim.x) {
-    const int c = int(q / vol);
-    const size_t r = q - c * vol;
-    const int kk = int(r % s.dims[2]), jj = int((r / s.dims[2]) % s.dims[1]), ii = int(r / (size_t(s.dims[2]) * s.dims[1]));
-    s.base[q] = s.field[size_t(c) * g.Ch + (size_t(s.begin[0] + ii) * g.Hx[1] + (s.begin[1] + jj)) * g.Hx[2] + (s.begin[2] + kk)];
+  B2P_GLOBAL(s.base); B2P_GLOBAL(s.field);
+  // 32-bit index arithmetic: a slab is at most one face of a tile lattice (checked when the plan is built)
+  const unsigned d1 = unsigned(s.dims[1]), d2 = unsigned(s.dims[2]), vol = unsigned(s.dims[0]) * d1 * d2;
+  const unsigned Hy = unsigned(g.Hx[1]), Hz = unsigned(g.Hx[2]);
+  const unsigned n0 = (unsigned(s.begin[0]) * Hy + unsigned(s.begin[1])) * Hz + unsigned(s.begin[2]);
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < 3u * vol; q += gridDim.x * blockDim.x) {
+    const unsigned c = q / vol, r = q - c * vol;
+    const unsigned t = r / d2, kk = r - t * d2, ii = t / d1, jj = t - ii * d1;
+    s.base[q] = s.field[size_t(c) * g.Ch + n0 + (ii * Hy + jj) * Hz + kk];
   }
 }
 
@@ -279,7 +282,7 @@ static void exchange_fields(b2p_grid* g, int mode) {
   for (size_t b = 0; b < pt.n; b += 65535) {
     ProfScope prof_(KC_HALO, 0.0);
     const unsigned nb = unsigned(std::min<size_t>(65535, pt.n - b));
-    k_pack_slabs<<<dim3(8, nb), 256, 0, ctx().stream>>>(pt.d.p + b, g->g);
+    k_pack_slabs<<<dim3(24, nb), 256, 0, ctx().stream>>>(pt.d.p + b, g->g);
     B2P_LAUNCH_CHECK();
   }
   Nccl& n = nccl();
