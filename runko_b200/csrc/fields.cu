@@ -107,25 +107,42 @@ __device__ __forceinline__ float stencil_deriv(const float* __restrict__ F, cons
   return acc;
 }
 
-// emf/yee_lattice_stencil.c++:18-295
-__global__ void __launch_bounds__(256)
+// emf/yee_lattice_stencil.c++:18-295.  One B component per block (blockIdx.z = 3 * tile + component, like the
+// reference's three per-component sweeps): two 54-point derivatives per thread instead of six keep the kernel at 64
+// registers and twice the resident warps of the all-components version (107 registers, 23 % occupancy, issue and L1
+// both under 50 %: it waited on its own loads).  Same operands and order => same bits.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_push_b_stencil(const FieldPtrs* __restrict__ tiles, const Geom g, const float dt, const StencilM c) {
-  INTERIOR_CELL_OR_RETURN();
+  const int jblocks = (g.N[1] + int(blockDim.y) - 1) / int(blockDim.y);
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y / jblocks;
+  const int j = (blockIdx.y - i * jblocks) * blockDim.y + threadIdx.y;
+  const int tile = blockIdx.z / 3, comp = blockIdx.z - 3 * tile;
+  if (k >= g.N[2] || j >= g.N[1]) return;
+  const long sj = g.Hx[2], si = long(g.Hx[1]) * g.Hx[2];
+  const long m = (long(i + H) * g.Hx[1] + (j + H)) * g.Hx[2] + (k + H);
+  const FieldPtrs f = tiles[tile];
+  const size_t Ch = g.Ch;
   const float* __restrict__ Ex = f.E;
   const float* __restrict__ Ey = f.E + Ch;
   const float* __restrict__ Ez = f.E + 2 * Ch;
-  const long s[3] = { long(si), long(sj), 1 };
-  const long m = long(n);
+  const long s[3] = { si, sj, 1 };
   // D*_a uses axis[a] with perp1=(a+1)%3, perp2=(a+2)%3
-  const float DzEy = stencil_deriv(Ey, m, c.M[2], s[2], s[0], s[1]);
-  const float DyEz = stencil_deriv(Ez, m, c.M[1], s[1], s[2], s[0]);
-  const float DxEz = stencil_deriv(Ez, m, c.M[0], s[0], s[1], s[2]);
-  const float DzEx = stencil_deriv(Ex, m, c.M[2], s[2], s[0], s[1]);
-  const float DyEx = stencil_deriv(Ex, m, c.M[1], s[1], s[2], s[0]);
-  const float DxEy = stencil_deriv(Ey, m, c.M[0], s[0], s[1], s[2]);
-  f.B[n] = f.B[n] + dt * (DzEy - DyEz);
-  f.B[Ch + n] = f.B[Ch + n] + dt * (DxEz - DzEx);
-  f.B[2 * Ch + n] = f.B[2 * Ch + n] + dt * (DyEx - DxEy);
+  float* __restrict__ B = f.B + size_t(comp) * Ch;
+  if (comp == 0) {
+    const float DzEy = stencil_deriv(Ey, m, c.M[2], s[2], s[0], s[1]);
+    const float DyEz = stencil_deriv(Ez, m, c.M[1], s[1], s[2], s[0]);
+    B[m] = B[m] + dt * (DzEy - DyEz);
+  } else if (comp == 1) {
+    const float DxEz = stencil_deriv(Ez, m, c.M[0], s[0], s[1], s[2]);
+    const float DzEx = stencil_deriv(Ex, m, c.M[2], s[2], s[0], s[1]);
+    B[m] = B[m] + dt * (DxEz - DzEx);
+  } else {
+    const float DyEx = stencil_deriv(Ex, m, c.M[1], s[1], s[2], s[0]);
+    const float DxEy = stencil_deriv(Ey, m, c.M[0], s[0], s[1], s[2]);
+    B[m] = B[m] + dt * (DyEx - DxEy);
+  }
 }
 
 // ---- edge boundary condition (emf/yee_lattice.c++:263-306) ---------------------
@@ -255,7 +272,7 @@ struct FilterTile { const float* src; float* dst; };
 // every load coalesced along k.  grid = ((Hy*Hz)/256, i chunks, tiles*3 components).
 template <bool UNROLLED>
 __global__ void __launch_bounds__(256)
-k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g, const int chunk) {
+k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g, const int chunk, const int ahead) {
   const int HyHz = g.Hx[1] * g.Hx[2];
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= HyHz) return;
@@ -288,6 +305,7 @@ k_filter_binomial2(const FilterTile* __restrict__ tiles, const Geom g, const int
     for (; i < iend; ++i) {
       const size_t n = size_t(i) * HyHz + q;
       if (i == g.Hx[0] - 1) { out[n] = J[n]; break; }
+      if (i + 1 + ahead < g.Hx[0]) asm volatile("prefetch.global.L2 [%0];" ::"l"(J + size_t(i + 1 + ahead) * HyHz + q));
       const float a2 = t2_of(i + 1);
       out[n] = __fmaf_rn(0.25f, a2, __fmaf_rn(0.5f, a1, 0.25f * a0));
       a0 = a1; a1 = a2;
@@ -600,7 +618,15 @@ void launch_push_b_stencil(const FieldPtrs* tiles, int ntiles, const Geom& g, fl
   check_tiles(ntiles);
   StencilM c;
   for (int a = 0; a < 3; ++a) for (int r = 0; r < 3; ++r) for (int q = 0; q < 5; ++q) c.M[a][r][q] = M[a][r][q];
-  k_push_b_stencil<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, g, dt, c);
+  if (ntiles * 3 > MAX_TILES_PER_LAUNCH) throw Error(B2P_ERR_RUNTIME, "more than 21845 local tiles per GPU are not supported");
+  dim3 grid = interior_grid(g, ntiles);
+  grid.z *= 3;
+  switch (tuning().stencil_minb) {
+    case 2: k_push_b_stencil<2><<<grid, cell_block(), 0, ctx().stream>>>(tiles, g, dt, c); break;
+    case 3: k_push_b_stencil<3><<<grid, cell_block(), 0, ctx().stream>>>(tiles, g, dt, c); break;
+    case 4: k_push_b_stencil<4><<<grid, cell_block(), 0, ctx().stream>>>(tiles, g, dt, c); break;
+    default: k_push_b_stencil<5><<<grid, cell_block(), 0, ctx().stream>>>(tiles, g, dt, c); break;
+  }
   B2P_LAUNCH_CHECK();
 }
 void launch_push_e_fdtd2(const FieldPtrs* tiles, int ntiles, const Geom& g, float dt, bool add_current) {
@@ -626,7 +652,7 @@ void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unr
   const int chunk = tuning().filter_chunk > 0 ? tuning().filter_chunk : 35;
   const dim3 grid((g.Hx[1] * g.Hx[2] + 255) / 256, (g.Hx[0] + chunk - 1) / chunk, unsigned(ntiles) * 3);
   const FilterTile* ft = static_cast<const FilterTile*>(filter_tiles);
-  if (unrolled) k_filter_binomial2<true><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk);
+  if (unrolled) k_filter_binomial2<true><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk, tuning().filter_ahead > 0 ? tuning().filter_ahead : 1 << 20);
   else if ((g.Hx[2] & 1) == 0 && tuning().filter_pairs) {
     // even Hz: two outputs per thread on the packed fp32x2 pipe + the zeroed outermost layer
     const int npair = (g.Hx[1] - 2) * ((g.Hx[2] - 2) / 2);
@@ -634,7 +660,7 @@ void launch_filter(const void* filter_tiles, int ntiles, const Geom& g, bool unr
     B2P_LAUNCH_CHECK();
     const int nshell = 2 * g.Hx[1] * g.Hx[2] + (g.Hx[0] - 2) * 2 * g.Hx[2] + (g.Hx[0] - 2) * (g.Hx[1] - 2) * 2;
     k_filter_binomial2_shell<<<dim3((nshell + 255) / 256, 1, grid.z), 256, 0, ctx().stream>>>(ft, g);
-  } else k_filter_binomial2<false><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk);
+  } else k_filter_binomial2<false><<<grid, 256, 0, ctx().stream>>>(ft, g, chunk, 0);
   B2P_LAUNCH_CHECK();
 }
 void launch_edge_bc(float* field, const Geom& g, const int lo[3], const int hi[3], unsigned mask, const float v[3]) {

@@ -59,6 +59,7 @@ static bool set_option(const std::string& name, int value) {
   else if (name == "fuse_deposit") g_tuning.fuse_deposit = value;
   else if (name == "filter_chunk") g_tuning.filter_chunk = value;
   else if (name == "filter_ahead") g_tuning.filter_ahead = value;
+  else if (name == "stencil_minb") g_tuning.stencil_minb = value;
   else if (name == "push_streams") g_tuning.push_streams = value;
   else if (name == "sort_streams") g_tuning.sort_streams = value;
   else if (name == "sort_batch") g_tuning.sort_batch = value;
