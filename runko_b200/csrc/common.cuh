@@ -75,6 +75,7 @@ struct Tuning {
   int filter_chunk = 35;  // i-planes per thread column of k_filter_binomial2
   int filter_ahead = 4;   // planes ahead the pair filter requests its own row into L2 (0 = off; measured 10.3 -> 7.9 ms per 1024^3 pass)
   int stencil_minb = 5;   // resident blocks per SM the extended-stencil push_b is compiled for (2..5; measured 21.1 / 19.1 / 16.1 / 15.6 ms per shock step)
+  int energy_cache = 1;   // kinetic-energy account kept by push / pack / append (particles.cuh: KE_SLOTS); 0 = always sum the containers
   int push_streams = 1;   // worker streams the groups of the particle phase are round-robined over (1 = library stream only: with 32 tiles per launch measured 3 % faster than 2)
   int sort_streams = 2;   // worker streams the sort's batches alternate over (0: library stream; at most 2)
   int comm_overlap = 1;   // multi-GPU b2p_grid_step_pic: the B halo exchange runs on its own stream under the pushes of the interior tiles

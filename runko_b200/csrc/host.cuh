@@ -46,6 +46,7 @@ struct b2p_tile {
   // (plus, after the particle exchange, of the arrivals); deposit_current adopts it when the
   // leavers of that same push were removed by pack_outgoing_particles, else it deposits afresh
   bool pendJ_valid = false, pend_packed = false;
+  unsigned long long ke_epoch = 0;   // phase_push_particles: detects a tile listed twice in one push
   b2p::DBuf<b2p::FieldPtrs> d_fp;   // 1-entry device tile table for per-tile launches
   bool fp_dirty = true;
   std::vector<b2p::Container> sp;
@@ -83,6 +84,11 @@ struct b2p_grid {
   b2p::CommPlan* comm = nullptr;              // owned; freed in ~b2p_grid (comm.cu)
   int rank = 0, nranks = 1;
   std::vector<int> owner;                     // cid -> rank
+  // kinetic-energy account (particles.cuh: KE_SLOTS): [species][KE_SLOTS] doubles, valid between a push of every
+  // container of the grid and the next change of a container that the account does not follow
+  b2p::DBuf<double> ke_acc;
+  bool ke_valid = false;
+  bool ke_asked = false;                      // b2p_grid_energies was called since the last whole-grid push: the next push keeps the account
 
   ~b2p_grid();
   const b2p::FieldPtrs* device_table();

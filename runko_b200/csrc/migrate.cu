@@ -124,6 +124,7 @@ k_pack_write(const PackJob* __restrict__ jobs) {
   }
   __syncthreads();
   // one thread per leaver of the compact list (the first L threads: full warps issue the seven gathers)
+  double ke = 0.0;
   for (unsigned e = threadIdx.x; e < L; e += 256u) {
     const unsigned sub = l_sub[e], n = seg_first + l_off[e];
     b2p_particle_state st;
@@ -134,7 +135,14 @@ k_pack_write(const PackJob* __restrict__ jobs) {
     for (unsigned q = 0; q < e; ++q) rank += unsigned(l_sub[q] == sub);
     jb.out[s_base[sub] + rank] = st;
     jb.s.id[n] = DEAD;
+    if (jb.ke) {
+      const V3 v = { st.vel[0], st.vel[1], st.vel[2] };
+      ke -= double(sqrtf(1.0f + dot(v, v)) - 1.0f);
+    }
   }
+  double* const account = jb.ke;
+  B2P_GLOBAL(account);
+  if (account && ke != 0.0) atomicAdd(account + (threadIdx.x & (KE_SLOTS - 1)), ke);   // the leavers leave the species' account
 }
 
 void launch_pack_count_scan(const PackJob* jobs, unsigned ncont, unsigned max_nseg, const PackTile* tiles, unsigned ntiles,

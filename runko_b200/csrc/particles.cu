@@ -153,6 +153,7 @@ struct AppendJob {            // one incoming span (pic/tile_communication.c++:1
   float* Jpend;               // != nullptr: the destination tile's pending nodal J (fused push+deposit)
   float3 origo;
   float charge;
+  double* ke;                 // kinetic-energy account of the species (arrivals are added), or nullptr
 };
 
 // ParticleContainer::append (pic/particle.h:511-571): AoS -> SoA after the last
@@ -163,8 +164,9 @@ struct AppendJob {            // one incoming span (pic/tile_communication.c++:1
 __global__ void __launch_bounds__(256)
 k_append(const AppendJob* __restrict__ jobs, const int wrap, const float3 wmin, const float3 wmax, const Geom g, const float cfl) {
   const AppendJob jb = jobs[blockIdx.y];
-  B2P_GLOBAL(jb.src); B2P_GLOBAL(jb.Jpend); B2P_GLOBAL_SPECIES(jb.dst);
+  B2P_GLOBAL(jb.src); B2P_GLOBAL(jb.Jpend); B2P_GLOBAL(jb.ke); B2P_GLOBAL_SPECIES(jb.dst);
   const float Lx = wmax.x - wmin.x, Ly = wmax.y - wmin.y, Lz = wmax.z - wmin.z;
+  double ke = 0.0;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.count; i += gridDim.x * blockDim.x) {
     const b2p_particle_state st = jb.src[i];
     const unsigned j = jb.dst_offset + i;
@@ -179,7 +181,12 @@ k_append(const AppendJob* __restrict__ jobs, const int wrap, const float3 wmin, 
     jb.dst.id[j] = st.id;
     if (jb.Jpend && st.id != DEAD)
       deposit_split_nodal(zigzag_split(p, V3{ st.vel[0], st.vel[1], st.vel[2] }, jb.origo, cfl, jb.charge, g), jb.Jpend, g);
+    if (jb.ke && st.id != DEAD) {
+      const V3 v = { st.vel[0], st.vel[1], st.vel[2] };
+      ke += double(sqrtf(1.0f + dot(v, v)) - 1.0f);
+    }
   }
+  if (jb.ke && ke != 0.0) atomicAdd(jb.ke + ((blockIdx.x * blockDim.x + threadIdx.x) & (KE_SLOTS - 1)), ke);
 }
 
 __global__ void __launch_bounds__(256)
@@ -210,19 +217,31 @@ k_kinetic_energy(const Species s, double* __restrict__ out) {
 
 // The same sum for many containers in one launch (blockIdx.y = job; the grid-wide diagnostics of every lap,
 // io_average_kinetic_energy): 12 + 8 B per slot, HBM-bound.
+constexpr unsigned KE_CHUNK = 16384;      // slots per block: 256 threads x 4 slots (one LDG.128 per stream) x 16 rounds
 __global__ void __launch_bounds__(256)
 k_kinetic_energy_batch(const EnergyJob* __restrict__ jobs) {
   const EnergyJob jb = jobs[blockIdx.y];
   const Species s = jb.s;
   B2P_GLOBAL_SPECIES(s); B2P_GLOBAL(jb.energy); B2P_GLOBAL(jb.alive);
-  if (blockIdx.x * blockDim.x >= s.n) return;
+  const unsigned first = blockIdx.x * KE_CHUNK;
+  if (first >= s.n) return;
+  const unsigned end = min(first + KE_CHUNK, s.n);
   double acc = 0.0;
   unsigned cnt = 0;
-  for (unsigned n = blockIdx.x * blockDim.x + threadIdx.x; n < s.n; n += gridDim.x * blockDim.x) {
-    const V3 v = { s.ux[n], s.uy[n], s.uz[n] };
+  auto one = [&](const float ux, const float uy, const float uz, const unsigned long long id) {
+    const V3 v = { ux, uy, uz };
     const float e = sqrtf(1.0f + dot(v, v)) - 1.0f;
-    if (s.id[n] != DEAD) { acc += double(e); ++cnt; }
+    if (id != DEAD) { acc += double(e); ++cnt; }
+  };
+  // the streams are 256-byte aligned and `first` is a multiple of 4: four slots per thread and round as 128-bit loads
+  const unsigned full = first + ((end - first) & ~3u);
+  for (unsigned n = first + 4u * threadIdx.x; n < full; n += 1024u) {
+    const float4 ux = *reinterpret_cast<const float4*>(s.ux + n), uy = *reinterpret_cast<const float4*>(s.uy + n),
+                 uz = *reinterpret_cast<const float4*>(s.uz + n);
+    const ulonglong2 i0 = *reinterpret_cast<const ulonglong2*>(s.id + n), i1 = *reinterpret_cast<const ulonglong2*>(s.id + n + 2);
+    one(ux.x, uy.x, uz.x, i0.x); one(ux.y, uy.y, uz.y, i0.y); one(ux.z, uy.z, uz.z, i1.x); one(ux.w, uy.w, uz.w, i1.y);
   }
+  for (unsigned n = full + threadIdx.x; n < end; n += 256u) one(s.ux[n], s.uy[n], s.uz[n], s.id[n]);
   for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
   __shared__ double sh[8];
   __shared__ unsigned sc[8];
@@ -231,7 +250,7 @@ k_kinetic_energy_batch(const EnergyJob* __restrict__ jobs) {
   if (threadIdx.x == 0) {
     double t = 0;
     unsigned long long c = 0;
-    for (int q = 0; q < int(blockDim.x >> 5); ++q) { t += sh[q]; c += sc[q]; }
+    for (int q = 0; q < 8; ++q) { t += sh[q]; c += sc[q]; }
     if (jb.energy) atomicAdd(jb.energy, t);
     if (jb.alive) atomicAdd(jb.alive, c);
   }
@@ -544,8 +563,7 @@ void launch_kinetic_energy(const Species& s, double* out) {
 void launch_kinetic_energy_batch(const EnergyJob* jobs, int njobs, unsigned max_n, double total_slots) {
   ProfScope prof_(KC_ENERGY, total_slots);
   if (!njobs || !max_n) return;
-  // about two waves of resident blocks over the whole batch, every block striding through its container
-  const unsigned per_job = std::max(1u, std::min(blocks_for(max_n), unsigned(ctx().sm_count) * 16u / unsigned(njobs) + 1u));
+  const unsigned per_job = (max_n + KE_CHUNK - 1) / KE_CHUNK;
   k_kinetic_energy_batch<<<dim3(per_job, unsigned(njobs)), 256, 0, ctx().stream>>>(jobs);
   B2P_LAUNCH_CHECK();
 }

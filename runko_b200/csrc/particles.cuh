@@ -12,6 +12,7 @@ struct AppendJobHost {        // mirrors particles.cu::AppendJob
   float* Jpend;               // destination tile's pending nodal J, or nullptr
   float3 origo;
   float charge;
+  double* ke;                 // kinetic-energy account of the container's species (KE_SLOTS doubles), or nullptr
 };
 
 
@@ -27,6 +28,14 @@ void launch_nodal_means(const float* E, const float* B, const Geom& g, float4* n
 // One container of a batched push launch (push.cu).  The push also publishes the leaver / stayer ballots of
 // every warp (masks: one uint2 per 32 slots, rounded up to whole blocks of 256 slots) for
 // pack_outgoing_particles; Jc != nullptr: fused push + deposit of the particles that stay inside the tile box.
+// Kinetic-energy account of a grid (pic/particle.c++:352-377, the per-lap io_average_kinetic_energy): when a push covers
+// every container of a grid it leaves, per species, the sum over the alive particles of sqrt(1 + u.u) - 1 of the
+// velocities it stored (fp32 per particle, summed pairwise inside a warp, fp64 across warps) in KE_SLOTS spread
+// accumulators; pack_outgoing subtracts the leavers, the particle exchange adds the arrivals, so the account keeps
+// equalling the sum over the containers and b2p_grid_energies reads 64 KB per species instead of 20 B per slot.  Any other
+// change of a container (injection, upload, reflector wall, ...) voids the account until the next whole-grid push.
+// The push keeps it (8 % of its time: 8 M double atomics per launch) only if the energies were read since the previous push.
+constexpr int KE_SLOTS = 8192;    // 2^13 accumulators per species: a push launch sends 8 M warp sums, 32 slots measured +90 % push time (L2 same-address atomics)
 struct PushJob {
   Species s;
   const float4* nod;          // nodal means of the container's tile (k_nodal_means layout)
@@ -34,6 +43,7 @@ struct PushJob {
   uint2* masks;               // leaver / stayer ballots, one uint2 per 32 slots
   float3 origo, mn, mx;       // lattice origin, tile box (float(mins/maxs))
   float qm, charge;           // sign(q)/m (pic/particle_boris.h:26-27), signed charge (zigzag)
+  double* ke;                 // kinetic-energy account of the species (KE_SLOTS doubles) or nullptr: see KE_SLOTS
 };
 // The job table travels as a kernel argument (CUDA >= 12.1 allows 32 KB of parameters): no upload, and the
 // compiler knows that every pointer in it addresses global memory.
@@ -74,6 +84,7 @@ struct PackJob {              // one container
   unsigned* last_alive;       // P = 1 + last slot that stays alive (zeroed by the caller)
   unsigned long long* ends;   // [27] subregion_particle_ends_ of this species (absolute offsets in the tile's buffer)
   b2p_particle_state* out;    // the tile's outgoing buffer (filled in for the write pass)
+  double* ke;                 // kinetic-energy account of the species (leavers are subtracted), or nullptr
 };
 struct PackTile { unsigned first, count; unsigned* total; };   // a tile's containers in the job table; its leaver total
 unsigned pack_segments(unsigned n_slots);

@@ -164,6 +164,16 @@ k_push(const __grid_constant__ PushJobs jobs, const Geom g, const float cfl, con
   jb.s.ux[n] = vel.x; jb.s.uy[n] = vel.y; jb.s.uz[n] = vel.z;
   jb.s.x[n] = nx; jb.s.y[n] = ny; jb.s.z[n] = nz;
   }
+  if (jb.ke) {
+    // kinetic-energy account (particles.cuh: KE_SLOTS): dead slots carry vel = 0, i.e. sqrt(1) - 1 = 0
+    float e = sqrtf(1.0f + dot(vel, vel)) - 1.0f;                   // pic/particle.c++:352-377
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0 && e != 0.0f) {
+      const unsigned gw = (blockIdx.y * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);   // warp of the launch
+      atomicAdd(jb.ke + ((gw * 2654435761u) >> 19), double(e));                                            // scattered over the 2^13 slots
+    }
+  }
   const bool inside = inside_box(nx, ny, nz, jb.mn, jb.mx);
   publish_masks(alive, inside, n, jb.masks);
   if (FUSE) {

@@ -124,6 +124,20 @@ def main():
     tot = [None] * world
     dist.all_gather_object(tot, n_local)
     assert sum(tot) == 2 * 4 * int(np.prod(n_cells)) * int(np.prod(n_tiles)), "particles lost in migration"
+    # the kinetic-energy account (particles.cuh: KE_SLOTS) follows particles across ranks: on every rank it equals the sum
+    # over that rank's containers (energy_cache = 0 forces the sum)
+    grid.energies()                                      # a read: the next push keeps the account
+    for lap in range(6, 9):
+        grid.step_pic(lap)
+        n0 = L.b2p_launch_count()
+        ke = np.array(grid.energies()[2])
+        n1 = L.b2p_launch_count()
+        check(L.b2p_set_option(b"energy_cache", 0))
+        full = np.array(grid.energies()[2])
+        check(L.b2p_set_option(b"energy_cache", 1))
+        n2 = L.b2p_launch_count()
+        assert n1 - n0 < n2 - n1, "energies() did not use the account on a multi-rank grid"
+        assert np.allclose(ke, full, rtol=2e-7, atol=0.0), (rank, lap, ke, full)
     dist.barrier()
     if rank == 0:
         print(f"multi-GPU parity OK on {world} ranks, tiles {n_tiles}")
