@@ -9,7 +9,7 @@ tail -c 600 gpurun_out/r02_bench_${TAG}_n1_512.json; echo; head -20 gpurun_out/r
 timeout 1200 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/r02_bench_${TAG}_reference_arm.json 2> gpurun_out/r02_bench_${TAG}_ref.err
 head -c 400 gpurun_out/r02_bench_${TAG}_reference_arm.json; echo
 export B2P_OPTS=push_streams=1,sort_streams=0
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_push -s 7 -c 1 -o /tmp/ncu/push -f python tools/microbench.py --cells 128 --laps 1 "" > gpurun_out/r02_ncu_${TAG}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k k_push -s 7 -c 1 -o /tmp/ncu/push -f python tools/microbench.py --cells 128 --laps 1 "" > gpurun_out/r02_ncu_${TAG}.log 2>&1
 ncu -i /tmp/ncu/push.ncu-rep --page raw --csv > gpurun_out/r02_${TAG}_push_raw.csv 2>/dev/null
 ncu -i /tmp/ncu/push.ncu-rep --page source --csv > gpurun_out/r02_${TAG}_push_source.csv 2>/dev/null
 timeout 900 ncu --set full --clock-control none -k regex:"k_pack_|k_append|k_nodal|k_edge_gather|k_filter|k_halo|k_push_b|k_push_e|k_J_exchange" -s 40 -c 40 -o /tmp/ncu/rest -f python tools/microbench.py --cells 128 --laps 1 "" >> gpurun_out/r02_ncu_${TAG}.log 2>&1
