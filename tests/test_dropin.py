@@ -91,6 +91,35 @@ print("reference package ok")
     assert r.returncode == 0 and "reference package ok" in r.stdout, r.stdout + r.stderr
 
 
+# The reference's OWN host-side unit tests (unmodified, where they lie) against the drop-in modules: everything below the
+# Python package that needs no device — configuration, module layout, TileGrid construction over pycorgi.Grid, virtual tile
+# specialisations, the Hilbert tile ordering.  (The tests that compute — test_emf*.py, test_pic*.py — need a GPU, which the
+# container holding /root/reference does not have; tests/test_reference_suite.py runs them on the oracle and
+# tests/test_kats.py restates their known answers for the CUDA path.)
+REF_HOST_TESTS = {
+    "test_configuration.py": "4 passed",
+    "test_module_meta.py": "1 passed",
+    "test_auto_outdir.py": "13 passed",
+    "test_auto_tile_grid.py": "1 passed",
+    "test_tile_grid.py": "3 passed",
+    "test_virtual_tile_specializations.py": "2 passed",
+    "test_hilbert.py": "7 passed",
+}
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "tests", "py")), reason="/root/reference is not present on this box")
+@pytest.mark.parametrize("fname", sorted(REF_HOST_TESTS))
+def test_reference_host_side_unit_tests_pass_on_the_dropin(fname):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([DROPIN, ROOT, REF])
+    env["PYTHONDONTWRITEBYTECODE"] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", os.path.join(REF, "tests", "py", fname)],
+                       cwd="/tmp", env=env, capture_output=True, text=True, timeout=600)
+    tail = (r.stdout + r.stderr)[-2000:]
+    assert r.returncode == 0, tail
+    assert REF_HOST_TESTS[fname] in r.stdout, tail
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("use_reference", [True, False])
 def test_pic_turbulence_lap_through_the_dropin_matches_the_oracle(use_reference, tmp_path):
