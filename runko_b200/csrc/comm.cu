@@ -119,6 +119,7 @@ struct CommPlan {
   std::vector<PeerBuffers> peers;
   DBuf<float> sendbuf, recvbuf;
   DBuf<SlabDesc> d_remote_fill, d_remote_exch;
+  DBuf<int> d_slot_of_entry;                    // entry -> local tile slot (k_unpack_halo)
   // Pack tables are persistent: one per (mode, which of a tile's two J buffers is current), rebuilt only when the
   // lattice pointers behind it change (the exchanges of a lap reuse four tables that are uploaded once).
   struct PackTable { std::vector<const float*> sig; DBuf<SlabDesc> d; size_t n = 0; };
@@ -153,6 +154,25 @@ k_pack_slabs(const SlabDesc* __restrict__ slabs, const Geom g) {
     const unsigned c = q / vol, r = q - c * vol;
     const unsigned t = r / d2, kk = r - t * d2, ii = t / d1, jj = t - ii * d1;
     s.base[q] = s.field[size_t(c) * g.Ch + n0 + (ii * Hy + jj) * Hz + kk];
+  }
+}
+
+// the inverse for the halo fill: every staged slab goes to the halo region of its tile that faces the remote neighbour
+// (what k_halo_fill does for these cells, driven by the slabs instead of by a sweep over every halo cell of every tile)
+__global__ void __launch_bounds__(256)
+k_unpack_halo(const FieldPtrs* __restrict__ tiles, const SlabDesc* __restrict__ slabs, const int* __restrict__ slot_of_entry,
+              const Geom g, const int which) {
+  const SlabDesc s = slabs[blockIdx.y];
+  const FieldPtrs f = tiles[slot_of_entry[blockIdx.y]];
+  float* __restrict__ dst = which == 0 ? f.E : (which == 1 ? f.B : f.J);
+  B2P_GLOBAL(s.base); B2P_GLOBAL(dst);
+  const unsigned d1 = unsigned(s.dims[1]), d2 = unsigned(s.dims[2]), vol = unsigned(s.dims[0]) * d1 * d2;
+  const unsigned Hy = unsigned(g.Hx[1]), Hz = unsigned(g.Hx[2]);
+  const unsigned n0 = (unsigned(s.begin[0]) * Hy + unsigned(s.begin[1])) * Hz + unsigned(s.begin[2]);
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < 3u * vol; q += gridDim.x * blockDim.x) {
+    const unsigned c = q / vol, r = q - c * vol;
+    const unsigned t = r / d2, kk = r - t * d2, ii = t / d1, jj = t - ii * d1;
+    dst[size_t(c) * g.Ch + n0 + (ii * Hy + jj) * Hz + kk] = s.base[q];
   }
 }
 
@@ -229,9 +249,19 @@ static void finalize_plan(b2p_grid* g) {
       SlabDesc& s = kind ? rx[i] : rf[i];
       s.base = p.recvbuf.p + p.recv_slab_off[kind][i];
       s.field = nullptr;
-      for (int d = 0; d < 3; ++d) { s.begin[d] = 0; s.dims[d] = p.entries[i].dims[d]; }
+      for (int d = 0; d < 3; ++d) {
+        // where the slab lands in the receiving lattice (k_unpack_halo): subregion(dir), the halo facing the neighbour
+        const int dr = p.entries[i].dir[d];
+        s.begin[d] = dr == 0 ? H : (dr == 1 ? H + g->cfg.n_cells[d] : 0);
+        s.dims[d] = p.entries[i].dims[d];
+      }
     }
   }
+  std::vector<int> slots(p.entries.size());
+  for (size_t i = 0; i < p.entries.size(); ++i) slots[i] = g->slot_of_cid[p.entries[i].cid];
+  p.d_slot_of_entry.reserve(std::max<size_t>(slots.size(), 1));
+  if (!slots.empty())
+    B2P_CUDA(cudaMemcpyAsync(p.d_slot_of_entry.p, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, ctx().stream));
   p.d_remote_fill.reserve(std::max<size_t>(rf.size(), 1));
   p.d_remote_exch.reserve(std::max<size_t>(rx.size(), 1));
   if (!rf.empty()) {
@@ -403,6 +433,17 @@ void comm_exchange_fields_on_comm_stream(b2p_grid* g, int mode) {
   try { exchange_fields(g, mode); } catch (...) { c.stream = saved; throw; }
   c.stream = saved;
   B2P_CUDA(cudaEventRecord(p.ev_done, p.cstream));
+}
+// the remote-fed halo cells of field `which` (0 E, 1 B, 2 J) from the slabs of the last exchange of that mode
+void comm_unpack_halo(b2p_grid* g, int which) {
+  CommPlan& p = *g->comm;
+  if (p.entries.empty()) return;
+  ProfScope prof_(KC_HALO, 0.0);
+  for (size_t b = 0; b < p.entries.size(); b += 65535) {
+    const unsigned nb = unsigned(std::min<size_t>(65535, p.entries.size() - b));
+    k_unpack_halo<<<dim3(24, nb), 256, 0, ctx().stream>>>(g->device_table(), p.d_remote_fill.p + b, p.d_slot_of_entry.p + b, g->g, which);
+    B2P_LAUNCH_CHECK();
+  }
 }
 void comm_wait_exchange(b2p_grid* g) {
   CommPlan& p = *g->comm;

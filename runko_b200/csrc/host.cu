@@ -1700,7 +1700,7 @@ int b2p_grid_step_pic(b2p_grid* g, int64_t lap) {
         if (pass == 0 && !remote) ++n_interior;
       }
     tr.mark("fields", lap);
-    phase_push_particles(order, n_interior, [&] { comm_wait_exchange(g); grid_local_communication(g, B2P_COMM_EMF_B, /*part=*/2); });
+    phase_push_particles(order, n_interior, [&] { comm_wait_exchange(g); comm_unpack_halo(g, /*B*/ 1); });
   } else {
     ext(B2P_COMM_EMF_B); grid_local_communication(g, B2P_COMM_EMF_B);
     tr.mark("fields", lap);

@@ -113,6 +113,7 @@ void phase_apply_edge_bcs(const std::vector<b2p_tile*>& tiles, int mode);
 void phase_reflect_particles(const std::vector<b2p_tile*>& tiles);
 void grid_local_communication(b2p_grid* g, int mode, int part = 0);   // part: fields.cuh launch_halo_fill
 void comm_exchange_fields_on_comm_stream(b2p_grid* g, int mode);      // comm.cu: exchange on the plan's own stream, ordered after the library stream
+void comm_unpack_halo(b2p_grid* g, int which);                          // the remote-fed halo cells of E / B / J from the staged slabs
 void comm_wait_exchange(b2p_grid* g);                                   // library stream waits for that exchange
 void flush_deferred();                      // executes the pending batch of per-tile calls (host.cu)
 void set_last_error(const std::string& s);
