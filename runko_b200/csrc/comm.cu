@@ -208,8 +208,30 @@ static void send_region_begin(const PlanEntry& e, const b2p_config& cfg, int kin
   }
 }
 
+// Tiles with a Moore neighbour on another rank first: a phase can then run on the boundary tiles, start their exchange,
+// and run on the interior tiles [n_boundary, n) of the same device table while the slabs travel.
+static void order_boundary_tiles_first(b2p_grid* g, int rank) {
+  const int* T = g->cfg.n_tiles;
+  auto is_boundary = [&](const b2p_tile* t) {
+    for (int kr = -1; kr <= 1; ++kr) for (int jr = -1; jr <= 1; ++jr) for (int ir = -1; ir <= 1; ++ir) {
+      const int oc = wrapc(t->idx[0] + ir, T[0]) + T[0] * (wrapc(t->idx[1] + jr, T[1]) + T[1] * wrapc(t->idx[2] + kr, T[2]));
+      if (g->owner[oc] != rank) return true;
+    }
+    return false;
+  };
+  const auto mid = std::stable_partition(g->tiles.begin(), g->tiles.end(), is_boundary);
+  g->n_boundary = size_t(mid - g->tiles.begin());
+  std::fill(g->slot_of_cid.begin(), g->slot_of_cid.end(), -1);
+  for (size_t i = 0; i < g->tiles.size(); ++i) {
+    g->tiles[i]->slot = int(i);
+    g->slot_of_cid[g->cid(g->tiles[i]->idx[0], g->tiles[i]->idx[1], g->tiles[i]->idx[2])] = int(i);
+  }
+  g->table_dirty = g->nbr_dirty = true;
+}
+
 static void finalize_plan(b2p_grid* g) {
   CommPlan& p = *g->comm;
+  order_boundary_tiles_first(g, p.rank);
   p.entries = build_plan(g->cfg, g->owner, p.rank);
   p.entry_of.clear();
   std::map<int, PeerBuffers> byp;

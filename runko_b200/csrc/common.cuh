@@ -78,7 +78,9 @@ struct Tuning {
   int energy_cache = 1;   // kinetic-energy account kept by push / pack / append (particles.cuh: KE_SLOTS); 0 = always sum the containers
   int push_streams = 1;   // worker streams the groups of the particle phase are round-robined over (1 = library stream only: with 32 tiles per launch measured 3 % faster than 2)
   int sort_streams = 2;   // worker streams the sort's batches alternate over (0: library stream; at most 2)
-  int comm_overlap = 1;   // multi-GPU b2p_grid_step_pic: the B halo exchange runs on its own stream under the pushes of the interior tiles
+  int comm_overlap = 1;   // multi-rank step_pic: 0 = blocking exchanges; 1 = the B exchange before the push flies under the interior tiles' pushes;
+                          // 2 = also every exchange of the field phase (boundary tiles first) - bit-identical, measured equal to 1 on 2 and 4 GPUs
+                          // (194.9 / 195.1 vs 194.5 / 195.2 ms per step at full size): what the exchanges cost is the wait for the slowest rank
   int filter_pairs = 1;   // binomial2 on lattices with even Hz: two k-adjacent outputs per thread, packed fp32x2 (0: one output per thread)
   int sort_batch = 16;    // containers per launch of the counting-sort kernels (scratch: ~200 MB per 4 M-slot container)
   int sort_overlap = 1;   // b2p_grid_step_pic leaves the sort running on the worker streams under the field phase of the lap

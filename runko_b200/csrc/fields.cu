@@ -12,12 +12,13 @@ namespace b2p {
 
 // thread <-> cell mapping shared by the interior sweeps: x->k, y->j, z->(tile,i)
 // grid = (k blocks, j blocks * planes, tiles): blockIdx.y carries (plane, j block)
-#define INTERIOR_CELL_OR_RETURN()                                              \
+#define INTERIOR_CELL_OR_RETURN() INTERIOR_CELL_OR_RETURN_AT(0)
+#define INTERIOR_CELL_OR_RETURN_AT(TILE0)                                      \
   const int jblocks = (g.N[1] + int(blockDim.y) - 1) / int(blockDim.y);        \
   const int k = blockIdx.x * blockDim.x + threadIdx.x;                         \
   const int i = blockIdx.y / jblocks;                                          \
   const int j = (blockIdx.y - i * jblocks) * blockDim.y + threadIdx.y;         \
-  const int tile = blockIdx.z;                                                 \
+  const int tile = int(blockIdx.z) + (TILE0);                                  \
   if (k >= g.N[2] || j >= g.N[1]) return;                                      \
   const size_t sj = g.Hx[2], si = size_t(g.Hx[1]) * g.Hx[2];                   \
   const size_t n = (size_t(i + H) * g.Hx[1] + (j + H)) * g.Hx[2] + (k + H);    \
@@ -514,8 +515,8 @@ k_halo_fill(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, co
 // contributions in the reference's order. One thread per interior cell/component.
 __global__ void __launch_bounds__(256)
 k_J_exchange(const FieldPtrs* __restrict__ tiles, const int* __restrict__ nbr, const Geom g,
-             const SlabDesc* __restrict__ remote) {
-  INTERIOR_CELL_OR_RETURN();
+             const SlabDesc* __restrict__ remote, const int tile0 /* the launch covers tiles [tile0, tile0 + gridDim.z) */) {
+  INTERIOR_CELL_OR_RETURN_AT(tile0);
   (void)sj; (void)si;
   const int a[3] = { i + H, j + H, k + H };
   // along one axis, cell a (haloed index) lies in corresponding_subregion(-d) for
@@ -725,11 +726,11 @@ void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const 
   k_halo_fill<<<dim3((nhalo + 255) / 256, 1, unsigned(ntiles)), 256, 0, ctx().stream>>>(tiles, nbr, g, which, remote, part);
   B2P_LAUNCH_CHECK();
 }
-void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, const SlabDesc* remote) {
+void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, const SlabDesc* remote, int tile0) {
   ProfScope prof_(KC_J_EXCHANGE, double(ntiles) * g.N[0] * g.N[1] * g.N[2]);
   if (!ntiles) return;
   check_tiles(ntiles);
-  k_J_exchange<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, nbr, g, remote);
+  k_J_exchange<<<interior_grid(g, ntiles), cell_block(), 0, ctx().stream>>>(tiles, nbr, g, remote, tile0);
   B2P_LAUNCH_CHECK();
 }
 void launch_field_energy(const FieldPtrs* tiles, int ntiles, const Geom& g, double* out) {

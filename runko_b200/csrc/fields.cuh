@@ -28,6 +28,6 @@ void launch_add_lattice(float* J, const float* add, size_t n);
 // nbr codes: >= 0 local tile slot; -1 none; <= -2 remote, staged slab remote[-(code+2)] (comm.cu)
 // part 0: every halo cell; 1: only those fed by a tile of this rank; 2: only those fed by a remote rank's staged slab
 void launch_halo_fill(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, int which, const SlabDesc* remote, int part = 0);
-void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, const SlabDesc* remote);
+void launch_J_exchange(const FieldPtrs* tiles, const int* nbr, int ntiles, const Geom& g, const SlabDesc* remote, int tile0 = 0);   // tiles [tile0, tile0 + ntiles) of the table
 void launch_field_energy(const FieldPtrs* tiles, int ntiles, const Geom& g, double* out);
 }  // namespace b2p

@@ -1033,6 +1033,11 @@ static void append_spans(std::vector<Container*>& conts, std::vector<b2p_tile*>&
 }
 
 // corgi::Grid::local_communication (external/corgi/src/corgi/corgi.h:1697-1718)
+// emf_J_exchange for the tiles [first, first + count) of the grid
+static void grid_J_exchange(b2p_grid* g, size_t first, size_t count) {
+  launch_J_exchange(g->device_table(), g->device_nbr(), int(count), g->g, static_cast<const SlabDesc*>(comm_remote_table(g, 1)), int(first));
+}
+
 void grid_local_communication(b2p_grid* g, int mode, int part) {
   const int nt = int(g->tiles.size());
   if (!nt) return;
@@ -1040,7 +1045,7 @@ void grid_local_communication(b2p_grid* g, int mode, int part) {
     case B2P_COMM_EMF_E: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 0, static_cast<const SlabDesc*>(comm_remote_table(g, 0)), part); return;
     case B2P_COMM_EMF_B: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 1, static_cast<const SlabDesc*>(comm_remote_table(g, 0)), part); return;
     case B2P_COMM_EMF_J: launch_halo_fill(g->device_table(), g->device_nbr(), nt, g->g, 2, static_cast<const SlabDesc*>(comm_remote_table(g, 0)), part); return;
-    case B2P_COMM_EMF_J_EXCHANGE: launch_J_exchange(g->device_table(), g->device_nbr(), nt, g->g, static_cast<const SlabDesc*>(comm_remote_table(g, 1))); return;
+    case B2P_COMM_EMF_J_EXCHANGE: grid_J_exchange(g, 0, size_t(nt)); return;
     case B2P_COMM_PIC_PARTICLE: break;
     default:
       throw Error(B2P_ERR_LOGIC, "local_communication does not support given communication mode: " + std::to_string(mode));
@@ -1715,6 +1720,42 @@ int b2p_grid_step_pic(b2p_grid* g, int64_t lap) {
   tr.mark("sort enqueue", lap);
   phase_deposit(g->tiles);
   tr.mark("deposit enqueue", lap);
+  if (multi && tuning().comm_overlap >= 2 && g->n_boundary > 0) {
+    // Every exchange of the field phase flies on the plan's own stream under work that does not need it.  The grid's
+    // tiles are ordered boundary-first (comm.cu: order_boundary_tiles_first), so a phase is: the boundary tiles, whose
+    // results the exchange sends; the exchange; the same phase on the interior tiles [nb, nt) and the fill of the
+    // locally fed halo cells meanwhile; then the remote slabs go into the boundary tiles' halos (comm_unpack_halo).
+    // Which tile is updated first does not change any operand: same bits as the sequential lap.
+    const size_t nb = g->n_boundary, nt = g->tiles.size();
+    const std::vector<b2p_tile*> bnd(g->tiles.begin(), g->tiles.begin() + nb), inte(g->tiles.begin() + nb, g->tiles.end());
+    auto round = [&](int mode, int which, const std::function<void()>& before_fill, const std::function<void()>& after_fill) {
+      comm_exchange_fields_on_comm_stream(g, mode);
+      if (before_fill) before_fill();                       // interior work the local fill reads
+      grid_local_communication(g, mode, /*part=*/1);
+      if (after_fill) after_fill();                         // interior work that needs only locally fed halos
+      comm_wait_exchange(g);
+      comm_unpack_halo(g, which);
+    };
+    comm_exchange_fields_on_comm_stream(g, B2P_COMM_EMF_J);   // the halos the J exchange adds (and the edges, unused here)
+    grid_J_exchange(g, nb, nt - nb);
+    comm_wait_exchange(g);
+    grid_J_exchange(g, 0, nb);
+    if (g->cfg.current_filter >= 0) {
+      round(B2P_COMM_EMF_J, 2, nullptr, [&] { phase_filter(inte); });
+      phase_filter(bnd);
+      round(B2P_COMM_EMF_J, 2, nullptr, [&] { phase_filter(inte); });
+      phase_filter(bnd);
+      phase_filter(g->tiles);
+    } else {
+      round(B2P_COMM_EMF_J, 2, nullptr, nullptr);
+    }
+    phase_push_half_b(bnd, g->device_table());
+    round(B2P_COMM_EMF_B, 1, [&] { phase_push_half_b(inte, g->device_table() + nb); }, nullptr);
+    phase_push_e(bnd, g->device_table(), true);
+    round(B2P_COMM_EMF_E, 0, [&] { phase_push_e(inte, g->device_table() + nb, true); }, nullptr);
+    tr.mark("J comm+filter+fields", lap);
+    return B2P_OK;
+  }
   ext(B2P_COMM_EMF_J); grid_local_communication(g, B2P_COMM_EMF_J_EXCHANGE);
   ext(B2P_COMM_EMF_J); grid_local_communication(g, B2P_COMM_EMF_J);
   if (g->cfg.current_filter >= 0) {

@@ -83,6 +83,7 @@ struct b2p_grid {
   bool table_dirty = true, nbr_dirty = true;
   b2p::CommPlan* comm = nullptr;              // owned; freed in ~b2p_grid (comm.cu)
   int rank = 0, nranks = 1;
+  size_t n_boundary = 0;                      // multi-rank grids: tiles[0, n_boundary) have a Moore neighbour on another rank (comm_init orders them first)
   std::vector<int> owner;                     // cid -> rank
   // kinetic-energy account (particles.cuh: KE_SLOTS): [species][KE_SLOTS] doubles, valid between a push of every
   // container of the grid and the next change of a container that the account does not follow
