@@ -734,9 +734,8 @@ void phase_reflect_particles(const std::vector<b2p_tile*>& tiles) {
 }
 
 // pic/tile.c++:419-438 + pic/particle.h:575-703: stable sort by cell key, dead last.
-// Fast path: counting sort by cell (particles.cu, "counting sort"); containers are processed in
-// batches of SORT_SLOTS so that one host read of the batch's largest cell populations decides, per
-// container, between the counting placement and the general radix sort (crowded cells).
+// Fast path: counting sort by cell (sort.cu), batched over containers; a container whose largest cell exceeded
+// SORT_RADIX_POP at its previous sort (page-locked hint, no host round trip) takes this general radix sort instead.
 static void sort_radix(b2p_tile* t, Container& c, int w) {
   Scratch& s = scratch();
   for (int b = 0; b < 2; ++b) { s.keys_w[w][b].reserve(c.n); s.vals_w[w][b].reserve(c.n); }
