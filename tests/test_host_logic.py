@@ -100,3 +100,27 @@ def test_exchange_plan_pairs_up(n_tiles, blocks):
             assert np.array_equal(send[:, 4], recv[:, 5]), "send/recv key order differs"
             assert np.array_equal(send[:, 6], recv[:, 6]), "slab sizes differ"
             assert np.array_equal(send[:, 1], recv[:, 3]) and np.array_equal(send[:, 3], recv[:, 1])
+
+
+def test_sorting_network_header_is_what_the_generator_writes():
+    """runko_b200/csrc/sortnet.cuh (the compare-exchange lists k_sort_cells orders a cell's member list with) is generated by
+    tools/gen_sortnet.py, which checks the networks against sorted() before writing: the committed header must be its output."""
+    import importlib.util
+    import os
+    import random
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_sortnet", os.path.join(root, "tools", "gen_sortnet.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text = open(os.path.join(root, "runko_b200", "csrc", "sortnet.cuh")).read()
+    for n, pairs in ((16, 63), (32, 191)):
+        ces = gen.batcher(n)
+        assert len(ces) == pairs
+        assert " ".join(f"CE({a},{b})" for a, b in ces) in " ".join(text.replace("\\\n", " ").split())
+        for _ in range(200):                                  # ... and they sort (ties included)
+            v = [random.randrange(40) for _ in range(n)]
+            w = v[:]
+            for a, b in ces:
+                if w[a] > w[b]:
+                    w[a], w[b] = w[b], w[a]
+            assert w == sorted(v)
